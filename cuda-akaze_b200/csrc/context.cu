@@ -1,0 +1,651 @@
+// C ABI implementation: context, scale schedule, the batched detect+describe pipeline and the
+// matcher front end.  Replaces Akazer::{init,allocMemory,detect,detectAndCompute} (akaze.cpp:80-503)
+// and akaze::cuMatch (akaze.cpp:55-64); the per-frame host round trips of the reference (contrast
+// maximum, histogram, keypoint counter) are gone: every data-dependent scalar stays on the device.
+#include "common.cuh"
+#include "kernels.h"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <algorithm>
+
+// ---- errors ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+int akz_set_error(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int akz_set_cuda_error(cudaError_t e, const char* what, const char* file, int line)
+{
+    snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return AKZ_E_CUDA;
+}
+
+extern "C" {
+
+int akz_version(void) { return 100; }
+const char* akz_last_error(void) { return g_err; }
+
+void akz_default_options(akz_options* o)
+{
+    memset(o, 0, sizeof(*o));
+    o->width = 0; o->height = 0;
+    o->noctaves = 4; o->max_scale = 4; o->per = 0.7f; o->kcontrast = 0.03f; o->soffset = 1.6f; o->reordering = 1;
+    o->derivative_factor = 1.5f; o->dthreshold = 0.001f; o->diffusivity = 1; o->descriptor_pattern_size = 10;
+    o->max_pts = 10000; o->max_batch = 8; o->device = -1; o->kcontrast_override = 0.f; o->fused = 1;
+}
+
+// ---- host math ----------------------------------------------------------------------------------------
+static bool is_prime_int(int v)
+{
+    if (v <= 1) return false;
+    if (v == 2 || v == 3 || v == 5 || v == 7) return true;
+    if (!(v % 2) || !(v % 3) || !(v % 5) || !(v % 7)) return false;
+    int upper = (int)sqrt(v + 1.0);
+    for (int d = 11; d <= upper; d += 2)
+        if (v % d == 0) return false;
+    return true;
+}
+
+// FED cycle time steps (Grewenig/Weickert/Bruhn): the smallest n with a stable cycle of stopping time
+// T/M, tau_k = d / cos^2(pi (2k+1)/(4n+2)), optionally permuted by the kappa-cycle (kappa = n/2) modulo
+// the next prime >= n+1.  The float/double mix mirrors fed.cpp:48-76 so the values are bit-identical.
+int akz_fed_tau(float T, int M, float tau_max, int reordering, float* tau, int cap)
+{
+    const float t = T / (float)M;
+    const int n = (int)(ceil(sqrt(3.0 * t / tau_max + 0.25f) - 0.5f - 1.0e-8f) + 0.5f);
+    if (n <= 0) return 0;
+    if (n > cap) return -n;
+    const float scale = (float)(3.0 * t / (tau_max * (float)(n * (n + 1))));
+    const float c = 1.0f / (4.0f * (float)n + 2.0f);
+    const float d = scale * tau_max / 2.0f;
+    std::vector<float> plain(n);
+    for (int k = 0; k < n; ++k) {
+        const float hc = (float)cos(M_PI * (2.0f * (float)k + 1.0f) * c);
+        plain[k] = d / (hc * hc);
+    }
+    if (!reordering) {
+        std::copy(plain.begin(), plain.end(), tau);
+        return n;
+    }
+    const int kappa = n / 2;
+    int prime = n + 1;
+    while (!is_prime_int(prime)) prime++;
+    for (int k = 0, l = 0; l < n; ++k, ++l) {
+        int index;
+        while ((index = ((k + 1) * kappa) % prime - 1) >= n) k++;
+        tau[l] = plain[index];
+    }
+    return n;
+}
+
+void akz_gauss_taps(float var, int radius, float* k)
+{
+    const float denom = 1.f / (2.f * var);
+    float ksum = 0.f;
+    for (int i = 0; i <= radius; i++) {
+        k[i] = expf(-i * i * denom);
+        ksum += (i == 0) ? k[i] : k[i] + k[i];
+    }
+    ksum = 1 / ksum;
+    for (int i = 0; i <= radius; i++) k[i] *= ksum;
+}
+
+void akz_compare_indices(int* c1, int* c2)
+{
+    // three grids (2x2: cells 0..3, 3x3: 4..12, 4x4: 13..28) x three channels, all ordered pairs (j<i);
+    // a value lives at 3*cell + channel
+    static const int lo[3] = { 0, 4, 13 }, hi[3] = { 4, 13, 29 };
+    int n = 0;
+    for (int g = 0; g < 3; g++)
+        for (int ch = 0; ch < 3; ch++)
+            for (int j = lo[g]; j + 1 < hi[g]; j++)
+                for (int i = j + 1; i < hi[g]; i++) { c1[n] = 3 * j + ch; c2[n] = 3 * i + ch; n++; }
+}
+
+}  // extern "C"
+
+// ---- context -----------------------------------------------------------------------------------------
+struct akz_ctx {
+    akz_options opt;
+    int device;
+    cudaStream_t stream;
+    int nlev, noct, psz;
+    AkzLevel lev[AKZ_MAX_LEVELS];
+    float tau[AKZ_MAX_LEVELS * AKZ_MAX_STEPS];
+    int mpitch;
+    long long mplane;
+    // device memory
+    std::vector<void*> allocs;
+    float *smooth, *flow, *tmpA, *tmpB;
+    unsigned long long* map;
+    unsigned* rowmask;
+    int *rowcount, *prefix, *hist, *counts_own;
+    unsigned* hmax;
+    float* kc;
+    akz_keypoint* kpts_own;
+    unsigned char* desc_own;
+    void* img_stage;
+    size_t img_stage_bytes;
+    akz_match_t* match_parts;
+    size_t match_parts_n;
+    void* match_stage; size_t match_stage_bytes;
+    int last_frames;
+    long long launches;
+    AkzLevelTable tab;
+};
+
+template <typename T>
+static int dalloc(akz_ctx* c, T** p, size_t n)
+{
+    void* q = nullptr;
+    AKZ_CUDA_TRY(cudaMalloc(&q, n * sizeof(T)));
+    c->allocs.push_back(q);
+    *p = (T*)q;
+    return AKZ_OK;
+}
+
+static int align_up(int a, int b) { return (a % b) ? a - a % b + b : a; }
+
+// scale schedule: akaze.cpp:204-237 (octave sizes) and :268-363 (sigma, evolution times, FED steps,
+// derivative scales, borders)
+static int build_schedule(akz_ctx* c)
+{
+    const akz_options& o = c->opt;
+    int ow[16], oh[16];
+    ow[0] = o.width; oh[0] = o.height; c->noct = 1;
+    for (int j = 1; j < o.noctaves; j++) {
+        ow[j] = ow[j - 1] >> 1; oh[j] = oh[j - 1] >> 1;
+        if (ow[j] < 80 || oh[j] < 80) break;
+        c->noct = j + 1;
+    }
+    const int S = o.max_scale;
+    if (c->noct * S > AKZ_MAX_LEVELS) return akz_set_error(AKZ_E_INVALID, "too many levels");
+    float last_etime = (float)(0.5 * o.soffset * o.soffset);
+    const float smax = (float)(10.0 * sqrtf(2.0f));
+    float psz = 10000.f;
+    int oratio = 1, toff = 0;
+    c->nlev = 0;
+    for (int i = 0; i < c->noct; i++) {
+        for (int j = 0; j < S; j++) {
+            AkzLevel& L = c->lev[c->nlev++];
+            memset(&L, 0, sizeof(L));
+            L.octave = i; L.sub = j; L.w = ow[i]; L.h = oh[i]; L.pitch = align_up(ow[i], 32);
+            L.plane = (long long)L.pitch * L.h;
+            L.tau_off = toff;
+            if (i == 0 && j == 0) {
+                L.esigma = o.soffset;
+                L.size = o.soffset * o.derivative_factor;
+                L.nsteps = 0;
+            } else {
+                L.esigma = o.soffset * powf(2, (float)j / S + i);
+                const float cur = 0.5f * L.esigma * L.esigma;
+                const float ttime = cur - last_etime;
+                int n = akz_fed_tau(ttime, 1, 0.25f, o.reordering, c->tau + toff, AKZ_MAX_STEPS);
+                if (n < 0) return akz_set_error(AKZ_E_UNSUPPORTED, "FED cycle of %d steps exceeds %d", -n, AKZ_MAX_STEPS);
+                L.nsteps = n; toff += n;
+                L.size = L.esigma * o.derivative_factor / oratio;
+                last_etime = cur;
+            }
+            L.sigma_size = (int)(L.size + 0.5f);
+            L.border = smax * L.sigma_size;
+        }
+        psz = std::min(psz, c->lev[i * S].border * oratio);
+        oratio *= 2;
+    }
+    c->psz = (int)psz;
+    return AKZ_OK;
+}
+
+extern "C" {
+
+int akz_create(const akz_options* o, akz_ctx** out)
+{
+    if (!o || !out) return akz_set_error(AKZ_E_INVALID, "null argument");
+    const bool matcher_only = (o->width == 0 && o->height == 0);
+    if (!matcher_only && (o->width < 16 || o->height < 16 || o->width > 4096)) return akz_set_error(AKZ_E_INVALID, "frame size %dx%d unsupported", o->width, o->height);
+    if (o->max_scale < 1 || o->max_scale > 5 || o->noctaves < 1 || o->noctaves > 8) return akz_set_error(AKZ_E_INVALID, "octaves/sublevels out of range");
+    if (o->dthreshold < 0.f) return akz_set_error(AKZ_E_INVALID, "dthreshold must be >= 0");
+    if (o->max_pts < 1 || o->max_batch < 1) return akz_set_error(AKZ_E_INVALID, "max_pts / max_batch must be positive");
+    int ndev = 0;
+    AKZ_CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) return akz_set_error(AKZ_E_CUDA, "no CUDA device: this library has no CPU fallback");
+    akz_ctx* c = new akz_ctx();
+    c->opt = *o;
+    c->launches = 0; c->last_frames = 0;
+    c->img_stage = nullptr; c->img_stage_bytes = 0; c->match_parts = nullptr; c->match_parts_n = 0;
+    c->match_stage = nullptr; c->match_stage_bytes = 0;
+    int rc = AKZ_OK;
+    do {
+        if (o->device >= 0) { if (cudaSetDevice(o->device) != cudaSuccess) { rc = akz_set_error(AKZ_E_CUDA, "cudaSetDevice(%d) failed", o->device); break; } }
+        cudaGetDevice(&c->device);
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamDefault) != cudaSuccess) { rc = akz_set_error(AKZ_E_CUDA, "stream creation failed"); break; }
+        const int B = o->max_batch;
+        // small per-frame scalars: needed by the stage seams even without a pyramid
+        if ((rc = dalloc(c, &c->prefix, (size_t)2 * B + 2)) != AKZ_OK) break;
+        if ((rc = dalloc(c, &c->hist, (size_t)AKZ_NBINS * B)) != AKZ_OK) break;
+        if ((rc = dalloc(c, &c->hmax, (size_t)B)) != AKZ_OK) break;
+        if ((rc = dalloc(c, &c->kc, (size_t)B)) != AKZ_OK) break;
+        if (matcher_only) { c->nlev = 0; c->noct = 0; break; }
+        if ((rc = build_schedule(c)) != AKZ_OK) break;
+        for (int l = 0; l < c->nlev && rc == AKZ_OK; l++) {
+            AkzLevel& L = c->lev[l];
+            size_t n = (size_t)L.plane * B;
+            if ((rc = dalloc(c, &L.lt, n)) != AKZ_OK) break;
+            if ((rc = dalloc(c, &L.det, n)) != AKZ_OK) break;
+            if ((rc = dalloc(c, &L.lx, n)) != AKZ_OK) break;
+            if ((rc = dalloc(c, &L.ly, n)) != AKZ_OK) break;
+        }
+        if (rc != AKZ_OK) break;
+        size_t n0 = (size_t)c->lev[0].plane * B;
+        if ((rc = dalloc(c, &c->smooth, n0)) != AKZ_OK) break;
+        if ((rc = dalloc(c, &c->flow, n0)) != AKZ_OK) break;
+        if ((rc = dalloc(c, &c->tmpA, n0)) != AKZ_OK) break;
+        if ((rc = dalloc(c, &c->tmpB, n0)) != AKZ_OK) break;
+        c->mpitch = c->lev[0].pitch;
+        c->mplane = (long long)c->mpitch * o->height;
+        if ((rc = dalloc(c, &c->map, (size_t)c->mplane * B)) != AKZ_OK) break;
+        int mwords = (o->width + 31) / 32;
+        if ((rc = dalloc(c, &c->rowmask, (size_t)mwords * o->height * B)) != AKZ_OK) break;
+        if ((rc = dalloc(c, &c->rowcount, (size_t)o->height * B)) != AKZ_OK) break;
+        if ((rc = dalloc(c, &c->counts_own, (size_t)B)) != AKZ_OK) break;
+        if ((rc = dalloc(c, &c->kpts_own, (size_t)o->max_pts * B)) != AKZ_OK) break;
+        if ((rc = dalloc(c, &c->desc_own, (size_t)o->max_pts * B * 64)) != AKZ_OK) break;
+        cudaMemsetAsync(c->rowcount, 0, sizeof(int) * (size_t)o->height * B, c->stream);
+        cudaMemsetAsync(c->rowmask, 0, sizeof(unsigned) * (size_t)mwords * o->height * B, c->stream);
+        // level table for the keypoint kernels
+        memset(&c->tab, 0, sizeof(c->tab));
+        c->tab.nlevels = c->nlev; c->tab.max_scale = o->max_scale;
+        for (int l = 0; l < c->nlev; l++) {
+            const AkzLevel& L = c->lev[l];
+            AkzLevelDev& D = c->tab.lv[l];
+            D.lt = L.lt; D.det = L.det; D.lx = L.lx; D.ly = L.ly; D.plane = L.plane;
+            D.w = L.w; D.h = L.h; D.pitch = L.pitch; D.octave = L.octave; D.size = L.size;
+        }
+        akzk::orient_table_init(c->stream);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = akz_set_cuda_error(cudaGetLastError(), "context init", __FILE__, __LINE__); break; }
+    } while (0);
+    if (rc != AKZ_OK) { akz_destroy(c); return rc; }
+    *out = c;
+    return AKZ_OK;
+}
+
+void akz_destroy(akz_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->img_stage) cudaFree(c->img_stage);
+    if (c->match_parts) cudaFree(c->match_parts);
+    if (c->match_stage) cudaFree(c->match_stage);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int akz_sync(akz_ctx* c)
+{
+    AKZ_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    AKZ_CUDA_TRY(cudaGetLastError());
+    return AKZ_OK;
+}
+void* akz_stream(akz_ctx* c) { return (void*)c->stream; }
+int akz_num_levels(const akz_ctx* c) { return c->nlev; }
+int akz_launch_count(const akz_ctx* c) { return (int)c->launches; }
+
+int akz_level_info(const akz_ctx* c, int l, int* w, int* h, int* pitch, int* nsteps, float* size, int* sigma_size, float* tau, int cap)
+{
+    if (l < 0 || l >= c->nlev) return akz_set_error(AKZ_E_INVALID, "level out of range");
+    const AkzLevel& L = c->lev[l];
+    if (w) *w = L.w; if (h) *h = L.h; if (pitch) *pitch = L.pitch; if (nsteps) *nsteps = L.nsteps;
+    if (size) *size = L.size; if (sigma_size) *sigma_size = L.sigma_size;
+    if (tau) for (int i = 0; i < L.nsteps && i < cap; i++) tau[i] = c->tau[L.tau_off + i];
+    return AKZ_OK;
+}
+
+const float* akz_level_plane(const akz_ctx* c, int l, int which, int frame)
+{
+    if (l < 0 || l >= c->nlev || frame < 0 || frame >= c->opt.max_batch) return nullptr;
+    const AkzLevel& L = c->lev[l];
+    const float* b = which == AKZ_PLANE_LT ? L.lt : which == AKZ_PLANE_DET ? L.det : which == AKZ_PLANE_LX ? L.lx : L.ly;
+    return b + (long long)frame * L.plane;
+}
+
+}  // extern "C"
+
+// ---- pipeline ------------------------------------------------------------------------------------------
+#define LAUNCHED(expr) do { int r_ = (expr); if (r_ < 0) return r_; c->launches += r_; } while (0)
+
+static int check_frame_args(akz_ctx* c, const void* img, int dtype, int nframes, int w, int h, int pitch)
+{
+    if (!c || !img) return akz_set_error(AKZ_E_INVALID, "null argument");
+    if (dtype != AKZ_F32 && dtype != AKZ_U8) return akz_set_error(AKZ_E_INVALID, "dtype must be AKZ_F32 or AKZ_U8");
+    if (c->nlev == 0) return akz_set_error(AKZ_E_INVALID, "matcher-only context");
+    if (w != c->opt.width || h != c->opt.height) return akz_set_error(AKZ_E_INVALID, "frame size %dx%d differs from the context's %dx%d", w, h, c->opt.width, c->opt.height);
+    if (pitch < w || nframes < 0) return akz_set_error(AKZ_E_INVALID, "bad pitch or frame count");
+    return AKZ_OK;
+}
+
+static int scale_space_chunk(akz_ctx* c, const void* img, int dtype, int nf, int ipitch, long long istride)
+{
+    cudaStream_t st = c->stream;
+    const akz_options& o = c->opt;
+    const int S = o.max_scale, fused = o.fused;
+    AkzLevel& L0 = c->lev[0];
+    const int w0 = L0.w, h0 = L0.h, p0 = L0.pitch;
+    // level (0,0): akaze.cpp:325-346
+    const float var0 = o.soffset * o.soffset;
+    const int ksz0 = (int)(2 * ceilf((o.soffset - 0.8f) / 0.3f) + 3);
+    if (dtype == AKZ_U8) {
+        if (!(o.kcontrast_override > 0.f))
+            LAUNCHED(akzk::lowpass_u8(st, (const unsigned char*)img, c->smooth, w0, h0, ipitch, istride, p0, L0.plane, nf, 1.f, 5));
+        LAUNCHED(akzk::lowpass_u8(st, (const unsigned char*)img, L0.lt, w0, h0, ipitch, istride, p0, L0.plane, nf, var0, ksz0));
+    } else {
+        if (!(o.kcontrast_override > 0.f))
+            LAUNCHED(akzk::lowpass(st, (const float*)img, c->smooth, w0, h0, ipitch, istride, p0, L0.plane, nf, 1.f, 5));
+        LAUNCHED(akzk::lowpass(st, (const float*)img, L0.lt, w0, h0, ipitch, istride, p0, L0.plane, nf, var0, ksz0));
+    }
+    LAUNCHED(akzk::contrast(st, c->smooth, c->hmax, c->hist, c->kc, o.per, o.kcontrast_override, w0, h0, p0, L0.plane, nf));
+    if (fused) LAUNCHED(akzk::level_prep(st, L0.lt, nullptr, L0.lx, L0.ly, L0.det, 0, o.diffusivity, c->kc, 0.75f, 0, L0.sigma_size, w0, h0, p0, L0.plane, nf));
+    else LAUNCHED(akzk::hessian(st, L0.lt, L0.lx, L0.ly, L0.det, L0.sigma_size, w0, h0, p0, L0.plane, nf));
+
+    for (int l = 1; l < c->nlev; l++) {
+        AkzLevel& L = c->lev[l];
+        const float* tau = c->tau + L.tau_off;
+        const int w = L.w, h = L.h, p = L.pitch;
+        if (L.sub == 0) {
+            // new octave (akaze.cpp:371-392): source is sublevel 0 of the previous octave; kcontrast *= 0.75
+            AkzLevel& P = c->lev[l - S];
+            if (fused) {
+                LAUNCHED(akzk::level_prep_down(st, P.lt, P.w, P.h, P.pitch, P.plane, c->tmpB, c->flow, L.lx, L.ly, L.det, o.diffusivity,
+                                               c->kc, 0.75f, L.octave, L.sigma_size, w, h, p, L.plane, nf));
+            } else {
+                LAUNCHED(akzk::down_with_smooth(st, P.lt, c->tmpB, c->smooth, P.w, P.h, P.pitch, P.plane, w, h, p, L.plane, nf));
+                LAUNCHED(akzk::flow(st, c->smooth, c->flow, o.diffusivity, c->kc, 0.75f, L.octave, w, h, p, L.plane, nf));
+            }
+            LAUNCHED(akzk::fed_cycle(st, c->tmpB, c->flow, L.lt, c->tmpA, tau, L.nsteps, w, h, p, L.plane, nf, fused));
+        } else {
+            // next sublevel (akaze.cpp:393-421)
+            AkzLevel& P = c->lev[l - 1];
+            if (fused) {
+                LAUNCHED(akzk::level_prep(st, P.lt, c->flow, L.lx, L.ly, L.det, 1, o.diffusivity, c->kc, 0.75f, L.octave, L.sigma_size, w, h, p, L.plane, nf));
+            } else {
+                LAUNCHED(akzk::lowpass(st, P.lt, c->smooth, w, h, p, L.plane, p, L.plane, nf, 1.f, 5));
+                LAUNCHED(akzk::flow(st, c->smooth, c->flow, o.diffusivity, c->kc, 0.75f, L.octave, w, h, p, L.plane, nf));
+            }
+            LAUNCHED(akzk::fed_cycle(st, P.lt, c->flow, L.lt, c->tmpA, tau, L.nsteps, w, h, p, L.plane, nf, fused));
+        }
+        if (!fused) LAUNCHED(akzk::hessian(st, c->smooth, L.lx, L.ly, L.det, L.sigma_size, w, h, p, L.plane, nf));   // akaze.cpp:423
+    }
+    c->last_frames = nf;
+    return AKZ_OK;
+}
+
+static int detect_chunk(akz_ctx* c, int nf, int describe, int* d_counts, akz_keypoint* d_kpts, unsigned char* d_desc)
+{
+    cudaStream_t st = c->stream;
+    const akz_options& o = c->opt;
+    const int S = o.max_scale;
+    AKZ_CUDA_TRY(cudaMemsetAsync(c->map, 0, sizeof(unsigned long long) * (size_t)c->mplane * nf, st));
+    for (int oc = 0; oc < c->noct; oc++) {
+        AkzExtremaArgs a;
+        memset(&a, 0, sizeof(a));
+        const AkzLevel& F = c->lev[oc * S];
+        a.nsub = S; a.w = F.w; a.h = F.h; a.pitch = F.pitch; a.octave = oc; a.psz = (int)F.border;     // akazed.cu:2571
+        for (int j = 0; j < S; j++) {
+            const AkzLevel& L = c->lev[oc * S + j];
+            a.lv[j].det = L.det; a.lv[j].plane = L.plane; a.lv[j].border = L.border; a.lv[j].threshold = o.dthreshold;
+            a.lv[j].layer = oc * S + j;
+        }
+        LAUNCHED(akzk::extrema(st, a, c->map, c->mpitch, c->mplane, nf));
+    }
+    LAUNCHED(akzk::nms_emit(st, c->map, c->mpitch, c->mplane, o.width, o.height, c->psz, c->tab, c->rowmask, c->rowcount,
+                            d_counts, c->prefix, d_kpts, o.max_pts, nf));
+    if (describe) {
+        LAUNCHED(akzk::orient(st, c->tab, d_counts, c->prefix, d_kpts, o.max_pts, nf));
+        LAUNCHED(akzk::describe(st, c->tab, d_counts, c->prefix, d_kpts, d_desc, o.max_pts, nf, o.descriptor_pattern_size));
+    }
+    return AKZ_OK;
+}
+
+extern "C" {
+
+int akz_build_scale_space(akz_ctx* c, const void* d_images, int dtype, int nframes, int w, int h, int pitch, long long stride)
+{
+    int rc = check_frame_args(c, d_images, dtype, nframes, w, h, pitch);
+    if (rc != AKZ_OK) return rc;
+    if (nframes > c->opt.max_batch) return akz_set_error(AKZ_E_INVALID, "nframes exceeds max_batch");
+    AKZ_CUDA_TRY(cudaSetDevice(c->device));
+    rc = scale_space_chunk(c, d_images, dtype, nframes, pitch, stride);
+    if (rc != AKZ_OK) return rc;
+    AKZ_CUDA_TRY(cudaGetLastError());
+    return AKZ_OK;
+}
+
+int akz_get_kcontrast(akz_ctx* c, float* h_k, int nframes)
+{
+    AKZ_CUDA_TRY(cudaMemcpyAsync(h_k, c->kc, sizeof(float) * nframes, cudaMemcpyDeviceToHost, c->stream));
+    return akz_sync(c);
+}
+
+int akz_detect_and_compute(akz_ctx* c, const void* d_images, int dtype, int nframes, int w, int h, int pitch, long long stride,
+                           int describe, int* d_counts, akz_keypoint* d_kpts, uint8_t* d_desc)
+{
+    int rc = check_frame_args(c, d_images, dtype, nframes, w, h, pitch);
+    if (rc != AKZ_OK) return rc;
+    if (!d_counts || !d_kpts || (describe && !d_desc)) return akz_set_error(AKZ_E_INVALID, "null result buffer");
+    AKZ_CUDA_TRY(cudaSetDevice(c->device));
+    const int B = c->opt.max_batch;
+    const size_t esz = dtype == AKZ_U8 ? 1 : 4;
+    for (int f0 = 0; f0 < nframes; f0 += B) {
+        int nf = std::min(B, nframes - f0);
+        const char* img = (const char*)d_images + (size_t)f0 * stride * esz;
+        if ((rc = scale_space_chunk(c, img, dtype, nf, pitch, stride)) != AKZ_OK) return rc;
+        if ((rc = detect_chunk(c, nf, describe, d_counts + f0, d_kpts + (size_t)f0 * c->opt.max_pts,
+                               d_desc ? d_desc + (size_t)f0 * c->opt.max_pts * 64 : nullptr)) != AKZ_OK) return rc;
+    }
+    AKZ_CUDA_TRY(cudaGetLastError());
+    return AKZ_OK;
+}
+
+int akz_detect_and_compute_host(akz_ctx* c, const void* h_images, int dtype, int nframes, int w, int h, int pitch, long long stride,
+                                int describe, int* h_counts, akz_keypoint* h_kpts, uint8_t* h_desc)
+{
+    int rc = check_frame_args(c, h_images, dtype, nframes, w, h, pitch);
+    if (rc != AKZ_OK) return rc;
+    if (!h_counts || !h_kpts || (describe && !h_desc)) return akz_set_error(AKZ_E_INVALID, "null result buffer");
+    AKZ_CUDA_TRY(cudaSetDevice(c->device));
+    const int B = c->opt.max_batch, MP = c->opt.max_pts;
+    const size_t esz = dtype == AKZ_U8 ? 1 : 4;
+    const size_t need = (size_t)B * stride * esz;
+    if (c->img_stage_bytes < need) {
+        if (c->img_stage) cudaFree(c->img_stage);
+        c->img_stage = nullptr; c->img_stage_bytes = 0;
+        AKZ_CUDA_TRY(cudaMalloc(&c->img_stage, need));
+        c->img_stage_bytes = need;
+    }
+    cudaStream_t st = c->stream;
+    for (int f0 = 0; f0 < nframes; f0 += B) {
+        int nf = std::min(B, nframes - f0);
+        const char* src = (const char*)h_images + (size_t)f0 * stride * esz;
+        AKZ_CUDA_TRY(cudaMemcpyAsync(c->img_stage, src, (size_t)nf * stride * esz, cudaMemcpyHostToDevice, st));
+        if ((rc = scale_space_chunk(c, c->img_stage, dtype, nf, pitch, stride)) != AKZ_OK) return rc;
+        if ((rc = detect_chunk(c, nf, describe, c->counts_own, c->kpts_own, c->desc_own)) != AKZ_OK) return rc;
+        AKZ_CUDA_TRY(cudaMemcpyAsync(h_counts + f0, c->counts_own, sizeof(int) * nf, cudaMemcpyDeviceToHost, st));
+        AKZ_CUDA_TRY(cudaStreamSynchronize(st));
+        for (int f = 0; f < nf; f++) {
+            int n = h_counts[f0 + f];
+            if (n <= 0) continue;
+            AKZ_CUDA_TRY(cudaMemcpyAsync(h_kpts + (size_t)(f0 + f) * MP, c->kpts_own + (size_t)f * MP, sizeof(akz_keypoint) * n, cudaMemcpyDeviceToHost, st));
+            if (describe)
+                AKZ_CUDA_TRY(cudaMemcpyAsync(h_desc + (size_t)(f0 + f) * MP * 64, c->desc_own + (size_t)f * MP * 64, (size_t)64 * n, cudaMemcpyDeviceToHost, st));
+        }
+        AKZ_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    AKZ_CUDA_TRY(cudaGetLastError());
+    return AKZ_OK;
+}
+
+// ---- stage seams ------------------------------------------------------------------------------------------
+#define STAGE_PROLOGUE() do { if (!c) return akz_set_error(AKZ_E_INVALID, "null context"); AKZ_CUDA_TRY(cudaSetDevice(c->device)); } while (0)
+#define STAGE_EPILOGUE() do { AKZ_CUDA_TRY(cudaGetLastError()); return AKZ_OK; } while (0)
+
+int akz_lowpass(akz_ctx* c, const float* src, float* dst, int w, int h, int pitch, long long stride, int n, float var, int ksz)
+{
+    STAGE_PROLOGUE();
+    LAUNCHED(akzk::lowpass(c->stream, src, dst, w, h, pitch, stride, pitch, stride, n, var, ksz));
+    STAGE_EPILOGUE();
+}
+
+int akz_down_with_smooth(akz_ctx* c, const float* src, float* dst, float* smooth, int sw, int sh, int sp, long long sstride,
+                         int dw, int dh, int dp, long long dstride, int n)
+{
+    STAGE_PROLOGUE();
+    LAUNCHED(akzk::down_with_smooth(c->stream, src, dst, smooth, sw, sh, sp, sstride, dw, dh, dp, dstride, n));
+    STAGE_EPILOGUE();
+}
+
+int akz_scharr_contrast(akz_ctx* c, const float* src, float* d_k, float per, int w, int h, int pitch, long long stride, int n)
+{
+    STAGE_PROLOGUE();
+    if (n > c->opt.max_batch) return akz_set_error(AKZ_E_INVALID, "nframes exceeds max_batch");
+    LAUNCHED(akzk::contrast(c->stream, src, c->hmax, c->hist, d_k, per, 0.f, w, h, pitch, stride, n));
+    STAGE_EPILOGUE();
+}
+
+int akz_flow(akz_ctx* c, const float* src, float* flow, int type, const float* d_k, float kscale, int w, int h, int pitch, long long stride, int n)
+{
+    STAGE_PROLOGUE();
+    LAUNCHED(akzk::flow(c->stream, src, flow, type, d_k, kscale, 1, w, h, pitch, stride, n));
+    STAGE_EPILOGUE();
+}
+
+int akz_nld_step(akz_ctx* c, const float* src, const float* flow, float* dst, float tau, int w, int h, int pitch, long long stride, int n)
+{
+    STAGE_PROLOGUE();
+    LAUNCHED(akzk::nld_step(c->stream, src, flow, dst, tau, w, h, pitch, stride, n));
+    STAGE_EPILOGUE();
+}
+
+int akz_fed_cycle(akz_ctx* c, const float* src, const float* flow, float* dst, float* tmp, const float* tau, int nsteps,
+                  int w, int h, int pitch, long long stride, int n)
+{
+    STAGE_PROLOGUE();
+    if (src == dst || src == tmp || dst == tmp) return akz_set_error(AKZ_E_INVALID, "src, dst and tmp must be distinct");
+    LAUNCHED(akzk::fed_cycle(c->stream, src, flow, dst, tmp, tau, nsteps, w, h, pitch, stride, n, c->opt.fused));
+    STAGE_EPILOGUE();
+}
+
+int akz_hessian(akz_ctx* c, const float* smooth, float* lx, float* ly, float* det, int step, int w, int h, int pitch, long long stride, int n)
+{
+    STAGE_PROLOGUE();
+    if (c->opt.fused) LAUNCHED(akzk::level_prep(c->stream, smooth, nullptr, lx, ly, det, 0, 1, c->kc, 1.f, 0, step, w, h, pitch, stride, n));
+    else LAUNCHED(akzk::hessian(c->stream, smooth, lx, ly, det, step, w, h, pitch, stride, n));
+    STAGE_EPILOGUE();
+}
+
+int akz_orient(akz_ctx* c, const int* d_counts, akz_keypoint* d_kpts, int n)
+{
+    STAGE_PROLOGUE();
+    if (n < 1 || n > c->opt.max_batch || c->nlev == 0) return akz_set_error(AKZ_E_INVALID, "bad frame count");
+    LAUNCHED(akzk::frame_prefix(c->stream, d_counts, c->prefix, n));
+    LAUNCHED(akzk::orient(c->stream, c->tab, d_counts, c->prefix, d_kpts, c->opt.max_pts, n));
+    STAGE_EPILOGUE();
+}
+
+int akz_describe(akz_ctx* c, const int* d_counts, const akz_keypoint* d_kpts, uint8_t* d_desc, int n)
+{
+    STAGE_PROLOGUE();
+    if (n < 1 || n > c->opt.max_batch || c->nlev == 0) return akz_set_error(AKZ_E_INVALID, "bad frame count");
+    LAUNCHED(akzk::frame_prefix(c->stream, d_counts, c->prefix, n));
+    LAUNCHED(akzk::describe(c->stream, c->tab, d_counts, c->prefix, d_kpts, d_desc, c->opt.max_pts, n, c->opt.descriptor_pattern_size));
+    STAGE_EPILOGUE();
+}
+
+int akz_detect_keypoints(akz_ctx* c, int n, int* d_counts, akz_keypoint* d_kpts)
+{
+    STAGE_PROLOGUE();
+    if (n < 1 || n > c->opt.max_batch || c->nlev == 0) return akz_set_error(AKZ_E_INVALID, "bad frame count");
+    int rc = detect_chunk(c, n, 0, d_counts, d_kpts, nullptr);
+    if (rc != AKZ_OK) return rc;
+    STAGE_EPILOGUE();
+}
+
+// ---- matcher ----------------------------------------------------------------------------------------------
+int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int t_index_base, int mode, int finalize, akz_match_t* d_out)
+{
+    STAGE_PROLOGUE();
+    if (mode != AKZ_MATCH_COMPAT && mode != AKZ_MATCH_KNN2) return akz_set_error(AKZ_E_INVALID, "bad matcher mode");
+    if (nq < 0 || nt < 0 || !d_out) return akz_set_error(AKZ_E_INVALID, "bad matcher arguments");
+    if (nq == 0) return AKZ_OK;
+    int qblocks = (nq + 127) / 128;
+    int nsplit = std::max(1, std::min((2 * 148 + qblocks - 1) / qblocks, (nt + 127) / 128));
+    size_t need = (size_t)nsplit * nq;
+    if (c->match_parts_n < need) {
+        if (c->match_parts) { cudaStreamSynchronize(c->stream); cudaFree(c->match_parts); }
+        c->match_parts = nullptr; c->match_parts_n = 0;
+        AKZ_CUDA_TRY(cudaMalloc((void**)&c->match_parts, need * sizeof(akz_match_t)));
+        c->match_parts_n = need;
+    }
+    LAUNCHED(akzk::match_partial(c->stream, d_q, nq, d_t, nt, t_index_base, mode, nsplit, c->match_parts));
+    LAUNCHED(akzk::match_merge(c->stream, c->match_parts, nsplit, nq, mode, finalize, d_out));
+    STAGE_EPILOGUE();
+}
+
+int akz_match_merge(akz_ctx* c, const akz_match_t* d_parts, int nparts, int nq, int mode, int finalize, akz_match_t* d_out)
+{
+    STAGE_PROLOGUE();
+    LAUNCHED(akzk::match_merge(c->stream, d_parts, nparts, nq, mode, finalize, d_out));
+    STAGE_EPILOGUE();
+}
+
+int akz_match_host(akz_ctx* c, const uint8_t* h_q, int nq, const uint8_t* h_t, int nt, int mode, akz_match_t* h_out)
+{
+    STAGE_PROLOGUE();
+    if (nq <= 0) return AKZ_OK;
+    size_t need = (size_t)(nq + nt) * 64 + (size_t)nq * sizeof(akz_match_t);
+    if (c->match_stage_bytes < need) {
+        if (c->match_stage) { cudaStreamSynchronize(c->stream); cudaFree(c->match_stage); }
+        c->match_stage = nullptr; c->match_stage_bytes = 0;
+        AKZ_CUDA_TRY(cudaMalloc(&c->match_stage, need));
+        c->match_stage_bytes = need;
+    }
+    uint8_t* dq = (uint8_t*)c->match_stage;
+    uint8_t* dt = dq + (size_t)nq * 64;
+    akz_match_t* dm = (akz_match_t*)(dt + (size_t)nt * 64);
+    AKZ_CUDA_TRY(cudaMemcpyAsync(dq, h_q, (size_t)nq * 64, cudaMemcpyHostToDevice, c->stream));
+    if (nt > 0) AKZ_CUDA_TRY(cudaMemcpyAsync(dt, h_t, (size_t)nt * 64, cudaMemcpyHostToDevice, c->stream));
+    int rc = akz_match(c, dq, nq, dt, nt, 0, mode, 1, dm);
+    if (rc != AKZ_OK) return rc;
+    AKZ_CUDA_TRY(cudaMemcpyAsync(h_out, dm, (size_t)nq * sizeof(akz_match_t), cudaMemcpyDeviceToHost, c->stream));
+    return akz_sync(c);
+}
+
+// ---- AoS bridge -----------------------------------------------------------------------------------------------
+int akz_pack_points(akz_ctx* c, const int* d_count, const akz_keypoint* d_kpts, const uint8_t* d_desc, void* d_points, int max_pts, int with_desc)
+{
+    STAGE_PROLOGUE();
+    LAUNCHED(akzk::pack_points(c->stream, d_count, d_kpts, d_desc, d_points, max_pts, with_desc));
+    STAGE_EPILOGUE();
+}
+int akz_unpack_desc(akz_ctx* c, const void* d_points, int n, uint8_t* d_desc)
+{
+    STAGE_PROLOGUE();
+    LAUNCHED(akzk::unpack_desc(c->stream, d_points, n, d_desc));
+    STAGE_EPILOGUE();
+}
+int akz_scatter_matches(akz_ctx* c, const akz_match_t* d_m, int nq, void* d_points_q, const void* d_points_t)
+{
+    STAGE_PROLOGUE();
+    LAUNCHED(akzk::scatter_matches(c->stream, d_m, nq, d_points_q, d_points_t));
+    STAGE_EPILOGUE();
+}
+
+}  // extern "C"

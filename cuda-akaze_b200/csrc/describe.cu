@@ -1,0 +1,322 @@
+// Dominant orientation and the 486-bit M-LDB descriptor, plus the AoS bridge for the akaze.h shim.
+// Reference: gCalcOrient (akazed.cu:1665-1736), dFastAtan2 (:173-185), gDescribe2 (:1869-2001),
+// comparison tables (:65-159), AkazePoint layout (akaze_structures.h:19-39).
+#include "common.cuh"
+#include "kernels.h"
+#include <math_constants.h>
+
+using namespace akz;
+
+namespace {
+
+// ---- orientation sample table: the 109 (i,j) of the 13x16 thread grid with i*i+j*j < 36, in thread
+// order, and their weights exp(-r2*0.08f) evaluated ON THE DEVICE with the same expf the reference uses
+__device__ float g_orient_w[36];            // weight by r2
+__device__ signed char g_orient_ij[128][2]; // (i, j) by sample rank; 109 valid
+__device__ int g_orient_n;
+
+__global__ void k_orient_table()
+{
+    if (threadIdx.x < 36) {
+        int r2 = threadIdx.x;
+        g_orient_w[r2] = exp(-r2 * 0.08f);                       // akazed.cu:1697
+    }
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int t = 0; t < 208; t++) {
+            int i = (t & 15) - 6, j = (t / 16) - 6;                // akazed.cu:1692-1693
+            if (i * i + j * j < 36) { g_orient_ij[n][0] = (signed char)i; g_orient_ij[n][1] = (signed char)j; n++; }
+        }
+        g_orient_n = n;
+    }
+}
+
+__device__ __forceinline__ float fast_atan2(float y, float x)     // akazed.cu:173-185
+{
+    const float absx = fabsf(x), absy = fabsf(y);
+    const float a = __fdiv_rn(fminf(absx, absy), fmaxf(absx, absy));
+    const float s = a * a;
+    float r = __fmaf_rn(__fmaf_rn(__fmaf_rn(-0.0464964749f, s, 0.15931422f), s, -0.327622764f), s * a, a);
+    r = (absy > absx ? 1.5707963267948966f - r : r);
+    r = (x < 0 ? (float)(3.14159265358979323846 - r) : r);
+    r = (y < 0 ? -r : r);
+    return r;
+}
+
+// locate keypoint g of the chunk: frame by linear search over the prefix (n <= a few dozen)
+__device__ __forceinline__ int find_frame(const int* __restrict__ prefix, int n, int g)
+{
+    int f = 0;
+    while (f + 1 < n && g >= prefix[f + 1]) f++;
+    return f;
+}
+
+constexpr int ORI_WARPS = 4;
+
+// one warp per keypoint; bins are summed in ascending sample order => deterministic (App. B-4)
+__global__ void __launch_bounds__(ORI_WARPS * 32) k_orient(const __grid_constant__ AkzLevelTable tab, const int* __restrict__ prefix, int nframes,
+                                                          akz_keypoint* __restrict__ kpts, int max_pts)
+{
+    __shared__ float4 s_samp[ORI_WARPS][128];
+    __shared__ float s_res[ORI_WARPS][2][64];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int total = prefix[nframes];
+    for (int g = blockIdx.x * ORI_WARPS + wid; g < total; g += gridDim.x * ORI_WARPS) {
+        int frame = find_frame(prefix, nframes, g);
+        akz_keypoint* kp = kpts + (long long)frame * max_pts + (g - prefix[frame]);
+        const AkzLevelDev& L = tab.lv[kp->layer];
+        int o = L.octave, p = L.pitch;
+        const float* lx = L.lx + (long long)frame * L.plane;
+        const float* ly = L.ly + (long long)frame * L.plane;
+        int step = (int)__fadd_rn(kp->size, 0.5f);
+        int x = (int)__fadd_rn(kp->x, 0.5f) >> o;
+        int y = (int)__fadd_rn(kp->y, 0.5f) >> o;
+        for (int s = lane; s < 128; s += 32) {
+            float4 v = make_float4(0.f, 0.f, __int_as_float(-1), 0.f);
+            if (s < 109) {
+                int i = g_orient_ij[s][0], j = g_orient_ij[s][1];
+                float gw = g_orient_w[i * i + j * j];
+                int yy = min(max(y + step * j, 0), L.h - 1), xx = min(max(x + step * i, 0), L.w - 1);
+                long long pos = (long long)yy * p + xx;
+                float dx = gw * __ldg(lx + pos);
+                float dy = gw * __ldg(ly + pos);
+                float ang = atan2f(dy, dx);
+                int a = max(min((int)(ang * (21 / 3.14159265358979323846)) + 21, 41), 0);   // akazed.cu:1702
+                v = make_float4(dx, dy, __int_as_float(a), 0.f);
+            }
+            s_samp[wid][s] = v;
+        }
+        __syncwarp();
+        // lane b owns bins b and b+32
+        float ax = 0.f, ay = 0.f, bx = 0.f, by = 0.f;
+        for (int s = 0; s < 109; s++) {
+            float4 v = s_samp[wid][s];
+            int a = __float_as_int(v.z);
+            if (a == lane) { ax = __fadd_rn(ax, v.x); ay = __fadd_rn(ay, v.y); }
+            if (a == lane + 32) { bx = __fadd_rn(bx, v.x); by = __fadd_rn(by, v.y); }
+        }
+        s_res[wid][0][lane] = ax; s_res[wid][1][lane] = ay;
+        s_res[wid][0][lane + 32] = bx; s_res[wid][1][lane + 32] = by;
+        __syncwarp();
+        // sliding window of 7 bins (akazed.cu:1708-1718), two windows per lane (k = lane, lane+32 < 42)
+        float best = -1.f, wx0 = 0.f, wy0 = 0.f;
+        int bestk = 0;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            int k = lane + 32 * half;
+            if (k < 42) {
+                float sx = s_res[wid][0][k], sy = s_res[wid][1][k];
+                for (int q = k + 1; q < k + 7; q++) {
+                    int qq = q < 42 ? q : q - 42;
+                    sx = __fadd_rn(sx, s_res[wid][0][qq]);
+                    sy = __fadd_rn(sy, s_res[wid][1][qq]);
+                }
+                float r = __fmaf_rn(sx, sx, __fmul_rn(sy, sy));
+                if (r > best) { best = r; bestk = k; wx0 = sx; wy0 = sy; }
+            }
+        }
+        // arg-max with "first strictly greater wins" (akazed.cu:1723-1733): larger r, then smaller k
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            float ob = __shfl_xor_sync(0xffffffffu, best, d);
+            int ok = __shfl_xor_sync(0xffffffffu, bestk, d);
+            float ox = __shfl_xor_sync(0xffffffffu, wx0, d);
+            float oy = __shfl_xor_sync(0xffffffffu, wy0, d);
+            if (ob > best || (ob == best && ok < bestk)) { best = ob; bestk = ok; wx0 = ox; wy0 = oy; }
+        }
+        if (lane == 0) {
+            // maxr starts at 0 and the test is '>': when every window is zero the reference keeps k = 0
+            if (!(best > 0.f)) {
+                float sx = s_res[wid][0][0], sy = s_res[wid][1][0];
+                for (int q = 1; q < 7; q++) { sx = __fadd_rn(sx, s_res[wid][0][q]); sy = __fadd_rn(sy, s_res[wid][1][q]); }
+                wx0 = sx; wy0 = sy;
+            }
+            float ang = fast_atan2(wy0, wx0);
+            kp->angle = (ang < 0.0f ? (float)(ang + 2.0f * 3.14159265358979323846) : ang);
+        }
+        __syncwarp();
+    }
+}
+
+// ---- M-LDB -------------------------------------------------------------------------------------------
+__constant__ short c_cmp[2][488];
+
+// 64 threads per keypoint exactly as the reference lays the work out; the per-thread accumulation
+// order and the reduction tree decide the bits, so both are kept (SURVEY A-13):
+//   a_t = acc_t + acc_{t+32} (t = 0..31), then the shuffle-down tree 1,2,4,8,16 -> lane 0.
+// Accumulators are stored value-major ([90][64]) so neighbouring threads hit different banks.
+__global__ void __launch_bounds__(64) k_describe(const __grid_constant__ AkzLevelTable tab, const int* __restrict__ prefix, int nframes,
+                                                 const akz_keypoint* __restrict__ kpts, unsigned char* __restrict__ desc,
+                                                 int max_pts, int size2, int size3, int size4)
+{
+    __shared__ float acc[90][64];
+    __shared__ float val[96];
+    int tix = threadIdx.x;
+    int total = prefix[nframes];
+    for (int g = blockIdx.x; g < total; g += gridDim.x) {
+        int frame = find_frame(prefix, nframes, g);
+        int local = g - prefix[frame];
+        const akz_keypoint* kp = kpts + (long long)frame * max_pts + local;
+        const AkzLevelDev& L = tab.lv[kp->layer];
+        int o = L.octave, p = L.pitch;
+        float iratio = 1.f / (1 << o);
+        int scale = (int)__fadd_rn(kp->size, 0.5f);
+        float xf = __fmul_rn(kp->x, iratio), yf = __fmul_rn(kp->y, iratio);
+        float ang = kp->angle;
+        float co = __cosf(ang), si = __sinf(ang);
+        const float* imd = L.lt + (long long)frame * L.plane;
+        const float* dxd = L.lx + (long long)frame * L.plane;
+        const float* dyd = L.ly + (long long)frame * L.plane;
+        int win = max(3 * size3, 4 * size4);
+#pragma unroll 6
+        for (int v = 0; v < 90; v++) acc[v][tix] = 0.f;
+        float fscale = (float)scale;
+        for (int i = tix; i < win * win; i += 64) {
+            int y = i / win, x = i - win * y, m = max(x, y);
+            if (m >= win) continue;
+            float l = (float)(x - size2), k = (float)(y - size2);
+            int xp = (int)__fadd_rn(__fmaf_rn(fscale, __fmaf_rn(co, k, -__fmul_rn(si, l)), xf), 0.5f);
+            int yp = (int)__fadd_rn(__fmaf_rn(fscale, __fmaf_rn(si, k, __fmul_rn(co, l)), yf), 0.5f);
+            xp = min(max(xp, 0), L.w - 1); yp = min(max(yp, 0), L.h - 1);       // no-op for in-range patches (border test)
+            long long pos = (long long)yp * p + xp;
+            float im = __ldg(imd + pos), dx = __ldg(dxd + pos), dy = __ldg(dyd + pos);
+            float rx = __fmaf_rn(co, dy, -__fmul_rn(si, dx));
+            float ry = __fmaf_rn(co, dx, __fmul_rn(si, dy));
+            if (m < 2 * size2) {
+                int c = 3 * ((y < size2 ? 0 : 1) * 2 + (x < size2 ? 0 : 1));
+                acc[c][tix] = __fadd_rn(acc[c][tix], im); acc[c + 1][tix] = __fadd_rn(acc[c + 1][tix], rx); acc[c + 2][tix] = __fadd_rn(acc[c + 2][tix], ry);
+            }
+            if (m < 3 * size3) {
+                int x3 = (x < size3 ? 0 : (x < 2 * size3 ? 1 : 2)), y3 = (y < size3 ? 0 : (y < 2 * size3 ? 1 : 2));
+                int c = 3 * (4 + y3 * 3 + x3);
+                acc[c][tix] = __fadd_rn(acc[c][tix], im); acc[c + 1][tix] = __fadd_rn(acc[c + 1][tix], rx); acc[c + 2][tix] = __fadd_rn(acc[c + 2][tix], ry);
+            }
+            if (m < 4 * size4) {
+                int x4 = (x < 2 * size4 ? (x < size4 ? 0 : 1) : (x < 3 * size4 ? 2 : 3));
+                int y4 = (y < 2 * size4 ? (y < size4 ? 0 : 1) : (y < 3 * size4 ? 2 : 3));
+                int c = 3 * (13 + y4 * 4 + x4);
+                acc[c][tix] = __fadd_rn(acc[c][tix], im); acc[c + 1][tix] = __fadd_rn(acc[c + 1][tix], rx); acc[c + 2][tix] = __fadd_rn(acc[c + 2][tix], ry);
+            }
+        }
+        __syncthreads();
+        // warp w reduces the values v = w, w+2, ...
+        int lane = tix & 31, w = tix >> 5;
+        for (int v = w; v < 87; v += 2) {
+            float a = __fadd_rn(acc[v][lane], acc[v][lane + 32]);
+            a = __fadd_rn(a, __shfl_down_sync(0xffffffffu, a, 1));
+            a = __fadd_rn(a, __shfl_down_sync(0xffffffffu, a, 2));
+            a = __fadd_rn(a, __shfl_down_sync(0xffffffffu, a, 4));
+            a = __fadd_rn(a, __shfl_down_sync(0xffffffffu, a, 8));
+            a = __fadd_rn(a, __shfl_down_sync(0xffffffffu, a, 16));
+            if (lane == 0) val[v] = a;
+        }
+        __syncthreads();
+        unsigned char* out = desc + ((long long)frame * max_pts + local) * 64;
+        unsigned r = 0;
+        if (tix < 61) {
+            int nb = (tix == 60 ? 6 : 8);
+            for (int i = 0; i < nb; i++)
+                r |= (val[c_cmp[0][tix * 8 + i]] > val[c_cmp[1][tix * 8 + i]] ? 1u : 0u) << i;
+        }
+        out[tix] = (unsigned char)r;                      // bytes 61..63 are written as zero
+        __syncthreads();
+    }
+}
+
+// ---- AoS bridge: reference AkazePoint (104 B) ------------------------------------------------------------
+struct RefPoint {
+    float x, y; int octave; float response, size, angle;
+    unsigned char features[61];
+    int match, distance; float match_x, match_y;
+};
+static_assert(sizeof(RefPoint) == 104, "AkazePoint layout (SURVEY App. C)");
+
+__global__ void k_pack(const int* __restrict__ count, const akz_keypoint* __restrict__ kpts, const unsigned char* __restrict__ desc,
+                       RefPoint* __restrict__ pts, int max_pts, int with_desc)
+{
+    int n = min(*count, max_pts);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        akz_keypoint k = kpts[i];
+        RefPoint* p = pts + i;
+        p->x = k.x; p->y = k.y; p->octave = k.layer; p->size = k.size; p->angle = k.angle;
+        if (with_desc) for (int b = 0; b < 61; b++) p->features[b] = desc[(long long)i * 64 + b];
+    }
+}
+
+__global__ void k_unpack(const RefPoint* __restrict__ pts, int n, unsigned char* __restrict__ desc)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int b = 0; b < 61; b++) desc[(long long)i * 64 + b] = pts[i].features[b];
+    desc[(long long)i * 64 + 61] = 0; desc[(long long)i * 64 + 62] = 0; desc[(long long)i * 64 + 63] = 0;
+}
+
+__global__ void k_scatter(const akz_match_t* __restrict__ m, int nq, RefPoint* __restrict__ pq, const RefPoint* __restrict__ pt)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    akz_match_t r = m[i];
+    if (r.idx1 >= 0) { pq[i].match = r.idx1; pq[i].distance = r.dist1; pq[i].match_x = pt[r.idx1].x; pq[i].match_y = pt[r.idx1].y; }
+    else { pq[i].match = -1; pq[i].distance = -1; pq[i].match_x = -1.f; pq[i].match_y = -1.f; }     // akazed.cu:2231-2237
+}
+
+bool g_cmp_uploaded = false;
+
+}  // namespace
+
+namespace akzk {
+
+int orient_table_init(cudaStream_t st)
+{
+    k_orient_table<<<1, 64, 0, st>>>();
+    if (!g_cmp_uploaded) {
+        int c1[488], c2[488];
+        short h[2][488];
+        akz_compare_indices(c1, c2);
+        for (int i = 0; i < 488; i++) { h[0][i] = (short)(i < 486 ? c1[i] : 0); h[1][i] = (short)(i < 486 ? c2[i] : 0); }
+        cudaMemcpyToSymbolAsync(c_cmp, h, sizeof(h), 0, cudaMemcpyHostToDevice, st);
+        cudaStreamSynchronize(st);
+        g_cmp_uploaded = true;
+    }
+    return 1;
+}
+
+int orient(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const int* prefix, akz_keypoint* kpts, int max_pts, int n)
+{
+    (void)counts;
+    k_orient<<<148 * 8, ORI_WARPS * 32, 0, st>>>(tab, prefix, n, kpts, max_pts);
+    return 1;
+}
+
+int describe(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const int* prefix, const akz_keypoint* kpts,
+             unsigned char* desc, int max_pts, int n, int pattern)
+{
+    (void)counts;
+    int size2 = pattern;                                          // akazed.cu:2681-2683
+    int size3 = (int)ceilf(2.0f * pattern / 3.0f);
+    int size4 = (int)ceilf(0.5f * pattern);
+    k_describe<<<148 * 8, 64, 0, st>>>(tab, prefix, n, kpts, desc, max_pts, size2, size3, size4);
+    return 1;
+}
+
+int pack_points(cudaStream_t st, const int* count, const akz_keypoint* kpts, const unsigned char* desc, void* points, int max_pts, int with_desc)
+{
+    k_pack<<<64, 256, 0, st>>>(count, kpts, desc, (RefPoint*)points, max_pts, with_desc);
+    return 1;
+}
+
+int unpack_desc(cudaStream_t st, const void* points, int n, unsigned char* desc)
+{
+    if (n <= 0) return 0;
+    k_unpack<<<(n + 255) / 256, 256, 0, st>>>((const RefPoint*)points, n, desc);
+    return 1;
+}
+
+int scatter_matches(cudaStream_t st, const akz_match_t* m, int nq, void* pq, const void* pt)
+{
+    if (nq <= 0) return 0;
+    k_scatter<<<(nq + 255) / 256, 256, 0, st>>>(m, nq, (RefPoint*)pq, (const RefPoint*)pt);
+    return 1;
+}
+
+}  // namespace akzk

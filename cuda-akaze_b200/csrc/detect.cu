@@ -1,0 +1,242 @@
+// Detector: per-level 3x3 extrema -> deterministic cross-level arg-max merge on a full-resolution
+// key map -> radius NMS -> sub-pixel refinement -> raster-ordered compaction.
+// Reference: gCalcExtremaMap (akazed.cu:1334-1393), gNmsRNaive (:1554-1613), gRefine (:1615-1662).
+// Differences from the reference, all deliberate:
+//   - the three float/int maps are one 64-bit key map merged with atomicMax: arg-max over levels,
+//     ties to the lowest layer, no tearing;
+//   - survivors are compacted in raster order (row counts -> scan -> emit), not atomicInc order;
+//   - the keypoint count never leaves the device.
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace akz;
+
+namespace {
+
+// grid: (ceil((w-2psz)/32), ceil((h-2psz)/8), nframes*nsub)
+__global__ void __launch_bounds__(256) k_extrema(const __grid_constant__ AkzExtremaArgs a, unsigned long long* __restrict__ map, int mpitch, long long mplane)
+{
+    int frame = blockIdx.z / a.nsub, sub = blockIdx.z - frame * a.nsub;
+    const AkzExtremaLevel& L = a.lv[sub];
+    int ix = blockIdx.x * 32 + threadIdx.x + a.psz;
+    int iy = blockIdx.y * 8 + threadIdx.y + a.psz;
+    if (ix >= a.w - 1 || iy >= a.h - 1) return;
+    float border = L.border;
+    // akazed.cu:1346-1353 (float arithmetic, truncating casts)
+    int left_x = (int)(__fadd_rn(__fsub_rn((float)ix, border), 0.5f)) - 1;
+    int right_x = (int)(__fadd_rn(__fadd_rn((float)ix, border), 0.5f)) + 1;
+    int up_y = (int)(__fadd_rn(__fsub_rn((float)iy, border), 0.5f)) - 1;
+    int down_y = (int)(__fadd_rn(__fadd_rn((float)iy, border), 0.5f)) + 1;
+    if (left_x < 0 || right_x >= a.w || up_y < 0 || down_y >= a.h) return;
+    const float* vp = L.det + (long long)frame * L.plane + (long long)iy * a.pitch + ix;
+    float v = __ldg(vp);
+    if (!(v > L.threshold)) return;
+    const float* v0 = vp - a.pitch;
+    const float* v2 = vp + a.pitch;
+    if (v > __ldg(v0) && v > __ldg(v2) && v > __ldg(vp - 1) && v > __ldg(vp + 1) &&
+        v > __ldg(v0 - 1) && v > __ldg(v0 + 1) && v > __ldg(v2 - 1) && v > __ldg(v2 + 1)) {
+        long long oi = (long long)frame * mplane + (long long)(iy << a.octave) * mpitch + (ix << a.octave);
+        atomicMax(map + oi, merge_key(v, L.layer));
+    }
+}
+
+// one block per (row, frame): radius NMS decision per pixel -> bit mask + row count
+__global__ void __launch_bounds__(256) k_nms_mark(const unsigned long long* __restrict__ map, int mpitch, long long mplane,
+                                                  int W, int H, int psz, const __grid_constant__ AkzLevelTable tab,
+                                                  unsigned* __restrict__ rowmask, int mwords, int* __restrict__ rowcount)
+{
+    int iy = blockIdx.x + psz, frame = blockIdx.y;
+    const unsigned long long* m = map + (long long)frame * mplane;
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    int cnt = 0;
+    int xend = W - psz;                                   // ix + psz < W
+    for (int x0 = 0; x0 < mwords * 32; x0 += 256) {
+        int ix = x0 + threadIdx.x;
+        bool keep = false;
+        if (ix >= psz && ix < xend) {
+            unsigned long long key = m[(long long)iy * mpitch + ix];
+            if (key != 0ull) {
+                float rc = key_resp(key);
+                float fsz = tab.lv[key_layer(key)].size;
+                int isz = (int)__fadd_rn(fsz, 0.5f);
+                int sq = (int)__fmul_rn(fsz, fsz);
+                keep = true;
+                for (int i = -isz; i <= isz && keep; i++) {
+                    const unsigned long long* row = m + (long long)(iy + i) * mpitch + ix;
+                    for (int j = -isz; j <= isz; j++) {
+                        if ((i == 0 && j == 0) || i * i + j * j >= sq) continue;
+                        unsigned long long kn = row[j];
+                        if (kn == 0ull) continue;
+                        float rn = key_resp(kn);
+                        if (rn > rc || (rn == rc && i <= 0 && j <= 0)) { keep = false; break; }
+                    }
+                }
+            }
+        }
+        unsigned b = __ballot_sync(0xffffffffu, keep);
+        if ((threadIdx.x & 31) == 0) {
+            int word = (x0 + threadIdx.x) >> 5;
+            if (word < mwords) rowmask[((long long)frame * H + iy) * mwords + word] = b;
+            cnt += __popc(b);
+        }
+    }
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) rowcount[(long long)frame * H + iy] = s_cnt;
+}
+
+// one block per frame: exclusive scan of the row counts (in place) -> per-frame total
+__global__ void __launch_bounds__(1024) k_row_scan(int* __restrict__ rowcount, int H, int psz, int* __restrict__ counts,
+                                                   int* __restrict__ totals, int max_pts)
+{
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    int frame = blockIdx.x;
+    int* rc = rowcount + (long long)frame * H;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    int lo = psz, hi = H - psz;
+    for (int base = lo; base < hi; base += 1024) {
+        int y = base + threadIdx.x;
+        int v = (y < hi) ? rc[y] : 0;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((threadIdx.x & 31) >= d) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int ws = warp_sums[threadIdx.x], wi = ws;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, wi, d);
+                if (threadIdx.x >= d) wi += t;
+            }
+            warp_sums[threadIdx.x] = wi - ws;            // exclusive
+        }
+        __syncthreads();
+        int excl = carry + warp_sums[threadIdx.x >> 5] + incl - v;
+        if (y < hi) rc[y] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        totals[frame] = carry;                            // survivors before clamping (reference: the raw counter)
+        counts[frame] = min(carry, max_pts);              // akaze.cpp:451
+    }
+}
+
+// exclusive prefix of the clamped counts over the frames of the chunk: prefix[0..n], prefix[n] = total
+__global__ void k_frame_prefix(const int* __restrict__ counts, int* __restrict__ prefix, int n)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int s = 0;
+        for (int i = 0; i < n; i++) { prefix[i] = s; s += counts[i]; }
+        prefix[n] = s;
+    }
+}
+
+// one block (128 threads) per (row, frame): rank the survivors of the row and write refined keypoints
+__global__ void __launch_bounds__(128) k_emit_refine(const unsigned long long* __restrict__ map, int mpitch, long long mplane,
+                                                     int H, int psz, const __grid_constant__ AkzLevelTable tab, const unsigned* __restrict__ rowmask, int mwords,
+                                                     const int* __restrict__ rowoff, akz_keypoint* __restrict__ kpts, int max_pts)
+{
+    int iy = blockIdx.x + psz, frame = blockIdx.y;
+    __shared__ int s_pref[129];
+    unsigned word = 0;
+    if ((int)threadIdx.x < mwords) word = rowmask[((long long)frame * H + iy) * mwords + threadIdx.x];
+    // mwords <= 128 (W <= 4096)
+    int c = __popc(word);
+    s_pref[threadIdx.x + 1] = c;
+    if (threadIdx.x == 0) s_pref[0] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) for (int i = 1; i <= 128; i++) s_pref[i] += s_pref[i - 1];
+    __syncthreads();
+    if (!word) return;
+    int rank = rowoff[(long long)frame * H + iy] + s_pref[threadIdx.x];
+    const unsigned long long* m = map + (long long)frame * mplane + (long long)iy * mpitch;
+    akz_keypoint* out = kpts + (long long)frame * max_pts;
+    while (word) {
+        int bit = __ffs(word) - 1;
+        word &= word - 1;
+        if (rank >= max_pts) break;
+        int ix = threadIdx.x * 32 + bit;
+        unsigned long long key = m[ix];
+        int layer = key_layer(key);
+        const AkzLevelDev& L = tab.lv[layer];
+        int o = L.octave, p = L.pitch;
+        int x = ix >> o, y = iy >> o;
+        const float* d = L.det + (long long)frame * L.plane + (long long)y * p + x;
+        // akazed.cu:1636-1657, operation order as compiled
+        float d0 = __ldg(d), dl = __ldg(d - 1), dr = __ldg(d + 1), du = __ldg(d - p), dd_ = __ldg(d + p);
+        float v2 = __fadd_rn(d0, d0);
+        float gx = __fmul_rn(0.5f, __fsub_rn(dr, dl));
+        float gy = __fmul_rn(0.5f, __fsub_rn(dd_, du));
+        float dxx = __fsub_rn(__fadd_rn(dr, dl), v2);
+        float dyy = __fsub_rn(__fadd_rn(dd_, du), v2);
+        float dxy = __fmul_rn(0.25f, __fsub_rn(__fsub_rn(__fadd_rn(__ldg(d + p + 1), __ldg(d - p - 1)), __ldg(d - p + 1)), __ldg(d + p - 1)));
+        float det = __fmaf_rn(dxx, dyy, -__fmul_rn(dxy, dxy));
+        float idd = det != 0.f ? __fdiv_rn(1.f, det) : 0.f;
+        float o0 = __fmul_rn(idd, __fmaf_rn(gy, dxy, -__fmul_rn(gx, dyy)));
+        float o1 = __fmul_rn(idd, __fmaf_rn(gx, dxy, -__fmul_rn(gy, dxx)));
+        bool weak = o0 < -1.f || o0 > 1.f || o1 < -1.f || o1 > 1.f;
+        akz_keypoint k;
+        k.ix = ix; k.iy = iy; k.layer = layer; k.size = L.size; k.response = key_resp(key); k.angle = 0.f;
+        if (weak) { k.x = (float)ix; k.y = (float)iy; }
+        else {
+            float ratio = (float)(1 << o);
+            k.x = __fmul_rn(ratio, __fadd_rn((float)x, o0));
+            k.y = __fmul_rn(ratio, __fadd_rn((float)y, o1));
+        }
+        out[rank] = k;
+        rank++;
+    }
+}
+
+}  // namespace
+
+namespace akzk {
+
+int extrema(cudaStream_t st, const AkzExtremaArgs& a, unsigned long long* map, int mpitch, long long mplane, int n)
+{
+    int ew = a.w - 2 * a.psz, eh = a.h - 2 * a.psz;
+    if (ew <= 0 || eh <= 0) return 0;
+    dim3 g((ew + 31) / 32, (eh + 7) / 8, n * a.nsub);
+    k_extrema<<<g, dim3(32, 8), 0, st>>>(a, map, mpitch, mplane);
+    return 1;
+}
+
+int frame_prefix(cudaStream_t st, const int* counts, int* prefix, int n)
+{
+    k_frame_prefix<<<1, 32, 0, st>>>(counts, prefix, n);
+    return 1;
+}
+
+int nms_emit(cudaStream_t st, const unsigned long long* map, int mpitch, long long mplane, int W, int H, int psz,
+             const AkzLevelTable& tab, unsigned* rowmask, int* rowcount, int* counts, int* prefix,
+             akz_keypoint* kpts, int max_pts, int n)
+{
+    int mwords = (W + 31) / 32;
+    if (mwords > 128) return akz_set_error(AKZ_E_UNSUPPORTED, "frame width above 4096 is not supported by the compaction kernel");
+    int rows = H - 2 * psz;
+    int launches = 0;
+    if (rows > 0) {
+        k_nms_mark<<<dim3(rows, n), 256, 0, st>>>(map, mpitch, mplane, W, H, psz, tab, rowmask, mwords, rowcount);
+        launches++;
+    }
+    k_row_scan<<<n, 1024, 0, st>>>(rowcount, H, rows > 0 ? psz : H, counts, prefix + n + 1, max_pts);
+    k_frame_prefix<<<1, 32, 0, st>>>(counts, prefix, n);
+    launches += 2;
+    if (rows > 0) {
+        k_emit_refine<<<dim3(rows, n), 128, 0, st>>>(map, mpitch, mplane, H, psz, tab, rowmask, mwords, rowcount, kpts, max_pts);
+        launches++;
+    }
+    return launches;
+}
+
+}  // namespace akzk

@@ -1,0 +1,81 @@
+// Internal launch-wrapper declarations (host side).  Every wrapper enqueues on the given stream,
+// never synchronises, and returns the number of kernels it launched (or a negative AKZ_E_* code).
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/akaze_b200.h"
+#include "common.cuh"
+
+struct AkzLevelTable {
+    AkzLevelDev lv[AKZ_MAX_LEVELS];
+    int nlevels, max_scale;
+};
+
+struct AkzExtremaLevel {
+    const float* det;
+    long long plane;
+    float border, threshold;
+    int layer, pad;
+};
+struct AkzExtremaArgs {
+    AkzExtremaLevel lv[8];
+    int nsub, w, h, pitch, octave, psz;
+};
+
+namespace akzk {
+
+int radius_from_ksz(int ksz);
+void hessian_factors(float* fac1, float* fac2);
+
+// ---- scale_space.cu: one kernel per reference stage --------------------------------------------
+int lowpass(cudaStream_t st, const float* src, float* dst, int w, int h, int sp, long long sstride, int dp, long long dstride,
+            int n, float var, int ksz);
+int lowpass_u8(cudaStream_t st, const unsigned char* src, float* dst, int w, int h, int sp, long long sstride, int dp, long long dstride,
+               int n, float var, int ksz);
+int down_with_smooth(cudaStream_t st, const float* src, float* dst, float* smooth, int sw, int sh, int sp, long long sstride,
+                     int dw, int dh, int dp, long long dstride, int n);
+int contrast(cudaStream_t st, const float* src, unsigned* hmax_bits, int* hist, float* kout, float per, float override_k,
+             int w, int h, int pitch, long long stride, int n);
+int flow(cudaStream_t st, const float* src, float* flowp, int type, const float* kc, float kscale, int nmul,
+         int w, int h, int pitch, long long stride, int n);
+int nld_step(cudaStream_t st, const float* src, const float* flowp, float* dst, float tau, int w, int h, int pitch, long long stride, int n);
+int hessian(cudaStream_t st, const float* smooth, float* lx, float* ly, float* det, int step, int w, int h, int pitch, long long stride, int n);
+
+// ---- scale_space_fused.cu: production kernels ------------------------------------------------------
+// base level from the input image: sigma=1 blur -> Scharr max / histogram -> k ; sigma0 blur -> Lt(0,0)
+int base_level(cudaStream_t st, const void* img, int dtype, int w, int h, int ipitch, long long istride,
+               float* lt, int pitch, long long plane, unsigned* hmax_bits, int* hist, float* kout, float per, float override_k,
+               float var0, int ksz0, int n);
+// Lt_prev -> (sigma=1 blur in smem) -> flow, Lx, Ly, det.  prev==cur plane for the base level (smooth := Lt)
+int level_prep(cudaStream_t st, const float* ltprev, float* flowp, float* lx, float* ly, float* det, int blur, int type,
+               const float* kc, float kscale, int nmul, int step, int w, int h, int pitch, long long plane, int n);
+// octave transition: Lt(o-1,0) -> Lt(o,0) (subsample) + flow, Lx, Ly, det from the coarse-lattice blur
+int level_prep_down(cudaStream_t st, const float* ltsrc, int sw, int sh, int sp, long long splane,
+                    float* ltdst, float* flowp, float* lx, float* ly, float* det, int type,
+                    const float* kc, float kscale, int nmul, int step, int w, int h, int pitch, long long plane, int n);
+// all n FED steps of a level (frozen conductance), temporally blocked in shared memory
+int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst, float* tmp, const float* tau, int nsteps,
+              int w, int h, int pitch, long long plane, int n, int fused);
+
+// ---- detect.cu ---------------------------------------------------------------------------------------
+int extrema(cudaStream_t st, const AkzExtremaArgs& a, unsigned long long* map, int mpitch, long long mplane, int n);
+int nms_emit(cudaStream_t st, const unsigned long long* map, int mpitch, long long mplane, int W, int H, int psz,
+             const AkzLevelTable& tab, unsigned* rowmask, int* rowcount, int* counts, int* prefix,
+             akz_keypoint* kpts, int max_pts, int n);
+
+int frame_prefix(cudaStream_t st, const int* counts, int* prefix, int n);
+
+// ---- describe.cu -------------------------------------------------------------------------------------
+int orient_table_init(cudaStream_t st);
+int orient(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const int* prefix, akz_keypoint* kpts, int max_pts, int n);
+int describe(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const int* prefix, const akz_keypoint* kpts,
+             unsigned char* desc, int max_pts, int n, int pattern);
+int pack_points(cudaStream_t st, const int* count, const akz_keypoint* kpts, const unsigned char* desc, void* points, int max_pts, int with_desc);
+int unpack_desc(cudaStream_t st, const void* points, int n, unsigned char* desc);
+int scatter_matches(cudaStream_t st, const akz_match_t* m, int nq, void* pq, const void* pt);
+
+// ---- match.cu ----------------------------------------------------------------------------------------
+int match_partial(cudaStream_t st, const unsigned char* q, int nq, const unsigned char* t, int nt, int tbase, int mode,
+                  int nsplit, akz_match_t* parts);
+int match_merge(cudaStream_t st, const akz_match_t* parts, int nparts, int nq, int mode, int finalize, akz_match_t* out);
+
+}  // namespace akzk

@@ -1,0 +1,391 @@
+// Production kernels of the nonlinear scale space.
+//
+//   k_level_prep<DOWN>  one pass per level: reads a tile (+halo) of the predecessor plane once and
+//                       produces everything of the level that does not depend on the diffusion:
+//                       the sigma=1 blur (shared memory only), the conductance plane g, the first
+//                       derivatives Lx, Ly and the Hessian determinant.  DOWN=1 additionally performs
+//                       the octave transition (point subsample + coarse-lattice blur).
+//                       Subsumes gConv2d<2> | gDownWithSmooth, gFlowNaive, gDerivate,
+//                       gHessianDeterminant (akazed.cu:204, :449, :1068, :1267, :1299).
+//   k_fed               all (up to 8) explicit diffusion steps of a FED cycle in one launch: the tile
+//                       and its halo live in shared memory, the valid region shrinks by one ring per
+//                       step (temporal blocking).  Subsumes n x gNldStepNaive + n D2D copies
+//                       (akazed.cu:1241, akaze.cpp:383-391, :412-420).
+//
+// Bit-exactness: every value is produced by the same rounded operations as in scale_space.cu; only
+// the data movement differs.  Reflect-101 is applied on INDICES (never by evaluating an operator on a
+// mirrored extension) wherever an operator is not symmetric: Lx/Ly are antisymmetric, the diffusion
+// update sums left/right/down/up in a fixed order, and the octave transition reflects in source
+// coordinates.
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace akz;
+
+namespace {
+
+// =====================================================================================================
+// level prep
+// =====================================================================================================
+constexpr int PT_W = 64, PT_H = 32;     // output tile
+constexpr int PB_X = 32, PB_Y = 8;      // threads
+
+struct PrepArgs {
+    const float* src;                    // predecessor Lt (same resolution) or source octave (DOWN)
+    float* ltdst;                        // DOWN: subsampled Lt
+    float *flow, *lx, *ly, *det;         // flow may be null (base level)
+    const float* kc;                     // per-frame contrast factor
+    long long splane, plane;
+    float kscale, fac1, fac2, k0, k1, k2;
+    int nmul, type, step, blur;
+    int sw, sh, sp;                      // source dims (== w,h,pitch unless DOWN)
+    int w, h, pitch;
+};
+
+// source-coordinate reflect of a coarse index (gDownWithSmooth reflects 2x+-2, 2x+-4 in the SOURCE image)
+__device__ __forceinline__ int coarse_src(int q, int sdim)
+{
+    int c = 2 * q;
+    if (c < 0) c = -c;
+    if (c >= sdim) c = sdim + sdim - 2 - c;
+    return c;
+}
+
+template <bool DOWN>
+__global__ void __launch_bounds__(PB_X * PB_Y) k_level_prep(const __grid_constant__ PrepArgs a)
+{
+    extern __shared__ float sm[];
+    const int s = a.step;
+    const int hb = a.blur ? 2 : 0;                    // blur halo
+    const int AW = PT_W + 4 * s + 2 * hb, AH = PT_H + 4 * s + 2 * hb;   // input tile
+    const int SW = PT_W + 4 * s, SH = PT_H + 4 * s;                     // smooth tile
+    const int DW = PT_W + 2 * s, DH = PT_H + 2 * s;                     // Lx/Ly tiles
+    float* A = sm;                                    // [AH][AW]
+    float* B = A + AW * AH;                           // [AH][SW]  row-filtered
+    float* S = B + SW * AH;                           // [SH][SW]
+    float* LX = sm;                                   // aliases A/B once S is complete
+    float* LY = LX + DW * DH;
+
+    const int frame = blockIdx.z;
+    const int X0 = blockIdx.x * PT_W, Y0 = blockIdx.y * PT_H;
+    const int w = a.w, h = a.h;
+    const float* src = a.src + (long long)frame * a.splane;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+
+    // ---- 1. input tile, extended by index reflection -------------------------------------------------
+    {
+        const int ax0 = X0 - 2 * s - hb, ay0 = Y0 - 2 * s - hb;
+        float* dstp = a.blur ? A : S;
+        for (int r = ty; r < AH; r += PB_Y) {
+            int gy = ay0 + r, sy;
+            if (DOWN) sy = min(max(coarse_src(gy, a.sh), 0), a.sh - 1);
+            else sy = min(max(refl(gy, h), 0), h - 1);
+            const float* row = src + (long long)sy * a.sp;
+            for (int c = tx; c < AW; c += PB_X) {
+                int gx = ax0 + c, sx;
+                if (DOWN) sx = min(max(coarse_src(gx, a.sw), 0), a.sw - 1);
+                else sx = min(max(refl(gx, w), 0), w - 1);
+                dstp[r * AW + c] = __ldg(row + sx);
+            }
+        }
+    }
+    __syncthreads();
+
+    if (DOWN) {
+        // subsampled plane: dst(x,y) = src(2x,2y)   (akazed.cu:505)
+        float* ltd = a.ltdst + (long long)frame * a.plane;
+        for (int r = ty; r < PT_H; r += PB_Y) {
+            int y = Y0 + r;
+            if (y >= h) break;
+            for (int c = tx; c < PT_W; c += PB_X) {
+                int x = X0 + c;
+                if (x < w) ltd[(long long)y * a.pitch + x] = A[(r + 2 * s + hb) * AW + (c + 2 * s + hb)];
+            }
+        }
+    }
+
+    if (a.blur) {
+        // ---- 2. row pass, evaluated at the REFLECTED column for cells outside the image -----------------
+        const int sx0 = X0 - 2 * s;
+        for (int r = ty; r < AH; r += PB_Y) {
+            const float* Ar = A + r * AW;
+            for (int c = tx; c < SW; c += PB_X) {
+                int q = min(max(refl(sx0 + c, w), 0), w - 1) - (X0 - 2 * s - hb);      // column in A
+                q = min(max(q, 2), AW - 3);
+                B[r * SW + c] = gauss_r2(Ar[q - 2], Ar[q - 1], Ar[q], Ar[q + 1], Ar[q + 2], a.k0, a.k1, a.k2);
+            }
+        }
+        __syncthreads();
+        // ---- 3. column pass, evaluated at the REFLECTED row ---------------------------------------------
+        const int sy0 = Y0 - 2 * s;
+        for (int r = ty; r < SH; r += PB_Y) {
+            int q = min(max(refl(sy0 + r, h), 0), h - 1) - (Y0 - 2 * s - hb);          // row in B
+            q = min(max(q, 2), AH - 3);
+            for (int c = tx; c < SW; c += PB_X)
+                S[r * SW + c] = gauss_r2(B[(q - 2) * SW + c], B[(q - 1) * SW + c], B[q * SW + c], B[(q + 1) * SW + c], B[(q + 2) * SW + c],
+                                         a.k0, a.k1, a.k2);
+        }
+        __syncthreads();
+    }
+
+    // ---- 4. conductance for the output pixels ----------------------------------------------------------
+    if (a.flow) {
+        float k = a.kc[frame];
+        for (int i = 0; i < a.nmul; i++) k = __fmul_rn(k, a.kscale);
+        const float ikc = __fdiv_rn(1.f, __fmul_rn(k, k));
+        float* fl = a.flow + (long long)frame * a.plane;
+        for (int r = ty; r < PT_H; r += PB_Y) {
+            int y = Y0 + r;
+            if (y >= h) break;
+            const float* S1 = S + (r + 2 * s) * SW + 2 * s;
+            for (int c = tx; c < PT_W; c += PB_X) {
+                int x = X0 + c;
+                if (x >= w) continue;
+                const float* p = S1 + c;
+                float ul = p[-SW - 1], uc = p[-SW], ur = p[-SW + 1], cl = p[-1], cr = p[1], ll = p[SW - 1], lc = p[SW], lr = p[SW + 1];
+                float dx = scharr_dx(ul, ur, cl, cr, ll, lr);
+                float dy = scharr_dy(ul, uc, ur, ll, lc, lr);
+                fl[(long long)y * a.pitch + x] = conductance(a.type, __fmul_rn(grad_sq(dx, dy), ikc));
+            }
+        }
+    }
+
+    // ---- 5. first derivatives on the tile extended by s, computed AT the reflected position -------------
+    // (LX/LY alias A/B: make sure every thread is done reading B)
+    __syncthreads();
+    {
+        const int dx0 = X0 - s, dy0 = Y0 - s;
+        float* lxg = a.lx + (long long)frame * a.plane;
+        float* lyg = a.ly + (long long)frame * a.plane;
+        for (int r = ty; r < DH; r += PB_Y) {
+            int gy = dy0 + r;
+            int qy = min(max(refl(gy, h), 0), h - 1) - (Y0 - 2 * s);                  // row in S
+            qy = min(max(qy, s), SH - 1 - s);
+            for (int c = tx; c < DW; c += PB_X) {
+                int gx = dx0 + c;
+                int qx = min(max(refl(gx, w), 0), w - 1) - (X0 - 2 * s);              // column in S
+                qx = min(max(qx, s), SW - 1 - s);
+                const float* p = S + qy * SW + qx;
+                float ul = p[-s * SW - s], uc = p[-s * SW], ur = p[-s * SW + s], cl = p[-s], cr = p[s];
+                float ll = p[s * SW - s], lc = p[s * SW], lr = p[s * SW + s];
+                float vx = deriv1(sum_x(ul, ur, ll, lr), __fsub_rn(cr, cl), a.fac1, a.fac2);
+                float vy = deriv1(sum_y(ul, ur, ll, lr), __fsub_rn(lc, uc), a.fac1, a.fac2);
+                // LX/LY overlap A/B but not S, and S is read-only from here on
+                LX[r * DW + c] = vx;
+                LY[r * DW + c] = vy;
+                if (gx >= X0 && gx < X0 + PT_W && gx < w && gy >= Y0 && gy < Y0 + PT_H && gy < h) {
+                    lxg[(long long)gy * a.pitch + gx] = vx;
+                    lyg[(long long)gy * a.pitch + gx] = vy;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 6. second derivatives and determinant ---------------------------------------------------------
+    {
+        float* dg = a.det + (long long)frame * a.plane;
+        for (int r = ty; r < PT_H; r += PB_Y) {
+            int y = Y0 + r;
+            if (y >= h) break;
+            for (int c = tx; c < PT_W; c += PB_X) {
+                int x = X0 + c;
+                if (x >= w) continue;
+                const float* px = LX + (r + s) * DW + (c + s);
+                const float* py = LY + (r + s) * DW + (c + s);
+                float xul = px[-s * DW - s], xuc = px[-s * DW], xur = px[-s * DW + s], xcl = px[-s], xcr = px[s];
+                float xll = px[s * DW - s], xlc = px[s * DW], xlr = px[s * DW + s];
+                float yul = py[-s * DW - s], yuc = py[-s * DW], yur = py[-s * DW + s];
+                float yll = py[s * DW - s], ylc = py[s * DW], ylr = py[s * DW + s];
+                float dxx = deriv2(sum_x(xul, xur, xll, xlr), __fsub_rn(xcr, xcl), a.fac1, a.fac2);
+                float dxy = deriv2(sum_y(xul, xur, xll, xlr), __fsub_rn(xlc, xuc), a.fac1, a.fac2);
+                float dyy = deriv2(sum_y(yul, yur, yll, ylr), __fsub_rn(ylc, yuc), a.fac1, a.fac2);
+                dg[(long long)y * a.pitch + x] = hess_det(dxx, dyy, dxy);
+            }
+        }
+    }
+}
+
+size_t prep_smem(int s, int blur)
+{
+    int hb = blur ? 2 : 0;
+    int AW = PT_W + 4 * s + 2 * hb, AH = PT_H + 4 * s + 2 * hb, SW = PT_W + 4 * s, SH = PT_H + 4 * s, DW = PT_W + 2 * s, DH = PT_H + 2 * s;
+    size_t ab = (size_t)AW * AH + (size_t)SW * AH;
+    size_t d2 = 2 * (size_t)DW * DH;
+    size_t front = ab > d2 ? ab : d2;
+    return (front + (size_t)SW * SH) * sizeof(float);
+}
+
+// =====================================================================================================
+// FED cycle, temporally blocked
+// =====================================================================================================
+constexpr int FE_W = 128, FE_H = 64;       // shared-memory tile (outputs + halo)
+constexpr int FE_TY = 4, FE_RUN = FE_H / FE_TY;
+constexpr int FE_MAXK = 8;
+
+struct FedArgs {
+    const float *src, *flow;
+    float* dst;
+    long long plane;
+    int w, h, pitch, n;
+    float stepfac[FE_MAXK];
+};
+
+__global__ void __launch_bounds__(FE_W * FE_TY) k_fed(const __grid_constant__ FedArgs a)
+{
+    extern __shared__ float sm[];
+    float* La = sm;
+    float* Lb = sm + FE_W * FE_H;
+    float* G = sm + 2 * FE_W * FE_H;
+    const int n = a.n, w = a.w, h = a.h;
+    const int TWo = FE_W - 2 * n, THo = FE_H - 2 * n;
+    const int X0 = blockIdx.x * TWo, Y0 = blockIdx.y * THo;
+    const int GX0 = X0 - n, GY0 = Y0 - n;
+    const long long base = (long long)blockIdx.z * a.plane;
+    const float* src = a.src + base;
+    const float* flw = a.flow + base;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int gx = GX0 + tx;
+    const bool xin = gx >= 0 && gx < w;
+
+    // load: column tx, all rows (coalesced along x)
+    for (int r = ty; r < FE_H; r += FE_TY) {
+        int gy = GY0 + r;
+        float lv = 0.f, gv = 0.f;
+        if (xin && gy >= 0 && gy < h) {
+            long long o = (long long)gy * a.pitch + gx;
+            lv = __ldg(src + o);
+            gv = __ldg(flw + o);
+        }
+        La[r * FE_W + tx] = lv;
+        G[r * FE_W + tx] = gv;
+    }
+    __syncthreads();
+
+    // reflect-101 neighbour offsets of this column (akazed.cu:1251-1254)
+    const int offl = (gx == 0) ? 1 : -1;
+    const int offr = (gx == w - 1) ? -1 : 1;
+    const int r0 = ty * FE_RUN;
+
+    float* Lin = La;
+    float* Lout = Lb;
+    for (int st = 1; st <= n; st++) {
+        // cells still exact after `st` steps: one ring lost per step on every side that is not an image border
+        const int xlo = (GX0 <= 0) ? -GX0 : st, xhi = (GX0 + FE_W >= w) ? w - GX0 : FE_W - st;
+        const int ylo = (GY0 <= 0) ? -GY0 : st, yhi = (GY0 + FE_H >= h) ? h - GY0 : FE_H - st;
+        const float sf = a.stepfac[st - 1];
+        if (tx >= xlo && tx < xhi) {
+            int ra = max(r0, ylo), rb = min(r0 + FE_RUN, yhi);
+            for (int r = ra; r < rb; r++) {
+                int gy = GY0 + r;
+                int up = (gy == 0) ? 1 : -1, dn = (gy == h - 1) ? -1 : 1;
+                const float* Lc = Lin + r * FE_W + tx;
+                const float* Gc = G + r * FE_W + tx;
+                float L0 = Lc[0], g0 = Gc[0];
+                Lout[r * FE_W + tx] = nld_update(L0, g0, Lc[offl], Gc[offl], Lc[offr], Gc[offr],
+                                                 Lc[dn * FE_W], Gc[dn * FE_W], Lc[up * FE_W], Gc[up * FE_W], sf);
+            }
+        }
+        __syncthreads();
+        float* t = Lin; Lin = Lout; Lout = t;
+    }
+
+    // store the interior
+    float* dst = a.dst + base;
+    if (gx >= X0 && gx < X0 + TWo && gx < w) {
+        for (int r = ty; r < FE_H; r += FE_TY) {
+            int gy = GY0 + r;
+            if (gy >= Y0 && gy < Y0 + THo && gy < h) dst[(long long)gy * a.pitch + gx] = Lin[r * FE_W + tx];
+        }
+    }
+}
+
+bool g_attr_done = false;
+
+}  // namespace
+
+namespace akzk {
+
+static void set_attrs()
+{
+    if (g_attr_done) return;
+    cudaFuncSetAttribute(k_fed, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * FE_W * FE_H * (int)sizeof(float));
+    cudaFuncSetAttribute(k_level_prep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_level_prep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    g_attr_done = true;
+}
+
+static int prep_common(cudaStream_t st, PrepArgs& a, bool down, int n)
+{
+    set_attrs();
+    hessian_factors(&a.fac1, &a.fac2);
+    float k[3];
+    akz_gauss_taps(1.f, 2, k);
+    a.k0 = k[0]; a.k1 = k[1]; a.k2 = k[2];
+    size_t smem = prep_smem(a.step, a.blur);
+    if (smem > 160 * 1024) return akz_set_error(AKZ_E_UNSUPPORTED, "derivative step %d too large for the fused level kernel", a.step);
+    dim3 g((a.w + PT_W - 1) / PT_W, (a.h + PT_H - 1) / PT_H, n), b(PB_X, PB_Y);
+    if (down) k_level_prep<true><<<g, b, smem, st>>>(a);
+    else k_level_prep<false><<<g, b, smem, st>>>(a);
+    return 1;
+}
+
+int level_prep(cudaStream_t st, const float* ltprev, float* flowp, float* lx, float* ly, float* det, int blur, int type,
+               const float* kc, float kscale, int nmul, int step, int w, int h, int pitch, long long plane, int n)
+{
+    PrepArgs a = {};
+    a.src = ltprev; a.ltdst = nullptr; a.flow = flowp; a.lx = lx; a.ly = ly; a.det = det; a.kc = kc;
+    a.splane = plane; a.plane = plane; a.kscale = kscale; a.nmul = nmul; a.type = type; a.step = step; a.blur = blur;
+    a.sw = w; a.sh = h; a.sp = pitch; a.w = w; a.h = h; a.pitch = pitch;
+    return prep_common(st, a, false, n);
+}
+
+int level_prep_down(cudaStream_t st, const float* ltsrc, int sw, int sh, int sp, long long splane,
+                    float* ltdst, float* flowp, float* lx, float* ly, float* det, int type,
+                    const float* kc, float kscale, int nmul, int step, int w, int h, int pitch, long long plane, int n)
+{
+    PrepArgs a = {};
+    a.src = ltsrc; a.ltdst = ltdst; a.flow = flowp; a.lx = lx; a.ly = ly; a.det = det; a.kc = kc;
+    a.splane = splane; a.plane = plane; a.kscale = kscale; a.nmul = nmul; a.type = type; a.step = step; a.blur = 1;
+    a.sw = sw; a.sh = sh; a.sp = sp; a.w = w; a.h = h; a.pitch = pitch;
+    return prep_common(st, a, true, n);
+}
+
+// dst receives the result of n steps applied to src; tmp is a scratch plane batch (never aliases src/dst).
+// fused != 0: ceil(n/8) launches of the temporally blocked kernel, else n single-step launches.
+int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst, float* tmp, const float* tau, int nsteps,
+              int w, int h, int pitch, long long plane, int n, int fused)
+{
+    if (nsteps <= 0) return 0;
+    set_attrs();
+    int launches = 0;
+    if (!fused) {
+        const float* cur = src;
+        for (int k = 0; k < nsteps; k++) {
+            float* out = ((nsteps - 1 - k) % 2 == 0) ? dst : tmp;
+            nld_step(st, cur, flowp, out, tau[k], w, h, pitch, plane, n);
+            cur = out;
+            launches++;
+        }
+        return launches;
+    }
+    int m = (nsteps + FE_MAXK - 1) / FE_MAXK;
+    int done = 0;
+    const float* cur = src;
+    for (int i = 0; i < m; i++) {
+        int cnt = (nsteps - done + (m - i) - 1) / (m - i);          // balanced split
+        FedArgs a = {};
+        a.src = cur; a.flow = flowp; a.dst = ((m - 1 - i) % 2 == 0) ? dst : tmp;
+        a.plane = plane; a.w = w; a.h = h; a.pitch = pitch; a.n = cnt;
+        for (int k = 0; k < cnt; k++) a.stepfac[k] = 0.5f * tau[done + k];      // akazed.cu:2515
+        int TWo = FE_W - 2 * cnt, THo = FE_H - 2 * cnt;
+        dim3 g((w + TWo - 1) / TWo, (h + THo - 1) / THo, n), b(FE_W, FE_TY);
+        k_fed<<<g, b, 3 * FE_W * FE_H * sizeof(float), st>>>(a);
+        cur = a.dst;
+        done += cnt;
+        launches++;
+    }
+    return launches;
+}
+
+}  // namespace akzk

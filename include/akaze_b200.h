@@ -1,0 +1,188 @@
+/*
+ * akaze_b200.h — C ABI of the B200-native AKAZE hot path (detect / describe / match).
+ *
+ * This is the drop-in boundary.  The C++ surface of the reference (akaze.h / akazed.h:
+ * akaze::Akazer, initAkazeData, freeAkazeData, cuMatch and the h* stage functions) is re-created in
+ * include/akaze.h ... on top of these entry points; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every "d_" pointer is CUDA device memory on the context's
+ *     device, every "h_" pointer is host memory (pinned gives the best transfer rate);
+ *   - images are row-major, `pitch` is in ELEMENTS (reference: whp.z, main.cpp:174-188), frame f of a
+ *     batch starts at base + f*frame_stride elements;
+ *   - every call returns AKZ_OK (0) or a negative AKZ_E_* code; akz_last_error() has the text.
+ *     (The reference prints and exit(-1)s instead, cuda_utils.h:18-37; the C++ shim restores that.)
+ *   - calls are asynchronous on the context's stream unless they return data to the host;
+ *     akz_sync() waits.  There is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with AKZ_E_CUDA.
+ */
+#ifndef AKAZE_B200_H
+#define AKAZE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AKZ_API __attribute__((visibility("default")))
+
+enum {
+    AKZ_OK = 0,
+    AKZ_E_INVALID = -1,     /* bad argument */
+    AKZ_E_CUDA = -2,        /* CUDA runtime error (text in akz_last_error) */
+    AKZ_E_NOMEM = -3,
+    AKZ_E_UNSUPPORTED = -4
+};
+
+enum { AKZ_F32 = 0, AKZ_U8 = 1 };                /* input pixel type: [0,1] float (main.cpp:149) or raw u8 */
+enum { AKZ_MATCH_COMPAT = 0, AKZ_MATCH_KNN2 = 1 };
+enum { AKZ_PLANE_LT = 0, AKZ_PLANE_DET = 1, AKZ_PLANE_LX = 2, AKZ_PLANE_LY = 3 };   /* akaze.cpp:315-320 */
+
+/* The reference has no options struct: these are the 11 arguments of Akazer::init (akaze.h:25-26)
+ * and the member defaults (akaze.h:34-54), plus the capacities a batched context needs. */
+typedef struct akz_options {
+    int   width, height;            /* frame size the context is sized for; 0 x 0 = matcher-only     */
+                                    /* context (no pyramid buffers)                                  */
+    int   noctaves;                 /* 4   */
+    int   max_scale;                /* 4 sublevels per octave, <= 5 (MAX_SCALE, akazed.cu:9)          */
+    float per;                      /* 0.7 percentile of the contrast histogram                       */
+    float kcontrast;                /* 0.03 — kept for signature parity; recomputed per frame         */
+    float soffset;                  /* 1.6  */
+    int   reordering;               /* 1    */
+    float derivative_factor;        /* 1.5  */
+    float dthreshold;               /* 0.001, must be >= 0                                            */
+    int   diffusivity;              /* 1 = PM_G2 (akaze_structures.h:51-57)                           */
+    int   descriptor_pattern_size;  /* 10   */
+    int   max_pts;                  /* per-frame keypoint capacity (main.cpp:157: 10000)              */
+    int   max_batch;                /* frames processed together (chunk size)                         */
+    int   device;                   /* CUDA device ordinal, -1 = current                              */
+    float kcontrast_override;       /* > 0: skip the percentile estimate and use this k (parity hook, */
+                                    /*      SURVEY App. B-1)                                          */
+    int   fused;                    /* 1 = fused production kernels, 0 = one kernel per reference     */
+                                    /*     stage (same results; used as a cross-check)                */
+} akz_options;
+
+/* One detected keypoint (32 bytes, device or host). */
+typedef struct akz_keypoint {
+    float x, y;          /* refined full-resolution position (akazed.cu:1655-1656)                    */
+    float response;      /* det(H) at the integer position (response_map entry)                       */
+    float size;          /* octave-relative derivative scale, as the reference stores it              */
+    float angle;         /* [0, 2*pi)                                                                  */
+    int   layer;         /* octave*max_scale + sublevel  (reference: AkazePoint::octave)              */
+    int   ix, iy;        /* full-resolution integer position before refinement                        */
+} akz_keypoint;
+
+/* Result of one matcher query (16 bytes).
+ * COMPAT: idx1 = match or -1, dist1 = distance or -1 (akazed.cu:2222-2237); idx2 = class mask, dist2 = 0.
+ * KNN2  : best and second best (distance, index), lowest index first on ties; -1 when absent. */
+typedef struct akz_match_t {
+    int idx1, dist1, idx2, dist2;
+} akz_match_t;
+
+typedef struct akz_ctx akz_ctx;
+
+/* ---- library ------------------------------------------------------------------------------ */
+AKZ_API int         akz_version(void);
+AKZ_API const char* akz_last_error(void);
+AKZ_API void        akz_default_options(akz_options* o);
+
+/* FED time steps, host only — replaces fed_tau_by_process_time (fed.cpp:41). Returns n (or -n if
+ * cap is too small). */
+AKZ_API int akz_fed_tau(float T, int M, float tau_max, int reordering, float* tau, int cap);
+/* Normalised Gaussian taps k[0..radius] — replaces createGaussKernel (akazed.cu:2298). */
+AKZ_API void akz_gauss_taps(float var, int radius, float* taps);
+/* M-LDB comparison table (486 pairs) — replaces setCompareIndices (akazed.cu:65). */
+AKZ_API void akz_compare_indices(int* idx1, int* idx2);
+
+/* ---- context ------------------------------------------------------------------------------ */
+AKZ_API int  akz_create(const akz_options* o, akz_ctx** out);
+AKZ_API void akz_destroy(akz_ctx* c);
+AKZ_API int  akz_sync(akz_ctx* c);
+AKZ_API void* akz_stream(akz_ctx* c);                 /* cudaStream_t */
+/* schedule introspection (replaces the scalars computed in akaze.cpp:268-363) */
+AKZ_API int  akz_num_levels(const akz_ctx* c);
+AKZ_API int  akz_level_info(const akz_ctx* c, int level, int* w, int* h, int* pitch, int* nsteps,
+                            float* size, int* sigma_size, float* tau, int tau_cap);
+/* device pointer of a plane of frame `frame` of the LAST processed chunk */
+AKZ_API const float* akz_level_plane(const akz_ctx* c, int level, int which, int frame);
+AKZ_API int  akz_launch_count(const akz_ctx* c);      /* kernels launched since creation */
+
+/* ---- the hot path: replaces Akazer::detectAndCompute (akaze.cpp:101-150) over a batch ------- */
+/* d_images: nframes frames of `dtype` on the device.  Results stay on the device:
+ *   d_counts[nframes]                      number of keypoints per frame (clamped to max_pts)
+ *   d_kpts  [nframes][max_pts]             akz_keypoint, raster order of (iy, ix)
+ *   d_desc  [nframes][max_pts][64]         M-LDB, 61 bytes + 3 zero bytes (may be NULL if !describe)
+ * nframes may exceed max_batch; frames are processed in chunks. */
+AKZ_API int akz_detect_and_compute(akz_ctx* c, const void* d_images, int dtype, int nframes,
+                                   int width, int height, int pitch, long long frame_stride,
+                                   int describe, int* d_counts, akz_keypoint* d_kpts, uint8_t* d_desc);
+
+/* Same call with HOST buffers: copies the frames in, runs the path, copies counts / keypoints /
+ * descriptors out, synchronises.  h_kpts / h_desc are [nframes][max_pts] strided like the device
+ * version; only the first counts[f] entries of each frame are valid. */
+AKZ_API int akz_detect_and_compute_host(akz_ctx* c, const void* h_images, int dtype, int nframes,
+                                        int width, int height, int pitch, long long frame_stride,
+                                        int describe, int* h_counts, akz_keypoint* h_kpts, uint8_t* h_desc);
+
+/* Build the scale space only (planes readable through akz_level_plane); nframes <= max_batch. */
+AKZ_API int akz_build_scale_space(akz_ctx* c, const void* d_images, int dtype, int nframes,
+                                  int width, int height, int pitch, long long frame_stride);
+/* contrast factors of the last chunk (device -> host, synchronises) */
+AKZ_API int akz_get_kcontrast(akz_ctx* c, float* h_k, int nframes);
+
+/* ---- stage seams: one entry per reference stage function (akazed.h:32-77), batched ----------- */
+/* Every plane argument is a batch: frame f at base + f*stride elements. stream = context stream. */
+AKZ_API int akz_lowpass(akz_ctx* c, const float* src, float* dst, int w, int h, int pitch, long long stride, int nframes,
+                        float var, int ksz);                                       /* hLowPass :2336 */
+AKZ_API int akz_down_with_smooth(akz_ctx* c, const float* src, float* dst, float* smooth,
+                                 int sw, int sh, int sp, long long sstride,
+                                 int dw, int dh, int dp, long long dstride, int nframes);   /* hDownWithSmooth :2389 */
+/* writes one contrast factor per frame to d_k; grad may be NULL (the gradient plane is not kept) */
+AKZ_API int akz_scharr_contrast(akz_ctx* c, const float* src, float* d_k, float per,
+                                int w, int h, int pitch, long long stride, int nframes);   /* hScharrContrast :2410 */
+/* d_k: per-frame contrast factor on the device; kscale multiplies it (0.75^octave, akaze.cpp:373) */
+AKZ_API int akz_flow(akz_ctx* c, const float* src, float* flow, int type, const float* d_k, float kscale,
+                     int w, int h, int pitch, long long stride, int nframes);               /* hFlow :2487 */
+AKZ_API int akz_nld_step(akz_ctx* c, const float* src, const float* flow, float* dst, float tau,
+                         int w, int h, int pitch, long long stride, int nframes);           /* hNldStep :2509 */
+/* n explicit steps with frozen conductance: dst = FED cycle applied to src (src != dst) */
+AKZ_API int akz_fed_cycle(akz_ctx* c, const float* src, const float* flow, float* dst, float* tmp,
+                          const float* tau, int n, int w, int h, int pitch, long long stride, int nframes);
+AKZ_API int akz_hessian(akz_ctx* c, const float* smooth, float* lx, float* ly, float* det, int step,
+                        int w, int h, int pitch, long long stride, int nframes);            /* hHessianDeterminant :2531 */
+
+/* keypoint stages on the planes of the LAST processed chunk (akz_build_scale_space / akz_detect_and_compute):
+ * d_counts[nframes], d_kpts[nframes][max_pts] as produced by akz_detect_and_compute (or supplied by a test) */
+AKZ_API int akz_orient(akz_ctx* c, const int* d_counts, akz_keypoint* d_kpts, int nframes);                 /* hCalcOrient :2655 */
+AKZ_API int akz_describe(akz_ctx* c, const int* d_counts, const akz_keypoint* d_kpts, uint8_t* d_desc, int nframes); /* hDescribe :2675 */
+/* extrema + NMS + refinement on the planes of the last processed chunk                     hCalcExtremaMap/hNmsR/hRefine */
+AKZ_API int akz_detect_keypoints(akz_ctx* c, int nframes, int* d_counts, akz_keypoint* d_kpts);
+
+/* ---- matcher: replaces akaze::cuMatch / hMatch (akaze.cpp:55, akazed.cu:2758) -------------------- */
+/* d_q [nq][64], d_t [nt][64] descriptors; train indices reported as t_index_base + local index
+ * (for sharded train sets).  d_out[nq].  finalize != 0 applies the acceptance rule (single shard);
+ * finalize == 0 leaves the associative partial form for akz_match_merge after a gather. */
+AKZ_API int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt,
+                      int t_index_base, int mode, int finalize, akz_match_t* d_out);
+/* merge `nparts` partial results (each [nq], e.g. gathered from shards) into d_out[nq];
+ * finalize != 0 applies the acceptance rule of the mode (COMPAT: unique class and < 96) */
+AKZ_API int akz_match_merge(akz_ctx* c, const akz_match_t* d_parts, int nparts, int nq, int mode,
+                            int finalize, akz_match_t* d_out);
+AKZ_API int akz_match_host(akz_ctx* c, const uint8_t* h_q, int nq, const uint8_t* h_t, int nt,
+                           int mode, akz_match_t* h_out);
+
+/* ---- AoS bridge for the akaze.h shim ------------------------------------------------------------ */
+/* writes x,y,octave,size,angle,features into reference-layout AkazePoint records (104 B, App. D) */
+AKZ_API int akz_pack_points(akz_ctx* c, const int* d_count, const akz_keypoint* d_kpts, const uint8_t* d_desc,
+                            void* d_points, int max_pts, int with_desc);
+/* gathers descriptors out of AkazePoint records into [n][64] */
+AKZ_API int akz_unpack_desc(akz_ctx* c, const void* d_points, int n, uint8_t* d_desc);
+/* scatters match results back into AkazePoint::match/distance/match_x/match_y (akazed.cu:2222-2237) */
+AKZ_API int akz_scatter_matches(akz_ctx* c, const akz_match_t* d_m, int nq, void* d_points_q, const void* d_points_t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AKAZE_B200_H */
