@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py — 1080p AKAZE detect + describe throughput (BASELINE.json metric 1) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames F] [--content shapes|noise]
+
+A "step" is one pass of the hot path (akz_detect_and_compute: nonlinear scale space, Hessian detector, NMS,
+refinement, orientation, M-LDB) over one batch of F synthetic 1920x1080 frames per GPU (BASELINE.json configs[2]:
+batch of 256 frames, frame-sharded: weak scaling, no data-path collective).  One JSON line is printed by rank 0:
+
+  value         frames/s with the batch already resident in HBM (device pointers in, device results out)
+  e2e           frames/s through akz_detect_and_compute_host: pinned HOST frames in, HOST keypoints/descriptors
+                out, H2D and D2H copies inside the timed region
+  roofline      the dominant kernel class of the step, timed with CUDA events on the library's stream
+                (akz_profile_*) in one extra pass over the same batch; achieved = algorithmic bytes / time
+  cpu_baseline  OpenCV cv::AKAZE (the reference's own CPU arm, main.cpp:344-399) and the C oracle port, on a
+                bounded sample of the same frames on the box's host cores (rank 0, N=1 only)
+
+--impl reference runs the UNMODIFIED reference CUDA library (oracle/_ref/libref_akaze.so, built from
+/root/reference by oracle/Makefile for sm_100a) through its own Akazer::detectAndCompute, frame by frame as
+main.cpp:199-205 does, on the same frames.  The reference has no CPU implementation of its own.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "cuda-akaze_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W, H = 1920, 1080
+L2_BYTES = 126 * 1024 * 1024
+
+
+def level_pixels(w, h, noct=4, S=4):
+    px = []
+    for o in range(noct):
+        ww, hh = w >> o, h >> o
+        if o and (ww < 80 or hh < 80):
+            break
+        px += [ww * hh] * S
+    return px
+
+
+def make_frames(nframes, content, seed0=0):
+    """F distinct u8 frames: 8 seeded base images (tests/bindings.py generators), each rolled by a
+    different offset so no two frames of the batch are equal."""
+    import bindings as B
+    nbase = min(8, nframes)
+    gen = B.synth_noise_u8 if content == "noise" else B.synth_shapes_u8
+    base = [gen(W, H, seed=seed0 + s) for s in range(nbase)]
+    out = np.empty((nframes, H, W), dtype=np.uint8)
+    for f in range(nframes):
+        b = base[f % nbase]
+        k = f // nbase
+        out[f] = np.roll(b, (37 * k, 53 * k), axis=(0, 1)) if k else b
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smmax, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smmax.append(float(r[1])); pw.append(float(r[2]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(ngpus):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def barrier_max(ms, world, device):
+    import torch
+    if world == 1:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def timed(fn, steps, stream, world, device):
+    """barrier + sync | K steps between two CUDA events on `stream` | barrier + sync; max over ranks (ms)."""
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    e1.synchronize()
+    barrier(world)
+    return barrier_max(e0.elapsed_time(e1), world, device)
+
+
+# ---- algorithmic bytes per kernel class, per frame (DESIGN.md "roofline") ---------------------------------------
+def algorithmic_bytes(cls, nkp):
+    px = level_pixels(W, H)
+    lv = sum(px)
+    if cls == "fed":       # per FED cycle: read Lt_prev and g, write Lt  (12 B/px), cycles = every level but (0,0)
+        return 12 * (lv - px[0])
+    if cls == "prep":      # read Lt_prev, write g, Lx, Ly, det (20 B/px); octave transitions also write Lt (+4)
+        return 20 * lv - 4 * px[0] + 4 * sum(px[i] for i in range(4, len(px), 4))
+    if cls == "base":      # read the frame twice-in-one (4 B/px), write smooth(sigma 1) and Lt(0,0)
+        return 12 * px[0]
+    if cls == "contrast":
+        return 4 * px[0]
+    if cls == "describe":  # 441 samples x 3 planes x 4 B + 64 B out per keypoint
+        return nkp * (441 * 12 + 64)
+    if cls == "orient":
+        return nkp * (109 * 8 + 32)
+    if cls == "extrema":
+        return 4 * lv
+    if cls == "nms":
+        return 8 * px[0]
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import akaze_b200 as ab
+    rank, world, local = dist_setup(args.gpus)
+    device = torch.device("cuda", local)
+    F = args.frames
+    frames8 = make_frames(F, args.content, seed0=100 * rank)
+    dtype = np.float32 if args.dtype == "f32" else np.uint8
+    host = torch.empty((F, H, W), dtype=torch.float32 if args.dtype == "f32" else torch.uint8).pin_memory()
+    if args.dtype == "f32":
+        host.numpy()[:] = frames8.astype(np.float32) * np.float32(1.0 / 255.0)       # main.cpp:149
+    else:
+        host.numpy()[:] = frames8
+    ctx = ab.Context(W, H, max_batch=args.chunk, max_pts=args.max_pts, device=local)
+    stream = ctx.torch_stream()
+    dev = host.to(device)
+    res = ctx.alloc_results(F, True)
+    mp = args.max_pts
+    h_counts = torch.zeros(F, dtype=torch.int32).pin_memory()
+    h_kpts = torch.zeros((F, mp, 8), dtype=torch.int32).pin_memory()
+    h_desc = torch.zeros((F, mp, 64), dtype=torch.uint8).pin_memory()
+    hout = (h_counts.numpy(), h_kpts.numpy().view(ab.KEYPOINT_DTYPE).reshape(F, mp), h_desc.numpy())
+
+    def step_dev():
+        ctx.detect_and_compute(dev, True, out=res)
+
+    def step_host():
+        ctx.detect_and_compute_host(host, True, out=hout)
+
+    for _ in range(args.warmup):
+        step_dev()
+    ctx.sync()
+    l0 = ctx.launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_dev, args.steps, stream, world, device)
+    launches = ctx.launches - l0
+    for _ in range(max(1, args.warmup // 2)):
+        step_host()
+    ms_e2e = timed(step_host, args.steps, stream, world, device)
+    clocks = sampler.stop() if rank == 0 else None
+    counts = res[0].cpu().numpy()
+    assert np.array_equal(counts, h_counts.numpy()), "host and device paths disagree"
+    nkp_mean = float(counts.mean())
+
+    # per-class device time: one extra pass of the same step with event pairs around every kernel group
+    ctx.profile(True)
+    step_dev()
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    tot_ms = sum(v[0] for v in prof.values())
+    top = max(prof, key=lambda k: prof[k][0])
+    top_ms, top_launches = prof[top]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg = algorithmic_bytes(top, nkp_mean) * F
+    achieved = alg / (top_ms * 1e-3) / 1e9 if top_ms > 0 else 0.0
+    step_alg = (4 * W * H + 20 * sum(level_pixels(W, H))) * F          # 228.6 MB / frame
+    roof = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 4), "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (sustained copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+            "kernel_ms_per_step": round(top_ms, 3), "kernel_share_of_step": round(top_ms / tot_ms, 3) if tot_ms else None,
+            "kernel_launches_per_step": int(top_launches), "algorithmic_bytes_per_launch": alg / max(1, top_launches),
+            "classes_ms_per_step": {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
+            "whole_step": {"algorithmic_gbs": round(step_alg / (ms / args.steps * 1e-3) / 1e9, 1),
+                           "frac_of_hbm": round(step_alg / (ms / args.steps * 1e-3) / 1e9 / peak, 4)}}
+    line = {
+        "metric": "1080p detect+describe images/sec", "value": round(F * world * args.steps / (ms * 1e-3), 2), "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"configs[2]: synthetic 1920x1080 grayscale, {F} frames per GPU per step ({args.content}), "
+                               "4 octaves x 4 sublevels, reference defaults (main.cpp:156-166), detect+describe",
+                   "frames_per_gpu": F, "chunk": args.chunk, "max_pts": mp, "keypoints_per_frame_mean": round(nkp_mean, 1),
+                   "parallelism": f"frame-sharded x{world}, no collective",
+                   "l2_policy": f"inputs larger than L2: {F} frames x {W * H * (4 if args.dtype == 'f32' else 1) / 1e6:.1f} MB in, "
+                                f"{args.chunk} x 176 MB of planes per chunk (L2 = 126 MB)",
+                   "roofline_pass": "one extra pass of the same step with CUDA event pairs around every kernel group"},
+        "e2e": {"value": round(F * world * args.steps / (ms_e2e * 1e-3), 2), "unit": "images/s",
+                "h2d_bytes_per_step": int(host.numel() * host.element_size()),
+                "d2h_bytes_per_step": int(F * 4 + counts.sum() * (32 + 64)), "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(frames8, args.cpu_frames)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def cpu_baseline(frames8, nsample):
+    """OpenCV cv::AKAZE (what main.cpp:344-399 times as the CPU arm) and the C oracle port on the first frames."""
+    cores = os.cpu_count() or 1
+    out = {"unit": "images/s", "cores": cores}
+    sample = frames8[:nsample]
+    try:
+        import cv2
+        cv2.setNumThreads(cores)
+        ak = cv2.AKAZE_create()
+        ak.detectAndCompute(sample[0], None)
+        t0 = time.perf_counter()
+        nk = 0
+        for f in sample:
+            kp, _ = ak.detectAndCompute(f, None)
+            nk += len(kp)
+        dt = time.perf_counter() - t0
+        out.update({"value": round(len(sample) / dt, 3), "kind": "reference",
+                    "sample": f"cv2 {cv2.__version__} AKAZE_create() defaults (main.cpp:373) on the first {len(sample)} frames of the batch, "
+                              f"{cv2.getNumThreads()} threads, {nk / len(sample):.0f} keypoints/frame"})
+    except Exception as e:                                     # cv2 missing on the box: the port below is the baseline
+        out["opencv_error"] = repr(e)[:120]
+    try:
+        import bindings as B
+        img = B.u8_to_unit(sample[0])
+        t0 = time.perf_counter()
+        k = B.oracle_detect_and_compute(img, True, threads=cores)
+        dt = time.perf_counter() - t0
+        port = {"value": round(1.0 / dt, 3), "kind": "port", "cores": cores,
+                "sample": f"oracle/akaze_oracle.c (OpenMP, {cores} threads) on the first frame, {len(k)} keypoints"}
+        if "value" in out:
+            out["port"] = port
+        else:
+            out.update(port)
+    except Exception as e:
+        out["port_error"] = repr(e)[:120]
+    return out
+
+
+def run_reference(args):
+    """The unmodified reference CUDA library through Akazer::detectAndCompute, one frame per call (main.cpp:199-205)."""
+    import torch
+    rank, world, local = dist_setup(args.gpus)
+    device = torch.device("cuda", local)
+    import bindings as B
+    if not B.have_ref():
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_akaze.so not built (needs /root/reference at build time)"}))
+        return
+    F = args.frames
+    frames8 = make_frames(F, args.content, seed0=100 * rank)
+    pitch = (W + 127) // 128 * 128                                  # main.cpp:174: iAlignUp(w, 128)
+    host = torch.zeros((F, H, pitch), dtype=torch.float32).pin_memory()
+    host.numpy()[:, :, :W] = frames8.astype(np.float32) * np.float32(1.0 / 255.0)
+    dev = host.to(device)
+    mp = args.max_pts
+    ref = B.RefAkazer(W, H, pitch)
+    L = ref.L
+    import ctypes as C
+    d_pts = torch.zeros(mp * 104, dtype=torch.uint8, device=device)
+    h_pts = torch.zeros(mp * 104, dtype=torch.uint8).pin_memory()
+    stage = torch.empty((H, pitch), dtype=torch.float32, device=device)
+    counts = np.zeros(F, dtype=np.int64)
+
+    def step_dev():
+        for f in range(F):
+            counts[f] = L.ref_akazer_detectAndCompute(ref.hnd, C.c_void_p(dev[f].data_ptr()), W, H, pitch, 1,
+                                                      C.c_void_p(d_pts.data_ptr()), None, mp)
+
+    def step_host():
+        for f in range(F):
+            stage.copy_(host[f], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            counts[f] = L.ref_akazer_detectAndCompute(ref.hnd, C.c_void_p(stage.data_ptr()), W, H, pitch, 1,
+                                                      C.c_void_p(d_pts.data_ptr()), C.c_void_p(h_pts.data_ptr()), mp)
+
+    stream = torch.cuda.current_stream()
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_dev, args.steps, stream, world, device)
+    ms_e2e = timed(step_host, args.steps, stream, world, device)
+    clocks = sampler.stop() if rank == 0 else None
+    v = F * world * args.steps / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": "1080p detect+describe images/sec", "value": round(v, 2), "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"configs[2]: synthetic 1920x1080 grayscale, {F} frames per GPU per step ({args.content}), "
+                               "4 octaves x 4 sublevels, reference defaults (main.cpp:156-166), detect+describe",
+                   "frames_per_gpu": F, "max_pts": mp, "keypoints_per_frame_mean": round(float(counts.mean()), 1),
+                   "how": "unmodified akazed.cu/akaze.cpp/fed.cpp compiled for sm_100a (oracle/Makefile), Akazer::detectAndCompute per frame "
+                          "on the reused-size path, legacy default stream; the reference is a CUDA library and has no CPU implementation"},
+        "e2e": {"value": round(F * world * args.steps / (ms_e2e * 1e-3), 2), "unit": "images/s",
+                "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": int(counts.sum() * 85),
+                "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "cpu_baseline": {"value": None, "unit": "images/s", "cores": 0, "kind": "reference",
+                         "sample": "not a CPU run: the reference implementation of this path is CUDA; its CPU comparison (cv::AKAZE) is in the main arm's cpu_baseline"},
+        "clocks": clocks,
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ref.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step (configs[2]: 256)")
+    ap.add_argument("--chunk", type=int, default=16, help="frames processed together (akz_options.max_batch)")
+    ap.add_argument("--max-pts", type=int, default=10000, help="per-frame keypoint capacity (main.cpp:157)")
+    ap.add_argument("--content", default="shapes", choices=["shapes", "noise"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "u8"])
+    ap.add_argument("--cpu-frames", type=int, default=8)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -36,7 +36,9 @@ EXPORTS = [
     "akz_get_kcontrast", "akz_lowpass", "akz_down_with_smooth", "akz_scharr_contrast", "akz_flow", "akz_nld_step",
     "akz_fed_cycle", "akz_hessian", "akz_match", "akz_match_merge", "akz_match_host", "akz_pack_points",
     "akz_unpack_desc", "akz_scatter_matches", "akz_orient", "akz_describe", "akz_detect_keypoints",
+    "akz_profile_enable", "akz_profile_read", "akz_profile_class_name",
 ]
+NUM_KCLASS = 13
 
 _lib = None
 
@@ -88,6 +90,10 @@ def lib():
     L.akz_pack_points.argtypes = [vp, vp, vp, vp, vp, i, i]
     L.akz_unpack_desc.argtypes = [vp, vp, i, vp]
     L.akz_scatter_matches.argtypes = [vp, vp, i, vp, vp]
+    L.akz_profile_enable.argtypes = [vp, i]
+    L.akz_profile_read.argtypes = [vp, i, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    L.akz_profile_class_name.argtypes = [i]
+    L.akz_profile_class_name.restype = C.c_char_p
     _lib = L
     return L
 
@@ -169,6 +175,16 @@ class Context:
     @property
     def launches(self):
         return lib().akz_launch_count(self.h)
+
+    def profile(self, on):
+        _check(lib().akz_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        """{class name: (milliseconds, launches)} accumulated since the last read (synchronises)."""
+        ms = (C.c_double * NUM_KCLASS)()
+        n = (C.c_longlong * NUM_KCLASS)()
+        _check(lib().akz_profile_read(self.h, NUM_KCLASS, ms, n))
+        return {lib().akz_profile_class_name(k).decode(): (ms[k], n[k]) for k in range(NUM_KCLASS) if n[k]}
 
     @property
     def num_levels(self):

@@ -140,7 +140,22 @@ struct akz_ctx {
     int last_frames;
     long long launches;
     AkzLevelTable tab;
+    // per-kernel-class device timing (akz_profile_*): event pairs around every wrapper call while enabled
+    bool prof_on;
+    struct ProfPair { cudaEvent_t a, b; int cls, launches; };
+    std::vector<ProfPair> prof_pairs;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[AKZ_NUM_KCLASS];
+    long long prof_launches[AKZ_NUM_KCLASS];
 };
+
+static cudaEvent_t prof_event(akz_ctx* c)
+{
+    cudaEvent_t e;
+    if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+}
 
 template <typename T>
 static int dalloc(akz_ctx* c, T** p, size_t n)
@@ -219,7 +234,8 @@ int akz_create(const akz_options* o, akz_ctx** out)
     if (ndev <= 0) return akz_set_error(AKZ_E_CUDA, "no CUDA device: this library has no CPU fallback");
     akz_ctx* c = new akz_ctx();
     c->opt = *o;
-    c->launches = 0; c->last_frames = 0;
+    c->launches = 0; c->last_frames = 0; c->prof_on = false;
+    memset(c->prof_ms, 0, sizeof(c->prof_ms)); memset(c->prof_launches, 0, sizeof(c->prof_launches));
     c->img_stage = nullptr; c->img_stage_bytes = 0; c->match_parts = nullptr; c->match_parts_n = 0;
     c->match_stage = nullptr; c->match_stage_bytes = 0;
     int rc = AKZ_OK;
@@ -286,6 +302,8 @@ void akz_destroy(akz_ctx* c)
     if (c->img_stage) cudaFree(c->img_stage);
     if (c->match_parts) cudaFree(c->match_parts);
     if (c->match_stage) cudaFree(c->match_stage);
+    for (auto& pp : c->prof_pairs) { cudaEventDestroy(pp.a); cudaEventDestroy(pp.b); }
+    for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -321,7 +339,15 @@ const float* akz_level_plane(const akz_ctx* c, int l, int which, int frame)
 }  // extern "C"
 
 // ---- pipeline ------------------------------------------------------------------------------------------
-#define LAUNCHED(expr) do { int r_ = (expr); if (r_ < 0) return r_; c->launches += r_; } while (0)
+#define LAUNCHED(cls_, expr) do {                                                              \
+        cudaEvent_t ea_ = nullptr;                                                             \
+        if (c->prof_on) { ea_ = prof_event(c); cudaEventRecord(ea_, c->stream); }              \
+        int r_ = (expr);                                                                       \
+        if (r_ < 0) return r_;                                                                 \
+        c->launches += r_;                                                                     \
+        if (ea_) { cudaEvent_t eb_ = prof_event(c); cudaEventRecord(eb_, c->stream);           \
+                   c->prof_pairs.push_back({ ea_, eb_, (cls_), r_ }); }                        \
+    } while (0)
 
 static int check_frame_args(akz_ctx* c, const void* img, int dtype, int nframes, int w, int h, int pitch)
 {
@@ -345,16 +371,16 @@ static int scale_space_chunk(akz_ctx* c, const void* img, int dtype, int nf, int
     const int ksz0 = (int)(2 * ceilf((o.soffset - 0.8f) / 0.3f) + 3);
     if (dtype == AKZ_U8) {
         if (!(o.kcontrast_override > 0.f))
-            LAUNCHED(akzk::lowpass_u8(st, (const unsigned char*)img, c->smooth, w0, h0, ipitch, istride, p0, L0.plane, nf, 1.f, 5));
-        LAUNCHED(akzk::lowpass_u8(st, (const unsigned char*)img, L0.lt, w0, h0, ipitch, istride, p0, L0.plane, nf, var0, ksz0));
+            LAUNCHED(AKZ_K_BASE, akzk::lowpass_u8(st, (const unsigned char*)img, c->smooth, w0, h0, ipitch, istride, p0, L0.plane, nf, 1.f, 5));
+        LAUNCHED(AKZ_K_BASE, akzk::lowpass_u8(st, (const unsigned char*)img, L0.lt, w0, h0, ipitch, istride, p0, L0.plane, nf, var0, ksz0));
     } else {
         if (!(o.kcontrast_override > 0.f))
-            LAUNCHED(akzk::lowpass(st, (const float*)img, c->smooth, w0, h0, ipitch, istride, p0, L0.plane, nf, 1.f, 5));
-        LAUNCHED(akzk::lowpass(st, (const float*)img, L0.lt, w0, h0, ipitch, istride, p0, L0.plane, nf, var0, ksz0));
+            LAUNCHED(AKZ_K_BASE, akzk::lowpass(st, (const float*)img, c->smooth, w0, h0, ipitch, istride, p0, L0.plane, nf, 1.f, 5));
+        LAUNCHED(AKZ_K_BASE, akzk::lowpass(st, (const float*)img, L0.lt, w0, h0, ipitch, istride, p0, L0.plane, nf, var0, ksz0));
     }
-    LAUNCHED(akzk::contrast(st, c->smooth, c->hmax, c->hist, c->kc, o.per, o.kcontrast_override, w0, h0, p0, L0.plane, nf));
-    if (fused) LAUNCHED(akzk::level_prep(st, L0.lt, nullptr, L0.lx, L0.ly, L0.det, 0, o.diffusivity, c->kc, 0.75f, 0, L0.sigma_size, w0, h0, p0, L0.plane, nf));
-    else LAUNCHED(akzk::hessian(st, L0.lt, L0.lx, L0.ly, L0.det, L0.sigma_size, w0, h0, p0, L0.plane, nf));
+    LAUNCHED(AKZ_K_CONTRAST, akzk::contrast(st, c->smooth, c->hmax, c->hist, c->kc, o.per, o.kcontrast_override, w0, h0, p0, L0.plane, nf));
+    if (fused) LAUNCHED(AKZ_K_PREP, akzk::level_prep(st, L0.lt, nullptr, L0.lx, L0.ly, L0.det, 0, o.diffusivity, c->kc, 0.75f, 0, L0.sigma_size, w0, h0, p0, L0.plane, nf));
+    else LAUNCHED(AKZ_K_HESSIAN, akzk::hessian(st, L0.lt, L0.lx, L0.ly, L0.det, L0.sigma_size, w0, h0, p0, L0.plane, nf));
 
     for (int l = 1; l < c->nlev; l++) {
         AkzLevel& L = c->lev[l];
@@ -364,25 +390,25 @@ static int scale_space_chunk(akz_ctx* c, const void* img, int dtype, int nf, int
             // new octave (akaze.cpp:371-392): source is sublevel 0 of the previous octave; kcontrast *= 0.75
             AkzLevel& P = c->lev[l - S];
             if (fused) {
-                LAUNCHED(akzk::level_prep_down(st, P.lt, P.w, P.h, P.pitch, P.plane, c->tmpB, c->flow, L.lx, L.ly, L.det, o.diffusivity,
+                LAUNCHED(AKZ_K_PREP, akzk::level_prep_down(st, P.lt, P.w, P.h, P.pitch, P.plane, c->tmpB, c->flow, L.lx, L.ly, L.det, o.diffusivity,
                                                c->kc, 0.75f, L.octave, L.sigma_size, w, h, p, L.plane, nf));
             } else {
-                LAUNCHED(akzk::down_with_smooth(st, P.lt, c->tmpB, c->smooth, P.w, P.h, P.pitch, P.plane, w, h, p, L.plane, nf));
-                LAUNCHED(akzk::flow(st, c->smooth, c->flow, o.diffusivity, c->kc, 0.75f, L.octave, w, h, p, L.plane, nf));
+                LAUNCHED(AKZ_K_BLUR, akzk::down_with_smooth(st, P.lt, c->tmpB, c->smooth, P.w, P.h, P.pitch, P.plane, w, h, p, L.plane, nf));
+                LAUNCHED(AKZ_K_FLOW, akzk::flow(st, c->smooth, c->flow, o.diffusivity, c->kc, 0.75f, L.octave, w, h, p, L.plane, nf));
             }
-            LAUNCHED(akzk::fed_cycle(st, c->tmpB, c->flow, L.lt, c->tmpA, tau, L.nsteps, w, h, p, L.plane, nf, fused));
+            LAUNCHED(AKZ_K_FED, akzk::fed_cycle(st, c->tmpB, c->flow, L.lt, c->tmpA, tau, L.nsteps, w, h, p, L.plane, nf, fused));
         } else {
             // next sublevel (akaze.cpp:393-421)
             AkzLevel& P = c->lev[l - 1];
             if (fused) {
-                LAUNCHED(akzk::level_prep(st, P.lt, c->flow, L.lx, L.ly, L.det, 1, o.diffusivity, c->kc, 0.75f, L.octave, L.sigma_size, w, h, p, L.plane, nf));
+                LAUNCHED(AKZ_K_PREP, akzk::level_prep(st, P.lt, c->flow, L.lx, L.ly, L.det, 1, o.diffusivity, c->kc, 0.75f, L.octave, L.sigma_size, w, h, p, L.plane, nf));
             } else {
-                LAUNCHED(akzk::lowpass(st, P.lt, c->smooth, w, h, p, L.plane, p, L.plane, nf, 1.f, 5));
-                LAUNCHED(akzk::flow(st, c->smooth, c->flow, o.diffusivity, c->kc, 0.75f, L.octave, w, h, p, L.plane, nf));
+                LAUNCHED(AKZ_K_BLUR, akzk::lowpass(st, P.lt, c->smooth, w, h, p, L.plane, p, L.plane, nf, 1.f, 5));
+                LAUNCHED(AKZ_K_FLOW, akzk::flow(st, c->smooth, c->flow, o.diffusivity, c->kc, 0.75f, L.octave, w, h, p, L.plane, nf));
             }
-            LAUNCHED(akzk::fed_cycle(st, P.lt, c->flow, L.lt, c->tmpA, tau, L.nsteps, w, h, p, L.plane, nf, fused));
+            LAUNCHED(AKZ_K_FED, akzk::fed_cycle(st, P.lt, c->flow, L.lt, c->tmpA, tau, L.nsteps, w, h, p, L.plane, nf, fused));
         }
-        if (!fused) LAUNCHED(akzk::hessian(st, c->smooth, L.lx, L.ly, L.det, L.sigma_size, w, h, p, L.plane, nf));   // akaze.cpp:423
+        if (!fused) LAUNCHED(AKZ_K_HESSIAN, akzk::hessian(st, c->smooth, L.lx, L.ly, L.det, L.sigma_size, w, h, p, L.plane, nf));   // akaze.cpp:423
     }
     c->last_frames = nf;
     return AKZ_OK;
@@ -404,13 +430,13 @@ static int detect_chunk(akz_ctx* c, int nf, int describe, int* d_counts, akz_key
             a.lv[j].det = L.det; a.lv[j].plane = L.plane; a.lv[j].border = L.border; a.lv[j].threshold = o.dthreshold;
             a.lv[j].layer = oc * S + j;
         }
-        LAUNCHED(akzk::extrema(st, a, c->map, c->mpitch, c->mplane, nf));
+        LAUNCHED(AKZ_K_EXTREMA, akzk::extrema(st, a, c->map, c->mpitch, c->mplane, nf));
     }
-    LAUNCHED(akzk::nms_emit(st, c->map, c->mpitch, c->mplane, o.width, o.height, c->psz, c->tab, c->rowmask, c->rowcount,
+    LAUNCHED(AKZ_K_NMS, akzk::nms_emit(st, c->map, c->mpitch, c->mplane, o.width, o.height, c->psz, c->tab, c->rowmask, c->rowcount,
                             d_counts, c->prefix, d_kpts, o.max_pts, nf));
     if (describe) {
-        LAUNCHED(akzk::orient(st, c->tab, d_counts, c->prefix, d_kpts, o.max_pts, nf));
-        LAUNCHED(akzk::describe(st, c->tab, d_counts, c->prefix, d_kpts, d_desc, o.max_pts, nf, o.descriptor_pattern_size));
+        LAUNCHED(AKZ_K_ORIENT, akzk::orient(st, c->tab, d_counts, c->prefix, d_kpts, o.max_pts, nf));
+        LAUNCHED(AKZ_K_DESCRIBE, akzk::describe(st, c->tab, d_counts, c->prefix, d_kpts, d_desc, o.max_pts, nf, o.descriptor_pattern_size));
     }
     return AKZ_OK;
 }
@@ -500,7 +526,7 @@ int akz_detect_and_compute_host(akz_ctx* c, const void* h_images, int dtype, int
 int akz_lowpass(akz_ctx* c, const float* src, float* dst, int w, int h, int pitch, long long stride, int n, float var, int ksz)
 {
     STAGE_PROLOGUE();
-    LAUNCHED(akzk::lowpass(c->stream, src, dst, w, h, pitch, stride, pitch, stride, n, var, ksz));
+    LAUNCHED(AKZ_K_BLUR, akzk::lowpass(c->stream, src, dst, w, h, pitch, stride, pitch, stride, n, var, ksz));
     STAGE_EPILOGUE();
 }
 
@@ -508,7 +534,7 @@ int akz_down_with_smooth(akz_ctx* c, const float* src, float* dst, float* smooth
                          int dw, int dh, int dp, long long dstride, int n)
 {
     STAGE_PROLOGUE();
-    LAUNCHED(akzk::down_with_smooth(c->stream, src, dst, smooth, sw, sh, sp, sstride, dw, dh, dp, dstride, n));
+    LAUNCHED(AKZ_K_BLUR, akzk::down_with_smooth(c->stream, src, dst, smooth, sw, sh, sp, sstride, dw, dh, dp, dstride, n));
     STAGE_EPILOGUE();
 }
 
@@ -516,21 +542,21 @@ int akz_scharr_contrast(akz_ctx* c, const float* src, float* d_k, float per, int
 {
     STAGE_PROLOGUE();
     if (n > c->opt.max_batch) return akz_set_error(AKZ_E_INVALID, "nframes exceeds max_batch");
-    LAUNCHED(akzk::contrast(c->stream, src, c->hmax, c->hist, d_k, per, 0.f, w, h, pitch, stride, n));
+    LAUNCHED(AKZ_K_CONTRAST, akzk::contrast(c->stream, src, c->hmax, c->hist, d_k, per, 0.f, w, h, pitch, stride, n));
     STAGE_EPILOGUE();
 }
 
 int akz_flow(akz_ctx* c, const float* src, float* flow, int type, const float* d_k, float kscale, int w, int h, int pitch, long long stride, int n)
 {
     STAGE_PROLOGUE();
-    LAUNCHED(akzk::flow(c->stream, src, flow, type, d_k, kscale, 1, w, h, pitch, stride, n));
+    LAUNCHED(AKZ_K_FLOW, akzk::flow(c->stream, src, flow, type, d_k, kscale, 1, w, h, pitch, stride, n));
     STAGE_EPILOGUE();
 }
 
 int akz_nld_step(akz_ctx* c, const float* src, const float* flow, float* dst, float tau, int w, int h, int pitch, long long stride, int n)
 {
     STAGE_PROLOGUE();
-    LAUNCHED(akzk::nld_step(c->stream, src, flow, dst, tau, w, h, pitch, stride, n));
+    LAUNCHED(AKZ_K_FED, akzk::nld_step(c->stream, src, flow, dst, tau, w, h, pitch, stride, n));
     STAGE_EPILOGUE();
 }
 
@@ -539,15 +565,15 @@ int akz_fed_cycle(akz_ctx* c, const float* src, const float* flow, float* dst, f
 {
     STAGE_PROLOGUE();
     if (src == dst || src == tmp || dst == tmp) return akz_set_error(AKZ_E_INVALID, "src, dst and tmp must be distinct");
-    LAUNCHED(akzk::fed_cycle(c->stream, src, flow, dst, tmp, tau, nsteps, w, h, pitch, stride, n, c->opt.fused));
+    LAUNCHED(AKZ_K_FED, akzk::fed_cycle(c->stream, src, flow, dst, tmp, tau, nsteps, w, h, pitch, stride, n, c->opt.fused));
     STAGE_EPILOGUE();
 }
 
 int akz_hessian(akz_ctx* c, const float* smooth, float* lx, float* ly, float* det, int step, int w, int h, int pitch, long long stride, int n)
 {
     STAGE_PROLOGUE();
-    if (c->opt.fused) LAUNCHED(akzk::level_prep(c->stream, smooth, nullptr, lx, ly, det, 0, 1, c->kc, 1.f, 0, step, w, h, pitch, stride, n));
-    else LAUNCHED(akzk::hessian(c->stream, smooth, lx, ly, det, step, w, h, pitch, stride, n));
+    if (c->opt.fused) LAUNCHED(AKZ_K_PREP, akzk::level_prep(c->stream, smooth, nullptr, lx, ly, det, 0, 1, c->kc, 1.f, 0, step, w, h, pitch, stride, n));
+    else LAUNCHED(AKZ_K_HESSIAN, akzk::hessian(c->stream, smooth, lx, ly, det, step, w, h, pitch, stride, n));
     STAGE_EPILOGUE();
 }
 
@@ -555,8 +581,8 @@ int akz_orient(akz_ctx* c, const int* d_counts, akz_keypoint* d_kpts, int n)
 {
     STAGE_PROLOGUE();
     if (n < 1 || n > c->opt.max_batch || c->nlev == 0) return akz_set_error(AKZ_E_INVALID, "bad frame count");
-    LAUNCHED(akzk::frame_prefix(c->stream, d_counts, c->prefix, n));
-    LAUNCHED(akzk::orient(c->stream, c->tab, d_counts, c->prefix, d_kpts, c->opt.max_pts, n));
+    LAUNCHED(AKZ_K_MISC, akzk::frame_prefix(c->stream, d_counts, c->prefix, n));
+    LAUNCHED(AKZ_K_ORIENT, akzk::orient(c->stream, c->tab, d_counts, c->prefix, d_kpts, c->opt.max_pts, n));
     STAGE_EPILOGUE();
 }
 
@@ -564,8 +590,8 @@ int akz_describe(akz_ctx* c, const int* d_counts, const akz_keypoint* d_kpts, ui
 {
     STAGE_PROLOGUE();
     if (n < 1 || n > c->opt.max_batch || c->nlev == 0) return akz_set_error(AKZ_E_INVALID, "bad frame count");
-    LAUNCHED(akzk::frame_prefix(c->stream, d_counts, c->prefix, n));
-    LAUNCHED(akzk::describe(c->stream, c->tab, d_counts, c->prefix, d_kpts, d_desc, c->opt.max_pts, n, c->opt.descriptor_pattern_size));
+    LAUNCHED(AKZ_K_MISC, akzk::frame_prefix(c->stream, d_counts, c->prefix, n));
+    LAUNCHED(AKZ_K_DESCRIBE, akzk::describe(c->stream, c->tab, d_counts, c->prefix, d_kpts, d_desc, c->opt.max_pts, n, c->opt.descriptor_pattern_size));
     STAGE_EPILOGUE();
 }
 
@@ -594,15 +620,15 @@ int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt
         AKZ_CUDA_TRY(cudaMalloc((void**)&c->match_parts, need * sizeof(akz_match_t)));
         c->match_parts_n = need;
     }
-    LAUNCHED(akzk::match_partial(c->stream, d_q, nq, d_t, nt, t_index_base, mode, nsplit, c->match_parts));
-    LAUNCHED(akzk::match_merge(c->stream, c->match_parts, nsplit, nq, mode, finalize, d_out));
+    LAUNCHED(AKZ_K_MATCH, akzk::match_partial(c->stream, d_q, nq, d_t, nt, t_index_base, mode, nsplit, c->match_parts));
+    LAUNCHED(AKZ_K_MATCH, akzk::match_merge(c->stream, c->match_parts, nsplit, nq, mode, finalize, d_out));
     STAGE_EPILOGUE();
 }
 
 int akz_match_merge(akz_ctx* c, const akz_match_t* d_parts, int nparts, int nq, int mode, int finalize, akz_match_t* d_out)
 {
     STAGE_PROLOGUE();
-    LAUNCHED(akzk::match_merge(c->stream, d_parts, nparts, nq, mode, finalize, d_out));
+    LAUNCHED(AKZ_K_MATCH, akzk::match_merge(c->stream, d_parts, nparts, nq, mode, finalize, d_out));
     STAGE_EPILOGUE();
 }
 
@@ -628,23 +654,52 @@ int akz_match_host(akz_ctx* c, const uint8_t* h_q, int nq, const uint8_t* h_t, i
     return akz_sync(c);
 }
 
+// ---- per-kernel-class device timing ------------------------------------------------------------------------------
+static const char* const k_class_names[AKZ_NUM_KCLASS] = { "base", "blur", "contrast", "prep", "hessian", "flow", "fed", "extrema", "nms",
+                                                           "orient", "describe", "match", "misc" };
+const char* akz_profile_class_name(int cls) { return (cls >= 0 && cls < AKZ_NUM_KCLASS) ? k_class_names[cls] : ""; }
+
+int akz_profile_enable(akz_ctx* c, int on)
+{
+    if (!c) return akz_set_error(AKZ_E_INVALID, "null context");
+    c->prof_on = on != 0;
+    return AKZ_OK;
+}
+
+int akz_profile_read(akz_ctx* c, int ncls, double* ms, long long* launches)
+{
+    if (!c || !ms || !launches) return akz_set_error(AKZ_E_INVALID, "null argument");
+    AKZ_CUDA_TRY(cudaSetDevice(c->device));
+    AKZ_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (auto& pp : c->prof_pairs) {
+        float t = 0.f;
+        AKZ_CUDA_TRY(cudaEventElapsedTime(&t, pp.a, pp.b));
+        c->prof_ms[pp.cls] += t; c->prof_launches[pp.cls] += pp.launches;
+        c->prof_pool.push_back(pp.a); c->prof_pool.push_back(pp.b);
+    }
+    c->prof_pairs.clear();
+    for (int i = 0; i < ncls && i < AKZ_NUM_KCLASS; i++) { ms[i] = c->prof_ms[i]; launches[i] = c->prof_launches[i]; }
+    memset(c->prof_ms, 0, sizeof(c->prof_ms)); memset(c->prof_launches, 0, sizeof(c->prof_launches));
+    return AKZ_OK;
+}
+
 // ---- AoS bridge -----------------------------------------------------------------------------------------------
 int akz_pack_points(akz_ctx* c, const int* d_count, const akz_keypoint* d_kpts, const uint8_t* d_desc, void* d_points, int max_pts, int with_desc)
 {
     STAGE_PROLOGUE();
-    LAUNCHED(akzk::pack_points(c->stream, d_count, d_kpts, d_desc, d_points, max_pts, with_desc));
+    LAUNCHED(AKZ_K_MISC, akzk::pack_points(c->stream, d_count, d_kpts, d_desc, d_points, max_pts, with_desc));
     STAGE_EPILOGUE();
 }
 int akz_unpack_desc(akz_ctx* c, const void* d_points, int n, uint8_t* d_desc)
 {
     STAGE_PROLOGUE();
-    LAUNCHED(akzk::unpack_desc(c->stream, d_points, n, d_desc));
+    LAUNCHED(AKZ_K_MISC, akzk::unpack_desc(c->stream, d_points, n, d_desc));
     STAGE_EPILOGUE();
 }
 int akz_scatter_matches(akz_ctx* c, const akz_match_t* d_m, int nq, void* d_points_q, const void* d_points_t)
 {
     STAGE_PROLOGUE();
-    LAUNCHED(akzk::scatter_matches(c->stream, d_m, nq, d_points_q, d_points_t));
+    LAUNCHED(AKZ_K_MISC, akzk::scatter_matches(c->stream, d_m, nq, d_points_q, d_points_t));
     STAGE_EPILOGUE();
 }
 

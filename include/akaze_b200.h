@@ -109,6 +109,15 @@ AKZ_API int  akz_level_info(const akz_ctx* c, int level, int* w, int* h, int* pi
 AKZ_API const float* akz_level_plane(const akz_ctx* c, int level, int which, int frame);
 AKZ_API int  akz_launch_count(const akz_ctx* c);      /* kernels launched since creation */
 
+/* ---- device timing per kernel class (bench.py roofline): while enabled, every kernel group of the pipeline is
+ * bracketed by CUDA events on the context's stream; akz_profile_read synchronises, returns the accumulated
+ * milliseconds and launch counts per class (AKZ_K_*) and resets them. */
+enum { AKZ_K_BASE = 0, AKZ_K_BLUR, AKZ_K_CONTRAST, AKZ_K_PREP, AKZ_K_HESSIAN, AKZ_K_FLOW, AKZ_K_FED, AKZ_K_EXTREMA,
+       AKZ_K_NMS, AKZ_K_ORIENT, AKZ_K_DESCRIBE, AKZ_K_MATCH, AKZ_K_MISC, AKZ_NUM_KCLASS };
+AKZ_API int         akz_profile_enable(akz_ctx* c, int on);
+AKZ_API int         akz_profile_read(akz_ctx* c, int ncls, double* ms, long long* launches);
+AKZ_API const char* akz_profile_class_name(int cls);
+
 /* ---- the hot path: replaces Akazer::detectAndCompute (akaze.cpp:101-150) over a batch ------- */
 /* d_images: nframes frames of `dtype` on the device.  Results stay on the device:
  *   d_counts[nframes]                      number of keypoints per frame (clamped to max_pts)
