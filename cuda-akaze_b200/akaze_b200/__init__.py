@@ -356,7 +356,7 @@ def _cudart_memcpy_d2d(dst, src, nbytes):
     class _Holder:
         pass
     h = _Holder()
-    h.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(src), True), "version": 2}
+    h.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(src), False), "version": 2}
     srct = torch.as_tensor(h, device="cuda")
     dstt_h = _Holder()
     dstt_h.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(dst), False), "version": 2}

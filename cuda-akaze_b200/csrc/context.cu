@@ -359,6 +359,22 @@ static int check_frame_args(akz_ctx* c, const void* img, int dtype, int nframes,
     return AKZ_OK;
 }
 
+// fused level kernel: second generation when it covers the case (fused == 1), else the first generation
+static int prep_level(akz_ctx* c, int mode, const float* src, int sw, int sh, int sp, long long splane, float* ltdst, float* flowp,
+                      float* lx, float* ly, float* det, int nmul, int step, int w, int h, int pitch, long long plane, int nf)
+{
+    const akz_options& o = c->opt;
+    if (o.fused == 1) {
+        int r = akzk::level_prep2(c->stream, mode, src, sw, sh, sp, splane, ltdst, flowp, lx, ly, det, o.diffusivity, c->kc, 0.75f, nmul,
+                                  step, w, h, pitch, plane, nf);
+        if (r != 0) return r;
+    }
+    if (mode == 2)
+        return akzk::level_prep_down(c->stream, src, sw, sh, sp, splane, ltdst, flowp, lx, ly, det, o.diffusivity, c->kc, 0.75f, nmul,
+                                     step, w, h, pitch, plane, nf);
+    return akzk::level_prep(c->stream, src, flowp, lx, ly, det, mode, o.diffusivity, c->kc, 0.75f, nmul, step, w, h, pitch, plane, nf);
+}
+
 static int scale_space_chunk(akz_ctx* c, const void* img, int dtype, int nf, int ipitch, long long istride)
 {
     cudaStream_t st = c->stream;
@@ -379,7 +395,7 @@ static int scale_space_chunk(akz_ctx* c, const void* img, int dtype, int nf, int
         LAUNCHED(AKZ_K_BASE, akzk::lowpass(st, (const float*)img, L0.lt, w0, h0, ipitch, istride, p0, L0.plane, nf, var0, ksz0));
     }
     LAUNCHED(AKZ_K_CONTRAST, akzk::contrast(st, c->smooth, c->hmax, c->hist, c->kc, o.per, o.kcontrast_override, w0, h0, p0, L0.plane, nf));
-    if (fused) LAUNCHED(AKZ_K_PREP, akzk::level_prep(st, L0.lt, nullptr, L0.lx, L0.ly, L0.det, 0, o.diffusivity, c->kc, 0.75f, 0, L0.sigma_size, w0, h0, p0, L0.plane, nf));
+    if (fused) LAUNCHED(AKZ_K_PREP, prep_level(c, 0, L0.lt, w0, h0, p0, L0.plane, nullptr, nullptr, L0.lx, L0.ly, L0.det, 0, L0.sigma_size, w0, h0, p0, L0.plane, nf));
     else LAUNCHED(AKZ_K_HESSIAN, akzk::hessian(st, L0.lt, L0.lx, L0.ly, L0.det, L0.sigma_size, w0, h0, p0, L0.plane, nf));
 
     for (int l = 1; l < c->nlev; l++) {
@@ -390,8 +406,8 @@ static int scale_space_chunk(akz_ctx* c, const void* img, int dtype, int nf, int
             // new octave (akaze.cpp:371-392): source is sublevel 0 of the previous octave; kcontrast *= 0.75
             AkzLevel& P = c->lev[l - S];
             if (fused) {
-                LAUNCHED(AKZ_K_PREP, akzk::level_prep_down(st, P.lt, P.w, P.h, P.pitch, P.plane, c->tmpB, c->flow, L.lx, L.ly, L.det, o.diffusivity,
-                                               c->kc, 0.75f, L.octave, L.sigma_size, w, h, p, L.plane, nf));
+                LAUNCHED(AKZ_K_PREP, prep_level(c, 2, P.lt, P.w, P.h, P.pitch, P.plane, c->tmpB, c->flow, L.lx, L.ly, L.det, L.octave,
+                                                L.sigma_size, w, h, p, L.plane, nf));
             } else {
                 LAUNCHED(AKZ_K_BLUR, akzk::down_with_smooth(st, P.lt, c->tmpB, c->smooth, P.w, P.h, P.pitch, P.plane, w, h, p, L.plane, nf));
                 LAUNCHED(AKZ_K_FLOW, akzk::flow(st, c->smooth, c->flow, o.diffusivity, c->kc, 0.75f, L.octave, w, h, p, L.plane, nf));
@@ -401,7 +417,7 @@ static int scale_space_chunk(akz_ctx* c, const void* img, int dtype, int nf, int
             // next sublevel (akaze.cpp:393-421)
             AkzLevel& P = c->lev[l - 1];
             if (fused) {
-                LAUNCHED(AKZ_K_PREP, akzk::level_prep(st, P.lt, c->flow, L.lx, L.ly, L.det, 1, o.diffusivity, c->kc, 0.75f, L.octave, L.sigma_size, w, h, p, L.plane, nf));
+                LAUNCHED(AKZ_K_PREP, prep_level(c, 1, P.lt, w, h, p, L.plane, nullptr, c->flow, L.lx, L.ly, L.det, L.octave, L.sigma_size, w, h, p, L.plane, nf));
             } else {
                 LAUNCHED(AKZ_K_BLUR, akzk::lowpass(st, P.lt, c->smooth, w, h, p, L.plane, p, L.plane, nf, 1.f, 5));
                 LAUNCHED(AKZ_K_FLOW, akzk::flow(st, c->smooth, c->flow, o.diffusivity, c->kc, 0.75f, L.octave, w, h, p, L.plane, nf));
@@ -572,7 +588,7 @@ int akz_fed_cycle(akz_ctx* c, const float* src, const float* flow, float* dst, f
 int akz_hessian(akz_ctx* c, const float* smooth, float* lx, float* ly, float* det, int step, int w, int h, int pitch, long long stride, int n)
 {
     STAGE_PROLOGUE();
-    if (c->opt.fused) LAUNCHED(AKZ_K_PREP, akzk::level_prep(c->stream, smooth, nullptr, lx, ly, det, 0, 1, c->kc, 1.f, 0, step, w, h, pitch, stride, n));
+    if (c->opt.fused) LAUNCHED(AKZ_K_PREP, prep_level(c, 0, smooth, w, h, pitch, stride, nullptr, nullptr, lx, ly, det, 0, step, w, h, pitch, stride, n));
     else LAUNCHED(AKZ_K_HESSIAN, akzk::hessian(c->stream, smooth, lx, ly, det, step, w, h, pitch, stride, n));
     STAGE_EPILOGUE();
 }

@@ -67,7 +67,10 @@ __global__ void __launch_bounds__(256) k_nms_mark(const unsigned long long* __re
                     const unsigned long long* row = m + (long long)(iy + i) * mpitch + ix;
                     for (int j = -isz; j <= isz; j++) {
                         if ((i == 0 && j == 0) || i * i + j * j >= sq) continue;
-                        unsigned long long kn = row[j];
+                        // akazed.cu:1578-1581: the reference's `continue` at the centre skips its `new_idx++`, so on
+                        // the centre row every j > 0 examines the pixel at offset j-1 (the centre itself for j = 1)
+                        // under the distance test of j.  Reproduced: the keypoint SET must equal the reference's.
+                        unsigned long long kn = row[(i == 0 && j > 0) ? j - 1 : j];
                         if (kn == 0ull) continue;
                         float rn = key_resp(kn);
                         if (rn > rc || (rn == rc && i <= 0 && j <= 0)) { keep = false; break; }

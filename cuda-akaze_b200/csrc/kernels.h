@@ -52,6 +52,12 @@ int level_prep(cudaStream_t st, const float* ltprev, float* flowp, float* lx, fl
 int level_prep_down(cudaStream_t st, const float* ltsrc, int sw, int sh, int sp, long long splane,
                     float* ltdst, float* flowp, float* lx, float* ly, float* det, int type,
                     const float* kc, float kscale, int nmul, int step, int w, int h, int pitch, long long plane, int n);
+// level_prep.cu: second-generation level kernel (templated on the derivative step, 64x64 tiles, vector shared-memory
+// traffic).  mode 0 = base level (no blur), 1 = blur, 2 = octave transition.  Returns 1 if launched, 0 if the
+// (step, size) combination is not covered and the caller must use level_prep / level_prep_down.
+int level_prep2(cudaStream_t st, int mode, const float* src, int sw, int sh, int sp, long long splane,
+                float* ltdst, float* flowp, float* lx, float* ly, float* det, int type,
+                const float* kc, float kscale, int nmul, int step, int w, int h, int pitch, long long plane, int n);
 // all n FED steps of a level (frozen conductance), temporally blocked in shared memory
 int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst, float* tmp, const float* tau, int nsteps,
               int w, int h, int pitch, long long plane, int n, int fused);

@@ -1,0 +1,333 @@
+// k_prep2<S, MODE>: the per-level "everything but the diffusion" kernel, second generation.
+//
+// Same contract as k_level_prep (scale_space_fused.cu): one read of the predecessor tile produces the
+// conductance plane g, the first derivatives Lx, Ly and the Hessian determinant of a level; the sigma=1
+// blur, its row-filtered intermediate and the derivative tiles live in shared memory only.
+// Subsumes gConv2d<2> | gDownWithSmooth (akazed.cu:204, :449), gFlowNaive (:1068), gDerivate (:1267) and
+// gHessianDeterminant (:1299).
+//
+// What changed against the first generation (ncu, profiles/r01_ncu_summary.md: 533 thread-instructions per
+// pixel, ALU pipe 54 % busy with index arithmetic, FMA pipe 30 %):
+//   * the derivative step S and the mode are template parameters and all tiles share ONE shared-memory
+//     coordinate frame (column = gx - X0 + 12, row = gy - Y0 + 2S + 2, pitch 88), so every neighbour offset
+//     is an immediate and every phase is a flat loop over "4 consecutive pixels" items: LDS.128 / STS.128 /
+//     STG.128 only, no per-element index arithmetic;
+//   * reflect-101 handling left the hot loops: interior tiles (82 % at 1080p) stream their input with
+//     cp.async 16-byte copies; border tiles load with reflected indices and, after the blur and after the
+//     first-derivative phase, overwrite the out-of-image cells of the tile with the value of their mirror
+//     cell (a copy, so operators are never evaluated on a mirrored extension: Lx/Ly are antisymmetric and
+//     the octave transition reflects in SOURCE coordinates);
+//   * 64x64 output tile (halo overhead 1.7x instead of 2.1x at S = 4), 512 threads, 2 CTAs per SM.
+// The arithmetic is the pinned sequence of common.cuh: results are bit-identical to the staged kernels.
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace akz;
+
+namespace {
+
+constexpr int P2_W = 64, P2_H = 64;          // output tile
+constexpr int P2_OX = 12;                    // shared-memory column of output column 0 (multiple of 4, >= 2*4 + 2)
+constexpr int P2_SP = P2_W + 2 * P2_OX;      // 88 floats per shared-memory row
+constexpr int P2_NT = 512;
+enum { PM_BASE = 0, PM_BLUR = 1, PM_DOWN = 2 };
+
+struct Prep2Args {
+    const float* src;                    // predecessor Lt (same resolution) or source octave (PM_DOWN)
+    float* ltdst;                        // PM_DOWN: subsampled Lt
+    float *flow, *lx, *ly, *det;         // flow may be null
+    const float* kc;                     // per-frame contrast factor
+    long long splane, plane;
+    float kscale, fac1, fac2, k0, k1, k2;
+    int nmul, type, vec_ok;
+    int sw, sh, sp;                      // source dims (== w, h, pitch unless PM_DOWN)
+    int w, h, pitch;
+};
+
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void sts4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// source-coordinate reflect of a coarse index (gDownWithSmooth reflects 2x+-2, 2x+-4 in the SOURCE image)
+__device__ __forceinline__ int coarse_src2(int q, int sdim)
+{
+    int c = 2 * q;
+    if (c < 0) c = -c;
+    if (c >= sdim) c = sdim + sdim - 2 - c;
+    return min(max(c, 0), sdim - 1);
+}
+
+// out-of-image cells of a tile := value of their reflect-101 mirror cell (border tiles only)
+template <int OY>
+__device__ __forceinline__ void ghost_fix(float* T, int r0, int r1, int c0, int c1, int X0, int Y0, int w, int h, int tid)
+{
+    const int nc = c1 - c0, tot = (r1 - r0) * nc;
+    for (int i = tid; i < tot; i += P2_NT) {
+        int r = r0 + i / nc, c = c0 + i % nc;
+        int gy = Y0 - OY + r, gx = X0 - P2_OX + c;
+        if (gy < 0 || gy >= h || gx < 0 || gx >= w) {
+            int mr = min(max(refl(gy, h) - Y0 + OY, r0), r1 - 1);
+            int mc = min(max(refl(gx, w) - X0 + P2_OX, c0), c1 - 1);
+            T[r * P2_SP + c] = T[mr * P2_SP + mc];
+        }
+    }
+}
+
+template <int S, int MODE>
+__global__ void __launch_bounds__(P2_NT, 2) k_prep2(const __grid_constant__ Prep2Args a)
+{
+    constexpr int OY = 2 * S + 2;                     // shared-memory row of output row 0
+    constexpr int AR = P2_H + 2 * OY;                 // rows of the input tile
+    constexpr int SP = P2_SP;
+    extern __shared__ __align__(16) float sm[];
+    float* A = sm;                                    // input tile            rows [0, AR)
+    float* Bf = A + AR * SP;                          // row-filtered          rows [0, AR)
+    float* Sm = Bf + AR * SP;                         // sigma = 1 blur        rows [2, AR-2)
+    float* LX = A;                                    // first derivatives     rows [OY-S, OY+64+S)   (alias A / Bf)
+    float* LY = Bf;
+
+    const int tid = threadIdx.x;
+    const int frame = blockIdx.z;
+    const int X0 = blockIdx.x * P2_W, Y0 = blockIdx.y * P2_H;
+    const int w = a.w, h = a.h;
+    const bool interior = X0 - P2_OX >= 0 && X0 + P2_W + P2_OX <= w && Y0 - OY >= 0 && Y0 + P2_H + OY <= h;
+    const bool fast = interior && a.vec_ok;
+    const float* __restrict__ src = a.src + (long long)frame * a.splane;
+
+    // ---- 1. input tile ------------------------------------------------------------------------------
+    {
+        float* dstp = (MODE == PM_BASE) ? Sm : A;
+        if (MODE != PM_DOWN && fast) {
+            for (int i = tid; i < AR * (SP / 4); i += P2_NT) {
+                int r = i / (SP / 4), g = i - r * (SP / 4);
+                cp_async16(dstp + r * SP + 4 * g, src + (long long)(Y0 - OY + r) * a.sp + (X0 - P2_OX + 4 * g));
+            }
+            cp_async_wait_all();
+        } else {
+            for (int i = tid; i < AR * SP; i += P2_NT) {
+                int r = i / SP, c = i - r * SP;
+                int gy = Y0 - OY + r, gx = X0 - P2_OX + c, sy, sx;
+                if (MODE == PM_DOWN) { sy = coarse_src2(gy, a.sh); sx = coarse_src2(gx, a.sw); }
+                else { sy = min(max(refl(gy, h), 0), h - 1); sx = min(max(refl(gx, w), 0), w - 1); }
+                dstp[i] = __ldg(src + (long long)sy * a.sp + sx);
+            }
+        }
+    }
+    __syncthreads();
+
+    if (MODE == PM_DOWN) {
+        // subsampled plane: dst(x, y) = src(2x, 2y)   (akazed.cu:505)
+        float* ltd = a.ltdst + (long long)frame * a.plane;
+        for (int i = tid; i < P2_H * P2_W; i += P2_NT) {
+            int r = i >> 6, c = i & 63;
+            int y = Y0 + r, x = X0 + c;
+            if (y < h && x < w) ltd[(long long)y * a.pitch + x] = A[(r + OY) * SP + P2_OX + c];
+        }
+    }
+
+    if (MODE != PM_BASE) {
+        const float k0 = a.k0, k1 = a.k1, k2 = a.k2;
+        // ---- 2. row pass: Bf[r][4..84) from A[r][2..86) -----------------------------------------------
+        for (int i = tid; i < AR * 20; i += P2_NT) {
+            int r = i / 20, g = i - r * 20;
+            const float* p = A + r * SP + 4 + 4 * g;
+            float4 v0 = lds4(p - 4), v1 = lds4(p), v2 = lds4(p + 4);
+            sts4(Bf + r * SP + 4 + 4 * g,
+                 gauss_r2(v0.z, v0.w, v1.x, v1.y, v1.z, k0, k1, k2), gauss_r2(v0.w, v1.x, v1.y, v1.z, v1.w, k0, k1, k2),
+                 gauss_r2(v1.x, v1.y, v1.z, v1.w, v2.x, k0, k1, k2), gauss_r2(v1.y, v1.z, v1.w, v2.x, v2.y, k0, k1, k2));
+        }
+        __syncthreads();
+        // ---- 3. column pass: Sm rows [2, AR-2), two rows per item --------------------------------------
+        for (int i = tid; i < ((AR - 4) / 2) * 20; i += P2_NT) {
+            int rb = i / 20, g = i - rb * 20;
+            int r = 2 + 2 * rb;
+            const float* p = Bf + (r - 2) * SP + 4 + 4 * g;
+            float4 b0 = lds4(p), b1 = lds4(p + SP), b2 = lds4(p + 2 * SP), b3 = lds4(p + 3 * SP), b4 = lds4(p + 4 * SP), b5 = lds4(p + 5 * SP);
+            float* q = Sm + r * SP + 4 + 4 * g;
+            sts4(q, gauss_r2(b0.x, b1.x, b2.x, b3.x, b4.x, k0, k1, k2), gauss_r2(b0.y, b1.y, b2.y, b3.y, b4.y, k0, k1, k2),
+                 gauss_r2(b0.z, b1.z, b2.z, b3.z, b4.z, k0, k1, k2), gauss_r2(b0.w, b1.w, b2.w, b3.w, b4.w, k0, k1, k2));
+            sts4(q + SP, gauss_r2(b1.x, b2.x, b3.x, b4.x, b5.x, k0, k1, k2), gauss_r2(b1.y, b2.y, b3.y, b4.y, b5.y, k0, k1, k2),
+                 gauss_r2(b1.z, b2.z, b3.z, b4.z, b5.z, k0, k1, k2), gauss_r2(b1.w, b2.w, b3.w, b4.w, b5.w, k0, k1, k2));
+        }
+        __syncthreads();
+    }
+    if (!interior) {
+        ghost_fix<OY>(Sm, 2, AR - 2, 4, 84, X0, Y0, w, h, tid);
+        __syncthreads();
+    }
+
+    // ---- 4. conductance of the output pixels ----------------------------------------------------------
+    if (a.flow) {
+        float k = a.kc[frame];
+        for (int i = 0; i < a.nmul; i++) k = __fmul_rn(k, a.kscale);
+        const float ikc = __fdiv_rn(1.f, __fmul_rn(k, k));
+        float* fl = a.flow + (long long)frame * a.plane;
+        for (int i = tid; i < P2_H * 16; i += P2_NT) {
+            int r = i >> 4, g = i & 15;
+            const float* p = Sm + (r + OY) * SP + P2_OX + 4 * g;
+            float u[6], c[6], l[6];
+            { float4 v = lds4(p - SP); u[0] = p[-SP - 1]; u[1] = v.x; u[2] = v.y; u[3] = v.z; u[4] = v.w; u[5] = p[-SP + 4]; }
+            { float4 v = lds4(p);      c[0] = p[-1];      c[1] = v.x; c[2] = v.y; c[3] = v.z; c[4] = v.w; c[5] = p[4]; }
+            { float4 v = lds4(p + SP); l[0] = p[SP - 1];  l[1] = v.x; l[2] = v.y; l[3] = v.z; l[4] = v.w; l[5] = p[SP + 4]; }
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float dx = scharr_dx(u[j], u[j + 2], c[j], c[j + 2], l[j], l[j + 2]);
+                float dy = scharr_dy(u[j], u[j + 1], u[j + 2], l[j], l[j + 1], l[j + 2]);
+                o[j] = conductance(a.type, __fmul_rn(grad_sq(dx, dy), ikc));
+            }
+            int y = Y0 + r, x = X0 + 4 * g;
+            float* d = fl + (long long)y * a.pitch + x;
+            if (fast) *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
+            else if (y < h) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (x + j < w) d[j] = o[j];
+            }
+        }
+    }
+
+    // ---- 5. first derivatives on the tile extended by S: rows [OY-S, OY+64+S), columns [8, 80) ----------
+    {
+        const float fac1 = a.fac1, fac2 = a.fac2;
+        float* lxg = a.lx + (long long)frame * a.plane;
+        float* lyg = a.ly + (long long)frame * a.plane;
+        for (int i = tid; i < (P2_H + 2 * S) * 18; i += P2_NT) {
+            int r = i / 18, g = i - r * 18;
+            int sr = OY - S + r, c4 = 8 + 4 * g;
+            const float* p = Sm + sr * SP + c4;
+            float u[12], c[12], l[12];
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                float4 vu = lds4(p - S * SP - 4 + 4 * q), vc = lds4(p - 4 + 4 * q), vl = lds4(p + S * SP - 4 + 4 * q);
+                u[4 * q] = vu.x; u[4 * q + 1] = vu.y; u[4 * q + 2] = vu.z; u[4 * q + 3] = vu.w;
+                c[4 * q] = vc.x; c[4 * q + 1] = vc.y; c[4 * q + 2] = vc.z; c[4 * q + 3] = vc.w;
+                l[4 * q] = vl.x; l[4 * q + 1] = vl.y; l[4 * q + 2] = vl.z; l[4 * q + 3] = vl.w;
+            }
+            float vx[4], vy[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int m = 4 + j;
+                float ul = u[m - S], uc = u[m], ur = u[m + S], cl = c[m - S], cr = c[m + S], ll = l[m - S], lc = l[m], lr = l[m + S];
+                vx[j] = deriv1(sum_x(ul, ur, ll, lr), __fsub_rn(cr, cl), fac1, fac2);
+                vy[j] = deriv1(sum_y(ul, ur, ll, lr), __fsub_rn(lc, uc), fac1, fac2);
+            }
+            sts4(LX + sr * SP + c4, vx[0], vx[1], vx[2], vx[3]);
+            sts4(LY + sr * SP + c4, vy[0], vy[1], vy[2], vy[3]);
+            if (r >= S && r < S + P2_H && g >= 1 && g <= 16) {
+                int y = Y0 + r - S, x = X0 + 4 * (g - 1);
+                long long o = (long long)y * a.pitch + x;
+                if (fast) {
+                    *reinterpret_cast<float4*>(lxg + o) = make_float4(vx[0], vx[1], vx[2], vx[3]);
+                    *reinterpret_cast<float4*>(lyg + o) = make_float4(vy[0], vy[1], vy[2], vy[3]);
+                } else if (y < h) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) if (x + j < w) { lxg[o + j] = vx[j]; lyg[o + j] = vy[j]; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (!interior) {
+        ghost_fix<OY>(LX, OY - S, OY + P2_H + S, 8, 80, X0, Y0, w, h, tid);
+        ghost_fix<OY>(LY, OY - S, OY + P2_H + S, 8, 80, X0, Y0, w, h, tid);
+        __syncthreads();
+    }
+
+    // ---- 6. second derivatives and determinant ----------------------------------------------------------
+    {
+        const float fac1 = a.fac1, fac2 = a.fac2;
+        float* dg = a.det + (long long)frame * a.plane;
+        for (int i = tid; i < P2_H * 16; i += P2_NT) {
+            int r = i >> 4, g = i & 15;
+            const float* px = LX + (r + OY) * SP + P2_OX + 4 * g;
+            const float* py = LY + (r + OY) * SP + P2_OX + 4 * g;
+            float xu[12], xc[12], xl[12], yu[12], yl[12];
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                float4 t;
+                t = lds4(px - S * SP - 4 + 4 * q); xu[4 * q] = t.x; xu[4 * q + 1] = t.y; xu[4 * q + 2] = t.z; xu[4 * q + 3] = t.w;
+                t = lds4(px + S * SP - 4 + 4 * q); xl[4 * q] = t.x; xl[4 * q + 1] = t.y; xl[4 * q + 2] = t.z; xl[4 * q + 3] = t.w;
+                t = lds4(py - S * SP - 4 + 4 * q); yu[4 * q] = t.x; yu[4 * q + 1] = t.y; yu[4 * q + 2] = t.z; yu[4 * q + 3] = t.w;
+                t = lds4(py + S * SP - 4 + 4 * q); yl[4 * q] = t.x; yl[4 * q + 1] = t.y; yl[4 * q + 2] = t.z; yl[4 * q + 3] = t.w;
+                if (S < 4 || q != 1) { t = lds4(px - 4 + 4 * q); xc[4 * q] = t.x; xc[4 * q + 1] = t.y; xc[4 * q + 2] = t.z; xc[4 * q + 3] = t.w; }
+            }
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int m = 4 + j;
+                float dxx = deriv2(sum_x(xu[m - S], xu[m + S], xl[m - S], xl[m + S]), __fsub_rn(xc[m + S], xc[m - S]), fac1, fac2);
+                float dxy = deriv2(sum_y(xu[m - S], xu[m + S], xl[m - S], xl[m + S]), __fsub_rn(xl[m], xu[m]), fac1, fac2);
+                float dyy = deriv2(sum_y(yu[m - S], yu[m + S], yl[m - S], yl[m + S]), __fsub_rn(yl[m], yu[m]), fac1, fac2);
+                o[j] = hess_det(dxx, dyy, dxy);
+            }
+            int y = Y0 + r, x = X0 + 4 * g;
+            float* d = dg + (long long)y * a.pitch + x;
+            if (fast) *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
+            else if (y < h) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (x + j < w) d[j] = o[j];
+            }
+        }
+    }
+}
+
+template <int S>
+constexpr int prep2_smem() { return 3 * (P2_H + 2 * (2 * S + 2)) * P2_SP * (int)sizeof(float); }
+
+template <int S, int MODE>
+void prep2_launch(cudaStream_t st, const Prep2Args& a, int n)
+{
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_prep2<S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, prep2_smem<S>()); attr = true; }
+    dim3 g((a.w + P2_W - 1) / P2_W, (a.h + P2_H - 1) / P2_H, n);
+    k_prep2<S, MODE><<<g, P2_NT, prep2_smem<S>(), st>>>(a);
+}
+
+template <int MODE>
+bool prep2_dispatch(cudaStream_t st, const Prep2Args& a, int step, int n)
+{
+    switch (step) {
+    case 2: prep2_launch<2, MODE>(st, a, n); return true;
+    case 3: prep2_launch<3, MODE>(st, a, n); return true;
+    case 4: prep2_launch<4, MODE>(st, a, n); return true;
+    default: return false;
+    }
+}
+
+}  // namespace
+
+namespace akzk {
+
+// mode: 0 = base level (smooth := src, no blur), 1 = same-resolution blur, 2 = octave transition.
+// Returns 1 when launched, 0 when this (step, size) combination is not covered (caller falls back to k_level_prep).
+int level_prep2(cudaStream_t st, int mode, const float* src, int sw, int sh, int sp, long long splane,
+                float* ltdst, float* flowp, float* lx, float* ly, float* det, int type,
+                const float* kc, float kscale, int nmul, int step, int w, int h, int pitch, long long plane, int n)
+{
+    if (step < 2 || step > 4 || w < 24 || h < 24) return 0;       // reflections must stay single (halo <= 10 + 2)
+    Prep2Args a = {};
+    a.src = src; a.ltdst = ltdst; a.flow = flowp; a.lx = lx; a.ly = ly; a.det = det; a.kc = kc;
+    a.splane = splane; a.plane = plane; a.kscale = kscale; a.nmul = nmul; a.type = type;
+    a.sw = sw; a.sh = sh; a.sp = sp; a.w = w; a.h = h; a.pitch = pitch;
+    hessian_factors(&a.fac1, &a.fac2);
+    float k[3];
+    akz_gauss_taps(1.f, 2, k);
+    a.k0 = k[0]; a.k1 = k[1]; a.k2 = k[2];
+    auto al16 = [](const void* p) { return p == nullptr || ((uintptr_t)p % 16) == 0; };
+    a.vec_ok = (pitch % 4 == 0) && (plane % 4 == 0) && (sp % 4 == 0) && (splane % 4 == 0) &&
+               al16(src) && al16(flowp) && al16(lx) && al16(ly) && al16(det);
+    bool ok = mode == 0 ? prep2_dispatch<PM_BASE>(st, a, step, n) : mode == 1 ? prep2_dispatch<PM_BLUR>(st, a, step, n)
+                                                                              : prep2_dispatch<PM_DOWN>(st, a, step, n);
+    return ok ? 1 : 0;
+}
+
+}  // namespace akzk

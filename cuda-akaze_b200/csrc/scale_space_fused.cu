@@ -300,6 +300,204 @@ __global__ void __launch_bounds__(FE_W * FE_TY) k_fed(const __grid_constant__ Fe
     }
 }
 
+
+// -----------------------------------------------------------------------------------------------------
+// k_fed2: register-blocked variant.  A 64x64 tile per CTA (512 threads), every thread owns a 4 (x) by
+// 2 (y) block of pixels for the whole launch: its Lt values AND the four conductance pair sums
+// g0+gL, g0+gR, g0+gD, g0+gU of every pixel stay in registers (g is frozen during a cycle, so the sums
+// are computed once; fadd is commutative, so neighbouring pixels share them bit-exactly: 22 sums per
+// 8 pixels).  Per step a thread exchanges only the rim of its block through shared memory (two row
+// float4s, two column float2s) and evaluates 9 FP instructions per pixel (4 sub, 1 mul, 4 fma) instead
+// of 13 FP + 10 shared-memory loads.  The valid region shrinks by one ring per step as in k_fed; cells
+// that have lost validity keep being computed (their garbage never reaches a valid cell).
+// Tile origin is aligned (x to 4, y to 2) so the image's left/top border always falls on a block edge.
+// -----------------------------------------------------------------------------------------------------
+constexpr int F2_T = 64;                     // tile edge
+constexpr int F2_BX = 16, F2_BY = 32;        // threads: 16 x 32, block 4 x 2 pixels
+constexpr int F2_CP = 66;                    // column-array pitch (floats): odd number of 8-byte units
+constexpr int F2_BUF = F2_T * F2_T + 2 * F2_BX * F2_CP;      // floats per exchange buffer
+constexpr int F2_SMEM = 2 * F2_BUF * (int)sizeof(float);
+
+struct Fed2Geom { int nhx, nhy, two, tho; };
+__host__ __device__ inline Fed2Geom fed2_geom(int n)
+{
+    Fed2Geom g;
+    g.nhx = (n + 3) & ~3; g.nhy = (n + 1) & ~1;
+    g.two = (F2_T - g.nhx - n) & ~3; g.tho = (F2_T - g.nhy - n) & ~1;
+    return g;
+}
+
+__device__ __forceinline__ float nld_update_s(float L0, float sL, float LL, float sR, float LR, float sD, float LD, float sU, float LU, float sf)
+{
+    float s = __fmul_rn(sL, __fsub_rn(LL, L0));
+    s = __fmaf_rn(sR, __fsub_rn(LR, L0), s);
+    s = __fmaf_rn(sD, __fsub_rn(LD, L0), s);
+    s = __fmaf_rn(sU, __fsub_rn(LU, L0), s);
+    return __fmaf_rn(s, sf, L0);
+}
+
+template <bool BORDER>
+__device__ __forceinline__ void fed2_body(const FedArgs& a, float* sm, int vec_ok)
+{
+    const int n = a.n, w = a.w, h = a.h;
+    const Fed2Geom ge = fed2_geom(n);
+    const int X0 = blockIdx.x * ge.two, Y0 = blockIdx.y * ge.tho;
+    const int GX0 = X0 - ge.nhx, GY0 = Y0 - ge.nhy;
+    const long long base = (long long)blockIdx.z * a.plane;
+    const float* __restrict__ src = a.src + base;
+    const float* __restrict__ flw = a.flow + base;
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * F2_BX + tx;
+    const int bx = 4 * tx, by = 2 * ty;                 // block origin in the tile
+    const int gx0 = GX0 + bx, gy0 = GY0 + by;
+
+    float* T0 = sm;                                     // buffer 0: tile [64][64], CL [16][66], CR [16][66]
+    float* T1 = sm + F2_BUF;                            // buffer 1 (its tile doubles as the G staging area)
+    float* Gs = T1;
+
+    // ---- conductance tile -> shared (reflected indices: pair sums at the image border come out right)
+    float L[2][4];
+    if (!BORDER && vec_ok) {
+        for (int i = tid; i < F2_T * (F2_T / 4); i += F2_BX * F2_BY) {
+            int r = i >> 4, c4 = (i & 15) * 4;
+            *(float4*)(Gs + r * F2_T + c4) = __ldg((const float4*)(flw + (long long)(GY0 + r) * a.pitch + GX0 + c4));
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            float4 v = __ldg((const float4*)(src + (long long)(gy0 + r) * a.pitch + gx0));
+            L[r][0] = v.x; L[r][1] = v.y; L[r][2] = v.z; L[r][3] = v.w;
+        }
+    } else {
+        for (int i = tid; i < F2_T * F2_T; i += F2_BX * F2_BY) {
+            int r = i >> 6, c = i & 63;
+            int sy = min(max(refl(GY0 + r, h), 0), h - 1), sx = min(max(refl(GX0 + c, w), 0), w - 1);
+            Gs[r * F2_T + c] = __ldg(flw + (long long)sy * a.pitch + sx);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            int sy = min(max(refl(gy0 + r, h), 0), h - 1);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                int sx = min(max(refl(gx0 + c, w), 0), w - 1);
+                L[r][c] = __ldg(src + (long long)sy * a.pitch + sx);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- pair sums: sh[r][j] = g(r, j-1) + g(r, j), j = 0..4 ; sv[k][c] = g(k-1, c) + g(k, c), k = 0..2
+    float sh[2][5], sv[3][4];
+    {
+        float g[4][6];                                   // rows by-1..by+2, cols bx-1..bx+4 (clamped at the tile rim)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int rr = min(max(by - 1 + k, 0), F2_T - 1);
+            const float* gr = Gs + rr * F2_T;
+            float4 v = *(const float4*)(gr + bx);
+            g[k][0] = gr[max(bx - 1, 0)]; g[k][1] = v.x; g[k][2] = v.y; g[k][3] = v.z; g[k][4] = v.w; g[k][5] = gr[min(bx + 4, F2_T - 1)];
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int j = 0; j < 5; j++) sh[r][j] = __fadd_rn(g[r + 1][j + 1], g[r + 1][j]);
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) sv[k][c] = __fadd_rn(g[k + 1][c + 1], g[k][c + 1]);
+    }
+
+    // border bookkeeping (BORDER tiles only)
+    bool bl = false, bt = false;
+    int ir = -1, jb = -1;
+    if (BORDER) {
+        bl = (gx0 == 0); bt = (gy0 == 0);
+        ir = (w - 1) - gx0; if (ir < 0 || ir > 3) ir = -1;
+        jb = (h - 1) - gy0; if (jb < 0 || jb > 1) jb = -1;
+    }
+
+    const int txl = max(tx - 1, 0), txr = min(tx + 1, F2_BX - 1);
+    const int ru = max(by - 1, 0), rd = min(by + 2, F2_T - 1);
+    const int o_row0 = by * F2_T + bx, o_up = ru * F2_T + bx, o_dn = rd * F2_T + bx;
+    const int o_cl = F2_T * F2_T + tx * F2_CP + by, o_cr = o_cl + F2_BX * F2_CP;
+    const int o_lf = F2_T * F2_T + F2_BX * F2_CP + txl * F2_CP + by;      // CR of the left neighbour
+    const int o_rt = F2_T * F2_T + txr * F2_CP + by;                      // CL of the right neighbour
+
+    // publish the rim of the block in buffer 0
+    *(float4*)(T0 + o_row0) = make_float4(L[0][0], L[0][1], L[0][2], L[0][3]);
+    *(float4*)(T0 + o_row0 + F2_T) = make_float4(L[1][0], L[1][1], L[1][2], L[1][3]);
+    *(float2*)(T0 + o_cl) = make_float2(L[0][0], L[1][0]);
+    *(float2*)(T0 + o_cr) = make_float2(L[0][3], L[1][3]);
+    __syncthreads();
+
+    float* cur = T0;
+    float* nxt = T1;
+    for (int st = 0; st < n; st++) {
+        const float sf = a.stepfac[st];
+        const float4 up4 = *(const float4*)(cur + o_up);
+        const float4 dn4 = *(const float4*)(cur + o_dn);
+        const float2 lf2 = *(const float2*)(cur + o_lf);
+        const float2 rt2 = *(const float2*)(cur + o_rt);
+        const float up[4] = { up4.x, up4.y, up4.z, up4.w }, dn[4] = { dn4.x, dn4.y, dn4.z, dn4.w };
+        const float lf[2] = { lf2.x, lf2.y }, rt[2] = { rt2.x, rt2.y };
+        float N[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                float LL = (c == 0) ? lf[r] : L[r][c - 1];
+                float LR = (c == 3) ? rt[r] : L[r][c + 1];
+                float LU = (r == 0) ? up[c] : L[0][c];
+                float LD = (r == 1) ? dn[c] : L[1][c];
+                if (BORDER) {
+                    if (c == 0 && bl) LL = LR;                 // x = 0: left neighbour is x = 1
+                    if (c == ir) LR = LL;                      // x = w-1: right neighbour is x = w-2
+                    if (r == 0 && bt) LU = LD;                 // y = 0
+                    if (r == jb) LD = LU;                      // y = h-1
+                }
+                N[r][c] = nld_update_s(L[r][c], sh[r][c], LL, sh[r][c + 1], LR, sv[r + 1][c], LD, sv[r][c], LU, sf);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) L[r][c] = N[r][c];
+        if (st + 1 < n) {
+            *(float4*)(nxt + o_row0) = make_float4(L[0][0], L[0][1], L[0][2], L[0][3]);
+            *(float4*)(nxt + o_row0 + F2_T) = make_float4(L[1][0], L[1][1], L[1][2], L[1][3]);
+            *(float2*)(nxt + o_cl) = make_float2(L[0][0], L[1][0]);
+            *(float2*)(nxt + o_cr) = make_float2(L[0][3], L[1][3]);
+            __syncthreads();
+            float* t = cur; cur = nxt; nxt = t;
+        }
+    }
+
+    // ---- store the output region of the tile
+    if (gx0 >= X0 && gx0 < X0 + ge.two && gx0 < w) {
+        float* dst = a.dst + base;
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            int gy = gy0 + r;
+            if (gy >= Y0 && gy < Y0 + ge.tho && gy < h) {
+                float* d = dst + (long long)gy * a.pitch + gx0;
+                if (vec_ok && gx0 + 3 < w) *(float4*)d = make_float4(L[r][0], L[r][1], L[r][2], L[r][3]);
+                else {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) if (gx0 + c < w) d[c] = L[r][c];
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(F2_BX * F2_BY, 2) k_fed2(const __grid_constant__ FedArgs a, int vec_ok)
+{
+    extern __shared__ __align__(16) float sm[];
+    const Fed2Geom ge = fed2_geom(a.n);
+    const int GX0 = blockIdx.x * ge.two - ge.nhx, GY0 = blockIdx.y * ge.tho - ge.nhy;
+    const bool border = GX0 <= 0 || GY0 <= 0 || GX0 + F2_T >= a.w || GY0 + F2_T >= a.h;
+    if (border) fed2_body<true>(a, sm, vec_ok);
+    else fed2_body<false>(a, sm, vec_ok);
+}
+
 bool g_attr_done = false;
 
 }  // namespace
@@ -310,6 +508,7 @@ static void set_attrs()
 {
     if (g_attr_done) return;
     cudaFuncSetAttribute(k_fed, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * FE_W * FE_H * (int)sizeof(float));
+    cudaFuncSetAttribute(k_fed2, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM);
     cudaFuncSetAttribute(k_level_prep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_level_prep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     g_attr_done = true;
@@ -352,7 +551,8 @@ int level_prep_down(cudaStream_t st, const float* ltsrc, int sw, int sh, int sp,
 }
 
 // dst receives the result of n steps applied to src; tmp is a scratch plane batch (never aliases src/dst).
-// fused != 0: ceil(n/8) launches of the temporally blocked kernel, else n single-step launches.
+// fused == 0: n single-step launches; fused == 1: ceil(n/8) launches of the register-blocked k_fed2;
+// fused == 2: the same split with the shared-memory-resident k_fed (kept as a cross-check).
 int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst, float* tmp, const float* tau, int nsteps,
               int w, int h, int pitch, long long plane, int n, int fused)
 {
@@ -378,9 +578,16 @@ int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst,
         a.src = cur; a.flow = flowp; a.dst = ((m - 1 - i) % 2 == 0) ? dst : tmp;
         a.plane = plane; a.w = w; a.h = h; a.pitch = pitch; a.n = cnt;
         for (int k = 0; k < cnt; k++) a.stepfac[k] = 0.5f * tau[done + k];      // akazed.cu:2515
-        int TWo = FE_W - 2 * cnt, THo = FE_H - 2 * cnt;
-        dim3 g((w + TWo - 1) / TWo, (h + THo - 1) / THo, n), b(FE_W, FE_TY);
-        k_fed<<<g, b, 3 * FE_W * FE_H * sizeof(float), st>>>(a);
+        if (fused == 2) {
+            int TWo = FE_W - 2 * cnt, THo = FE_H - 2 * cnt;
+            dim3 g((w + TWo - 1) / TWo, (h + THo - 1) / THo, n), b(FE_W, FE_TY);
+            k_fed<<<g, b, 3 * FE_W * FE_H * sizeof(float), st>>>(a);
+        } else {
+            Fed2Geom ge = fed2_geom(cnt);
+            dim3 g((w + ge.two - 1) / ge.two, (h + ge.tho - 1) / ge.tho, n), b(F2_BX, F2_BY);
+            int vec_ok = (pitch % 4 == 0) && (plane % 4 == 0) && (((uintptr_t)a.src | (uintptr_t)flowp | (uintptr_t)a.dst) % 16 == 0);
+            k_fed2<<<g, b, F2_SMEM, st>>>(a, vec_ok);
+        }
         cur = a.dst;
         done += cnt;
         launches++;

@@ -498,7 +498,11 @@ int orc_pyramid_detect(orc_pyramid* P, orc_keypoint* out, int cap)
                 for (int j = -isz; j <= isz; j++) {
                     if (i == 0 && j == 0) continue;
                     if (i * i + j * j >= sq) continue;
-                    size_t ni = (size_t)(iy + i) * W + (ix + j);
+                    /* akazed.cu:1578-1581: the `continue` at the centre skips `new_idx++`, so in the centre row every
+                     * j > 0 reads the pixel at offset j - 1 (the centre itself for j = 1) under the distance test of j;
+                     * the farthest in-radius pixel to the right on the centre row is never examined. */
+                    int jj = (i == 0 && j > 0) ? j - 1 : j;
+                    size_t ni = (size_t)(iy + i) * W + (ix + jj);
                     if (P->layer[ni] < 0) continue;      /* non-candidates hold a value below any response */
                     float rn = P->resp[ni];
                     if (rn > rc || (rn == rc && i <= 0 && j <= 0)) { kill = 1; break; }

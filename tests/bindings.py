@@ -207,6 +207,41 @@ def ref():
     return L
 
 
+
+def _wrap_device(ptr, nbytes):
+    """A uint8 torch view of foreign device memory (no ownership)."""
+    import torch
+
+    class _H:
+        pass
+    h = _H()
+    h.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(h, device="cuda")
+
+
+def ref_schedule(noct, S=4, soffset=1.6, derivative_factor=1.5):
+    """(sizes, sigma_sizes, borders) per octave exactly as akaze.cpp:268-363 computes them (float arithmetic, libm powf)."""
+    libm = C.CDLL("libm.so.6")
+    libm.powf.restype = C.c_float
+    libm.powf.argtypes = [C.c_float, C.c_float]
+    f = np.float32
+    smax = f(10.0 * float(np.sqrt(f(2.0))))
+    out = []
+    for i in range(noct):
+        oratio = f(1 << i)
+        sizes, ss, borders = [], [], []
+        for j in range(S):
+            if i == 0 and j == 0:
+                size = f(f(soffset) * f(derivative_factor))
+            else:
+                esigma = f(f(soffset) * f(libm.powf(f(2), f(f(j) / f(S)) + f(i))))
+                size = f(f(esigma * f(derivative_factor)) / oratio)
+            sg = int(f(size + f(0.5)))
+            sizes.append(size); ss.append(sg); borders.append(f(smax * f(sg)))
+        out.append((np.array(sizes, dtype=f), ss, np.array(borders, dtype=f)))
+    return out
+
+
 class RefAkazer:
     """The reference's Akazer (akaze.h:19-66) behind the shim; images are torch CUDA tensors (h, pitch)."""
 
@@ -265,6 +300,80 @@ class RefAkazer:
                 planes.append(grp)
         k = self.L.ref_last_kcontrast()
         return pts.cpu().numpy().view(REF_POINT)[:n].copy(), planes, float(k)
+
+
+    def detect_serialized(self, img_t, max_pts=100000, desc=True, dthreshold=0.001):
+        """The reference pipeline with its sublevel merge made race-free WITHOUT touching its code.
+
+        gCalcExtremaMap merges the sublevels of an octave with an unsynchronised check-then-write
+        (akazed.cu:1364-1373, App. B-2); on a B200 the z-slices of a small octave are co-resident and the outcome varies.
+        Here the stock scale space is built first (detect_keep), then hCalcExtremaMap is called once per sublevel on a
+        copy of the octave's determinant planes in which every OTHER sublevel is zeroed (zero never passes the
+        threshold), then the stock hNmsR, hRefine, hCalcOrient and hDescribe run on the same pyramid.
+        Returns (points, planes, kcontrast)."""
+        import torch
+        L = self.L
+        dev = img_t.device
+        pts = torch.zeros(max_pts * 104, dtype=torch.uint8, device=dev)
+        tmem = C.c_void_p()
+        oparams = (C.c_int * 64)()
+        noct = C.c_int()
+        torch.cuda.synchronize()
+        L.ref_akazer_detect_keep(self.hnd, C.c_void_p(img_t.data_ptr()), self.w, self.h, self.pitch, 0,
+                                 C.c_void_p(pts.data_ptr()), max_pts, C.byref(tmem), oparams, C.byref(noct))
+        torch.cuda.synchronize()
+        no, S = noct.value, self.S
+        osizes = list(oparams[0:no])
+        offsets = list(oparams[no:2 * no + 1])
+        owhps = [tuple(oparams[2 * no + 1 + 3 * k: 2 * no + 4 + 3 * k]) for k in range(no)]
+        total = offsets[no]
+        mem = _wrap_device(tmem.value, total * 4).view(torch.int32)
+        W, H, P0 = owhps[0]
+        msz = H * P0
+        mem[0:2 * msz] = int(np.array([0xBDBDBDBD], dtype=np.uint32).view(np.int32)[0])     # akaze.cpp:253-258 (App. B-8)
+        mem[2 * msz:3 * msz] = -1
+        sched = ref_schedule(no, S)
+        psz, neigh = 10000.0, 0
+        f32 = mem.view(torch.float32)
+        for o in range(no):
+            w, h, p = owhps[o]
+            sizes, ss, borders = sched[o]
+            params = np.concatenate([borders, sizes]).astype(np.float32)
+            psz = min(psz, float(borders[0]) * (1 << o))
+            neigh = max(neigh, max(ss))
+            dets = f32[offsets[o] + S * osizes[o]: offsets[o] + 2 * S * osizes[o]]           # group 1 = det (akaze.cpp:315-320)
+            for j in range(S):
+                scratch = torch.zeros_like(dets)
+                scratch[j * osizes[o]:(j + 1) * osizes[o]] = dets[j * osizes[o]:(j + 1) * osizes[o]]
+                torch.cuda.synchronize()
+                L.ref_hCalcExtremaMap(C.c_void_p(scratch.data_ptr()), C.c_void_p(tmem.value), C.c_void_p(tmem.value + 4 * msz),
+                                      C.c_void_p(tmem.value + 8 * msz), params.ctypes.data_as(C.POINTER(C.c_float)),
+                                      o, S, dthreshold, w, h, p, P0)
+        pts.zero_()
+        L.ref_setMaxNumPoints(max_pts)
+        L.ref_resetPointCounter()
+        L.ref_hNmsR(C.c_void_p(pts.data_ptr()), C.c_void_p(tmem.value), C.c_void_p(tmem.value + 4 * msz), C.c_void_p(tmem.value + 8 * msz),
+                    int(psz), neigh, W, H, P0)
+        n = min(int(L.ref_readPointCounter()), max_pts)
+        L.ref_hRefine(C.c_void_p(pts.data_ptr()), n, max_pts, C.c_void_p(tmem.value), no, S)
+        if desc:
+            L.ref_hCalcOrient(C.c_void_p(pts.data_ptr()), n, max_pts, C.c_void_p(tmem.value), no, S)
+            L.ref_hDescribe(C.c_void_p(pts.data_ptr()), n, max_pts, C.c_void_p(tmem.value), no, S, 10)
+        torch.cuda.synchronize()
+        host = f32.cpu().numpy()
+        planes = []
+        for o in range(no):
+            w, h, p = owhps[o]
+            for sidx in range(S):
+                grp = []
+                for which in range(4):
+                    off = offsets[o] + (which * S + sidx) * osizes[o]
+                    grp.append(host[off:off + osizes[o]].reshape(h, p)[:, :w].copy())
+                planes.append(grp)
+        out = pts.cpu().numpy().view(REF_POINT)[:n].copy()
+        del mem, f32
+        L.ref_cuda_free(tmem)
+        return out, planes, float(L.ref_last_kcontrast())
 
 
 # ---- seeded inputs ------------------------------------------------------------------------------------------

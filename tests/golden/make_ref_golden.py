@@ -5,7 +5,8 @@ The reference is a CUDA library, so this runs under gpurun:
 and the file is then copied to tests/golden/.  It pins the CPU oracle (tests/test_cpu.py::
 test_oracle_against_reference_golden_fixture): sha256 of every Lt/det/Lx/Ly plane of the reference's pyramid plus
 an 8x-subsampled copy of each, the reference's keypoints, angles and descriptors, and the contrast factor the
-reference's (racy, App. B-1) reduction produced in that run.  320x240 with 2 octaves is a size at which the
+reference's (racy, App. B-1) reduction produced in that run.  The keypoints come from the reference's own kernels with
+the sublevel merge serialised (bindings.RefAkazer.detect_serialized: the stock merge is a data race, App. B-2).  320x240 with 2 octaves is a size at which the
 reference's blur kernels have no uninitialised halo rows (App. B-7).
 """
 import hashlib
@@ -29,7 +30,7 @@ def main(out):
     buf[:, :w] = img
     d = torch.from_numpy(buf).cuda()
     ref = B.RefAkazer(w, h, pitch, noctaves=2)
-    pts, planes, k = ref.detect_keep(d, max_pts=20000, desc=True)
+    pts, planes, k = ref.detect_serialized(d, max_pts=20000, desc=True)
     g = {"seed": seed, "img_sha256": hashlib.sha256(img.tobytes()).hexdigest(), "kcontrast": np.float32(k), "nlevels": len(planes)}
     for l, grp in enumerate(planes):
         for which, nm in enumerate(("lt", "det", "lx", "ly")):

@@ -356,9 +356,13 @@ def test_keypoints_vs_reference(ref_left):
     rep = same.mean()
     print(f"\n[keypoints] ours={len(mine)} reference={len(refp)} identical-position fraction={rep:.5f} "
           f"max position error among matched={d[same].max() if same.any() else -1:.2e}")
-    assert abs(len(mine) - len(refp)) <= max(3, 0.002 * len(refp))
-    assert rep >= 0.99                                   # north-star: repeatability >= 99 %
-    assert np.all(mine["size"][j][same] == refp["size"][same])
+    # The whole-pipeline reference run merges sublevels with a data race (App. B-2) that is live on a B200 at octaves >= 1
+    # (all z-slices of gCalcExtremaMap are co-resident): a racing pixel can keep the SMALLER response, which changes
+    # what the radius NMS around it suppresses.  The exact, race-free comparison is test_detector_vs_serialized_reference
+    # (set equality); here the racy run must still agree on the bulk.
+    assert abs(len(mine) - len(refp)) <= 0.04 * len(refp)
+    assert rep >= 0.93
+    assert np.mean(mine["size"][j][same] == refp["size"][same]) >= 0.995      # torn (layer, size) pairs of the racy merge
     # orientation: <= 1e-4 rad modulo 2 pi (App. B-4: the reference sums its histogram with float atomics)
     da = np.abs(mine["angle"][j][same] - refp["angle"][same])
     da = np.minimum(da, 2 * np.pi - da)
@@ -377,6 +381,39 @@ def test_keypoints_vs_reference(ref_left):
     assert nbad == 0
     assert not dm[:, 61:].any()
     ctx.close()
+
+
+def test_detector_vs_serialized_reference():
+    """Extrema merge + radius NMS + refinement + orientation + M-LDB against the reference's own kernels run race-free
+    (bindings.RefAkazer.detect_serialized): keypoint SETS must be equal, positions within 1e-4 px, descriptors of
+    keypoints with identical (x, y, angle) bit-identical."""
+    if not B.have_ref():
+        pytest.skip("reference not built")
+    for name, img in (("left.pgm", left_image()), ("right.pgm", right_image())):
+        h, w = img.shape
+        r = B.RefAkazer(w, h, w)
+        rp, _, k = r.detect_serialized(dev(img)[0], max_pts=30000)
+        r.close()
+        ctx = ab().Context(w, h, max_batch=1, max_pts=30000, kcontrast_override=k)
+        counts, kpts, desc = ctx.detect_and_compute(dev(img))
+        ctx.sync()
+        mine = _kp_array(counts, kpts)
+        dm = desc[0].cpu().numpy()
+        ctx.close()
+        from scipy.spatial import cKDTree
+        d, j = cKDTree(np.stack([mine["x"], mine["y"]], 1)).query(np.stack([rp["x"], rp["y"]], 1))
+        same = (d <= 1e-4) & (mine["layer"][j] == rp["octave"])
+        da = np.abs(mine["angle"][j] - rp["angle"])
+        da = np.minimum(da, 2 * np.pi - da)
+        exact = same & (mine["angle"][j].view(np.uint32) == rp["angle"].view(np.uint32)) & \
+            (mine["x"][j].view(np.uint32) == rp["x"].view(np.uint32)) & (mine["y"][j].view(np.uint32) == rp["y"].view(np.uint32))
+        nbad = int((dm[j[exact]][:, :61] != rp["features"][exact]).any(axis=1).sum())
+        print(f"\n[{name} | serialised reference] ours={len(mine)} reference={len(rp)} same position+layer={same.mean():.5f} "
+              f"max |dpos|={d.max():.2e} angle<=1e-4: {(da[same] <= 1e-4).mean():.5f} exact (x,y,angle)={int(exact.sum())} descriptors differing={nbad}")
+        assert len(mine) == len(rp) and same.all()
+        assert np.array_equal(mine["size"][j], rp["size"])
+        assert (da <= 1e-4).mean() >= 0.995
+        assert nbad == 0 and exact.mean() >= 0.75          # the rest differ in the last bits of the angle (App. B-4)
 
 
 def test_orientation_and_descriptor_given_reference_keypoints(ref_left):
@@ -538,7 +575,9 @@ def test_matcher_vs_cpu_oracle(nq, nt):
 
 @needs_ref
 def test_matcher_vs_reference():
-    nq, nt = 1200, 1700
+    # nt must be a multiple of 16: gHammingMatch calls __syncthreads() inside a loop whose trip count differs per
+    # thread otherwise (akazed.cu:2176-2187, App. B-15) -- on sm_100a that deadlocks (observed: the kernel never returns)
+    nq, nt = 1200, 1696
     q, t = _planted(nq, nt, seed=99)
     pq = np.zeros(nq, dtype=B.REF_POINT)
     pt = np.zeros(nt, dtype=B.REF_POINT)
