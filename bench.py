@@ -172,6 +172,69 @@ def algorithmic_bytes(cls, nkp):
     return 0
 
 
+def match_metric(ab, device, rank, world, clock_mhz):
+    """BASELINE metric 2: brute-force Hamming matching, 10k x 10k on one GPU and 10k x 1M with the TRAIN set sharded over
+    the ranks (akz_match(finalize=0) per shard -> one all_gather of nq x 16 B per rank over NCCL -> akz_match_merge)."""
+    import torch
+    import bindings as B
+    from akaze_b200 import distributed as D
+    ctx = ab.Context(0, 0, device=device.index)
+    stream = ctx.torch_stream()
+    out = {}
+    q = torch.from_numpy(B.random_descriptors(10000, 0)).to(device)
+    t = torch.from_numpy(B.random_descriptors(10000, 1)).to(device)
+    res = torch.zeros(10000, 4, dtype=torch.int32, device=device)
+
+    def time_it(fn, iters):
+        for _ in range(3):
+            fn()
+        ctx.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(iters):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    for mode, name in ((ab.MATCH_KNN2, "knn2"), (ab.MATCH_COMPAT, "compat")):
+        out[f"{name}_10kx10k_ms"] = round(time_it(lambda: ctx.match(q, t, mode, out=res), 20), 4)
+    popc = 10000 * 10000 * 16 / (out["knn2_10kx10k_ms"] * 1e-3)
+    peak = 148 * 16 * (clock_mhz or 1965.0) * 1e6                  # POPC.32: 16 lanes / clk / SM (cc 10.0 throughput table)
+    out["popc32_per_s"] = float(f"{popc:.4g}")
+    out["popc_frac_of_peak"] = round(popc / peak, 3)
+    out["popc_peak_assumed"] = "148 SMs x 16 POPC/clk x SM clock"
+    # 10k x 1M, train sharded over the ranks (config 4)
+    nt_total = 1_000_000
+    lo, hi = D.shard_bounds(nt_total, world, rank)
+    g = torch.Generator(device=device)
+    g.manual_seed(1234 + rank)
+    tl = torch.randint(0, 256, (hi - lo, 64), dtype=torch.uint8, device=device, generator=g)
+    tl[:, 61:] = 0
+    tl[:, 60] &= 0x3F
+    if world > 1:
+        import torch.distributed as dist
+        fn = lambda: D.match_sharded_gpu(ctx, q, tl, lo, ab.MATCH_KNN2)
+        for _ in range(2):
+            fn()
+        barrier(world)
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            fn()
+        e1.record()
+        e1.synchronize()
+        ms = barrier_max(e0.elapsed_time(e1) / 3, world, device)
+    else:
+        ms = time_it(lambda: ctx.match(q, tl, ab.MATCH_KNN2, out=res), 3)
+    out["knn2_10kx1M_ms"] = round(ms, 3)
+    out["knn2_10kx1M_shards"] = world
+    out["knn2_10kx1M_popc_frac_of_peak"] = round(10000 * nt_total * 16 / (ms * 1e-3) / (peak * world), 3)
+    ctx.close()
+    return out
+
+
 def run_ours(args):
     import torch
     import akaze_b200 as ab
@@ -259,11 +322,15 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(F * 4 + counts.sum() * (32 + 64)), "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
     }
+    ctx.close()
+    del dev
+    if not args.no_match:
+        m = match_metric(ab, device, rank, world, (clocks or {}).get("sm_mhz") if clocks else None)
+        line["match"] = m
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(frames8, args.cpu_frames)
     if rank == 0:
         print(json.dumps(line), flush=True)
-    ctx.close()
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -391,6 +458,7 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "u8"])
     ap.add_argument("--cpu-frames", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-match", action="store_true", help="skip the brute-force matching metric (BASELINE metric 2)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = max(args.warmup, 1)

@@ -127,13 +127,16 @@ struct akz_ctx {
     float *smooth, *flow, *tmpA, *tmpB;
     unsigned long long* map;
     unsigned* rowmask;
-    int *rowcount, *prefix, *hist, *counts_own;
+    int *rowcount, *prefix, *hist, *counts_own;      // counts_own / kpts_own / desc_own: two result sets (host API pipeline)
     unsigned* hmax;
     float* kc;
     akz_keypoint* kpts_own;
     unsigned char* desc_own;
-    void* img_stage;
+    void* img_stage[2];
     size_t img_stage_bytes;
+    cudaStream_t h2d_stream, d2h_stream;
+    cudaEvent_t ev_h2d[2], ev_comp[2], ev_cnt[2], ev_d2h[2];
+    int* h_cnt_pinned;                               // [2][max_batch] pinned landing zone of the per-chunk counts
     akz_match_t* match_parts;
     size_t match_parts_n;
     void* match_stage; size_t match_stage_bytes;
@@ -236,7 +239,9 @@ int akz_create(const akz_options* o, akz_ctx** out)
     c->opt = *o;
     c->launches = 0; c->last_frames = 0; c->prof_on = false;
     memset(c->prof_ms, 0, sizeof(c->prof_ms)); memset(c->prof_launches, 0, sizeof(c->prof_launches));
-    c->img_stage = nullptr; c->img_stage_bytes = 0; c->match_parts = nullptr; c->match_parts_n = 0;
+    c->img_stage[0] = c->img_stage[1] = nullptr; c->img_stage_bytes = 0; c->match_parts = nullptr; c->match_parts_n = 0;
+    c->h2d_stream = c->d2h_stream = nullptr; c->h_cnt_pinned = nullptr;
+    for (int i = 0; i < 2; i++) { c->ev_h2d[i] = c->ev_comp[i] = c->ev_cnt[i] = c->ev_d2h[i] = nullptr; }
     c->match_stage = nullptr; c->match_stage_bytes = 0;
     int rc = AKZ_OK;
     do {
@@ -271,9 +276,16 @@ int akz_create(const akz_options* o, akz_ctx** out)
         int mwords = (o->width + 31) / 32;
         if ((rc = dalloc(c, &c->rowmask, (size_t)mwords * o->height * B)) != AKZ_OK) break;
         if ((rc = dalloc(c, &c->rowcount, (size_t)o->height * B)) != AKZ_OK) break;
-        if ((rc = dalloc(c, &c->counts_own, (size_t)B)) != AKZ_OK) break;
-        if ((rc = dalloc(c, &c->kpts_own, (size_t)o->max_pts * B)) != AKZ_OK) break;
-        if ((rc = dalloc(c, &c->desc_own, (size_t)o->max_pts * B * 64)) != AKZ_OK) break;
+        if ((rc = dalloc(c, &c->counts_own, (size_t)2 * B)) != AKZ_OK) break;
+        if ((rc = dalloc(c, &c->kpts_own, (size_t)2 * o->max_pts * B)) != AKZ_OK) break;
+        if ((rc = dalloc(c, &c->desc_own, (size_t)2 * o->max_pts * B * 64)) != AKZ_OK) break;
+        if (cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = akz_set_error(AKZ_E_CUDA, "stream creation failed"); break; }
+        for (int i = 0; i < 2; i++) {
+            cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&c->ev_cnt[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming);
+        }
+        if (cudaMallocHost((void**)&c->h_cnt_pinned, sizeof(int) * 2 * B) != cudaSuccess) { rc = akz_set_error(AKZ_E_NOMEM, "pinned allocation failed"); break; }
         cudaMemsetAsync(c->rowcount, 0, sizeof(int) * (size_t)o->height * B, c->stream);
         cudaMemsetAsync(c->rowmask, 0, sizeof(unsigned) * (size_t)mwords * o->height * B, c->stream);
         // level table for the keypoint kernels
@@ -299,7 +311,16 @@ void akz_destroy(akz_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (void* p : c->allocs) cudaFree(p);
-    if (c->img_stage) cudaFree(c->img_stage);
+    for (int i = 0; i < 2; i++) {
+        if (c->img_stage[i]) cudaFree(c->img_stage[i]);
+        if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
+        if (c->ev_comp[i]) cudaEventDestroy(c->ev_comp[i]);
+        if (c->ev_cnt[i]) cudaEventDestroy(c->ev_cnt[i]);
+        if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
+    }
+    if (c->h_cnt_pinned) cudaFreeHost(c->h_cnt_pinned);
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->match_parts) cudaFree(c->match_parts);
     if (c->match_stage) cudaFree(c->match_stage);
     for (auto& pp : c->prof_pairs) { cudaEventDestroy(pp.a); cudaEventDestroy(pp.b); }
@@ -508,29 +529,67 @@ int akz_detect_and_compute_host(akz_ctx* c, const void* h_images, int dtype, int
     const size_t esz = dtype == AKZ_U8 ? 1 : 4;
     const size_t need = (size_t)B * stride * esz;
     if (c->img_stage_bytes < need) {
-        if (c->img_stage) cudaFree(c->img_stage);
-        c->img_stage = nullptr; c->img_stage_bytes = 0;
-        AKZ_CUDA_TRY(cudaMalloc(&c->img_stage, need));
+        for (int i = 0; i < 2; i++) {
+            if (c->img_stage[i]) cudaFree(c->img_stage[i]);
+            c->img_stage[i] = nullptr;
+        }
+        c->img_stage_bytes = 0;
+        AKZ_CUDA_TRY(cudaMalloc(&c->img_stage[0], need));
+        AKZ_CUDA_TRY(cudaMalloc(&c->img_stage[1], need));
         c->img_stage_bytes = need;
     }
+    // Three-stage pipeline over chunks of max_batch frames, two buffer sets:
+    //   h2d stream : frames of chunk i+1 -> staging[(i+1)&1]      (overlaps the kernels of chunk i)
+    //   main stream: scale space + detector + descriptors of chunk i -> result set i&1
+    //   d2h stream : counts of chunk i, then (once the host knows them) one strided copy of keypoints and one of
+    //                descriptors, width = the largest count of the chunk (overlaps the kernels of chunk i+1)
     cudaStream_t st = c->stream;
-    for (int f0 = 0; f0 < nframes; f0 += B) {
-        int nf = std::min(B, nframes - f0);
-        const char* src = (const char*)h_images + (size_t)f0 * stride * esz;
-        AKZ_CUDA_TRY(cudaMemcpyAsync(c->img_stage, src, (size_t)nf * stride * esz, cudaMemcpyHostToDevice, st));
-        if ((rc = scale_space_chunk(c, c->img_stage, dtype, nf, pitch, stride)) != AKZ_OK) return rc;
-        if ((rc = detect_chunk(c, nf, describe, c->counts_own, c->kpts_own, c->desc_own)) != AKZ_OK) return rc;
-        AKZ_CUDA_TRY(cudaMemcpyAsync(h_counts + f0, c->counts_own, sizeof(int) * nf, cudaMemcpyDeviceToHost, st));
-        AKZ_CUDA_TRY(cudaStreamSynchronize(st));
-        for (int f = 0; f < nf; f++) {
-            int n = h_counts[f0 + f];
-            if (n <= 0) continue;
-            AKZ_CUDA_TRY(cudaMemcpyAsync(h_kpts + (size_t)(f0 + f) * MP, c->kpts_own + (size_t)f * MP, sizeof(akz_keypoint) * n, cudaMemcpyDeviceToHost, st));
+    const int nchunks = (nframes + B - 1) / B;
+    auto chunk_frames = [&](int i) { return std::min(B, nframes - i * B); };
+    auto issue_h2d = [&](int i) -> int {
+        const char* src = (const char*)h_images + (size_t)i * B * stride * esz;
+        AKZ_CUDA_TRY(cudaMemcpyAsync(c->img_stage[i & 1], src, (size_t)chunk_frames(i) * stride * esz, cudaMemcpyHostToDevice, c->h2d_stream));
+        AKZ_CUDA_TRY(cudaEventRecord(c->ev_h2d[i & 1], c->h2d_stream));
+        return AKZ_OK;
+    };
+    auto drain = [&](int i) -> int {          // host side of the result download of chunk i
+        const int s = i & 1, nf = chunk_frames(i), f0 = i * B;
+        AKZ_CUDA_TRY(cudaEventSynchronize(c->ev_cnt[s]));
+        int maxc = 0;
+        for (int f = 0; f < nf; f++) { h_counts[f0 + f] = c->h_cnt_pinned[s * B + f]; maxc = std::max(maxc, h_counts[f0 + f]); }
+        if (maxc > 0) {
+            AKZ_CUDA_TRY(cudaMemcpy2DAsync(h_kpts + (size_t)f0 * MP, sizeof(akz_keypoint) * (size_t)MP, c->kpts_own + (size_t)s * B * MP,
+                                           sizeof(akz_keypoint) * (size_t)MP, sizeof(akz_keypoint) * (size_t)maxc, nf, cudaMemcpyDeviceToHost, c->d2h_stream));
             if (describe)
-                AKZ_CUDA_TRY(cudaMemcpyAsync(h_desc + (size_t)(f0 + f) * MP * 64, c->desc_own + (size_t)f * MP * 64, (size_t)64 * n, cudaMemcpyDeviceToHost, st));
+                AKZ_CUDA_TRY(cudaMemcpy2DAsync(h_desc + (size_t)f0 * MP * 64, (size_t)MP * 64, c->desc_own + (size_t)s * B * MP * 64, (size_t)MP * 64,
+                                               (size_t)maxc * 64, nf, cudaMemcpyDeviceToHost, c->d2h_stream));
         }
-        AKZ_CUDA_TRY(cudaStreamSynchronize(st));
+        AKZ_CUDA_TRY(cudaEventRecord(c->ev_d2h[s], c->d2h_stream));
+        return AKZ_OK;
+    };
+    if (nchunks > 0 && (rc = issue_h2d(0)) != AKZ_OK) return rc;
+    for (int i = 0; i < nchunks; i++) {
+        const int s = i & 1, nf = chunk_frames(i);
+        AKZ_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_h2d[s], 0));
+        if (i >= 2) AKZ_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_d2h[s], 0));          // result set s is free again
+        if ((rc = scale_space_chunk(c, c->img_stage[s], dtype, nf, pitch, stride)) != AKZ_OK) return rc;
+        if ((rc = detect_chunk(c, nf, describe, c->counts_own + (size_t)s * B, c->kpts_own + (size_t)s * B * MP,
+                               c->desc_own + (size_t)s * B * MP * 64)) != AKZ_OK) return rc;
+        AKZ_CUDA_TRY(cudaEventRecord(c->ev_comp[s], st));
+        // staging[(i+1)&1] was last read by the kernels of chunk i-1, which precede ev_comp of chunk i-1
+        if (i + 1 < nchunks) {
+            if (i >= 1) AKZ_CUDA_TRY(cudaStreamWaitEvent(c->h2d_stream, c->ev_comp[(i + 1) & 1], 0));
+            if ((rc = issue_h2d(i + 1)) != AKZ_OK) return rc;
+        }
+        // results of chunk i-1 first (the GPU is already busy with chunk i), so that they do not queue behind the wait below
+        if (i >= 1 && (rc = drain(i - 1)) != AKZ_OK) return rc;
+        AKZ_CUDA_TRY(cudaStreamWaitEvent(c->d2h_stream, c->ev_comp[s], 0));
+        AKZ_CUDA_TRY(cudaMemcpyAsync(c->h_cnt_pinned + s * B, c->counts_own + (size_t)s * B, sizeof(int) * nf, cudaMemcpyDeviceToHost, c->d2h_stream));
+        AKZ_CUDA_TRY(cudaEventRecord(c->ev_cnt[s], c->d2h_stream));
     }
+    if (nchunks > 0 && (rc = drain(nchunks - 1)) != AKZ_OK) return rc;
+    AKZ_CUDA_TRY(cudaStreamSynchronize(c->d2h_stream));
+    AKZ_CUDA_TRY(cudaStreamSynchronize(st));
     AKZ_CUDA_TRY(cudaGetLastError());
     return AKZ_OK;
 }

@@ -223,6 +223,109 @@ __global__ void __launch_bounds__(64) k_describe(const __grid_constant__ AkzLeve
     }
 }
 
+// ---- M-LDB, pattern size fixed at compile time (PAT = 10 is the reference default, akaze.h:54) ---------------
+// Same numbers as k_describe, produced with a third of the instructions (ncu r01b: 2160 thread-instructions per
+// thread per keypoint, 18.7 % issue utilisation, stalls on the global gathers and on shared memory):
+//   * all 7 x 3 gathers of a thread are issued before the first accumulation (memory-level parallelism 21);
+//   * window size and cell geometry are immediates (no runtime division);
+//   * the reduction is transposed: thread v owns output value v and evaluates the reference's tree itself,
+//     a_t = acc_t + acc_{t+32}, then the shuffle-down pairing ((a0+a1)+(a2+a3))+... serially from shared memory
+//     (row stride 65: conflict-free both for the per-thread accumulation columns and for the transposed reads).
+template <int PAT>
+__global__ void __launch_bounds__(64) k_describe_t(const __grid_constant__ AkzLevelTable tab, const int* __restrict__ prefix, int nframes,
+                                                   const akz_keypoint* __restrict__ kpts, unsigned char* __restrict__ desc, int max_pts)
+{
+    constexpr int S2 = PAT, S3 = (2 * PAT + 2) / 3, S4 = (PAT + 1) / 2;      // akazed.cu:2681-2683 (ceil)
+    constexpr int WIN = (3 * S3 > 4 * S4) ? 3 * S3 : 4 * S4;
+    constexpr int NS = WIN * WIN, NK = (NS + 63) / 64, RS = 65;
+    __shared__ float acc[87 * RS];
+    __shared__ float val[96];
+    const int tix = threadIdx.x;
+    const int total = prefix[nframes];
+    for (int g = blockIdx.x; g < total; g += gridDim.x) {
+        int frame = find_frame(prefix, nframes, g);
+        int local = g - prefix[frame];
+        const akz_keypoint* kp = kpts + (long long)frame * max_pts + local;
+        const AkzLevelDev& L = tab.lv[kp->layer];
+        const int o = L.octave, p = L.pitch;
+        const float iratio = 1.f / (1 << o);
+        const float fscale = (float)(int)__fadd_rn(kp->size, 0.5f);
+        const float xf = __fmul_rn(kp->x, iratio), yf = __fmul_rn(kp->y, iratio);
+        const float ang = kp->angle;
+        const float co = __cosf(ang), si = __sinf(ang);
+        const float* imd = L.lt + (long long)frame * L.plane;
+        const float* dxd = L.lx + (long long)frame * L.plane;
+        const float* dyd = L.ly + (long long)frame * L.plane;
+        // 1. gather
+        float im[NK], dx[NK], dy[NK];
+#pragma unroll
+        for (int k = 0; k < NK; k++) {
+            int i = tix + 64 * k;
+            im[k] = 0.f; dx[k] = 0.f; dy[k] = 0.f;
+            if (i < NS) {
+                int y = i / WIN, x = i - WIN * y;
+                float l = (float)(x - S2), kk = (float)(y - S2);
+                int xp = (int)__fadd_rn(__fmaf_rn(fscale, __fmaf_rn(co, kk, -__fmul_rn(si, l)), xf), 0.5f);
+                int yp = (int)__fadd_rn(__fmaf_rn(fscale, __fmaf_rn(si, kk, __fmul_rn(co, l)), yf), 0.5f);
+                xp = min(max(xp, 0), L.w - 1); yp = min(max(yp, 0), L.h - 1);       // no-op for in-range patches (border test)
+                long long pos = (long long)yp * p + xp;
+                im[k] = __ldg(imd + pos); dx[k] = __ldg(dxd + pos); dy[k] = __ldg(dyd + pos);
+            }
+        }
+        // 2. clear this thread's accumulator column
+#pragma unroll
+        for (int v = 0; v < 87; v++) acc[v * RS + tix] = 0.f;
+        // 3. accumulate in sample order (each thread touches only its own column: no synchronisation needed)
+#pragma unroll
+        for (int k = 0; k < NK; k++) {
+            int i = tix + 64 * k;
+            if (i < NS) {
+                int y = i / WIN, x = i - WIN * y, m = max(x, y);
+                float rx = __fmaf_rn(co, dy[k], -__fmul_rn(si, dx[k]));
+                float ry = __fmaf_rn(co, dx[k], __fmul_rn(si, dy[k]));
+                if (m < 2 * S2) {
+                    float* a = acc + (3 * ((y < S2 ? 0 : 1) * 2 + (x < S2 ? 0 : 1))) * RS + tix;
+                    a[0] = __fadd_rn(a[0], im[k]); a[RS] = __fadd_rn(a[RS], rx); a[2 * RS] = __fadd_rn(a[2 * RS], ry);
+                }
+                if (m < 3 * S3) {
+                    int x3 = (x < S3 ? 0 : (x < 2 * S3 ? 1 : 2)), y3 = (y < S3 ? 0 : (y < 2 * S3 ? 1 : 2));
+                    float* a = acc + (3 * (4 + y3 * 3 + x3)) * RS + tix;
+                    a[0] = __fadd_rn(a[0], im[k]); a[RS] = __fadd_rn(a[RS], rx); a[2 * RS] = __fadd_rn(a[2 * RS], ry);
+                }
+                if (m < 4 * S4) {
+                    int x4 = (x < 2 * S4 ? (x < S4 ? 0 : 1) : (x < 3 * S4 ? 2 : 3));
+                    int y4 = (y < 2 * S4 ? (y < S4 ? 0 : 1) : (y < 3 * S4 ? 2 : 3));
+                    float* a = acc + (3 * (13 + y4 * 4 + x4)) * RS + tix;
+                    a[0] = __fadd_rn(a[0], im[k]); a[RS] = __fadd_rn(a[RS], rx); a[2 * RS] = __fadd_rn(a[2 * RS], ry);
+                }
+            }
+        }
+        __syncthreads();
+        // 4. transposed reduction: the reference's tree for value v, evaluated by one thread
+        for (int v = tix; v < 87; v += 64) {
+            const float* a = acc + v * RS;
+            float r[32];
+#pragma unroll
+            for (int t = 0; t < 32; t++) r[t] = __fadd_rn(a[t], a[t + 32]);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+#pragma unroll
+                for (int t = 0; t + d < 32; t += 2 * d) r[t] = __fadd_rn(r[t], r[t + d]);
+            val[v] = r[0];
+        }
+        __syncthreads();
+        unsigned char* out = desc + ((long long)frame * max_pts + local) * 64;
+        unsigned rbits = 0;
+        if (tix < 61) {
+            int nb = (tix == 60 ? 6 : 8);
+            for (int i = 0; i < nb; i++)
+                rbits |= (val[c_cmp[0][tix * 8 + i]] > val[c_cmp[1][tix * 8 + i]] ? 1u : 0u) << i;
+        }
+        out[tix] = (unsigned char)rbits;                  // bytes 61..63 are written as zero
+        __syncthreads();
+    }
+}
+
 // ---- AoS bridge: reference AkazePoint (104 B) ------------------------------------------------------------
 struct RefPoint {
     float x, y; int octave; float response, size, angle;
@@ -295,7 +398,8 @@ int describe(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const
     int size2 = pattern;                                          // akazed.cu:2681-2683
     int size3 = (int)ceilf(2.0f * pattern / 3.0f);
     int size4 = (int)ceilf(0.5f * pattern);
-    k_describe<<<148 * 8, 64, 0, st>>>(tab, prefix, n, kpts, desc, max_pts, size2, size3, size4);
+    if (pattern == 10) k_describe_t<10><<<148 * 9, 64, 0, st>>>(tab, prefix, n, kpts, desc, max_pts);
+    else k_describe<<<148 * 8, 64, 0, st>>>(tab, prefix, n, kpts, desc, max_pts, size2, size3, size4);
     return 1;
 }
 

@@ -13,30 +13,43 @@ using namespace akz;
 
 namespace {
 
-// grid: (ceil((w-2psz)/32), ceil((h-2psz)/8), nframes*nsub)
+// grid: (ceil((w - x_base)/128), ceil((h-2psz)/8), nframes*nsub); 4 consecutive pixels per thread.
+// Almost every pixel fails the threshold, so a thread first looks at one float4 of the centre row and only
+// candidates pay for the two neighbour rows (ncu r01b: the one-pixel-per-thread version was latency bound,
+// 9.4 warps stalled on the long scoreboard per issue).
 __global__ void __launch_bounds__(256) k_extrema(const __grid_constant__ AkzExtremaArgs a, unsigned long long* __restrict__ map, int mpitch, long long mplane)
 {
     int frame = blockIdx.z / a.nsub, sub = blockIdx.z - frame * a.nsub;
     const AkzExtremaLevel& L = a.lv[sub];
-    int ix = blockIdx.x * 32 + threadIdx.x + a.psz;
-    int iy = blockIdx.y * 8 + threadIdx.y + a.psz;
-    if (ix >= a.w - 1 || iy >= a.h - 1) return;
-    float border = L.border;
+    const int x0 = (a.psz & ~3) + (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int iy = blockIdx.y * 8 + threadIdx.y + a.psz;
+    if (x0 >= a.w - 1 || iy >= a.h - 1) return;
+    const float* row = L.det + (long long)frame * L.plane + (long long)iy * a.pitch + x0;
+    const float4 c4 = __ldg(reinterpret_cast<const float4*>(row));
+    const float thr = L.threshold;
+    if (!(c4.x > thr || c4.y > thr || c4.z > thr || c4.w > thr)) return;
+    const float4 u4 = __ldg(reinterpret_cast<const float4*>(row - a.pitch));
+    const float4 d4 = __ldg(reinterpret_cast<const float4*>(row + a.pitch));
+    const float u[6] = { __ldg(row - a.pitch - 1), u4.x, u4.y, u4.z, u4.w, __ldg(row - a.pitch + 4) };
+    const float c[6] = { __ldg(row - 1), c4.x, c4.y, c4.z, c4.w, __ldg(row + 4) };
+    const float d[6] = { __ldg(row + a.pitch - 1), d4.x, d4.y, d4.z, d4.w, __ldg(row + a.pitch + 4) };
+    const float border = L.border;
     // akazed.cu:1346-1353 (float arithmetic, truncating casts)
-    int left_x = (int)(__fadd_rn(__fsub_rn((float)ix, border), 0.5f)) - 1;
-    int right_x = (int)(__fadd_rn(__fadd_rn((float)ix, border), 0.5f)) + 1;
     int up_y = (int)(__fadd_rn(__fsub_rn((float)iy, border), 0.5f)) - 1;
     int down_y = (int)(__fadd_rn(__fadd_rn((float)iy, border), 0.5f)) + 1;
-    if (left_x < 0 || right_x >= a.w || up_y < 0 || down_y >= a.h) return;
-    const float* vp = L.det + (long long)frame * L.plane + (long long)iy * a.pitch + ix;
-    float v = __ldg(vp);
-    if (!(v > L.threshold)) return;
-    const float* v0 = vp - a.pitch;
-    const float* v2 = vp + a.pitch;
-    if (v > __ldg(v0) && v > __ldg(v2) && v > __ldg(vp - 1) && v > __ldg(vp + 1) &&
-        v > __ldg(v0 - 1) && v > __ldg(v0 + 1) && v > __ldg(v2 - 1) && v > __ldg(v2 + 1)) {
-        long long oi = (long long)frame * mplane + (long long)(iy << a.octave) * mpitch + (ix << a.octave);
-        atomicMax(map + oi, merge_key(v, L.layer));
+    if (up_y < 0 || down_y >= a.h) return;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int ix = x0 + j;
+        float v = c[j + 1];
+        if (ix < a.psz || ix >= a.w - 1 || !(v > thr)) continue;
+        int left_x = (int)(__fadd_rn(__fsub_rn((float)ix, border), 0.5f)) - 1;
+        int right_x = (int)(__fadd_rn(__fadd_rn((float)ix, border), 0.5f)) + 1;
+        if (left_x < 0 || right_x >= a.w) continue;
+        if (v > u[j + 1] && v > d[j + 1] && v > c[j] && v > c[j + 2] && v > u[j] && v > u[j + 2] && v > d[j] && v > d[j + 2]) {
+            long long oi = (long long)frame * mplane + (long long)(iy << a.octave) * mpitch + (ix << a.octave);
+            atomicMax(map + oi, merge_key(v, L.layer));
+        }
     }
 }
 
@@ -209,7 +222,8 @@ int extrema(cudaStream_t st, const AkzExtremaArgs& a, unsigned long long* map, i
 {
     int ew = a.w - 2 * a.psz, eh = a.h - 2 * a.psz;
     if (ew <= 0 || eh <= 0) return 0;
-    dim3 g((ew + 31) / 32, (eh + 7) / 8, n * a.nsub);
+    int xb = a.psz & ~3;
+    dim3 g((a.w - xb + 127) / 128, (eh + 7) / 8, n * a.nsub);
     k_extrema<<<g, dim3(32, 8), 0, st>>>(a, map, mpitch, mplane);
     return 1;
 }

@@ -44,7 +44,16 @@ struct Prep2Args {
     int w, h, pitch;
 };
 
-__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// 128-bit shared-memory load that the compiler may not narrow: when only some components are used (S = 2, 3) nvcc
+// splits a float4 load into LDS.32 / LDS.64 pieces, which at a 16-byte lane stride are 4-way / 2-way bank conflicts
+// (ncu r01b source page: 36 % of the shared-memory wavefronts of this kernel were conflict replays).
+__device__ __forceinline__ float4 lds4(const float* p)
+{
+    float4 v;
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ void sts4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src)
@@ -137,8 +146,10 @@ __global__ void __launch_bounds__(P2_NT, 2) k_prep2(const __grid_constant__ Prep
     if (MODE != PM_BASE) {
         const float k0 = a.k0, k1 = a.k1, k2 = a.k2;
         // ---- 2. row pass: Bf[r][4..84) from A[r][2..86) -----------------------------------------------
-        for (int i = tid; i < AR * 20; i += P2_NT) {
-            int r = i / 20, g = i - r * 20;
+        // (24 lanes per row, 20 active: a quarter-warp never straddles two rows, which would be a 2-way bank conflict)
+        for (int i = tid; i < AR * 24; i += P2_NT) {
+            int r = i / 24, g = i - r * 24;
+            if (g >= 20) continue;
             const float* p = A + r * SP + 4 + 4 * g;
             float4 v0 = lds4(p - 4), v1 = lds4(p), v2 = lds4(p + 4);
             sts4(Bf + r * SP + 4 + 4 * g,
@@ -147,8 +158,9 @@ __global__ void __launch_bounds__(P2_NT, 2) k_prep2(const __grid_constant__ Prep
         }
         __syncthreads();
         // ---- 3. column pass: Sm rows [2, AR-2), two rows per item --------------------------------------
-        for (int i = tid; i < ((AR - 4) / 2) * 20; i += P2_NT) {
-            int rb = i / 20, g = i - rb * 20;
+        for (int i = tid; i < ((AR - 4) / 2) * 24; i += P2_NT) {
+            int rb = i / 24, g = i - rb * 24;
+            if (g >= 20) continue;
             int r = 2 + 2 * rb;
             const float* p = Bf + (r - 2) * SP + 4 + 4 * g;
             float4 b0 = lds4(p), b1 = lds4(p + SP), b2 = lds4(p + 2 * SP), b3 = lds4(p + 3 * SP), b4 = lds4(p + 4 * SP), b5 = lds4(p + 5 * SP);
@@ -174,10 +186,21 @@ __global__ void __launch_bounds__(P2_NT, 2) k_prep2(const __grid_constant__ Prep
         for (int i = tid; i < P2_H * 16; i += P2_NT) {
             int r = i >> 4, g = i & 15;
             const float* p = Sm + (r + OY) * SP + P2_OX + 4 * g;
+            // the two values beside the float4 come from the neighbouring lanes (same row: 16 items per row, all 32
+            // lanes active); only the row ends read shared memory (a 4-float-strided scalar LDS is a 4-way bank conflict)
             float u[6], c[6], l[6];
-            { float4 v = lds4(p - SP); u[0] = p[-SP - 1]; u[1] = v.x; u[2] = v.y; u[3] = v.z; u[4] = v.w; u[5] = p[-SP + 4]; }
-            { float4 v = lds4(p);      c[0] = p[-1];      c[1] = v.x; c[2] = v.y; c[3] = v.z; c[4] = v.w; c[5] = p[4]; }
-            { float4 v = lds4(p + SP); l[0] = p[SP - 1];  l[1] = v.x; l[2] = v.y; l[3] = v.z; l[4] = v.w; l[5] = p[SP + 4]; }
+#define AKZ_ROW6(arr, q)                                                                         \
+            {                                                                                        \
+                float4 v = lds4(q);                                                                  \
+                float lft = __shfl_up_sync(0xffffffffu, v.w, 1), rgt = __shfl_down_sync(0xffffffffu, v.x, 1); \
+                if (g == 0) lft = (q)[-1];                                                           \
+                if (g == 15) rgt = (q)[4];                                                           \
+                arr[0] = lft; arr[1] = v.x; arr[2] = v.y; arr[3] = v.z; arr[4] = v.w; arr[5] = rgt; \
+            }
+            AKZ_ROW6(u, p - SP)
+            AKZ_ROW6(c, p)
+            AKZ_ROW6(l, p + SP)
+#undef AKZ_ROW6
             float o[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -200,8 +223,9 @@ __global__ void __launch_bounds__(P2_NT, 2) k_prep2(const __grid_constant__ Prep
         const float fac1 = a.fac1, fac2 = a.fac2;
         float* lxg = a.lx + (long long)frame * a.plane;
         float* lyg = a.ly + (long long)frame * a.plane;
-        for (int i = tid; i < (P2_H + 2 * S) * 18; i += P2_NT) {
-            int r = i / 18, g = i - r * 18;
+        for (int i = tid; i < (P2_H + 2 * S) * 24; i += P2_NT) {
+            int r = i / 24, g = i - r * 24;
+            if (g >= 18) continue;
             int sr = OY - S + r, c4 = 8 + 4 * g;
             const float* p = Sm + sr * SP + c4;
             float u[12], c[12], l[12];
