@@ -452,7 +452,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step (configs[2]: 256)")
-    ap.add_argument("--chunk", type=int, default=16, help="frames processed together (akz_options.max_batch)")
+    ap.add_argument("--chunk", type=int, default=32, help="frames processed together (akz_options.max_batch)")
     ap.add_argument("--max-pts", type=int, default=10000, help="per-frame keypoint capacity (main.cpp:157)")
     ap.add_argument("--content", default="shapes", choices=["shapes", "noise"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "u8"])

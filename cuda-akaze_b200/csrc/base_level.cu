@@ -1,0 +1,305 @@
+// k_base2<Tin>: the base level (0,0) in one pass over the input frame.
+//
+// One read of a 64x64 input tile (+4 halo, float [0,1] or raw u8) produces
+//   * Lt(0,0)   = Gaussian blur with sigma0^2 = soffset^2, radius 4        (akaze.cpp:331, gConv2d<4> akazed.cu:204)
+//   * the Scharr gradient magnitude of the sigma = 1 blur (radius 2), written to a scratch plane, and its
+//     per-frame maximum (atomicMax on the float bits)                       (akaze.cpp:329-330, akazed.cu:644-667, :2410-2449)
+// k_hist2 then bins the magnitude plane with the now known maximum          (akazed.cu:901-938, in-image pixels only)
+// and k_contrast_scan (scale_space.cu) turns the histogram into k on the device.
+// Replaces 2 x k_lowpass + k_scharr_max + k_contrast_hist (24 B/px of traffic, two recomputations of the gradient)
+// by 16 B/px.  Both blurs are symmetric operators, so evaluating them on the reflect-101 extended tile gives the
+// value at the mirrored pixel bit for bit; no border fix-up is needed here.
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace akz;
+
+namespace {
+
+constexpr int B2_T = 64, B2_O = 8, B2_SP = B2_T + 2 * B2_O;      // tile, frame offset (cols), pitch 80
+constexpr int B2_R = B2_T + 8;                                   // 72 rows: Y0-4 .. Y0+67
+constexpr int B2_NT = 512;
+
+struct Base2Args {
+    const void* img;
+    float* lt;            // Lt(0,0)
+    float* mag;           // gradient magnitude scratch plane (may be null: skip the contrast part)
+    unsigned* hmax_bits;
+    long long istride, plane;
+    int w, h, ipitch, pitch, vec_ok;
+    float a0, a1, a2, a3, a4;      // sigma0 taps (radius 4)
+    float k0, k1, k2;              // sigma = 1 taps (radius 2)
+};
+
+__device__ __forceinline__ float4 lds4(const float* p)
+{
+    float4 v;
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
+
+// radius-4 Gaussian in the reference's operation order (akazed.cu:225-238): (x-1 + x+1)*k1, fma(x0,k0), fma(x-i + x+i, ki) i = 2..4
+__device__ __forceinline__ float gauss_r4(float m4, float m3, float m2, float m1, float c, float p1, float p2, float p3, float p4,
+                                          float k0, float k1, float k2, float k3, float k4)
+{
+    float acc = __fmul_rn(__fadd_rn(m1, p1), k1);
+    acc = __fmaf_rn(c, k0, acc);
+    acc = __fmaf_rn(__fadd_rn(m2, p2), k2, acc);
+    acc = __fmaf_rn(__fadd_rn(m3, p3), k3, acc);
+    return __fmaf_rn(__fadd_rn(m4, p4), k4, acc);
+}
+
+__device__ __forceinline__ float to_unit(float v) { return v; }
+__device__ __forceinline__ float to_unit(unsigned char v) { return u8_to_unit(v); }
+
+template <typename Tin>
+__global__ void __launch_bounds__(B2_NT, 2) k_base2(const __grid_constant__ Base2Args a)
+{
+    constexpr int SP = B2_SP;
+    extern __shared__ __align__(16) float sm[];
+    float* In = sm;                         // [72][80]  input tile; later the sigma = 1 blur S1 (rows 3..68)
+    float* R0 = In + B2_R * SP;             // sigma0 row pass, cols [8, 72)
+    float* R1 = R0 + B2_R * SP;             // sigma1 row pass, cols [4, 76)
+    const int tid = threadIdx.x, frame = blockIdx.z;
+    const int X0 = blockIdx.x * B2_T, Y0 = blockIdx.y * B2_T;
+    const int w = a.w, h = a.h;
+    const bool interior = X0 - B2_O >= 0 && X0 + B2_T + B2_O <= w && Y0 - 4 >= 0 && Y0 + B2_T + 4 <= h;
+    const bool fast = interior && a.vec_ok;
+    const Tin* __restrict__ src = (const Tin*)a.img + (long long)frame * a.istride;
+
+    // ---- 1. input tile ------------------------------------------------------------------------------------
+    if (fast && sizeof(Tin) == 4) {
+        for (int i = tid; i < B2_R * (SP / 4); i += B2_NT) {
+            int r = i / (SP / 4), g = i - r * (SP / 4);
+            cp_async16(In + r * SP + 4 * g, (const float*)src + (long long)(Y0 - 4 + r) * a.ipitch + (X0 - B2_O + 4 * g));
+        }
+        cp_async_wait_all();
+    } else if (fast) {
+        for (int i = tid; i < B2_R * (SP / 8); i += B2_NT) {               // 8 bytes = 8 pixels per item
+            int r = i / (SP / 8), g = i - r * (SP / 8);
+            uint2 v = __ldg(reinterpret_cast<const uint2*>((const unsigned char*)src + (long long)(Y0 - 4 + r) * a.ipitch + (X0 - B2_O + 8 * g)));
+            float* d = In + r * SP + 8 * g;
+            sts4(d, u8_to_unit((unsigned char)(v.x)), u8_to_unit((unsigned char)(v.x >> 8)), u8_to_unit((unsigned char)(v.x >> 16)), u8_to_unit((unsigned char)(v.x >> 24)));
+            sts4(d + 4, u8_to_unit((unsigned char)(v.y)), u8_to_unit((unsigned char)(v.y >> 8)), u8_to_unit((unsigned char)(v.y >> 16)), u8_to_unit((unsigned char)(v.y >> 24)));
+        }
+    } else {
+        for (int i = tid; i < B2_R * SP; i += B2_NT) {
+            int r = i / SP, c = i - r * SP;
+            int sy = min(max(refl(Y0 - 4 + r, h), 0), h - 1), sx = min(max(refl(X0 - B2_O + c, w), 0), w - 1);
+            In[i] = to_unit(__ldg(src + (long long)sy * a.ipitch + sx));
+        }
+    }
+    __syncthreads();
+
+    // ---- 2. both row passes from the same three float4 loads: cols [4, 76), 18 items per row (24 lanes) --------
+    for (int i = tid; i < B2_R * 24; i += B2_NT) {
+        int r = i / 24, g = i - r * 24;
+        if (g >= 18) continue;
+        const float* p = In + r * SP + 4 + 4 * g;
+        float4 v0 = lds4(p - 4), v1 = lds4(p), v2 = lds4(p + 4);
+        const float e[12] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w };
+        float o1[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) o1[j] = gauss_r2(e[2 + j], e[3 + j], e[4 + j], e[5 + j], e[6 + j], a.k0, a.k1, a.k2);
+        sts4(R1 + r * SP + 4 + 4 * g, o1[0], o1[1], o1[2], o1[3]);
+        if (g >= 1 && g <= 16) {
+            float o0[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                o0[j] = gauss_r4(e[j], e[1 + j], e[2 + j], e[3 + j], e[4 + j], e[5 + j], e[6 + j], e[7 + j], e[8 + j], a.a0, a.a1, a.a2, a.a3, a.a4);
+            sts4(R0 + r * SP + 4 + 4 * g, o0[0], o0[1], o0[2], o0[3]);
+        }
+    }
+    __syncthreads();
+
+    // ---- 3a. sigma0 column pass -> Lt(0,0), two rows per item ---------------------------------------------------
+    {
+        float* ltg = a.lt + (long long)frame * a.plane;
+        for (int i = tid; i < (B2_T / 2) * 16; i += B2_NT) {
+            int rb = i >> 4, g = i & 15;
+            int r = 4 + 2 * rb;                                           // tile row of the first output
+            const float* p = R0 + (r - 4) * SP + B2_O + 4 * g;
+            float4 q[10];
+#pragma unroll
+            for (int k = 0; k < 10; k++) q[k] = lds4(p + k * SP);
+            float o[2][4];
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                o[t][0] = gauss_r4(q[t].x, q[t + 1].x, q[t + 2].x, q[t + 3].x, q[t + 4].x, q[t + 5].x, q[t + 6].x, q[t + 7].x, q[t + 8].x, a.a0, a.a1, a.a2, a.a3, a.a4);
+                o[t][1] = gauss_r4(q[t].y, q[t + 1].y, q[t + 2].y, q[t + 3].y, q[t + 4].y, q[t + 5].y, q[t + 6].y, q[t + 7].y, q[t + 8].y, a.a0, a.a1, a.a2, a.a3, a.a4);
+                o[t][2] = gauss_r4(q[t].z, q[t + 1].z, q[t + 2].z, q[t + 3].z, q[t + 4].z, q[t + 5].z, q[t + 6].z, q[t + 7].z, q[t + 8].z, a.a0, a.a1, a.a2, a.a3, a.a4);
+                o[t][3] = gauss_r4(q[t].w, q[t + 1].w, q[t + 2].w, q[t + 3].w, q[t + 4].w, q[t + 5].w, q[t + 6].w, q[t + 7].w, q[t + 8].w, a.a0, a.a1, a.a2, a.a3, a.a4);
+            }
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                int y = Y0 + 2 * rb + t, x = X0 + 4 * g;
+                float* d = ltg + (long long)y * a.pitch + x;
+                if (fast) *reinterpret_cast<float4*>(d) = make_float4(o[t][0], o[t][1], o[t][2], o[t][3]);
+                else if (y < h) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) if (x + j < w) d[j] = o[t][j];
+                }
+            }
+        }
+    }
+    if (a.mag == nullptr) return;
+
+    // ---- 3b. sigma = 1 column pass -> S1 (over In): tile rows 3..68 (Y0-1 .. Y0+64), cols [4, 76) ----------------
+    for (int i = tid; i < 33 * 24; i += B2_NT) {
+        int rb = i / 24, g = i - rb * 24;
+        if (g >= 18) continue;
+        int r = 3 + 2 * rb;
+        const float* p = R1 + (r - 2) * SP + 4 + 4 * g;
+        float4 b0 = lds4(p), b1 = lds4(p + SP), b2 = lds4(p + 2 * SP), b3 = lds4(p + 3 * SP), b4 = lds4(p + 4 * SP), b5 = lds4(p + 5 * SP);
+        float* q = In + r * SP + 4 + 4 * g;
+        sts4(q, gauss_r2(b0.x, b1.x, b2.x, b3.x, b4.x, a.k0, a.k1, a.k2), gauss_r2(b0.y, b1.y, b2.y, b3.y, b4.y, a.k0, a.k1, a.k2),
+             gauss_r2(b0.z, b1.z, b2.z, b3.z, b4.z, a.k0, a.k1, a.k2), gauss_r2(b0.w, b1.w, b2.w, b3.w, b4.w, a.k0, a.k1, a.k2));
+        sts4(q + SP, gauss_r2(b1.x, b2.x, b3.x, b4.x, b5.x, a.k0, a.k1, a.k2), gauss_r2(b1.y, b2.y, b3.y, b4.y, b5.y, a.k0, a.k1, a.k2),
+             gauss_r2(b1.z, b2.z, b3.z, b4.z, b5.z, a.k0, a.k1, a.k2), gauss_r2(b1.w, b2.w, b3.w, b4.w, b5.w, a.k0, a.k1, a.k2));
+    }
+    __syncthreads();
+
+    // ---- 4. Scharr magnitude of S1 -> scratch plane, maximum -> hmax_bits[frame] -----------------------------------
+    {
+        float* mg = a.mag + (long long)frame * a.plane;
+        unsigned best = 0u;
+        for (int i = tid; i < B2_T * 16; i += B2_NT) {
+            int r = i >> 4, g = i & 15;
+            const float* p = In + (r + 4) * SP + B2_O + 4 * g;
+            float u[6], c[6], l[6];
+#define AKZ_ROW6(arr, q)                                                                         \
+            {                                                                                        \
+                float4 v = lds4(q);                                                                  \
+                float lft = __shfl_up_sync(0xffffffffu, v.w, 1), rgt = __shfl_down_sync(0xffffffffu, v.x, 1); \
+                if (g == 0) lft = (q)[-1];                                                           \
+                if (g == 15) rgt = (q)[4];                                                           \
+                arr[0] = lft; arr[1] = v.x; arr[2] = v.y; arr[3] = v.z; arr[4] = v.w; arr[5] = rgt; \
+            }
+            AKZ_ROW6(u, p - SP)
+            AKZ_ROW6(c, p)
+            AKZ_ROW6(l, p + SP)
+#undef AKZ_ROW6
+            float o[4];
+            int y = Y0 + r, x = X0 + 4 * g;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float dx = scharr_dx(u[j], u[j + 2], c[j], c[j + 2], l[j], l[j + 2]);
+                float dy = scharr_dy(u[j], u[j + 1], u[j + 2], l[j], l[j + 1], l[j + 2]);
+                o[j] = __fsqrt_rn(grad_sq(dx, dy));
+                if (y < h && x + j < w) best = max(best, __float_as_uint(o[j]));      // o >= 0: bit patterns order like the floats
+            }
+            float* d = mg + (long long)y * a.pitch + x;
+            if (fast) *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
+            else if (y < h) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (x + j < w) d[j] = o[j];
+            }
+        }
+        best = __reduce_max_sync(0xffffffffu, best);
+        __shared__ unsigned smax[B2_NT / 32];
+        if ((tid & 31) == 0) smax[tid >> 5] = best;
+        __syncthreads();
+        if (tid < 32) {
+            unsigned v = tid < B2_NT / 32 ? smax[tid] : 0u;
+            v = __reduce_max_sync(0xffffffffu, v);
+            if (tid == 0) atomicMax(a.hmax_bits + frame, v);
+        }
+    }
+}
+
+// 300-bin histogram of mag * 300 / hmax (truncating multiply, clamp to 299) over the in-image pixels (akazed.cu:901-938,
+// App. B-3); one block bins 8 rows; per-warp privatised shared histograms keep the atomics apart.
+__global__ void __launch_bounds__(256) k_hist2(const float* __restrict__ mag, const unsigned* __restrict__ hmax_bits, int* __restrict__ hist,
+                                               int w, int h, int pitch, long long plane, int vec_ok)
+{
+    __shared__ int sh[8][AKZ_NBINS + 4];
+    const int tid = threadIdx.x, wid = tid >> 5, frame = blockIdx.y;
+    for (int i = tid; i < 8 * (AKZ_NBINS + 4); i += 256) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const float hfactor = __fdiv_rn((float)AKZ_NBINS, __uint_as_float(hmax_bits[frame]));
+    const float* m = mag + (long long)frame * plane;
+    const int y0 = blockIdx.x * 8;
+    if (vec_ok && (w & 3) == 0) {
+        const int w4 = w >> 2;
+        for (int i = tid; i < 8 * w4; i += 256) {
+            int r = i / w4, g = i - r * w4, y = y0 + r;
+            if (y >= h) break;
+            float4 v = __ldg(reinterpret_cast<const float4*>(m + (long long)y * pitch + 4 * g));
+            atomicAdd(&sh[wid][min((int)__fmul_rz(v.x, hfactor), AKZ_NBINS - 1)], 1);
+            atomicAdd(&sh[wid][min((int)__fmul_rz(v.y, hfactor), AKZ_NBINS - 1)], 1);
+            atomicAdd(&sh[wid][min((int)__fmul_rz(v.z, hfactor), AKZ_NBINS - 1)], 1);
+            atomicAdd(&sh[wid][min((int)__fmul_rz(v.w, hfactor), AKZ_NBINS - 1)], 1);
+        }
+    } else {
+        for (int i = tid; i < 8 * w; i += 256) {
+            int r = i / w, x = i - r * w, y = y0 + r;
+            if (y >= h) break;
+            atomicAdd(&sh[wid][min((int)__fmul_rz(__ldg(m + (long long)y * pitch + x), hfactor), AKZ_NBINS - 1)], 1);
+        }
+    }
+    __syncthreads();
+    int* g = hist + (long long)frame * AKZ_NBINS;
+    for (int i = tid; i < AKZ_NBINS; i += 256) {
+        int s = sh[0][i] + sh[1][i] + sh[2][i] + sh[3][i] + sh[4][i] + sh[5][i] + sh[6][i] + sh[7][i];
+        if (s) atomicAdd(g + i, s);
+    }
+}
+
+__global__ void k_contrast_init2(unsigned* hmax_bits, int* hist, int nframes)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nframes) hmax_bits[i] = __float_as_uint(0.03f);       // akazed.cu:2413
+    if (i < nframes * AKZ_NBINS) hist[i] = 0;
+}
+
+constexpr int B2_SMEM = 3 * B2_R * B2_SP * (int)sizeof(float);
+
+}  // namespace
+
+namespace akzk {
+
+// Fused base level: Lt(0,0) and (unless mag == nullptr) the gradient-magnitude plane + per-frame maximum + histogram.
+// Covers sigma0 kernels of radius 4 (ksz0 = 9, the reference default soffset = 1.6); returns 0 when not applicable.
+int base_level2(cudaStream_t st, const void* img, int dtype, int w, int h, int ipitch, long long istride,
+                float* lt, int pitch, long long plane, float* mag, unsigned* hmax_bits, int* hist, float var0, int ksz0, int n)
+{
+    if (radius_from_ksz(ksz0) != 4 || w < 16 || h < 16) return 0;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_base2<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
+        cudaFuncSetAttribute(k_base2<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
+        attr = true;
+    }
+    Base2Args a = {};
+    a.img = img; a.lt = lt; a.mag = mag; a.hmax_bits = hmax_bits; a.istride = istride; a.plane = plane;
+    a.w = w; a.h = h; a.ipitch = ipitch; a.pitch = pitch;
+    float t0[5], t1[3];
+    akz_gauss_taps(var0, 4, t0);
+    akz_gauss_taps(1.f, 2, t1);
+    a.a0 = t0[0]; a.a1 = t0[1]; a.a2 = t0[2]; a.a3 = t0[3]; a.a4 = t0[4];
+    a.k0 = t1[0]; a.k1 = t1[1]; a.k2 = t1[2];
+    const size_t esz = dtype == AKZ_U8 ? 1 : 4;
+    a.vec_ok = (pitch % 4 == 0) && (plane % 4 == 0) && ((uintptr_t)lt % 16 == 0) && (mag == nullptr || (uintptr_t)mag % 16 == 0) &&
+               ((uintptr_t)img % 16 == 0) && (((size_t)ipitch * esz) % 16 == 0) && (((size_t)istride * esz) % 16 == 0);
+    int launches = 0;
+    if (mag) { int tot = n * AKZ_NBINS; k_contrast_init2<<<(tot + 255) / 256, 256, 0, st>>>(hmax_bits, hist, n); launches++; }
+    dim3 g((w + B2_T - 1) / B2_T, (h + B2_T - 1) / B2_T, n);
+    if (dtype == AKZ_U8) k_base2<unsigned char><<<g, B2_NT, B2_SMEM, st>>>(a);
+    else k_base2<float><<<g, B2_NT, B2_SMEM, st>>>(a);
+    launches++;
+    if (mag) {
+        k_hist2<<<dim3((h + 7) / 8, n), 256, 0, st>>>(mag, hmax_bits, hist, w, h, pitch, plane, a.vec_ok);
+        launches++;
+    }
+    return launches;
+}
+
+}  // namespace akzk

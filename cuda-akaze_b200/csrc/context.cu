@@ -406,16 +406,29 @@ static int scale_space_chunk(akz_ctx* c, const void* img, int dtype, int nf, int
     // level (0,0): akaze.cpp:325-346
     const float var0 = o.soffset * o.soffset;
     const int ksz0 = (int)(2 * ceilf((o.soffset - 0.8f) / 0.3f) + 3);
-    if (dtype == AKZ_U8) {
-        if (!(o.kcontrast_override > 0.f))
-            LAUNCHED(AKZ_K_BASE, akzk::lowpass_u8(st, (const unsigned char*)img, c->smooth, w0, h0, ipitch, istride, p0, L0.plane, nf, 1.f, 5));
-        LAUNCHED(AKZ_K_BASE, akzk::lowpass_u8(st, (const unsigned char*)img, L0.lt, w0, h0, ipitch, istride, p0, L0.plane, nf, var0, ksz0));
-    } else {
-        if (!(o.kcontrast_override > 0.f))
-            LAUNCHED(AKZ_K_BASE, akzk::lowpass(st, (const float*)img, c->smooth, w0, h0, ipitch, istride, p0, L0.plane, nf, 1.f, 5));
-        LAUNCHED(AKZ_K_BASE, akzk::lowpass(st, (const float*)img, L0.lt, w0, h0, ipitch, istride, p0, L0.plane, nf, var0, ksz0));
+    bool base_done = false;
+    if (fused == 1) {
+        // one pass over the input: Lt(0,0) + gradient magnitude plane (c->smooth) + maximum + histogram
+        int r = 0;
+        LAUNCHED(AKZ_K_BASE, (r = akzk::base_level2(st, img, dtype, w0, h0, ipitch, istride, L0.lt, p0, L0.plane,
+                                                    o.kcontrast_override > 0.f ? nullptr : c->smooth, c->hmax, c->hist, var0, ksz0, nf)));
+        if (r > 0) {
+            base_done = true;
+            LAUNCHED(AKZ_K_CONTRAST, akzk::contrast_scan(st, c->hmax, c->hist, c->kc, o.per, o.kcontrast_override, w0, h0, nf));
+        }
     }
-    LAUNCHED(AKZ_K_CONTRAST, akzk::contrast(st, c->smooth, c->hmax, c->hist, c->kc, o.per, o.kcontrast_override, w0, h0, p0, L0.plane, nf));
+    if (!base_done) {
+        if (dtype == AKZ_U8) {
+            if (!(o.kcontrast_override > 0.f))
+                LAUNCHED(AKZ_K_BASE, akzk::lowpass_u8(st, (const unsigned char*)img, c->smooth, w0, h0, ipitch, istride, p0, L0.plane, nf, 1.f, 5));
+            LAUNCHED(AKZ_K_BASE, akzk::lowpass_u8(st, (const unsigned char*)img, L0.lt, w0, h0, ipitch, istride, p0, L0.plane, nf, var0, ksz0));
+        } else {
+            if (!(o.kcontrast_override > 0.f))
+                LAUNCHED(AKZ_K_BASE, akzk::lowpass(st, (const float*)img, c->smooth, w0, h0, ipitch, istride, p0, L0.plane, nf, 1.f, 5));
+            LAUNCHED(AKZ_K_BASE, akzk::lowpass(st, (const float*)img, L0.lt, w0, h0, ipitch, istride, p0, L0.plane, nf, var0, ksz0));
+        }
+        LAUNCHED(AKZ_K_CONTRAST, akzk::contrast(st, c->smooth, c->hmax, c->hist, c->kc, o.per, o.kcontrast_override, w0, h0, p0, L0.plane, nf));
+    }
     if (fused) LAUNCHED(AKZ_K_PREP, prep_level(c, 0, L0.lt, w0, h0, p0, L0.plane, nullptr, nullptr, L0.lx, L0.ly, L0.det, 0, L0.sigma_size, w0, h0, p0, L0.plane, nf));
     else LAUNCHED(AKZ_K_HESSIAN, akzk::hessian(st, L0.lt, L0.lx, L0.ly, L0.det, L0.sigma_size, w0, h0, p0, L0.plane, nf));
 

@@ -52,6 +52,11 @@ int level_prep(cudaStream_t st, const float* ltprev, float* flowp, float* lx, fl
 int level_prep_down(cudaStream_t st, const float* ltsrc, int sw, int sh, int sp, long long splane,
                     float* ltdst, float* flowp, float* lx, float* ly, float* det, int type,
                     const float* kc, float kscale, int nmul, int step, int w, int h, int pitch, long long plane, int n);
+// base_level.cu: Lt(0,0), gradient-magnitude plane, its maximum and histogram in one pass over the input (+ one over the
+// magnitude plane).  Returns the number of launches, 0 when the sigma0 radius is not 4 (caller uses the staged kernels).
+int base_level2(cudaStream_t st, const void* img, int dtype, int w, int h, int ipitch, long long istride,
+                float* lt, int pitch, long long plane, float* mag, unsigned* hmax_bits, int* hist, float var0, int ksz0, int n);
+int contrast_scan(cudaStream_t st, const unsigned* hmax_bits, const int* hist, float* kout, float per, float override_k, int w, int h, int n);
 // level_prep.cu: second-generation level kernel (templated on the derivative step, 64x64 tiles, vector shared-memory
 // traffic).  mode 0 = base level (no blur), 1 = blur, 2 = octave transition.  Returns 1 if launched, 0 if the
 // (step, size) combination is not covered and the caller must use level_prep / level_prep_down.

@@ -314,6 +314,13 @@ int contrast(cudaStream_t st, const float* src, unsigned* hmax_bits, int* hist, 
     return launches;
 }
 
+// only the percentile scan (the histogram and the maximum were produced by base_level2)
+int contrast_scan(cudaStream_t st, const unsigned* hmax_bits, const int* hist, float* kout, float per, float override_k, int w, int h, int n)
+{
+    k_contrast_scan<<<(n + 63) / 64, 64, 0, st>>>(hist, hmax_bits, kout, per, w, h, n, override_k);
+    return 1;
+}
+
 int flow(cudaStream_t st, const float* src, float* flowp, int type, const float* kc, float kscale, int nmul,
          int w, int h, int pitch, long long stride, int n)
 {
