@@ -76,10 +76,11 @@ __device__ __forceinline__ int coarse_src2(int q, int sdim)
 }
 
 // out-of-image cells of a tile := value of their reflect-101 mirror cell (border tiles only)
-template <int OY>
-__device__ __forceinline__ void ghost_fix(float* T, int r0, int r1, int c0, int c1, int X0, int Y0, int w, int h, int tid)
+template <int OY, int C0, int C1>
+__device__ __forceinline__ void ghost_fix(float* T, int r0, int r1, int X0, int Y0, int w, int h, int tid)
 {
-    const int nc = c1 - c0, tot = (r1 - r0) * nc;
+    constexpr int c0 = C0, c1 = C1, nc = C1 - C0;
+    const int tot = (r1 - r0) * nc;
     for (int i = tid; i < tot; i += P2_NT) {
         int r = r0 + i / nc, c = c0 + i % nc;
         int gy = Y0 - OY + r, gx = X0 - P2_OX + c;
@@ -121,13 +122,24 @@ __global__ void __launch_bounds__(P2_NT, 2) k_prep2(const __grid_constant__ Prep
                 cp_async16(dstp + r * SP + 4 * g, src + (long long)(Y0 - OY + r) * a.sp + (X0 - P2_OX + 4 * g));
             }
             cp_async_wait_all();
-        } else {
+        } else if (MODE == PM_DOWN) {
             for (int i = tid; i < AR * SP; i += P2_NT) {
                 int r = i / SP, c = i - r * SP;
-                int gy = Y0 - OY + r, gx = X0 - P2_OX + c, sy, sx;
-                if (MODE == PM_DOWN) { sy = coarse_src2(gy, a.sh); sx = coarse_src2(gx, a.sw); }
-                else { sy = min(max(refl(gy, h), 0), h - 1); sx = min(max(refl(gx, w), 0), w - 1); }
+                int sy = coarse_src2(Y0 - OY + r, a.sh), sx = coarse_src2(X0 - P2_OX + c, a.sw);
                 dstp[i] = __ldg(src + (long long)sy * a.sp + sx);
+            }
+        } else {
+            // border tile: rows by reflected index; a group of 4 columns that lies inside the image is one float4 load
+            for (int i = tid; i < AR * (SP / 4); i += P2_NT) {
+                int r = i / (SP / 4), g = i - r * (SP / 4);
+                int sy = min(max(refl(Y0 - OY + r, h), 0), h - 1), gx = X0 - P2_OX + 4 * g;
+                const float* row = src + (long long)sy * a.sp;
+                float* d = dstp + r * SP + 4 * g;
+                if (a.vec_ok && gx >= 0 && gx + 3 < w) *reinterpret_cast<float4*>(d) = __ldg(reinterpret_cast<const float4*>(row + gx));
+                else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) d[j] = __ldg(row + min(max(refl(gx + j, w), 0), w - 1));
+                }
             }
         }
     }
@@ -173,7 +185,7 @@ __global__ void __launch_bounds__(P2_NT, 2) k_prep2(const __grid_constant__ Prep
         __syncthreads();
     }
     if (!interior) {
-        ghost_fix<OY>(Sm, 2, AR - 2, 4, 84, X0, Y0, w, h, tid);
+        ghost_fix<OY, 4, 84>(Sm, 2, AR - 2, X0, Y0, w, h, tid);
         __syncthreads();
     }
 
@@ -261,8 +273,8 @@ __global__ void __launch_bounds__(P2_NT, 2) k_prep2(const __grid_constant__ Prep
     }
     __syncthreads();
     if (!interior) {
-        ghost_fix<OY>(LX, OY - S, OY + P2_H + S, 8, 80, X0, Y0, w, h, tid);
-        ghost_fix<OY>(LY, OY - S, OY + P2_H + S, 8, 80, X0, Y0, w, h, tid);
+        ghost_fix<OY, 8, 80>(LX, OY - S, OY + P2_H + S, X0, Y0, w, h, tid);
+        ghost_fix<OY, 8, 80>(LY, OY - S, OY + P2_H + S, X0, Y0, w, h, tid);
         __syncthreads();
     }
 

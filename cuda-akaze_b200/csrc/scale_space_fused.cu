@@ -498,6 +498,226 @@ __global__ void __launch_bounds__(F2_BX * F2_BY, 2) k_fed2(const __grid_constant
     else fed2_body<false>(a, sm, vec_ok);
 }
 
+// -----------------------------------------------------------------------------------------------------
+// k_fed3: k_fed2 made persistent with a software prefetch.  ncu on k_fed2 (profiles/r01a_k_fed2_raw.txt):
+// issue slots 51 % busy, 5.1 warps per issue waiting on the global loads of the tile prologue -- with two
+// register-limited CTAs per SM nothing overlaps a tile's load latency.  Here each CTA walks a strided list
+// of tiles; while it runs the steps of tile t, cp.async copies the Lt and g tiles of tile t+1 into a
+// shared-memory staging area (interior tiles; border tiles fill the stage with reflected scalar loads).
+// Arithmetic and tiling are those of k_fed2.
+// -----------------------------------------------------------------------------------------------------
+constexpr int F3_STAGE = 2 * F2_T * F2_T;                               // floats: Lt tile, g tile
+constexpr int F3_SMEM = (2 * F2_BUF + F3_STAGE) * (int)sizeof(float);
+
+struct Fed3Args {
+    FedArgs f;
+    int gx, gy, ntiles, vec_ok;
+    int nhx, nhy, two, tho;                       // fed2_geom(n), computed on the host
+    unsigned long long inv_per, inv_gx;           // floor(2^40 / d) + 1: t / d == (t * inv) >> 40 for t < 2^24, d < 2^16
+};
+
+__device__ __forceinline__ int f3_div(int t, unsigned long long inv) { return (int)(((unsigned long long)(unsigned)t * inv) >> 40); }
+
+__device__ __forceinline__ void f3_cp_async16(float* smem_dst, const float* gmem_src)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+
+struct F3Tile { int X0, Y0, GX0, GY0; long long base; bool border; };
+
+// (ncu source view of the first version: the two integer divisions of this decode were 14 % of all executed
+// instructions of the kernel, hence the multiplicative inverses)
+__device__ __forceinline__ F3Tile f3_decode(const Fed3Args& a, int t)
+{
+    F3Tile T;
+    int per = a.gx * a.gy;
+    int frame = f3_div(t, a.inv_per), rem = t - frame * per;
+    int by = f3_div(rem, a.inv_gx), bx = rem - by * a.gx;
+    T.X0 = bx * a.two; T.Y0 = by * a.tho;
+    T.GX0 = T.X0 - a.nhx; T.GY0 = T.Y0 - a.nhy;
+    T.base = (long long)frame * a.f.plane;
+    T.border = T.GX0 <= 0 || T.GY0 <= 0 || T.GX0 + F2_T >= a.f.w || T.GY0 + F2_T >= a.f.h || !a.vec_ok;
+    return T;
+}
+
+// fill the staging area with the Lt and g tiles of T (asynchronously for interior tiles)
+__device__ __forceinline__ void f3_stage(const Fed3Args& a, const F3Tile& T, float* St, int tid)
+{
+    const float* __restrict__ src = a.f.src + T.base;
+    const float* __restrict__ flw = a.f.flow + T.base;
+    if (!T.border) {
+        for (int i = tid; i < F2_T * (F2_T / 4); i += F2_BX * F2_BY) {
+            int r = i >> 4, c4 = (i & 15) * 4;
+            long long o = (long long)(T.GY0 + r) * a.f.pitch + T.GX0 + c4;
+            f3_cp_async16(St + r * F2_T + c4, src + o);
+            f3_cp_async16(St + F2_T * F2_T + r * F2_T + c4, flw + o);
+        }
+    } else {
+        // border tile: rows by reflected index; a group of 4 columns inside the image is one float4 load per plane
+        const int w = a.f.w, h = a.f.h;
+        for (int i = tid; i < F2_T * (F2_T / 4); i += F2_BX * F2_BY) {
+            int r = i >> 4, c4 = (i & 15) * 4;
+            int sy = min(max(refl(T.GY0 + r, h), 0), h - 1), gx = T.GX0 + c4;
+            long long ro = (long long)sy * a.f.pitch;
+            float* dl = St + r * F2_T + c4;
+            float* dg = dl + F2_T * F2_T;
+            if (a.vec_ok && gx >= 0 && gx + 3 < w) {
+                *(float4*)dl = __ldg((const float4*)(src + ro + gx));
+                *(float4*)dg = __ldg((const float4*)(flw + ro + gx));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    int sx = min(max(refl(gx + j, w), 0), w - 1);
+                    dl[j] = __ldg(src + ro + sx);
+                    dg[j] = __ldg(flw + ro + sx);
+                }
+            }
+        }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+
+__global__ void __launch_bounds__(F2_BX * F2_BY, 2) k_fed3(const __grid_constant__ Fed3Args a)
+{
+    extern __shared__ __align__(16) float sm[];
+    float* T0 = sm;
+    float* T1 = sm + F2_BUF;
+    float* St = sm + 2 * F2_BUF;
+    float* Gs = St + F2_T * F2_T;
+    const int n = a.f.n, w = a.f.w, h = a.f.h;
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * F2_BX + tx;
+    const int bx = 4 * tx, by = 2 * ty;
+
+    const int txl = max(tx - 1, 0), txr = min(tx + 1, F2_BX - 1);
+    const int ru = max(by - 1, 0), rd = min(by + 2, F2_T - 1);
+    const int o_row0 = by * F2_T + bx, o_up = ru * F2_T + bx, o_dn = rd * F2_T + bx;
+    const int o_cl = F2_T * F2_T + tx * F2_CP + by, o_cr = o_cl + F2_BX * F2_CP;
+    const int o_lf = F2_T * F2_T + F2_BX * F2_CP + txl * F2_CP + by;      // CR of the left neighbour
+    const int o_rt = F2_T * F2_T + txr * F2_CP + by;                      // CL of the right neighbour
+
+    int t = blockIdx.x;
+    if (t < a.ntiles) { F3Tile Tn = f3_decode(a, t); f3_stage(a, Tn, St, tid); }
+    for (; t < a.ntiles; t += gridDim.x) {
+        const F3Tile T = f3_decode(a, t);
+        const int gx0 = T.GX0 + bx, gy0 = T.GY0 + by;
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        __syncthreads();                                                   // stage(t) complete and visible
+
+        float L[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            float4 v = *(const float4*)(St + (by + r) * F2_T + bx);
+            L[r][0] = v.x; L[r][1] = v.y; L[r][2] = v.z; L[r][3] = v.w;
+        }
+        float sh[2][5], sv[3][4];
+        {
+            float g[4][6];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int rr = min(max(by - 1 + k, 0), F2_T - 1);
+                const float* gr = Gs + rr * F2_T;
+                float4 v = *(const float4*)(gr + bx);
+                g[k][0] = gr[max(bx - 1, 0)]; g[k][1] = v.x; g[k][2] = v.y; g[k][3] = v.z; g[k][4] = v.w; g[k][5] = gr[min(bx + 4, F2_T - 1)];
+            }
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int j = 0; j < 5; j++) sh[r][j] = __fadd_rn(g[r + 1][j + 1], g[r + 1][j]);
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) sv[k][c] = __fadd_rn(g[k + 1][c + 1], g[k][c + 1]);
+        }
+        // publish the rim of the block in buffer 0 (its last readers finished before the barrier above)
+        *(float4*)(T0 + o_row0) = make_float4(L[0][0], L[0][1], L[0][2], L[0][3]);
+        *(float4*)(T0 + o_row0 + F2_T) = make_float4(L[1][0], L[1][1], L[1][2], L[1][3]);
+        *(float2*)(T0 + o_cl) = make_float2(L[0][0], L[1][0]);
+        *(float2*)(T0 + o_cr) = make_float2(L[0][3], L[1][3]);
+        __syncthreads();                                                   // stage fully consumed, rim visible
+        if (t + (int)gridDim.x < a.ntiles) { F3Tile Tn = f3_decode(a, t + gridDim.x); f3_stage(a, Tn, St, tid); }
+
+        // image-border bookkeeping (only tiles that touch the border pay for it)
+        const bool border = T.GX0 <= 0 || T.GY0 <= 0 || T.GX0 + F2_T >= w || T.GY0 + F2_T >= h;
+        bool bl = false, bt = false;
+        int ir = -1, jb = -1;
+        if (border) {
+            bl = (gx0 == 0); bt = (gy0 == 0);
+            ir = (w - 1) - gx0; if (ir < 0 || ir > 3) ir = -1;
+            jb = (h - 1) - gy0; if (jb < 0 || jb > 1) jb = -1;
+        }
+
+        float* cur = T0;
+        float* nxt = T1;
+        for (int st = 0; st < n; st++) {
+            const float sf = a.f.stepfac[st];
+            const float4 up4 = *(const float4*)(cur + o_up);
+            const float4 dn4 = *(const float4*)(cur + o_dn);
+            const float2 lf2 = *(const float2*)(cur + o_lf);
+            const float2 rt2 = *(const float2*)(cur + o_rt);
+            const float up[4] = { up4.x, up4.y, up4.z, up4.w }, dn[4] = { dn4.x, dn4.y, dn4.z, dn4.w };
+            const float lf[2] = { lf2.x, lf2.y }, rt[2] = { rt2.x, rt2.y };
+            float N[2][4];
+            if (!border) {
+#pragma unroll
+                for (int r = 0; r < 2; r++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        float LL = (c == 0) ? lf[r] : L[r][c - 1];
+                        float LR = (c == 3) ? rt[r] : L[r][c + 1];
+                        float LU = (r == 0) ? up[c] : L[0][c];
+                        float LD = (r == 1) ? dn[c] : L[1][c];
+                        N[r][c] = nld_update_s(L[r][c], sh[r][c], LL, sh[r][c + 1], LR, sv[r + 1][c], LD, sv[r][c], LU, sf);
+                    }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 2; r++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        float LL = (c == 0) ? lf[r] : L[r][c - 1];
+                        float LR = (c == 3) ? rt[r] : L[r][c + 1];
+                        float LU = (r == 0) ? up[c] : L[0][c];
+                        float LD = (r == 1) ? dn[c] : L[1][c];
+                        if (c == 0 && bl) LL = LR;                 // x = 0: left neighbour is x = 1
+                        if (c == ir) LR = LL;                      // x = w-1: right neighbour is x = w-2
+                        if (r == 0 && bt) LU = LD;                 // y = 0
+                        if (r == jb) LD = LU;                      // y = h-1
+                        N[r][c] = nld_update_s(L[r][c], sh[r][c], LL, sh[r][c + 1], LR, sv[r + 1][c], LD, sv[r][c], LU, sf);
+                    }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) L[r][c] = N[r][c];
+            if (st + 1 < n) {
+                *(float4*)(nxt + o_row0) = make_float4(L[0][0], L[0][1], L[0][2], L[0][3]);
+                *(float4*)(nxt + o_row0 + F2_T) = make_float4(L[1][0], L[1][1], L[1][2], L[1][3]);
+                *(float2*)(nxt + o_cl) = make_float2(L[0][0], L[1][0]);
+                *(float2*)(nxt + o_cr) = make_float2(L[0][3], L[1][3]);
+                __syncthreads();
+                float* tt = cur; cur = nxt; nxt = tt;
+            }
+        }
+
+        // store the output region of the tile
+        if (gx0 >= T.X0 && gx0 < T.X0 + a.two && gx0 < w) {
+            float* dst = a.f.dst + T.base;
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                int gy = gy0 + r;
+                if (gy >= T.Y0 && gy < T.Y0 + a.tho && gy < h) {
+                    float* d = dst + (long long)gy * a.f.pitch + gx0;
+                    if (a.vec_ok && gx0 + 3 < w) *(float4*)d = make_float4(L[r][0], L[r][1], L[r][2], L[r][3]);
+                    else {
+#pragma unroll
+                        for (int c = 0; c < 4; c++) if (gx0 + c < w) d[c] = L[r][c];
+                    }
+                }
+            }
+        }
+    }
+}
+
 bool g_attr_done = false;
 
 }  // namespace
@@ -509,6 +729,7 @@ static void set_attrs()
     if (g_attr_done) return;
     cudaFuncSetAttribute(k_fed, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * FE_W * FE_H * (int)sizeof(float));
     cudaFuncSetAttribute(k_fed2, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM);
+    cudaFuncSetAttribute(k_fed3, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
     cudaFuncSetAttribute(k_level_prep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_level_prep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     g_attr_done = true;
@@ -551,8 +772,8 @@ int level_prep_down(cudaStream_t st, const float* ltsrc, int sw, int sh, int sp,
 }
 
 // dst receives the result of n steps applied to src; tmp is a scratch plane batch (never aliases src/dst).
-// fused == 0: n single-step launches; fused == 1: ceil(n/8) launches of the register-blocked k_fed2;
-// fused == 2: the same split with the shared-memory-resident k_fed (kept as a cross-check).
+// fused == 0: n single-step launches; fused == 1: ceil(n/8) launches of the persistent, prefetching k_fed3;
+// fused == 2: the same split with the shared-memory-resident k_fed, fused == 3: with k_fed2 (kept as cross-checks).
 int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst, float* tmp, const float* tau, int nsteps,
               int w, int h, int pitch, long long plane, int n, int fused)
 {
@@ -586,7 +807,16 @@ int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst,
             Fed2Geom ge = fed2_geom(cnt);
             dim3 g((w + ge.two - 1) / ge.two, (h + ge.tho - 1) / ge.tho, n), b(F2_BX, F2_BY);
             int vec_ok = (pitch % 4 == 0) && (plane % 4 == 0) && (((uintptr_t)a.src | (uintptr_t)flowp | (uintptr_t)a.dst) % 16 == 0);
-            k_fed2<<<g, b, F2_SMEM, st>>>(a, vec_ok);
+            if (fused == 3) k_fed2<<<g, b, F2_SMEM, st>>>(a, vec_ok);
+            else {
+                Fed3Args a3;
+                a3.f = a; a3.gx = g.x; a3.gy = g.y; a3.ntiles = (int)(g.x * g.y * g.z); a3.vec_ok = vec_ok;
+                a3.nhx = ge.nhx; a3.nhy = ge.nhy; a3.two = ge.two; a3.tho = ge.tho;
+                a3.inv_per = (1ull << 40) / (unsigned long long)(g.x * g.y) + 1; a3.inv_gx = (1ull << 40) / (unsigned long long)g.x + 1;
+                if (a3.ntiles >= (1 << 24) || g.x * g.y >= (1u << 16)) return akz_set_error(AKZ_E_UNSUPPORTED, "FED tile count out of range");
+                int nb = a3.ntiles < 2 * 148 ? a3.ntiles : 2 * 148;
+                k_fed3<<<nb, b, F3_SMEM, st>>>(a3);
+            }
         }
         cur = a.dst;
         done += cnt;
