@@ -699,7 +699,7 @@ int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt
     if (mode != AKZ_MATCH_COMPAT && mode != AKZ_MATCH_KNN2) return akz_set_error(AKZ_E_INVALID, "bad matcher mode");
     if (nq < 0 || nt < 0 || !d_out) return akz_set_error(AKZ_E_INVALID, "bad matcher arguments");
     if (nq == 0) return AKZ_OK;
-    int qblocks = (nq + 127) / 128;
+    int qblocks = (nq + 255) / 256;                 // match.cu: 256 queries per block
     int nsplit = std::max(1, std::min((2 * 148 + qblocks - 1) / qblocks, (nt + 127) / 128));
     size_t need = (size_t)nsplit * nq;
     if (c->match_parts_n < need) {

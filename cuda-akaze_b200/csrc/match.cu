@@ -2,10 +2,11 @@
 // Reference: gHammingMatch (akazed.cu:2144-2241, the live 1-NN with the 16-stride uniqueness gate
 // and the <96 gate) and gMatch (akazed.cu:2028-2122, the top-2 variant).
 //
-// Layout: each thread keeps ONE query descriptor in 16 registers; the block stages tiles of train
-// descriptors in shared memory and every thread walks the tile with broadcast LDS.128 reads, so the
-// inner loop is 16 LOP3 + 16 POPC + adds per pair and touches no global memory.  The train range is
-// split across blockIdx.y so the grid covers all 148 SMs even for a few thousand queries; partial
+// Layout: each thread keeps TWO query descriptors in 32 registers; the block stages tiles of train
+// descriptors in shared memory and every thread walks the tile with broadcast LDS.128 reads (one read serves
+// both queries), so the inner loop touches no global memory.  The 512-bit distance is a carry-save
+// (Harley-Seal) tree: 16 XOR + 30 LOP3 + 5 POPC per pair instead of 16 XOR + 16 POPC + 15 IADD.  The train
+// range is split across blockIdx.y so the grid covers all 148 SMs even for a few thousand queries; partial
 // results are merged by k_match_merge with an associative rule, which is also what the train-sharded
 // multi-GPU path applies to the per-shard results after the NCCL gather.
 //
@@ -19,54 +20,129 @@
 
 namespace {
 
-constexpr int QPB = 128;        // queries per block (one per thread)
-constexpr int TILE = 128;       // train descriptors per shared-memory tile (8 KB)
+constexpr int QPT = 2;                   // queries per thread
+constexpr int NTH = 128;                 // threads per block
+constexpr int QPB = QPT * NTH;           // queries per block
+constexpr int TILE = 128;                // train descriptors per shared-memory tile (8 KB)
 
-struct Best { int d1, i1, d2, i2; };
+// 3-input logic, written as PTX so that ptxas keeps the carry-save structure (left to itself the compiler re-associates
+// the tree into ~95 LOP3 per pair instead of 46: ncu r01e, ALU pipe 89.5 % busy)
+__device__ __forceinline__ unsigned xor3(unsigned a, unsigned b, unsigned c)
+{
+    unsigned d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned maj3(unsigned a, unsigned b, unsigned c)
+{
+    unsigned d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+#define AKZ_CSA(h, l, a, b, c) { unsigned a_ = (a), b_ = (b), c_ = (c); (h) = maj3(a_, b_, c_); (l) = xor3(a_, b_, c_); }
+#define AKZ_HA(h, l, a, b)     { unsigned a_ = (a), b_ = (b); (h) = a_ & b_; (l) = a_ ^ b_; }
+
+// Hamming distance of two 512-bit strings as a Harley-Seal carry-save tree: 16 XOR + 30 LOP3 + 5 POPC instead of
+// 16 XOR + 16 POPC + 15 IADD.  POPC issues at 4 lanes/clk/SMSP (the plain form is POPC bound: 128 of 216 SMSP cycles per
+// warp-pair, ncu r01c), LOP3 at 16 lanes/clk/SMSP.
+__device__ __forceinline__ int hamming512(const unsigned (&q)[16], const uint4& t0, const uint4& t1, const uint4& t2, const uint4& t3)
+{
+    const unsigned x0 = q[0] ^ t0.x, x1 = q[1] ^ t0.y, x2 = q[2] ^ t0.z, x3 = q[3] ^ t0.w;
+    const unsigned x4 = q[4] ^ t1.x, x5 = q[5] ^ t1.y, x6 = q[6] ^ t1.z, x7 = q[7] ^ t1.w;
+    const unsigned x8 = q[8] ^ t2.x, x9 = q[9] ^ t2.y, x10 = q[10] ^ t2.z, x11 = q[11] ^ t2.w;
+    const unsigned x12 = q[12] ^ t3.x, x13 = q[13] ^ t3.y, x14 = q[14] ^ t3.z, x15 = q[15] ^ t3.w;
+    unsigned ones, twos, fours, eights, sixteens, tA, tB, fA, fB, eA, eB;
+    AKZ_CSA(tA, ones, x0, x1, x2)
+    AKZ_CSA(tB, ones, ones, x3, x4)
+    AKZ_HA(fA, twos, tA, tB)
+    AKZ_CSA(tA, ones, ones, x5, x6)
+    AKZ_CSA(tB, ones, ones, x7, x8)
+    AKZ_CSA(fB, twos, twos, tA, tB)
+    AKZ_HA(eA, fours, fA, fB)
+    AKZ_CSA(tA, ones, ones, x9, x10)
+    AKZ_CSA(tB, ones, ones, x11, x12)
+    AKZ_CSA(fA, twos, twos, tA, tB)
+    AKZ_CSA(tA, ones, ones, x13, x14)
+    AKZ_HA(tB, ones, ones, x15)
+    AKZ_CSA(fB, twos, twos, tA, tB)
+    AKZ_CSA(eB, fours, fours, fA, fB)
+    AKZ_HA(sixteens, eights, eA, eB)
+    return __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights) + 16 * __popc(sixteens);
+}
+
+// Running best of a query.  A candidate is ordered by key = distance << 22 | (index relative to the block's train
+// range): unsigned order of the key IS the lexicographic (distance, index) order the matcher contract asks for.
+//   KNN2  : two smallest keys (min / max network, 3 instructions per pair)
+//   COMPAT: smallest key + the 16-bit mask of (index mod 16) classes that attain the smallest DISTANCE
+struct Best { unsigned k1, k2; };
+constexpr unsigned KEY_NONE = 0xFFFFFFFFu;
+constexpr int KEY_IDX_BITS = 22;
 
 template <int MODE>
-__device__ __forceinline__ void consider(Best& b, int d, int j)
+__device__ __forceinline__ void consider(Best& b, int d, int jrel, unsigned classbit)
 {
+    const unsigned key = ((unsigned)d << KEY_IDX_BITS) | (unsigned)jrel;
     if (MODE == AKZ_MATCH_KNN2) {
-        if (d < b.d1) { b.d2 = b.d1; b.i2 = b.i1; b.d1 = d; b.i1 = j; }
-        else if (d < b.d2) { b.d2 = d; b.i2 = j; }
+        const unsigned hi = max(b.k1, key);
+        b.k1 = min(b.k1, key);
+        b.k2 = min(b.k2, hi);
     } else {
-        if (d < b.d1) { b.d1 = d; b.i1 = j; b.i2 = 1 << (j & 15); }
-        else if (d == b.d1) b.i2 |= 1 << (j & 15);
+        const unsigned dcur = b.k1 >> KEY_IDX_BITS;                    // KEY_NONE >> 22 = 1023 > any distance
+        b.k2 = (unsigned)d < dcur ? classbit : ((unsigned)d == dcur ? (b.k2 | classbit) : b.k2);
+        b.k1 = min(b.k1, key);
     }
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(QPB) k_match(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t, int nt, int tbase,
+__global__ void __launch_bounds__(NTH) k_match(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t, int nt, int tbase,
                                                int per_split, akz_match_t* __restrict__ parts)
 {
     __shared__ uint4 tile[TILE * 4];
-    int qi = blockIdx.x * QPB + threadIdx.x;
-    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, a2 = a0, a3 = a0;
-    if (qi < nq) { a0 = __ldg(q + 4 * qi); a1 = __ldg(q + 4 * qi + 1); a2 = __ldg(q + 4 * qi + 2); a3 = __ldg(q + 4 * qi + 3); }
-    int t0 = blockIdx.y * per_split, t1 = min(nt, t0 + per_split);
-    Best b;
-    b.d1 = 1 << 20; b.i1 = -1; b.d2 = (MODE == AKZ_MATCH_KNN2) ? (1 << 20) : 0; b.i2 = (MODE == AKZ_MATCH_KNN2) ? -1 : 0;
+    unsigned qa[QPT][16];
+    int qi[QPT];
+    Best b[QPT];
+#pragma unroll
+    for (int k = 0; k < QPT; k++) {
+        qi[k] = blockIdx.x * QPB + k * NTH + threadIdx.x;
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            uint4 w = qi[k] < nq ? __ldg(q + 4 * (long long)qi[k] + v) : make_uint4(0, 0, 0, 0);
+            qa[k][4 * v] = w.x; qa[k][4 * v + 1] = w.y; qa[k][4 * v + 2] = w.z; qa[k][4 * v + 3] = w.w;
+        }
+        b[k].k1 = KEY_NONE; b[k].k2 = (MODE == AKZ_MATCH_KNN2) ? KEY_NONE : 0u;
+    }
+    const int t0 = blockIdx.y * per_split, t1 = min(nt, t0 + per_split);
     for (int base = t0; base < t1; base += TILE) {
         int cnt = min(TILE, t1 - base);
         __syncthreads();
-        for (int i = threadIdx.x; i < cnt * 4; i += QPB) tile[i] = __ldg(t + 4 * (long long)base + i);
+        for (int i = threadIdx.x; i < cnt * 4; i += NTH) tile[i] = __ldg(t + 4 * (long long)base + i);
         __syncthreads();
 #pragma unroll 2
         for (int j = 0; j < cnt; j++) {
-            uint4 b0 = tile[4 * j], b1 = tile[4 * j + 1], b2 = tile[4 * j + 2], b3 = tile[4 * j + 3];
-            int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w)
-                  + __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w)
-                  + __popc(a2.x ^ b2.x) + __popc(a2.y ^ b2.y) + __popc(a2.z ^ b2.z) + __popc(a2.w ^ b2.w)
-                  + __popc(a3.x ^ b3.x) + __popc(a3.y ^ b3.y) + __popc(a3.z ^ b3.z) + __popc(a3.w ^ b3.w);
-            consider<MODE>(b, d, tbase + base + j);
+            const uint4 b0 = tile[4 * j], b1 = tile[4 * j + 1], b2 = tile[4 * j + 2], b3 = tile[4 * j + 3];
+            const int jrel = base - t0 + j;
+            const unsigned classbit = 1u << ((tbase + base + j) & 15);
+#pragma unroll
+            for (int k = 0; k < QPT; k++) consider<MODE>(b[k], hamming512(qa[k], b0, b1, b2, b3), jrel, classbit);
         }
     }
-    if (qi < nq) {
-        akz_match_t m;
-        m.idx1 = b.i1; m.dist1 = b.i1 < 0 ? -1 : b.d1; m.idx2 = b.i2;
-        m.dist2 = (MODE == AKZ_MATCH_KNN2) ? (b.i2 < 0 ? -1 : b.d2) : 0;
-        parts[(long long)blockIdx.y * nq + qi] = m;
+    const unsigned imask = (1u << KEY_IDX_BITS) - 1;
+#pragma unroll
+    for (int k = 0; k < QPT; k++) {
+        if (qi[k] < nq) {
+            akz_match_t m;
+            const bool has1 = b[k].k1 != KEY_NONE;
+            m.idx1 = has1 ? tbase + t0 + (int)(b[k].k1 & imask) : -1;
+            m.dist1 = has1 ? (int)(b[k].k1 >> KEY_IDX_BITS) : -1;
+            if (MODE == AKZ_MATCH_KNN2) {
+                const bool has2 = b[k].k2 != KEY_NONE;
+                m.idx2 = has2 ? tbase + t0 + (int)(b[k].k2 & imask) : -1;
+                m.dist2 = has2 ? (int)(b[k].k2 >> KEY_IDX_BITS) : -1;
+            } else {
+                m.idx2 = (int)b[k].k2; m.dist2 = 0;
+            }
+            parts[(long long)blockIdx.y * nq + qi[k]] = m;
+        }
     }
 }
 
@@ -116,11 +192,12 @@ int match_partial(cudaStream_t st, const unsigned char* q, int nq, const unsigne
     int per = (nt + nsplit - 1) / nsplit;
     per = ((per + TILE - 1) / TILE) * TILE;
     if (per <= 0) per = TILE;
+    if (per >= (1 << KEY_IDX_BITS)) return akz_set_error(AKZ_E_UNSUPPORTED, "train range per block exceeds 2^22 descriptors: shard the train set");
     dim3 g((nq + QPB - 1) / QPB, nsplit);
     if (mode == AKZ_MATCH_KNN2)
-        k_match<AKZ_MATCH_KNN2><<<g, QPB, 0, st>>>((const uint4*)q, nq, (const uint4*)t, nt, tbase, per, parts);
+        k_match<AKZ_MATCH_KNN2><<<g, NTH, 0, st>>>((const uint4*)q, nq, (const uint4*)t, nt, tbase, per, parts);
     else
-        k_match<AKZ_MATCH_COMPAT><<<g, QPB, 0, st>>>((const uint4*)q, nq, (const uint4*)t, nt, tbase, per, parts);
+        k_match<AKZ_MATCH_COMPAT><<<g, NTH, 0, st>>>((const uint4*)q, nq, (const uint4*)t, nt, tbase, per, parts);
     return 1;
 }
 

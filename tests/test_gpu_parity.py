@@ -471,6 +471,34 @@ def test_keypoints_equal_cpu_oracle():
         ctx.close()
 
 
+def test_five_octaves_equal_cpu_oracle():
+    """configs[4] uses 5 octaves x 4 sublevels (FED cycles of up to 57 steps): planes of every level and the keypoints are
+    bit-identical to the CPU oracle at a size whose fifth octave is 81x81."""
+    w, h = 1296, 1300
+    img = B.u8_to_unit(B.synth_shapes_u8(w, h, seed=31))
+    ctx = ab().Context(w, h, noctaves=5, max_batch=1, max_pts=30000)
+    assert ctx.num_levels == 20 and ctx.level_info(19)["nsteps"] == 57
+    counts, kpts, desc = ctx.detect_and_compute(dev(img))
+    ctx.sync()
+    P = B.OraclePyramid(w, h, noctaves=5)
+    P.build(img)
+    assert P.levels == 20
+    names = ["Lt", "det", "Lx", "Ly"]
+    for l in (0, 3, 4, 11, 15, 16, 17, 18, 19):
+        for which in range(4):
+            assert_bits_equal(ctx.plane(l, which), P.plane(l, which), f"level {l} {names[which]}")
+    mine = _kp_array(counts, kpts)
+    ok = P.detect()
+    assert len(mine) == len(ok) and len(ok) > 100
+    for fld in ("ix", "iy", "layer"):
+        assert np.array_equal(mine[fld], ok[fld]), fld
+    for fld in ("x", "y", "response"):
+        assert np.array_equal(mine[fld].view(np.uint32), ok[fld].view(np.uint32)), fld
+    assert mine["layer"].max() >= 16                      # the fifth octave contributes keypoints
+    P.close()
+    ctx.close()
+
+
 def test_u8_ingest_batching_host_api_and_determinism():
     w, h = 640, 480
     frames8 = np.stack([B.synth_shapes_u8(w, h, seed=s) for s in range(5)])
