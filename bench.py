@@ -278,9 +278,18 @@ def run_ours(args):
     for _ in range(max(1, args.warmup // 2)):
         step_host()
     ms_e2e = timed(step_host, args.steps, stream, world, device)
-    clocks = sampler.stop() if rank == 0 else None
     counts = res[0].cpu().numpy()
     assert np.array_equal(counts, h_counts.numpy()), "host and device paths disagree"
+    # the same end-to-end call with raw 8-bit frames (the reference's fastDetectAndCompute ingest; a quarter of the H2D bytes)
+    ms_e2e_u8 = None
+    if args.dtype == "f32":
+        host8 = torch.from_numpy(frames8).pin_memory()
+        step8 = lambda: ctx.detect_and_compute_host(host8, True, out=hout)
+        step8()
+        ms_e2e_u8 = timed(step8, args.steps, stream, world, device)
+        assert np.array_equal(counts, h_counts.numpy()), "u8 and f32 ingest disagree"
+        del host8
+    clocks = sampler.stop() if rank == 0 else None
     nkp_mean = float(counts.mean())
 
     # per-class device time: one extra pass of the same step with event pairs around every kernel group
@@ -322,6 +331,8 @@ def run_ours(args):
         "e2e": {"value": round(F * world * args.steps / (ms_e2e * 1e-3), 2), "unit": "images/s",
                 "h2d_bytes_per_step": int(host.numel() * host.element_size()),
                 "d2h_bytes_per_step": int(F * 4 + counts.sum() * (32 + 64)), "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "e2e_u8": None if ms_e2e_u8 is None else {"value": round(F * world * args.steps / (ms_e2e_u8 * 1e-3), 2), "unit": "images/s",
+                                                  "h2d_bytes_per_step": int(F * W * H), "note": "same call with raw u8 host frames (AKZ_U8)"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
     }
     ctx.close()

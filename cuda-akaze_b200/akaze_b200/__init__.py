@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libakaze_b200.so")
 
 AKZ_F32, AKZ_U8 = 0, 1
-MATCH_COMPAT, MATCH_KNN2 = 0, 1
+MATCH_COMPAT, MATCH_KNN2, MATCH_UNIQUE2 = 0, 1, 2
 PLANE_LT, PLANE_DET, PLANE_LX, PLANE_LY = 0, 1, 2, 3
 
 
@@ -36,7 +36,7 @@ EXPORTS = [
     "akz_get_kcontrast", "akz_lowpass", "akz_down_with_smooth", "akz_scharr_contrast", "akz_flow", "akz_nld_step",
     "akz_fed_cycle", "akz_hessian", "akz_match", "akz_match_merge", "akz_match_host", "akz_pack_points",
     "akz_unpack_desc", "akz_scatter_matches", "akz_orient", "akz_describe", "akz_detect_keypoints",
-    "akz_profile_enable", "akz_profile_read", "akz_profile_class_name",
+    "akz_profile_enable", "akz_profile_read", "akz_profile_class_name", "akz_keypoints_to_opencv", "akz_matches_to_opencv",
 ]
 NUM_KCLASS = 13
 
@@ -90,6 +90,8 @@ def lib():
     L.akz_pack_points.argtypes = [vp, vp, vp, vp, vp, i, i]
     L.akz_unpack_desc.argtypes = [vp, vp, i, vp]
     L.akz_scatter_matches.argtypes = [vp, vp, i, vp, vp]
+    L.akz_keypoints_to_opencv.argtypes = [vp, i, i, vp]
+    L.akz_matches_to_opencv.argtypes = [vp, i, vp]
     L.akz_profile_enable.argtypes = [vp, i]
     L.akz_profile_read.argtypes = [vp, i, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     L.akz_profile_class_name.argtypes = [i]
@@ -363,6 +365,24 @@ def _cudart_memcpy_d2d(dst, src, nbytes):
     dstt = torch.as_tensor(dstt_h, device="cuda")
     dstt.copy_(srct)
     torch.cuda.synchronize()
+
+
+def keypoints_to_opencv(kpts, max_scale=4):
+    """KEYPOINT_DTYPE array (host) -> (n, 7) float32: pt.x, pt.y, size, angle (deg), response, octave, class_id."""
+    k = np.ascontiguousarray(kpts)
+    out = np.zeros((len(k), 7), dtype=np.float32)
+    _check(lib().akz_keypoints_to_opencv(C.c_void_p(k.ctypes.data), len(k), max_scale, C.c_void_p(out.ctypes.data)))
+    return out
+
+
+def matches_to_opencv(m):
+    """(nq, 4) int32 match results (host) -> (n_accepted, 3) int32: queryIdx, trainIdx, distance."""
+    a = np.ascontiguousarray(m, dtype=np.int32)
+    out = np.zeros((len(a), 3), dtype=np.int32)
+    n = lib().akz_matches_to_opencv(C.c_void_p(a.ctypes.data), len(a), C.c_void_p(out.ctypes.data))
+    if n < 0:
+        _check(n)
+    return out[:n]
 
 
 def keypoints_from_words(words):

@@ -696,7 +696,7 @@ int akz_detect_keypoints(akz_ctx* c, int n, int* d_counts, akz_keypoint* d_kpts)
 int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int t_index_base, int mode, int finalize, akz_match_t* d_out)
 {
     STAGE_PROLOGUE();
-    if (mode != AKZ_MATCH_COMPAT && mode != AKZ_MATCH_KNN2) return akz_set_error(AKZ_E_INVALID, "bad matcher mode");
+    if (mode != AKZ_MATCH_COMPAT && mode != AKZ_MATCH_KNN2 && mode != AKZ_MATCH_UNIQUE2) return akz_set_error(AKZ_E_INVALID, "bad matcher mode");
     if (nq < 0 || nt < 0 || !d_out) return akz_set_error(AKZ_E_INVALID, "bad matcher arguments");
     if (nq == 0) return AKZ_OK;
     int qblocks = (nq + 255) / 256;                 // match.cu: 256 queries per block
@@ -769,6 +769,31 @@ int akz_profile_read(akz_ctx* c, int ncls, double* ms, long long* launches)
     for (int i = 0; i < ncls && i < AKZ_NUM_KCLASS; i++) { ms[i] = c->prof_ms[i]; launches[i] = c->prof_launches[i]; }
     memset(c->prof_ms, 0, sizeof(c->prof_ms)); memset(c->prof_launches, 0, sizeof(c->prof_launches));
     return AKZ_OK;
+}
+
+// ---- host format: OpenCV conventions --------------------------------------------------------------
+// cv::KeyPoint fields for keypoints already on the host: pt = (x, y), size = derivative scale in FULL-resolution pixels
+// (size * 2^octave), angle in degrees, response, octave, class_id = sublevel.  out: n rows of 7 floats.
+int akz_keypoints_to_opencv(const akz_keypoint* h_kpts, int n, int max_scale, float* out)
+{
+    if (!h_kpts || !out || n < 0 || max_scale < 1) return akz_set_error(AKZ_E_INVALID, "bad argument");
+    for (int i = 0; i < n; i++) {
+        const akz_keypoint& k = h_kpts[i];
+        int oct = k.layer / max_scale, sub = k.layer - oct * max_scale;
+        float* o = out + 7 * (size_t)i;
+        o[0] = k.x; o[1] = k.y; o[2] = k.size * (float)(1 << oct); o[3] = k.angle * (float)(180.0 / M_PI);
+        o[4] = k.response; o[5] = (float)oct; o[6] = (float)sub;
+    }
+    return AKZ_OK;
+}
+// cv::DMatch fields for accepted matches: out rows (queryIdx, trainIdx, distance); returns the number of rows written
+int akz_matches_to_opencv(const akz_match_t* h_m, int nq, int* out)
+{
+    if (!h_m || !out || nq < 0) return akz_set_error(AKZ_E_INVALID, "bad argument");
+    int n = 0;
+    for (int i = 0; i < nq; i++)
+        if (h_m[i].idx1 >= 0) { out[3 * n] = i; out[3 * n + 1] = h_m[i].idx1; out[3 * n + 2] = h_m[i].dist1; n++; }
+    return n;
 }
 
 // ---- AoS bridge -----------------------------------------------------------------------------------------------

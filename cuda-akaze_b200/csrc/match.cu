@@ -153,11 +153,12 @@ __global__ void k_match_merge(const akz_match_t* __restrict__ parts, int nparts,
     int qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
     akz_match_t r;
-    r.idx1 = -1; r.dist1 = -1; r.idx2 = (mode == AKZ_MATCH_KNN2) ? -1 : 0; r.dist2 = (mode == AKZ_MATCH_KNN2) ? -1 : 0;
+    const bool top2 = mode != AKZ_MATCH_COMPAT;                // KNN2 and UNIQUE2 share the partial form
+    r.idx1 = -1; r.dist1 = -1; r.idx2 = top2 ? -1 : 0; r.dist2 = top2 ? -1 : 0;
     for (int p = 0; p < nparts; p++) {
         akz_match_t m = parts[(long long)p * nq + qi];
         if (m.idx1 < 0) continue;
-        if (mode == AKZ_MATCH_KNN2) {
+        if (top2) {
             // merge two sorted pairs, lowest (distance, index) first
             int cd[4] = { r.dist1, r.dist2, m.dist1, m.dist2 };
             int ci[4] = { r.idx1, r.idx2, m.idx1, m.idx2 };
@@ -172,6 +173,11 @@ __global__ void k_match_merge(const akz_match_t* __restrict__ parts, int nparts,
             if (r.idx1 < 0 || m.dist1 < r.dist1) r = m;
             else if (m.dist1 == r.dist1) { r.idx1 = min(r.idx1, m.idx1); r.idx2 |= m.idx2; }
         }
+    }
+    if (finalize && mode == AKZ_MATCH_UNIQUE2) {
+        // gMatch (akazed.cu:2103): the best must be strictly better than the second best and below MAX_DIST
+        bool ok = r.idx1 >= 0 && r.dist1 < AKZ_MAX_DIST && (r.idx2 < 0 || r.dist1 < r.dist2);
+        if (!ok) { r.idx1 = -1; r.dist1 = -1; }
     }
     if (finalize && mode == AKZ_MATCH_COMPAT) {
         // akazed.cu:2222: the minimum must be strictly unique across the 16 strides and below MAX_DIST
@@ -194,7 +200,7 @@ int match_partial(cudaStream_t st, const unsigned char* q, int nq, const unsigne
     if (per <= 0) per = TILE;
     if (per >= (1 << KEY_IDX_BITS)) return akz_set_error(AKZ_E_UNSUPPORTED, "train range per block exceeds 2^22 descriptors: shard the train set");
     dim3 g((nq + QPB - 1) / QPB, nsplit);
-    if (mode == AKZ_MATCH_KNN2)
+    if (mode != AKZ_MATCH_COMPAT)
         k_match<AKZ_MATCH_KNN2><<<g, NTH, 0, st>>>((const uint4*)q, nq, (const uint4*)t, nt, tbase, per, parts);
     else
         k_match<AKZ_MATCH_COMPAT><<<g, NTH, 0, st>>>((const uint4*)q, nq, (const uint4*)t, nt, tbase, per, parts);

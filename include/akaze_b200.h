@@ -37,7 +37,7 @@ enum {
 };
 
 enum { AKZ_F32 = 0, AKZ_U8 = 1 };                /* input pixel type: [0,1] float (main.cpp:149) or raw u8 */
-enum { AKZ_MATCH_COMPAT = 0, AKZ_MATCH_KNN2 = 1 };
+enum { AKZ_MATCH_COMPAT = 0, AKZ_MATCH_KNN2 = 1, AKZ_MATCH_UNIQUE2 = 2 };
 enum { AKZ_PLANE_LT = 0, AKZ_PLANE_DET = 1, AKZ_PLANE_LX = 2, AKZ_PLANE_LY = 3 };   /* akaze.cpp:315-320 */
 
 /* The reference has no options struct: these are the 11 arguments of Akazer::init (akaze.h:25-26)
@@ -76,7 +76,8 @@ typedef struct akz_keypoint {
 
 /* Result of one matcher query (16 bytes).
  * COMPAT: idx1 = match or -1, dist1 = distance or -1 (akazed.cu:2222-2237); idx2 = class mask, dist2 = 0.
- * KNN2  : best and second best (distance, index), lowest index first on ties; -1 when absent. */
+ * KNN2  : best and second best (distance, index), lowest index first on ties; -1 when absent.
+ * UNIQUE2: as KNN2, but idx1/dist1 = -1 unless dist1 < dist2 and dist1 < 96 (the reference's gMatch rule, akazed.cu:2103). */
 typedef struct akz_match_t {
     int idx1, dist1, idx2, dist2;
 } akz_match_t;
@@ -181,6 +182,13 @@ AKZ_API int akz_match_merge(akz_ctx* c, const akz_match_t* d_parts, int nparts, 
                             int finalize, akz_match_t* d_out);
 AKZ_API int akz_match_host(akz_ctx* c, const uint8_t* h_q, int nq, const uint8_t* h_t, int nt,
                            int mode, akz_match_t* h_out);
+
+/* ---- host format in OpenCV conventions (beside cv::AKAZE; reference main.cpp:373-388 uses cv::KeyPoint / cv::DMatch) -- */
+/* out: n rows of 7 floats = pt.x, pt.y, size (full-resolution pixels: size * 2^octave), angle (degrees), response,
+ * octave, class_id (sublevel).  Host arrays. */
+AKZ_API int akz_keypoints_to_opencv(const akz_keypoint* h_kpts, int n, int max_scale, float* out);
+/* out: rows (queryIdx, trainIdx, distance) of the accepted matches; returns their number.  Host arrays. */
+AKZ_API int akz_matches_to_opencv(const akz_match_t* h_m, int nq, int* out);
 
 /* ---- AoS bridge for the akaze.h shim ------------------------------------------------------------ */
 /* writes x,y,octave,size,angle,features into reference-layout AkazePoint records (104 B, App. D) */

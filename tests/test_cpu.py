@@ -171,6 +171,17 @@ def test_schedule_of_the_1080p_configuration():
     P.close()
 
 
+def test_opencv_export_host_only():
+    """akz_keypoints_to_opencv / akz_matches_to_opencv are host-only format conversions (no device needed)."""
+    k = np.zeros(3, dtype=ab().KEYPOINT_DTYPE)
+    k["x"], k["y"], k["size"], k["angle"], k["layer"], k["response"] = [1.5, 2.5, 3.5], [4, 5, 6], [2.4, 2.854, 4.036], [0, np.pi / 2, np.pi], [0, 5, 14], [.1, .2, .3]
+    o = ab().keypoints_to_opencv(k, 4)
+    assert np.allclose(o[:, 0], [1.5, 2.5, 3.5]) and np.allclose(o[:, 2], [2.4, 2.854 * 2, 4.036 * 8]) and np.allclose(o[:, 3], [0, 90, 180])
+    assert o[:, 5].tolist() == [0, 1, 3] and o[:, 6].tolist() == [0, 1, 2]
+    m = np.array([[5, 10, -1, 0], [-1, -1, 0, 0], [7, 95, 3, 100]], dtype=np.int32)
+    assert ab().matches_to_opencv(m).tolist() == [[0, 5, 10], [2, 7, 95]]
+
+
 def test_reference_point_layout():
     assert B.REF_POINT.itemsize == 104
     assert [B.REF_POINT.fields[n][1] for n in ("x", "y", "octave", "response", "size", "angle", "features", "match", "distance", "match_x", "match_y")] == \

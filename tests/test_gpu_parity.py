@@ -140,7 +140,7 @@ def test_down_with_smooth_odd_sizes_vs_oracle(stage_ctx):
 
 
 @needs_ref
-@pytest.mark.parametrize("dtype_k", [(1, 0.0123), (1, 0.0021), (0, 0.02), (3, 0.02)])
+@pytest.mark.parametrize("dtype_k", [(1, 0.0123), (1, 0.0021), (0, 0.02), (3, 0.02), (2, 0.02)])
 def test_flow_vs_reference(stage_ctx, dtype_k):
     typ, k = dtype_k
     img = left_image()
@@ -589,6 +589,13 @@ def test_matcher_vs_cpu_oracle(nq, nt):
     o2 = B.oracle_match(q, t, "knn2")
     assert np.array_equal(r2.cpu().numpy(), o2)
     assert np.array_equal(ctx.match_host(q, t, ab().MATCH_KNN2), o2)
+    # UNIQUE2 = the reference's gMatch acceptance (akazed.cu:2103) on top of the exact top-2
+    r3 = ctx.match(qt, tt, ab().MATCH_UNIQUE2)
+    ctx.sync()
+    r3 = r3.cpu().numpy()
+    ok = (o2[:, 0] >= 0) & (o2[:, 1] < 96) & ((o2[:, 2] < 0) | (o2[:, 1] < o2[:, 3]))
+    assert np.array_equal(r3[:, 0], np.where(ok, o2[:, 0], -1)) and np.array_equal(r3[:, 1], np.where(ok, o2[:, 1], -1))
+    assert np.array_equal(r3[:, 2:], o2[:, 2:])
     # sharded: split the train set in 3 ranges, merge the partial results (what the NCCL path does after its gather)
     for mode, ref_out in ((ab().MATCH_COMPAT, o), (ab().MATCH_KNN2, o2)):
         cuts = [0, nt // 3, (2 * nt) // 3, nt]
