@@ -308,9 +308,17 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     alg = algorithmic_bytes(top, nkp_mean) * F
     achieved = alg / (top_ms * 1e-3) / 1e9 if top_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    try:                                     # DRAM bytes of the captured launch, scaled by the algorithmic bytes (profiles/traffic.json)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if top in tr:
+            traffic = tr[top]["ratio"] * alg / max(1, top_launches)
+            traffic_src = f"ncu {tr[top]['kernel']}: {tr[top]['dram_bytes']} B DRAM for {tr[top]['algorithmic_bytes']} B algorithmic ({tr['source']})"
+    except Exception:
+        pass
     step_alg = (4 * W * H + 20 * sum(level_pixels(W, H))) * F          # 228.6 MB / frame
     roof = {"bound": "hbm", "kernel": top, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(achieved / peak, 4), "traffic": None,
+            "frac": round(achieved / peak, 4), "traffic": None if traffic is None else round(traffic), "traffic_source": traffic_src,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (sustained copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
             "kernel_ms_per_step": round(top_ms, 3), "kernel_share_of_step": round(top_ms / tot_ms, 3) if tot_ms else None,
             "kernel_launches_per_step": int(top_launches), "algorithmic_bytes_per_launch": alg / max(1, top_launches),

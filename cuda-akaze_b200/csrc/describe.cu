@@ -52,6 +52,7 @@ __device__ __forceinline__ int find_frame(const int* __restrict__ prefix, int n,
 }
 
 constexpr int ORI_WARPS = 4;
+#define AKZ_MAX_FRAMES_SEARCH 256
 
 // one warp per keypoint; bins are summed in ascending sample order => deterministic (App. B-4)
 __global__ void __launch_bounds__(ORI_WARPS * 32) k_orient(const __grid_constant__ AkzLevelTable tab, const int* __restrict__ prefix, int nframes,
@@ -238,13 +239,26 @@ __global__ void __launch_bounds__(64) k_describe_t(const __grid_constant__ AkzLe
     constexpr int S2 = PAT, S3 = (2 * PAT + 2) / 3, S4 = (PAT + 1) / 2;      // akazed.cu:2681-2683 (ceil)
     constexpr int WIN = (3 * S3 > 4 * S4) ? 3 * S3 : 4 * S4;
     constexpr int NS = WIN * WIN, NK = (NS + 63) / 64, RS = 65;
-    __shared__ float acc[87 * RS];
+    __shared__ __align__(16) float acc[87 * RS + 4];
     __shared__ float val[96];
     const int tix = threadIdx.x;
-    const int total = prefix[nframes];
+    // frame of a keypoint: binary search in a shared-memory copy of the prefix (the linear search through global memory
+    // was 14 % of the stall samples, ncu r01f; one block per frame instead leaves the busiest frame as a long tail)
+    __shared__ int s_prefix[AKZ_MAX_FRAMES_SEARCH + 1];
+    for (int i = tix; i <= nframes && i <= AKZ_MAX_FRAMES_SEARCH; i += 64) s_prefix[i] = prefix[i];
+    __syncthreads();
+    const int total = s_prefix[min(nframes, AKZ_MAX_FRAMES_SEARCH)];
+    // this thread's 8 comparison pairs, fetched once (per-lane different constant addresses serialise in the constant cache)
+    unsigned cmp[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int b = min(tix, 60) * 8 + i;
+        cmp[i] = (unsigned)c_cmp[0][b] | ((unsigned)c_cmp[1][b] << 16);
+    }
     for (int g = blockIdx.x; g < total; g += gridDim.x) {
-        int frame = find_frame(prefix, nframes, g);
-        int local = g - prefix[frame];
+        int lo = 0, hi = nframes - 1;                      // largest f with s_prefix[f] <= g
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_prefix[mid] <= g) lo = mid; else hi = mid - 1; }
+        const int frame = lo, local = g - s_prefix[lo];
         const akz_keypoint* kp = kpts + (long long)frame * max_pts + local;
         const AkzLevelDev& L = tab.lv[kp->layer];
         const int o = L.octave, p = L.pitch;
@@ -272,9 +286,9 @@ __global__ void __launch_bounds__(64) k_describe_t(const __grid_constant__ AkzLe
                 im[k] = __ldg(imd + pos); dx[k] = __ldg(dxd + pos); dy[k] = __ldg(dyd + pos);
             }
         }
-        // 2. clear this thread's accumulator column
-#pragma unroll
-        for (int v = 0; v < 87; v++) acc[v * RS + tix] = 0.f;
+        // 2. clear the accumulators: the block zeroes the whole array with 128-bit stores (22 per thread instead of 87 scalar)
+        for (int i = tix; i < (87 * RS + 3) / 4; i += 64) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
         // 3. accumulate in sample order (each thread touches only its own column: no synchronisation needed)
 #pragma unroll
         for (int k = 0; k < NK; k++) {
@@ -317,9 +331,10 @@ __global__ void __launch_bounds__(64) k_describe_t(const __grid_constant__ AkzLe
         unsigned char* out = desc + ((long long)frame * max_pts + local) * 64;
         unsigned rbits = 0;
         if (tix < 61) {
-            int nb = (tix == 60 ? 6 : 8);
-            for (int i = 0; i < nb; i++)
-                rbits |= (val[c_cmp[0][tix * 8 + i]] > val[c_cmp[1][tix * 8 + i]] ? 1u : 0u) << i;
+            const int nb = (tix == 60 ? 6 : 8);
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (i < nb) rbits |= (val[cmp[i] & 0xFFFFu] > val[cmp[i] >> 16] ? 1u : 0u) << i;
         }
         out[tix] = (unsigned char)rbits;                  // bytes 61..63 are written as zero
         __syncthreads();
@@ -398,7 +413,7 @@ int describe(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const
     int size2 = pattern;                                          // akazed.cu:2681-2683
     int size3 = (int)ceilf(2.0f * pattern / 3.0f);
     int size4 = (int)ceilf(0.5f * pattern);
-    if (pattern == 10) k_describe_t<10><<<148 * 9, 64, 0, st>>>(tab, prefix, n, kpts, desc, max_pts);
+    if (pattern == 10 && n <= AKZ_MAX_FRAMES_SEARCH) k_describe_t<10><<<148 * 9, 64, 0, st>>>(tab, prefix, n, kpts, desc, max_pts);
     else k_describe<<<148 * 8, 64, 0, st>>>(tab, prefix, n, kpts, desc, max_pts, size2, size3, size4);
     return 1;
 }

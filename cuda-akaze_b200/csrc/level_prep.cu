@@ -75,19 +75,35 @@ __device__ __forceinline__ int coarse_src2(int q, int sdim)
     return min(max(c, 0), sdim - 1);
 }
 
-// out-of-image cells of a tile := value of their reflect-101 mirror cell (border tiles only)
+// out-of-image cells of a tile := value of their reflect-101 mirror cell (border tiles only).
+// Only the ghost band is visited: the rows above the image / below it over the full width, then the columns left /
+// right of it over the remaining rows (visiting every cell of the region was 9 % of the kernel's instructions, ncu r01f).
 template <int OY, int C0, int C1>
 __device__ __forceinline__ void ghost_fix(float* T, int r0, int r1, int X0, int Y0, int w, int h, int tid)
 {
-    constexpr int c0 = C0, c1 = C1, nc = C1 - C0;
-    const int tot = (r1 - r0) * nc;
-    for (int i = tid; i < tot; i += P2_NT) {
-        int r = r0 + i / nc, c = c0 + i % nc;
-        int gy = Y0 - OY + r, gx = X0 - P2_OX + c;
-        if (gy < 0 || gy >= h || gx < 0 || gx >= w) {
-            int mr = min(max(refl(gy, h) - Y0 + OY, r0), r1 - 1);
-            int mc = min(max(refl(gx, w) - X0 + P2_OX, c0), c1 - 1);
-            T[r * P2_SP + c] = T[mr * P2_SP + mc];
+    constexpr int nc = C1 - C0;
+    const int nr = r1 - r0;
+    const int gy0 = Y0 - OY + r0, gx0 = X0 - P2_OX + C0;           // image coordinates of the region's first cell
+    const int top = min(max(-gy0, 0), nr), bot = min(max(h - gy0, top), nr);      // in-image rows of the region: [top, bot)
+    const int lft = min(max(-gx0, 0), nc), rgt = min(max(w - gx0, lft), nc);      // in-image columns:           [lft, rgt)
+    auto fix = [&](int rr, int cc) {
+        int r = r0 + rr, c = C0 + cc;
+        int mr = min(max(refl(gy0 + rr, h) - Y0 + OY, r0), r1 - 1);
+        int mc = min(max(refl(gx0 + cc, w) - X0 + P2_OX, C0), C1 - 1);
+        T[r * P2_SP + c] = T[mr * P2_SP + mc];
+    };
+    const int nghost_rows = top + (nr - bot);
+    for (int i = tid; i < nghost_rows * nc; i += P2_NT) {
+        int rr = i / nc, cc = i - rr * nc;
+        if (rr >= top) rr += bot - top;
+        fix(rr, cc);
+    }
+    const int nghost_cols = lft + (nc - rgt);
+    if (nghost_cols > 0) {
+        for (int i = tid; i < (bot - top) * nghost_cols; i += P2_NT) {
+            int rr = i / nghost_cols, cc = i - rr * nghost_cols;
+            if (cc >= lft) cc += rgt - lft;
+            fix(top + rr, cc);
         }
     }
 }
