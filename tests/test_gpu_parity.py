@@ -550,6 +550,79 @@ def test_small_image_drops_octaves_and_empty_image():
     ctx.close()
 
 
+def test_full_size_1080p_properties():
+    """BASELINE configs[2] size (1920x1080, 4x4): size-independent properties instead of an oracle pass --
+    the fused production kernels equal the one-kernel-per-stage path bit for bit on every plane, and a frame's result
+    does not depend on its position in the batch or on the chunking."""
+    w, h = 1920, 1080
+    f0 = B.u8_to_unit(B.synth_shapes_u8(w, h, seed=41))
+    f1 = B.u8_to_unit(B.synth_noise_u8(w, h, seed=42))
+    t = torch.from_numpy(np.stack([f0, f1, f0])).cuda()
+    planes = {}
+    for fused in (0, 1):
+        ctx = ab().Context(w, h, fused=fused, max_batch=3, max_pts=40000)
+        ctx.build_scale_space(t)
+        ctx.sync()
+        planes[fused] = [[ctx.plane(l, which, 1) for which in range(4)] for l in (0, 1, 5, 10, 15)]
+        if fused:
+            c3, k3, d3 = ctx.detect_and_compute(t)
+            ctx.sync()
+        ctx.close()
+    for a, b in zip(planes[0], planes[1]):
+        for which in range(4):
+            assert_bits_equal(a[which], b[which], "1080p stages vs fused")
+    n0, n1 = int(c3[0]), int(c3[1])
+    assert n0 == int(c3[2]) and n0 > 500 and n1 > 5000
+    assert torch.equal(k3[0, :n0], k3[2, :n0]) and torch.equal(d3[0, :n0], d3[2, :n0])          # position in the batch
+    ctx = ab().Context(w, h, max_batch=2, max_pts=40000)                                              # different chunking
+    c2, k2, d2 = ctx.detect_and_compute(t)
+    ctx.sync()
+    assert torch.equal(c2, c3)
+    for f in range(3):
+        n = int(c3[f])
+        assert torch.equal(k2[f, :n], k3[f, :n]) and torch.equal(d2[f, :n], d3[f, :n])
+    ctx.close()
+
+
+def test_keypoint_capacity_is_clamped_in_raster_order():
+    """App. B-10: more survivors than max_pts -> the count is clamped and the FIRST max_pts keypoints in raster order are
+    kept (the reference keeps an order-dependent subset and indexes past the buffer)."""
+    w, h = 640, 480
+    img = B.u8_to_unit(B.synth_noise_u8(w, h, seed=3))
+    big = ab().Context(w, h, max_batch=1, max_pts=20000)
+    cb, kb, db = big.detect_and_compute(dev(img))
+    big.sync()
+    n = int(cb[0])
+    assert n > 300
+    small = ab().Context(w, h, max_batch=1, max_pts=200)
+    cs, ks, ds = small.detect_and_compute(dev(img))
+    small.sync()
+    assert int(cs[0]) == 200
+    assert torch.equal(ks[0, :200], kb[0, :200]) and torch.equal(ds[0, :200], db[0, :200])
+    big.close(); small.close()
+
+
+def test_report_overlap_with_opencv_akaze():
+    """Report only (App. B-11: the reference differs from OpenCV/upstream AKAZE by design): fraction of our keypoints on
+    left.pgm that have an OpenCV cv::AKAZE keypoint within 3 px, and the other way round."""
+    cv2 = pytest.importorskip("cv2")
+    img = left_image()
+    h, w = img.shape
+    ctx = ab().Context(w, h, max_batch=1, max_pts=30000)
+    counts, kpts, _ = ctx.detect_and_compute(dev(img))
+    ctx.sync()
+    mine = _kp_array(counts, kpts)
+    ctx.close()
+    kp = cv2.AKAZE_create().detect(np.clip(np.rint(img * 255.0), 0, 255).astype(np.uint8), None)
+    cvxy = np.array([k.pt for k in kp], dtype=np.float32)
+    from scipy.spatial import cKDTree
+    d1, _ = cKDTree(cvxy).query(np.stack([mine["x"], mine["y"]], 1))
+    d2, _ = cKDTree(np.stack([mine["x"], mine["y"]], 1)).query(cvxy)
+    print(f"\n[vs OpenCV cv::AKAZE on left.pgm] ours={len(mine)} opencv={len(kp)}; ours within 3 px of an OpenCV keypoint: {(d1 <= 3).mean():.3f}; "
+          f"OpenCV within 3 px of ours: {(d2 <= 3).mean():.3f}")
+    assert len(mine) > 1000 and len(kp) > 1000 and (d2 <= 3).mean() > 0.3
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # matcher
 # ---------------------------------------------------------------------------------------------------------------
