@@ -21,7 +21,8 @@ class Options(C.Structure):
                 ("per", C.c_float), ("kcontrast", C.c_float), ("soffset", C.c_float), ("reordering", C.c_int),
                 ("derivative_factor", C.c_float), ("dthreshold", C.c_float), ("diffusivity", C.c_int),
                 ("descriptor_pattern_size", C.c_int), ("max_pts", C.c_int), ("max_batch", C.c_int),
-                ("device", C.c_int), ("kcontrast_override", C.c_float), ("fused", C.c_int)]
+                ("device", C.c_int), ("kcontrast_override", C.c_float), ("fused", C.c_int),
+                ("fast_kcontrast_override", C.c_int)]
 
 
 KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("response", "<f4"), ("size", "<f4"), ("angle", "<f4"),
@@ -37,6 +38,8 @@ EXPORTS = [
     "akz_fed_cycle", "akz_hessian", "akz_match", "akz_match_merge", "akz_match_host", "akz_pack_points",
     "akz_unpack_desc", "akz_scatter_matches", "akz_orient", "akz_describe", "akz_detect_keypoints",
     "akz_profile_enable", "akz_profile_read", "akz_profile_class_name", "akz_keypoints_to_opencv", "akz_matches_to_opencv",
+    "akz_fast_detect_and_compute", "akz_fast_build_scale_space", "akz_fast_get_kcontrast", "akz_fast_lowpass",
+    "akz_fast_down_with_smooth", "akz_fast_scharr_contrast", "akz_fast_flow", "akz_fast_nld_step", "akz_fast_hessian",
 ]
 NUM_KCLASS = 13
 
@@ -90,6 +93,15 @@ def lib():
     L.akz_pack_points.argtypes = [vp, vp, vp, vp, vp, i, i]
     L.akz_unpack_desc.argtypes = [vp, vp, i, vp]
     L.akz_scatter_matches.argtypes = [vp, vp, i, vp, vp]
+    L.akz_fast_detect_and_compute.argtypes = [vp, vp, i, i, i, i, ll, i, vp, vp, vp]
+    L.akz_fast_build_scale_space.argtypes = [vp, vp, i, i, i, i, ll]
+    L.akz_fast_get_kcontrast.argtypes = [vp, C.POINTER(C.c_int), i]
+    L.akz_fast_lowpass.argtypes = [vp, vp, i, vp, vp, i, i, i, ll, i, f, i]
+    L.akz_fast_down_with_smooth.argtypes = [vp, vp, vp, vp, i, i, i, ll, i, i, i, ll, i]
+    L.akz_fast_scharr_contrast.argtypes = [vp, vp, vp, vp, f, i, i, i, ll, i]
+    L.akz_fast_flow.argtypes = [vp, vp, vp, i, vp, i, i, i, ll, i]
+    L.akz_fast_nld_step.argtypes = [vp, vp, vp, vp, f, i, i, i, ll, i]
+    L.akz_fast_hessian.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, ll, i]
     L.akz_keypoints_to_opencv.argtypes = [vp, i, i, vp]
     L.akz_matches_to_opencv.argtypes = [vp, i, vp]
     L.akz_profile_enable.argtypes = [vp, i]
@@ -251,6 +263,31 @@ class Context:
         _check(lib().akz_detect_and_compute(self.h, _ptr(images), dtype, n, w, h, pitch, pitch * h, int(describe),
                                             _ptr(counts), _ptr(kpts), _ptr(desc)))
         return counts, kpts, desc
+
+    # ---- integer ("fast") pipeline -------------------------------------------------------------------
+    def fast_detect_and_compute(self, images, describe=True, out=None, width=None):
+        """images: (n, h, pitch) uint8 on the device -> (counts, kpts, desc) as detect_and_compute, integer arithmetic."""
+        n, h, pitch, dtype = self._img_args(images)
+        assert dtype == AKZ_U8
+        w = width or self.opt.width
+        counts, kpts, desc = out if out is not None else self.alloc_results(n, describe)
+        _check(lib().akz_fast_detect_and_compute(self.h, _ptr(images), n, w, h, pitch, pitch * h, int(describe),
+                                                 _ptr(counts), _ptr(kpts), _ptr(desc)))
+        return counts, kpts, desc
+
+    def fast_build_scale_space(self, images, width=None):
+        n, h, pitch, dtype = self._img_args(images)
+        assert dtype == AKZ_U8
+        _check(lib().akz_fast_build_scale_space(self.h, _ptr(images), n, width or self.opt.width, h, pitch, pitch * h))
+
+    def fast_kcontrast(self, nframes=1):
+        buf = (C.c_int * nframes)()
+        _check(lib().akz_fast_get_kcontrast(self.h, buf, nframes))
+        return np.array(buf[:], dtype=np.int32)
+
+    def plane_int(self, level, which, frame=0):
+        """A plane of the integer pipeline as int32 (the buffers are shared with the float pipeline)."""
+        return self.plane(level, which, frame).view(np.int32)
 
     def detect_and_compute_host(self, images, describe=True, out=None, width=None):
         """images: (n, h, pitch) numpy array (or pinned torch CPU tensor).  Returns numpy arrays."""

@@ -172,11 +172,15 @@ namespace akaze
             CHECK(cudaMalloc((void**)&d_desc, (size_t)64 * max_pts));
             cap = max_pts;
         }
-        void run(const void* image, int dtype, AkazeData& result, int3 whp0, bool desc)
+        void run(const void* image, int dtype, AkazeData& result, int3 whp0, bool desc, bool fast = false)
         {
             ensure(whp0.x, whp0.y, result.max_pts);
-            AKZ_DO(akz_detect_and_compute(ctx, image, dtype, 1, whp0.x, whp0.y, whp0.z, (long long)whp0.y * whp0.z,
-                                          desc ? 1 : 0, d_count, d_kpts, d_desc));
+            if (fast)
+                AKZ_DO(akz_fast_detect_and_compute(ctx, (const uint8_t*)image, 1, whp0.x, whp0.y, whp0.z, (long long)whp0.y * whp0.z,
+                                                   desc ? 1 : 0, d_count, d_kpts, d_desc));
+            else
+                AKZ_DO(akz_detect_and_compute(ctx, image, dtype, 1, whp0.x, whp0.y, whp0.z, (long long)whp0.y * whp0.z,
+                                              desc ? 1 : 0, d_count, d_kpts, d_desc));
             AKZ_DO(akz_pack_points(ctx, d_count, d_kpts, d_desc, result.d_data, result.max_pts, desc ? 1 : 0));
             CHECK(cudaMemcpyAsync(&result.num_pts, d_count, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)akz_stream(ctx)));
             AKZ_DO(akz_sync(ctx));
@@ -215,12 +219,10 @@ namespace akaze
         state->run(image, AKZ_F32, result, whp0, desc);
     }
 
-    // Integer entry point of the reference (akaze.cpp:153-201).  This build ingests the 8-bit frame
-    // directly (u8 -> [0,1] folded into the first blur) and runs the float pipeline; the reference's
-    // 16.16 fixed-point arithmetic is a documented "next" row.
+    // Integer entry point of the reference (akaze.cpp:153-201): the 16.16 fixed-point pipeline (fast_pipeline.cu)
     void Akazer::fastDetectAndCompute(unsigned char* image, AkazeData& result, int3 whp0, const bool desc)
     {
-        state->run(image, AKZ_U8, result, whp0, desc);
+        state->run(image, AKZ_U8, result, whp0, desc, true);
     }
 
     // ---- akazed.h: float stage functions, synchronous like the reference's wrappers --------------------------

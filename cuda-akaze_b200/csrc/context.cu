@@ -39,7 +39,7 @@ void akz_default_options(akz_options* o)
     o->width = 0; o->height = 0;
     o->noctaves = 4; o->max_scale = 4; o->per = 0.7f; o->kcontrast = 0.03f; o->soffset = 1.6f; o->reordering = 1;
     o->derivative_factor = 1.5f; o->dthreshold = 0.001f; o->diffusivity = 1; o->descriptor_pattern_size = 10;
-    o->max_pts = 10000; o->max_batch = 8; o->device = -1; o->kcontrast_override = 0.f; o->fused = 1;
+    o->max_pts = 10000; o->max_batch = 8; o->device = -1; o->kcontrast_override = 0.f; o->fused = 1; o->fast_kcontrast_override = 0;
 }
 
 // ---- host math ----------------------------------------------------------------------------------------
@@ -464,7 +464,50 @@ static int scale_space_chunk(akz_ctx* c, const void* img, int dtype, int nf, int
     return AKZ_OK;
 }
 
-static int detect_chunk(akz_ctx* c, int nf, int describe, int* d_counts, akz_keypoint* d_kpts, unsigned char* d_desc)
+// integer pipeline, Akazer::fastDetect (akaze.cpp:506-743): the plane buffers of the context are reused as int32 planes
+static int fast_scale_space_chunk(akz_ctx* c, const unsigned char* img, int nf, int ipitch, long long istride)
+{
+    cudaStream_t st = c->stream;
+    const akz_options& o = c->opt;
+    const int S = o.max_scale;
+    AkzLevel& L0 = c->lev[0];
+    const int w0 = L0.w, h0 = L0.h, p0 = L0.pitch;
+    int* smooth = (int*)c->smooth; int* flow = (int*)c->flow; int* tA = (int*)c->tmpA; int* tB = (int*)c->tmpB;
+    int* ikc = (int*)c->kc; int* ihmax = (int*)c->hmax;
+    const float var0 = o.soffset * o.soffset;
+    const int ksz0 = (int)(2 * ceilf((o.soffset - 0.8f) / 0.3f) + 3);
+    // level (0,0): akaze.cpp:593-617
+    LAUNCHED(AKZ_K_BASE, akzk::fast_lowpass(st, img, 1, smooth, tA, w0, h0, ipitch, istride, p0, L0.plane, nf, 1.f, 5));
+    LAUNCHED(AKZ_K_CONTRAST, akzk::fast_contrast(st, smooth, tB, ihmax, c->hist, ikc, o.per, o.fast_kcontrast_override, w0, h0, p0, L0.plane, nf));
+    LAUNCHED(AKZ_K_BASE, akzk::fast_lowpass(st, img, 1, (int*)L0.lt, tA, w0, h0, ipitch, istride, p0, L0.plane, nf, var0, ksz0));
+    LAUNCHED(AKZ_K_HESSIAN, akzk::fast_hessian(st, (const int*)L0.lt, (int*)L0.lx, (int*)L0.ly, (int*)L0.det, L0.sigma_size, w0, h0, p0, L0.plane, nf));
+    for (int l = 1; l < c->nlev; l++) {
+        AkzLevel& L = c->lev[l];
+        const float* tau = c->tau + L.tau_off;
+        const int w = L.w, h = L.h, p = L.pitch;
+        const int* cur;
+        if (L.sub == 0) {
+            AkzLevel& P = c->lev[l - S];                                   // sublevel 0 of the previous octave (akaze.cpp:650)
+            LAUNCHED(AKZ_K_BLUR, akzk::fast_down(st, (const int*)P.lt, tB, smooth, P.w, P.h, P.pitch, P.plane, w, h, p, L.plane, nf));
+            cur = tB;
+        } else {
+            AkzLevel& P = c->lev[l - 1];
+            LAUNCHED(AKZ_K_BLUR, akzk::fast_lowpass(st, P.lt, 0, smooth, tA, w, h, p, L.plane, p, L.plane, nf, 1.f, 5));
+            cur = (const int*)P.lt;
+        }
+        LAUNCHED(AKZ_K_FLOW, akzk::fast_flow(st, smooth, flow, o.diffusivity, ikc, L.octave, w, h, p, L.plane, nf));
+        for (int k = 0; k < L.nsteps; k++) {
+            int* out = ((L.nsteps - 1 - k) % 2 == 0) ? (int*)L.lt : tA;
+            LAUNCHED(AKZ_K_FED, akzk::fast_nld_step(st, cur, flow, out, tau[k], w, h, p, L.plane, nf));
+            cur = out;
+        }
+        LAUNCHED(AKZ_K_HESSIAN, akzk::fast_hessian(st, smooth, (int*)L.lx, (int*)L.ly, (int*)L.det, L.sigma_size, w, h, p, L.plane, nf));
+    }
+    c->last_frames = nf;
+    return AKZ_OK;
+}
+
+static int detect_chunk(akz_ctx* c, int nf, int describe, int* d_counts, akz_keypoint* d_kpts, unsigned char* d_desc, int fast = 0)
 {
     cudaStream_t st = c->stream;
     const akz_options& o = c->opt;
@@ -475,18 +518,19 @@ static int detect_chunk(akz_ctx* c, int nf, int describe, int* d_counts, akz_key
         memset(&a, 0, sizeof(a));
         const AkzLevel& F = c->lev[oc * S];
         a.nsub = S; a.w = F.w; a.h = F.h; a.pitch = F.pitch; a.octave = oc; a.psz = (int)F.border;     // akazed.cu:2571
+        a.int_planes = fast;
         for (int j = 0; j < S; j++) {
             const AkzLevel& L = c->lev[oc * S + j];
             a.lv[j].det = L.det; a.lv[j].plane = L.plane; a.lv[j].border = L.border; a.lv[j].threshold = o.dthreshold;
-            a.lv[j].layer = oc * S + j;
+            a.lv[j].layer = oc * S + j; a.lv[j].ithreshold = 65;                      // akaze.cpp:560
         }
         LAUNCHED(AKZ_K_EXTREMA, akzk::extrema(st, a, c->map, c->mpitch, c->mplane, nf));
     }
     LAUNCHED(AKZ_K_NMS, akzk::nms_emit(st, c->map, c->mpitch, c->mplane, o.width, o.height, c->psz, c->tab, c->rowmask, c->rowcount,
-                            d_counts, c->prefix, d_kpts, o.max_pts, nf));
+                            d_counts, c->prefix, d_kpts, o.max_pts, nf, fast));
     if (describe) {
-        LAUNCHED(AKZ_K_ORIENT, akzk::orient(st, c->tab, d_counts, c->prefix, d_kpts, o.max_pts, nf));
-        LAUNCHED(AKZ_K_DESCRIBE, akzk::describe(st, c->tab, d_counts, c->prefix, d_kpts, d_desc, o.max_pts, nf, o.descriptor_pattern_size));
+        LAUNCHED(AKZ_K_ORIENT, akzk::orient(st, c->tab, d_counts, c->prefix, d_kpts, o.max_pts, nf, fast));
+        LAUNCHED(AKZ_K_DESCRIBE, akzk::describe(st, c->tab, d_counts, c->prefix, d_kpts, d_desc, o.max_pts, nf, o.descriptor_pattern_size, fast));
     }
     return AKZ_OK;
 }
@@ -526,6 +570,41 @@ int akz_detect_and_compute(akz_ctx* c, const void* d_images, int dtype, int nfra
         if ((rc = scale_space_chunk(c, img, dtype, nf, pitch, stride)) != AKZ_OK) return rc;
         if ((rc = detect_chunk(c, nf, describe, d_counts + f0, d_kpts + (size_t)f0 * c->opt.max_pts,
                                d_desc ? d_desc + (size_t)f0 * c->opt.max_pts * 64 : nullptr)) != AKZ_OK) return rc;
+    }
+    AKZ_CUDA_TRY(cudaGetLastError());
+    return AKZ_OK;
+}
+
+int akz_fast_build_scale_space(akz_ctx* c, const uint8_t* d_images, int nframes, int w, int h, int pitch, long long stride)
+{
+    int rc = check_frame_args(c, d_images, AKZ_U8, nframes, w, h, pitch);
+    if (rc != AKZ_OK) return rc;
+    if (nframes > c->opt.max_batch) return akz_set_error(AKZ_E_INVALID, "nframes exceeds max_batch");
+    AKZ_CUDA_TRY(cudaSetDevice(c->device));
+    if ((rc = fast_scale_space_chunk(c, d_images, nframes, pitch, stride)) != AKZ_OK) return rc;
+    AKZ_CUDA_TRY(cudaGetLastError());
+    return AKZ_OK;
+}
+
+int akz_fast_get_kcontrast(akz_ctx* c, int* h_k, int nframes)
+{
+    AKZ_CUDA_TRY(cudaMemcpyAsync(h_k, c->kc, sizeof(int) * nframes, cudaMemcpyDeviceToHost, c->stream));
+    return akz_sync(c);
+}
+
+int akz_fast_detect_and_compute(akz_ctx* c, const uint8_t* d_images, int nframes, int w, int h, int pitch, long long stride,
+                                int describe, int* d_counts, akz_keypoint* d_kpts, uint8_t* d_desc)
+{
+    int rc = check_frame_args(c, d_images, AKZ_U8, nframes, w, h, pitch);
+    if (rc != AKZ_OK) return rc;
+    if (!d_counts || !d_kpts || (describe && !d_desc)) return akz_set_error(AKZ_E_INVALID, "null result buffer");
+    AKZ_CUDA_TRY(cudaSetDevice(c->device));
+    const int B = c->opt.max_batch;
+    for (int f0 = 0; f0 < nframes; f0 += B) {
+        int nf = std::min(B, nframes - f0);
+        if ((rc = fast_scale_space_chunk(c, d_images + (size_t)f0 * stride, nf, pitch, stride)) != AKZ_OK) return rc;
+        if ((rc = detect_chunk(c, nf, describe, d_counts + f0, d_kpts + (size_t)f0 * c->opt.max_pts,
+                               d_desc ? d_desc + (size_t)f0 * c->opt.max_pts * 64 : nullptr, 1)) != AKZ_OK) return rc;
     }
     AKZ_CUDA_TRY(cudaGetLastError());
     return AKZ_OK;
@@ -662,6 +741,46 @@ int akz_hessian(akz_ctx* c, const float* smooth, float* lx, float* ly, float* de
     STAGE_PROLOGUE();
     if (c->opt.fused) LAUNCHED(AKZ_K_PREP, prep_level(c, 0, smooth, w, h, pitch, stride, nullptr, nullptr, lx, ly, det, 0, step, w, h, pitch, stride, n));
     else LAUNCHED(AKZ_K_HESSIAN, akzk::hessian(c->stream, smooth, lx, ly, det, step, w, h, pitch, stride, n));
+    STAGE_EPILOGUE();
+}
+
+// ---- integer pipeline stage seams ---------------------------------------------------------------------------------------
+int akz_fast_lowpass(akz_ctx* c, const void* src, int src_is_u8, int* dst, int* tmp, int w, int h, int pitch, long long stride, int n, float var, int ksz)
+{
+    STAGE_PROLOGUE();
+    LAUNCHED(AKZ_K_BLUR, akzk::fast_lowpass(c->stream, src, src_is_u8, dst, tmp, w, h, pitch, stride, pitch, stride, n, var, ksz));
+    STAGE_EPILOGUE();
+}
+int akz_fast_down_with_smooth(akz_ctx* c, const int* src, int* dst, int* smooth, int sw, int sh, int sp, long long sstride,
+                              int dw, int dh, int dp, long long dstride, int n)
+{
+    STAGE_PROLOGUE();
+    LAUNCHED(AKZ_K_BLUR, akzk::fast_down(c->stream, src, dst, smooth, sw, sh, sp, sstride, dw, dh, dp, dstride, n));
+    STAGE_EPILOGUE();
+}
+int akz_fast_scharr_contrast(akz_ctx* c, const int* src, int* mag, int* d_k, float per, int w, int h, int pitch, long long stride, int n)
+{
+    STAGE_PROLOGUE();
+    if (n > c->opt.max_batch) return akz_set_error(AKZ_E_INVALID, "nframes exceeds max_batch");
+    LAUNCHED(AKZ_K_CONTRAST, akzk::fast_contrast(c->stream, src, mag, (int*)c->hmax, c->hist, d_k, per, 0, w, h, pitch, stride, n));
+    STAGE_EPILOGUE();
+}
+int akz_fast_flow(akz_ctx* c, const int* src, int* flow, int type, const int* d_k, int w, int h, int pitch, long long stride, int n)
+{
+    STAGE_PROLOGUE();
+    LAUNCHED(AKZ_K_FLOW, akzk::fast_flow(c->stream, src, flow, type, d_k, 0, w, h, pitch, stride, n));
+    STAGE_EPILOGUE();
+}
+int akz_fast_nld_step(akz_ctx* c, const int* src, const int* flow, int* dst, float tau, int w, int h, int pitch, long long stride, int n)
+{
+    STAGE_PROLOGUE();
+    LAUNCHED(AKZ_K_FED, akzk::fast_nld_step(c->stream, src, flow, dst, tau, w, h, pitch, stride, n));
+    STAGE_EPILOGUE();
+}
+int akz_fast_hessian(akz_ctx* c, const int* smooth, int* lx, int* ly, int* det, int step, int w, int h, int pitch, long long stride, int n)
+{
+    STAGE_PROLOGUE();
+    LAUNCHED(AKZ_K_HESSIAN, akzk::fast_hessian(c->stream, smooth, lx, ly, det, step, w, h, pitch, stride, n));
     STAGE_EPILOGUE();
 }
 

@@ -12,6 +12,7 @@ namespace {
 // ---- orientation sample table: the 109 (i,j) of the 13x16 thread grid with i*i+j*j < 36, in thread
 // order, and their weights exp(-r2*0.08f) evaluated ON THE DEVICE with the same expf the reference uses
 __device__ float g_orient_w[36];            // weight by r2
+__device__ float g_orient_wf[36];           // integer pipeline: __expf(-r2 * 0.08f) (akazed.cu:3681)
 __device__ signed char g_orient_ij[128][2]; // (i, j) by sample rank; 109 valid
 __device__ int g_orient_n;
 
@@ -20,6 +21,7 @@ __global__ void k_orient_table()
     if (threadIdx.x < 36) {
         int r2 = threadIdx.x;
         g_orient_w[r2] = exp(-r2 * 0.08f);                       // akazed.cu:1697
+        g_orient_wf[r2] = __expf(-r2 * 0.08f);
     }
     if (threadIdx.x == 0) {
         int n = 0;
@@ -55,6 +57,9 @@ constexpr int ORI_WARPS = 4;
 #define AKZ_MAX_FRAMES_SEARCH 256
 
 // one warp per keypoint; bins are summed in ascending sample order => deterministic (App. B-4)
+// FAST = true: the integer pipeline's gCalcOrient (akazed.cu:3649-3720): int Lx/Ly planes, __expf weights, and the
+// polynomial dFastAtan2 for the bin as well as for the final angle
+template <bool FAST>
 __global__ void __launch_bounds__(ORI_WARPS * 32) k_orient(const __grid_constant__ AkzLevelTable tab, const int* __restrict__ prefix, int nframes,
                                                           akz_keypoint* __restrict__ kpts, int max_pts)
 {
@@ -76,12 +81,19 @@ __global__ void __launch_bounds__(ORI_WARPS * 32) k_orient(const __grid_constant
             float4 v = make_float4(0.f, 0.f, __int_as_float(-1), 0.f);
             if (s < 109) {
                 int i = g_orient_ij[s][0], j = g_orient_ij[s][1];
-                float gw = g_orient_w[i * i + j * j];
+                float gw = FAST ? g_orient_wf[i * i + j * j] : g_orient_w[i * i + j * j];
                 int yy = min(max(y + step * j, 0), L.h - 1), xx = min(max(x + step * i, 0), L.w - 1);
                 long long pos = (long long)yy * p + xx;
-                float dx = gw * __ldg(lx + pos);
-                float dy = gw * __ldg(ly + pos);
-                float ang = atan2f(dy, dx);
+                float dx, dy, ang;
+                if (FAST) {
+                    dx = gw * __ldg(reinterpret_cast<const int*>(lx) + pos);
+                    dy = gw * __ldg(reinterpret_cast<const int*>(ly) + pos);
+                    ang = fast_atan2(dy, dx);
+                } else {
+                    dx = gw * __ldg(lx + pos);
+                    dy = gw * __ldg(ly + pos);
+                    ang = atan2f(dy, dx);
+                }
                 int a = max(min((int)(ang * (21 / 3.14159265358979323846)) + 21, 41), 0);   // akazed.cu:1702
                 v = make_float4(dx, dy, __int_as_float(a), 0.f);
             }
@@ -341,6 +353,85 @@ __global__ void __launch_bounds__(64) k_describe_t(const __grid_constant__ AkzLe
     }
 }
 
+// ---- M-LDB of the integer pipeline (gDescribe2 akazed.cu:3723-3855): int planes, int rotated derivatives
+// (float product sums truncated to int), int cell sums (associative: any reduction order), int comparisons.
+__global__ void __launch_bounds__(64) k_describe_int(const __grid_constant__ AkzLevelTable tab, const int* __restrict__ prefix, int nframes,
+                                                     const akz_keypoint* __restrict__ kpts, unsigned char* __restrict__ desc,
+                                                     int max_pts, int size2, int size3, int size4)
+{
+    __shared__ int acc[87][65];
+    __shared__ int val[96];
+    const int tix = threadIdx.x;
+    const int total = prefix[nframes];
+    for (int g = blockIdx.x; g < total; g += gridDim.x) {
+        int frame = find_frame(prefix, nframes, g);
+        int local = g - prefix[frame];
+        const akz_keypoint* pt = kpts + (long long)frame * max_pts + local;
+        const AkzLevelDev& L = tab.lv[pt->layer];
+        int o = L.octave, p = L.pitch;
+        float iratio = 1.f / (1 << o);
+        int scale = (int)(pt->size + 0.5f);
+        float xf = pt->x * iratio;
+        float yf = pt->y * iratio;
+        float ang = pt->angle;
+        float co = __cosf(ang);
+        float si = __sinf(ang);
+        const int* imd = reinterpret_cast<const int*>(L.lt) + (long long)frame * L.plane;
+        const int* dxd = reinterpret_cast<const int*>(L.lx) + (long long)frame * L.plane;
+        const int* dyd = reinterpret_cast<const int*>(L.ly) + (long long)frame * L.plane;
+        int winsize = max(3 * size3, 4 * size4);
+        for (int v = 0; v < 87; v++) acc[v][tix] = 0;
+        for (int i = tix; i < winsize * winsize; i += 64) {
+            int y = i / winsize;
+            int x = i - winsize * y;
+            int m = max(x, y);
+            if (m >= winsize) continue;
+            int l = x - size2;
+            int k = y - size2;
+            int xp = (int)(xf + scale * (k * co - l * si) + 0.5f);
+            int yp = (int)(yf + scale * (k * si + l * co) + 0.5f);
+            xp = min(max(xp, 0), L.w - 1); yp = min(max(yp, 0), L.h - 1);       // no-op for in-range patches (border test)
+            long long pos = (long long)yp * p + xp;
+            int im = __ldg(imd + pos);
+            int dx = __ldg(dxd + pos);
+            int dy = __ldg(dyd + pos);
+            int rx = -dx * si + dy * co;
+            int ry = dx * co + dy * si;
+            if (m < 2 * size2) {
+                int c = 3 * ((y < size2 ? 0 : 1) * 2 + (x < size2 ? 0 : 1));
+                acc[c][tix] += im; acc[c + 1][tix] += rx; acc[c + 2][tix] += ry;
+            }
+            if (m < 3 * size3) {
+                int x3 = (x < size3 ? 0 : (x < 2 * size3 ? 1 : 2)), y3 = (y < size3 ? 0 : (y < 2 * size3 ? 1 : 2));
+                int c = 3 * (4 + y3 * 3 + x3);
+                acc[c][tix] += im; acc[c + 1][tix] += rx; acc[c + 2][tix] += ry;
+            }
+            if (m < 4 * size4) {
+                int x4 = (x < 2 * size4 ? (x < size4 ? 0 : 1) : (x < 3 * size4 ? 2 : 3));
+                int y4 = (y < 2 * size4 ? (y < size4 ? 0 : 1) : (y < 3 * size4 ? 2 : 3));
+                int c = 3 * (13 + y4 * 4 + x4);
+                acc[c][tix] += im; acc[c + 1][tix] += rx; acc[c + 2][tix] += ry;
+            }
+        }
+        __syncthreads();
+        for (int v = tix; v < 87; v += 64) {
+            int sum = 0;
+            for (int t = 0; t < 64; t++) sum += acc[v][t];
+            val[v] = sum;
+        }
+        __syncthreads();
+        unsigned char* out = desc + ((long long)frame * max_pts + local) * 64;
+        unsigned r = 0;
+        if (tix < 61) {
+            int nb = (tix == 60 ? 6 : 8);
+            for (int i = 0; i < nb; i++)
+                r |= (val[c_cmp[0][tix * 8 + i]] > val[c_cmp[1][tix * 8 + i]] ? 1u : 0u) << i;
+        }
+        out[tix] = (unsigned char)r;
+        __syncthreads();
+    }
+}
+
 // ---- AoS bridge: reference AkazePoint (104 B) ------------------------------------------------------------
 struct RefPoint {
     float x, y; int octave; float response, size, angle;
@@ -399,20 +490,22 @@ int orient_table_init(cudaStream_t st)
     return 1;
 }
 
-int orient(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const int* prefix, akz_keypoint* kpts, int max_pts, int n)
+int orient(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const int* prefix, akz_keypoint* kpts, int max_pts, int n, int fast)
 {
     (void)counts;
-    k_orient<<<148 * 8, ORI_WARPS * 32, 0, st>>>(tab, prefix, n, kpts, max_pts);
+    if (fast) k_orient<true><<<148 * 8, ORI_WARPS * 32, 0, st>>>(tab, prefix, n, kpts, max_pts);
+    else k_orient<false><<<148 * 8, ORI_WARPS * 32, 0, st>>>(tab, prefix, n, kpts, max_pts);
     return 1;
 }
 
 int describe(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const int* prefix, const akz_keypoint* kpts,
-             unsigned char* desc, int max_pts, int n, int pattern)
+             unsigned char* desc, int max_pts, int n, int pattern, int fast)
 {
     (void)counts;
     int size2 = pattern;                                          // akazed.cu:2681-2683
     int size3 = (int)ceilf(2.0f * pattern / 3.0f);
     int size4 = (int)ceilf(0.5f * pattern);
+    if (fast) { k_describe_int<<<148 * 8, 64, 0, st>>>(tab, prefix, n, kpts, desc, max_pts, size2, size3, size4); return 1; }
     if (pattern == 10 && n <= AKZ_MAX_FRAMES_SEARCH) k_describe_t<10><<<148 * 9, 64, 0, st>>>(tab, prefix, n, kpts, desc, max_pts);
     else k_describe<<<148 * 8, 64, 0, st>>>(tab, prefix, n, kpts, desc, max_pts, size2, size3, size4);
     return 1;

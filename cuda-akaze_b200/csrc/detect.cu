@@ -17,22 +17,34 @@ namespace {
 // Almost every pixel fails the threshold, so a thread first looks at one float4 of the centre row and only
 // candidates pay for the two neighbour rows (ncu r01b: the one-pixel-per-thread version was latency bound,
 // 9.4 warps stalled on the long scoreboard per issue).
+// T = float: the float pipeline; T = int: the integer "fast" pipeline (gCalcExtremaMap akazed.cu:3476, threshold 65)
+template <typename T> struct ExtVec;
+template <> struct ExtVec<float> { typedef float4 type; };
+template <> struct ExtVec<int> { typedef int4 type; };
+__device__ __forceinline__ unsigned long long ext_key(float v, int layer) { return merge_key(v, layer); }
+__device__ __forceinline__ unsigned long long ext_key(int v, int layer) { return ((unsigned long long)(unsigned)v << 32) | (unsigned)(0xFFFF - layer); }
+
+__device__ __forceinline__ float ext_thr(const AkzExtremaLevel& L, float) { return L.threshold; }
+__device__ __forceinline__ int ext_thr(const AkzExtremaLevel& L, int) { return L.ithreshold; }
+
+template <typename T>
 __global__ void __launch_bounds__(256) k_extrema(const __grid_constant__ AkzExtremaArgs a, unsigned long long* __restrict__ map, int mpitch, long long mplane)
 {
+    typedef typename ExtVec<T>::type V4;
     int frame = blockIdx.z / a.nsub, sub = blockIdx.z - frame * a.nsub;
     const AkzExtremaLevel& L = a.lv[sub];
     const int x0 = (a.psz & ~3) + (blockIdx.x * 32 + threadIdx.x) * 4;
     const int iy = blockIdx.y * 8 + threadIdx.y + a.psz;
     if (x0 >= a.w - 1 || iy >= a.h - 1) return;
-    const float* row = L.det + (long long)frame * L.plane + (long long)iy * a.pitch + x0;
-    const float4 c4 = __ldg(reinterpret_cast<const float4*>(row));
-    const float thr = L.threshold;
+    const T* row = reinterpret_cast<const T*>(L.det) + (long long)frame * L.plane + (long long)iy * a.pitch + x0;
+    const V4 c4 = __ldg(reinterpret_cast<const V4*>(row));
+    const T thr = ext_thr(L, T());
     if (!(c4.x > thr || c4.y > thr || c4.z > thr || c4.w > thr)) return;
-    const float4 u4 = __ldg(reinterpret_cast<const float4*>(row - a.pitch));
-    const float4 d4 = __ldg(reinterpret_cast<const float4*>(row + a.pitch));
-    const float u[6] = { __ldg(row - a.pitch - 1), u4.x, u4.y, u4.z, u4.w, __ldg(row - a.pitch + 4) };
-    const float c[6] = { __ldg(row - 1), c4.x, c4.y, c4.z, c4.w, __ldg(row + 4) };
-    const float d[6] = { __ldg(row + a.pitch - 1), d4.x, d4.y, d4.z, d4.w, __ldg(row + a.pitch + 4) };
+    const V4 u4 = __ldg(reinterpret_cast<const V4*>(row - a.pitch));
+    const V4 d4 = __ldg(reinterpret_cast<const V4*>(row + a.pitch));
+    const T u[6] = { __ldg(row - a.pitch - 1), u4.x, u4.y, u4.z, u4.w, __ldg(row - a.pitch + 4) };
+    const T c[6] = { __ldg(row - 1), c4.x, c4.y, c4.z, c4.w, __ldg(row + 4) };
+    const T d[6] = { __ldg(row + a.pitch - 1), d4.x, d4.y, d4.z, d4.w, __ldg(row + a.pitch + 4) };
     const float border = L.border;
     // akazed.cu:1346-1353 (float arithmetic, truncating casts)
     int up_y = (int)(__fadd_rn(__fsub_rn((float)iy, border), 0.5f)) - 1;
@@ -41,14 +53,14 @@ __global__ void __launch_bounds__(256) k_extrema(const __grid_constant__ AkzExtr
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         int ix = x0 + j;
-        float v = c[j + 1];
+        T v = c[j + 1];
         if (ix < a.psz || ix >= a.w - 1 || !(v > thr)) continue;
         int left_x = (int)(__fadd_rn(__fsub_rn((float)ix, border), 0.5f)) - 1;
         int right_x = (int)(__fadd_rn(__fadd_rn((float)ix, border), 0.5f)) + 1;
         if (left_x < 0 || right_x >= a.w) continue;
         if (v > u[j + 1] && v > d[j + 1] && v > c[j] && v > c[j + 2] && v > u[j] && v > u[j + 2] && v > d[j] && v > d[j + 2]) {
             long long oi = (long long)frame * mplane + (long long)(iy << a.octave) * mpitch + (ix << a.octave);
-            atomicMax(map + oi, merge_key(v, L.layer));
+            atomicMax(map + oi, ext_key(v, L.layer));
         }
     }
 }
@@ -71,7 +83,7 @@ __global__ void __launch_bounds__(256) k_nms_mark(const unsigned long long* __re
         if (ix >= psz && ix < xend) {
             unsigned long long key = m[(long long)iy * mpitch + ix];
             if (key != 0ull) {
-                float rc = key_resp(key);
+                unsigned rc = (unsigned)(key >> 32);          // positive float bits and positive ints order like unsigned
                 float fsz = tab.lv[key_layer(key)].size;
                 int isz = (int)__fadd_rn(fsz, 0.5f);
                 int sq = (int)__fmul_rn(fsz, fsz);
@@ -85,7 +97,7 @@ __global__ void __launch_bounds__(256) k_nms_mark(const unsigned long long* __re
                         // under the distance test of j.  Reproduced: the keypoint SET must equal the reference's.
                         unsigned long long kn = row[(i == 0 && j > 0) ? j - 1 : j];
                         if (kn == 0ull) continue;
-                        float rn = key_resp(kn);
+                        unsigned rn = (unsigned)(kn >> 32);
                         if (rn > rc || (rn == rc && i <= 0 && j <= 0)) { keep = false; break; }
                     }
                 }
@@ -158,6 +170,7 @@ __global__ void k_frame_prefix(const int* __restrict__ counts, int* __restrict__
 }
 
 // one block (128 threads) per (row, frame): rank the survivors of the row and write refined keypoints
+template <bool INT>
 __global__ void __launch_bounds__(128) k_emit_refine(const unsigned long long* __restrict__ map, int mpitch, long long mplane,
                                                      int H, int psz, const __grid_constant__ AkzLevelTable tab, const unsigned* __restrict__ rowmask, int mwords,
                                                      const int* __restrict__ rowoff, akz_keypoint* __restrict__ kpts, int max_pts)
@@ -187,27 +200,52 @@ __global__ void __launch_bounds__(128) k_emit_refine(const unsigned long long* _
         const AkzLevelDev& L = tab.lv[layer];
         int o = L.octave, p = L.pitch;
         int x = ix >> o, y = iy >> o;
-        const float* d = L.det + (long long)frame * L.plane + (long long)y * p + x;
-        // akazed.cu:1636-1657, operation order as compiled
-        float d0 = __ldg(d), dl = __ldg(d - 1), dr = __ldg(d + 1), du = __ldg(d - p), dd_ = __ldg(d + p);
-        float v2 = __fadd_rn(d0, d0);
-        float gx = __fmul_rn(0.5f, __fsub_rn(dr, dl));
-        float gy = __fmul_rn(0.5f, __fsub_rn(dd_, du));
-        float dxx = __fsub_rn(__fadd_rn(dr, dl), v2);
-        float dyy = __fsub_rn(__fadd_rn(dd_, du), v2);
-        float dxy = __fmul_rn(0.25f, __fsub_rn(__fsub_rn(__fadd_rn(__ldg(d + p + 1), __ldg(d - p - 1)), __ldg(d - p + 1)), __ldg(d + p - 1)));
-        float det = __fmaf_rn(dxx, dyy, -__fmul_rn(dxy, dxy));
-        float idd = det != 0.f ? __fdiv_rn(1.f, det) : 0.f;
-        float o0 = __fmul_rn(idd, __fmaf_rn(gy, dxy, -__fmul_rn(gx, dyy)));
-        float o1 = __fmul_rn(idd, __fmaf_rn(gx, dxy, -__fmul_rn(gy, dxx)));
-        bool weak = o0 < -1.f || o0 > 1.f || o1 < -1.f || o1 > 1.f;
         akz_keypoint k;
-        k.ix = ix; k.iy = iy; k.layer = layer; k.size = L.size; k.response = key_resp(key); k.angle = 0.f;
-        if (weak) { k.x = (float)ix; k.y = (float)iy; }
-        else {
-            float ratio = (float)(1 << o);
-            k.x = __fmul_rn(ratio, __fadd_rn((float)x, o0));
-            k.y = __fmul_rn(ratio, __fadd_rn((float)y, o1));
+        k.ix = ix; k.iy = iy; k.layer = layer; k.size = L.size; k.angle = 0.f;
+        if (!INT) {
+            const float* d = L.det + (long long)frame * L.plane + (long long)y * p + x;
+            // akazed.cu:1636-1657, operation order as compiled
+            float d0 = __ldg(d), dl = __ldg(d - 1), dr = __ldg(d + 1), du = __ldg(d - p), dd_ = __ldg(d + p);
+            float v2 = __fadd_rn(d0, d0);
+            float gx = __fmul_rn(0.5f, __fsub_rn(dr, dl));
+            float gy = __fmul_rn(0.5f, __fsub_rn(dd_, du));
+            float dxx = __fsub_rn(__fadd_rn(dr, dl), v2);
+            float dyy = __fsub_rn(__fadd_rn(dd_, du), v2);
+            float dxy = __fmul_rn(0.25f, __fsub_rn(__fsub_rn(__fadd_rn(__ldg(d + p + 1), __ldg(d - p - 1)), __ldg(d - p + 1)), __ldg(d + p - 1)));
+            float det = __fmaf_rn(dxx, dyy, -__fmul_rn(dxy, dxy));
+            float idd = det != 0.f ? __fdiv_rn(1.f, det) : 0.f;
+            float o0 = __fmul_rn(idd, __fmaf_rn(gy, dxy, -__fmul_rn(gx, dyy)));
+            float o1 = __fmul_rn(idd, __fmaf_rn(gx, dxy, -__fmul_rn(gy, dxx)));
+            bool weak = o0 < -1.f || o0 > 1.f || o1 < -1.f || o1 > 1.f;
+            k.response = key_resp(key);
+            if (weak) { k.x = (float)ix; k.y = (float)iy; }
+            else {
+                float ratio = (float)(1 << o);
+                k.x = __fmul_rn(ratio, __fadd_rn((float)x, o0));
+                k.y = __fmul_rn(ratio, __fadd_rn((float)y, o1));
+            }
+        } else {
+            // integer pipeline, gRefine akazed.cu:3600-3646: integer differences (arithmetic shifts), float quotient
+            const int* d = reinterpret_cast<const int*>(L.det) + (long long)frame * L.plane + (long long)y * p + x;
+            int d0 = __ldg(d), dl = __ldg(d - 1), dr = __ldg(d + 1), du = __ldg(d - p), dd_ = __ldg(d + p);
+            int v2 = d0 + d0;
+            int gx = (dr - dl) >> 1;
+            int gy = (dd_ - du) >> 1;
+            int dxx = dr + dl - v2;
+            int dyy = dd_ + du - v2;
+            int dxy = (__ldg(d + p + 1) + __ldg(d - p - 1) - __ldg(d - p + 1) - __ldg(d + p - 1)) >> 2;
+            int det = dxx * dyy - dxy * dxy;
+            float idd = det != 0 ? (1.f / det) : 0.f;
+            float o0 = idd * (dxy * gy - dyy * gx);
+            float o1 = idd * (dxy * gx - dxx * gy);
+            bool weak = o0 < -1.f || o0 > 1.f || o1 < -1.f || o1 > 1.f;
+            k.response = (float)(int)(key >> 32);
+            if (weak) { k.x = (float)ix; k.y = (float)iy; }
+            else {
+                int ratio = 1 << o;
+                k.y = ratio * (y + o1);
+                k.x = ratio * (x + o0);
+            }
         }
         out[rank] = k;
         rank++;
@@ -224,7 +262,8 @@ int extrema(cudaStream_t st, const AkzExtremaArgs& a, unsigned long long* map, i
     if (ew <= 0 || eh <= 0) return 0;
     int xb = a.psz & ~3;
     dim3 g((a.w - xb + 127) / 128, (eh + 7) / 8, n * a.nsub);
-    k_extrema<<<g, dim3(32, 8), 0, st>>>(a, map, mpitch, mplane);
+    if (a.int_planes) k_extrema<int><<<g, dim3(32, 8), 0, st>>>(a, map, mpitch, mplane);
+    else k_extrema<float><<<g, dim3(32, 8), 0, st>>>(a, map, mpitch, mplane);
     return 1;
 }
 
@@ -236,7 +275,7 @@ int frame_prefix(cudaStream_t st, const int* counts, int* prefix, int n)
 
 int nms_emit(cudaStream_t st, const unsigned long long* map, int mpitch, long long mplane, int W, int H, int psz,
              const AkzLevelTable& tab, unsigned* rowmask, int* rowcount, int* counts, int* prefix,
-             akz_keypoint* kpts, int max_pts, int n)
+             akz_keypoint* kpts, int max_pts, int n, int int_planes)
 {
     int mwords = (W + 31) / 32;
     if (mwords > 128) return akz_set_error(AKZ_E_UNSUPPORTED, "frame width above 4096 is not supported by the compaction kernel");
@@ -250,7 +289,8 @@ int nms_emit(cudaStream_t st, const unsigned long long* map, int mpitch, long lo
     k_frame_prefix<<<1, 32, 0, st>>>(counts, prefix, n);
     launches += 2;
     if (rows > 0) {
-        k_emit_refine<<<dim3(rows, n), 128, 0, st>>>(map, mpitch, mplane, H, psz, tab, rowmask, mwords, rowcount, kpts, max_pts);
+        if (int_planes) k_emit_refine<true><<<dim3(rows, n), 128, 0, st>>>(map, mpitch, mplane, H, psz, tab, rowmask, mwords, rowcount, kpts, max_pts);
+        else k_emit_refine<false><<<dim3(rows, n), 128, 0, st>>>(map, mpitch, mplane, H, psz, tab, rowmask, mwords, rowcount, kpts, max_pts);
         launches++;
     }
     return launches;

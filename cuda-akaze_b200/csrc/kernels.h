@@ -14,11 +14,11 @@ struct AkzExtremaLevel {
     const float* det;
     long long plane;
     float border, threshold;
-    int layer, pad;
+    int layer, ithreshold;              // ithreshold: integer pipeline (akaze.cpp:560: 65)
 };
 struct AkzExtremaArgs {
     AkzExtremaLevel lv[8];
-    int nsub, w, h, pitch, octave, psz;
+    int nsub, w, h, pitch, octave, psz, int_planes;
 };
 
 namespace akzk {
@@ -67,19 +67,30 @@ int level_prep2(cudaStream_t st, int mode, const float* src, int sw, int sh, int
 int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst, float* tmp, const float* tau, int nsteps,
               int w, int h, int pitch, long long plane, int n, int fused);
 
+// ---- fast_pipeline.cu: integer ("fast") scale-space stages, reference namespace fastakaze (akazed.cu:2781-4366) ----------
+int fast_lowpass(cudaStream_t st, const void* src, int src_u8, int* dst, int* tmp, int w, int h, int sp, long long sstride,
+                 int dp, long long dstride, int n, float var, int ksz);
+int fast_down(cudaStream_t st, const int* src, int* dst, int* smooth, int sw, int sh, int sp, long long sstride,
+              int dw, int dh, int dp, long long dstride, int n);
+int fast_contrast(cudaStream_t st, const int* src, int* mag, int* hmax, int* hist, int* kout, float per, int override_k,
+                  int w, int h, int pitch, long long stride, int n);
+int fast_flow(cudaStream_t st, const int* src, int* flow, int type, const int* kc, int nmul, int w, int h, int pitch, long long stride, int n);
+int fast_nld_step(cudaStream_t st, const int* src, const int* flow, int* dst, float tau, int w, int h, int pitch, long long stride, int n);
+int fast_hessian(cudaStream_t st, const int* smooth, int* lx, int* ly, int* det, int step, int w, int h, int pitch, long long stride, int n);
+
 // ---- detect.cu ---------------------------------------------------------------------------------------
 int extrema(cudaStream_t st, const AkzExtremaArgs& a, unsigned long long* map, int mpitch, long long mplane, int n);
 int nms_emit(cudaStream_t st, const unsigned long long* map, int mpitch, long long mplane, int W, int H, int psz,
              const AkzLevelTable& tab, unsigned* rowmask, int* rowcount, int* counts, int* prefix,
-             akz_keypoint* kpts, int max_pts, int n);
+             akz_keypoint* kpts, int max_pts, int n, int int_planes = 0);
 
 int frame_prefix(cudaStream_t st, const int* counts, int* prefix, int n);
 
 // ---- describe.cu -------------------------------------------------------------------------------------
 int orient_table_init(cudaStream_t st);
-int orient(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const int* prefix, akz_keypoint* kpts, int max_pts, int n);
+int orient(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const int* prefix, akz_keypoint* kpts, int max_pts, int n, int fast = 0);
 int describe(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const int* prefix, const akz_keypoint* kpts,
-             unsigned char* desc, int max_pts, int n, int pattern);
+             unsigned char* desc, int max_pts, int n, int pattern, int fast = 0);
 int pack_points(cudaStream_t st, const int* count, const akz_keypoint* kpts, const unsigned char* desc, void* points, int max_pts, int with_desc);
 int unpack_desc(cudaStream_t st, const void* points, int n, unsigned char* desc);
 int scatter_matches(cudaStream_t st, const akz_match_t* m, int nq, void* pq, const void* pt);

@@ -62,6 +62,7 @@ typedef struct akz_options {
                                     /*      SURVEY App. B-1)                                          */
     int   fused;                    /* 1 = fused production kernels, 0 = one kernel per reference     */
                                     /*     stage (same results; used as a cross-check)                */
+    int   fast_kcontrast_override;  /* > 0: integer pipeline only, use this integer contrast factor   */
 } akz_options;
 
 /* One detected keypoint (32 bytes, device or host). */
@@ -135,6 +136,24 @@ AKZ_API int akz_detect_and_compute(akz_ctx* c, const void* d_images, int dtype, 
 AKZ_API int akz_detect_and_compute_host(akz_ctx* c, const void* h_images, int dtype, int nframes,
                                         int width, int height, int pitch, long long frame_stride,
                                         int describe, int* h_counts, akz_keypoint* h_kpts, uint8_t* h_desc);
+
+/* ---- the integer ("fast") pipeline: replaces Akazer::fastDetectAndCompute (akaze.cpp:153-201, :506-743) --------------
+ * Raw 8-bit frames in, the reference's 16.16 fixed-point arithmetic (namespace fastakaze, akazed.cu:2781-4366): integer
+ * planes (readable through akz_level_plane as int32), integer contrast factor, determinant threshold 65.  Results have
+ * the layout of akz_detect_and_compute; `response` holds the integer determinant converted to float. */
+AKZ_API int akz_fast_detect_and_compute(akz_ctx* c, const uint8_t* d_images, int nframes, int width, int height, int pitch,
+                                        long long frame_stride, int describe, int* d_counts, akz_keypoint* d_kpts, uint8_t* d_desc);
+AKZ_API int akz_fast_build_scale_space(akz_ctx* c, const uint8_t* d_images, int nframes, int width, int height, int pitch, long long frame_stride);
+AKZ_API int akz_fast_get_kcontrast(akz_ctx* c, int* h_k, int nframes);
+/* stage seams of the integer pipeline (akazed.h:88-110), batched like the float ones; tmp: scratch plane batch */
+AKZ_API int akz_fast_lowpass(akz_ctx* c, const void* src, int src_is_u8, int* dst, int* tmp, int w, int h, int pitch, long long stride,
+                             int nframes, float var, int ksz);                              /* hConv2dR2 / hLowPass */
+AKZ_API int akz_fast_down_with_smooth(akz_ctx* c, const int* src, int* dst, int* smooth, int sw, int sh, int sp, long long sstride,
+                                      int dw, int dh, int dp, long long dstride, int nframes);
+AKZ_API int akz_fast_scharr_contrast(akz_ctx* c, const int* src, int* mag, int* d_k, float per, int w, int h, int pitch, long long stride, int nframes);
+AKZ_API int akz_fast_flow(akz_ctx* c, const int* src, int* flow, int type, const int* d_k, int w, int h, int pitch, long long stride, int nframes);
+AKZ_API int akz_fast_nld_step(akz_ctx* c, const int* src, const int* flow, int* dst, float tau, int w, int h, int pitch, long long stride, int nframes);
+AKZ_API int akz_fast_hessian(akz_ctx* c, const int* smooth, int* lx, int* ly, int* det, int step, int w, int h, int pitch, long long stride, int nframes);
 
 /* Build the scale space only (planes readable through akz_level_plane); nframes <= max_batch. */
 AKZ_API int akz_build_scale_space(akz_ctx* c, const void* d_images, int dtype, int nframes,

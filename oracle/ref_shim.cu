@@ -40,13 +40,21 @@ void hScharrContrastHook(float* src, float* grad, float& kcontrast, float per, i
 }
 }
 
+namespace {
+int g_ik_mode = 0, g_ik_inject = 0, g_ik_seen = 0;
+}
 namespace fastakaze {
-// the -D rename also hits the integer overload's declaration in akazed.h; keep it linkable
+// the -D rename also hits the integer overload's declaration in akazed.h: same record / override hook for the
+// integer pipeline's contrast factor (akaze.cpp:599)
 void hScharrContrastHook(int* src, int* grad, int& kcontrast, float per, int width, int height, int pitch)
 {
     hScharrContrast(src, grad, kcontrast, per, width, height, pitch);
+    g_ik_seen = kcontrast;
+    if (g_ik_mode == 1) kcontrast = g_ik_inject;
 }
 }
+REF_API void ref_fast_set_kcontrast_mode(int mode, int k) { g_ik_mode = mode; g_ik_inject = k; }
+REF_API int ref_fast_last_kcontrast() { return g_ik_seen; }
 
 REF_API void ref_set_kcontrast_mode(int mode, float k) { g_k_mode = mode; g_k_inject = k; }
 REF_API float ref_last_kcontrast() { return g_k_seen; }
@@ -106,6 +114,25 @@ REF_API void ref_hMatch(void* d_q, int nq, void* d_t, int nt)
     akaze::AkazeData a = mkdata(d_q, nq, nq), b = mkdata(d_t, nt, nt);
     if (nq > 0) akaze::hMatch(a, b);
 }
+
+// ---- integer pipeline stage seams (akazed.h:88-124) ------------------------------------------
+REF_API void ref_fast_hConv2dR2_u8(unsigned char* src, int* dst, int w, int h, int p, float var) { fastakaze::hConv2dR2(src, dst, w, h, p, var); }
+REF_API void ref_fast_hConv2dR2_i(int* src, int* dst, int w, int h, int p, float var) { fastakaze::hConv2dR2(src, dst, w, h, p, var); }
+REF_API void ref_fast_hLowPass(unsigned char* src, int* dst, int w, int h, int p, float var, int ksz) { fastakaze::hLowPass(src, dst, w, h, p, var, ksz); cudaDeviceSynchronize(); }
+REF_API void ref_fast_hDownWithSmooth(int* src, int* dst, int* smooth, int sw, int sh, int sp, int dw, int dh, int dp)
+{ fastakaze::hDownWithSmooth(src, dst, smooth, make_int3(sw, sh, sp), make_int3(dw, dh, dp)); }
+REF_API int ref_fast_hScharrContrast(int* src, int* grad, float per, int w, int h, int p)
+{ int k = 1; fastakaze::hScharrContrast(src, grad, k, per, w, h, p); return k; }
+REF_API void ref_fast_hFlow(int* src, int* flow, int type, int k, int w, int h, int p)
+{ fastakaze::hFlow(src, flow, (akaze::DiffusivityType)type, k, w, h, p); }
+REF_API void ref_fast_hNldStep(int* img, int* flow, int* dst, float tau, int w, int h, int p) { fastakaze::hNldStep(img, flow, dst, tau, w, h, p); }
+REF_API void ref_fast_hHessianDeterminant(int* src, int* dx, int* dy, int step, int w, int h, int p)
+{ fastakaze::hHessianDeterminant(src, dx, dy, step, w, h, p); }
+REF_API void ref_fast_hCalcExtremaMap(int* dets, int* resp, float* size, int* layer, float* params,
+                                      int octave, int max_scale, int thr, int w, int h, int p, int op)
+{ fastakaze::hCalcExtremaMap(dets, resp, size, layer, params, octave, max_scale, thr, w, h, p, op); }
+REF_API void ref_fast_hNmsR(void* pts, int* resp, float* size, int* layer, int psz, int neigh, int w, int h, int p)
+{ fastakaze::hNmsR((akaze::AkazePoint*)pts, resp, size, layer, psz, neigh, w, h, p); }
 
 // ---- whole pipeline (akaze.h) -------------------------------------------------------------
 struct RefAkazer {
@@ -169,6 +196,49 @@ REF_API int ref_akazer_detect_keep(void* hnd, float* d_img, int w, int h, int p,
     *noct_out = n;
     return d.num_pts;
 }
+// Integer pipeline (akaze.cpp:153-201, :506-743) with the pyramid kept, as ref_akazer_detect_keep does for the float one.
+REF_API int ref_akazer_fast_detect_keep(void* hnd, unsigned char* d_img, int w, int h, int p, int desc,
+                                        void* d_pts, int cap, void** tmem_out, int* oparams_out, int* noct_out)
+{
+    RefAkazer* r = (RefAkazer*)hnd;
+    akaze::Akazer& az = r->az;
+    int3 whp0 = make_int3(w, h, p);
+    {
+        int wq = w, hq = h, n = 1;
+        for (int j = 1; j < az.noctaves; j++) { wq >>= 1; hq >>= 1; if (wq < 80 || hq < 80) break; n++; }
+        az.noctaves = n;
+    }
+    int n = az.noctaves;
+    int* osizes = r->oparams;
+    int* offsets = osizes + n;
+    int3* owhps = (int3*)(offsets + n + 1);
+    void* tmem = NULL;
+    az.allocMemory(&tmem, whp0, owhps, osizes, offsets, false);
+    akaze::AkazeData d = mkdata(d_pts, 0, cap);
+    az.fastDetect(d, tmem, d_img, owhps, osizes, offsets);
+    if (desc && d.num_pts > 0) {
+        fastakaze::hCalcOrient(d, tmem, az.noctaves, az.max_scale);
+        fastakaze::hDescribe(d, tmem, az.noctaves, az.max_scale, az.descriptor_pattern_size);
+    }
+    *tmem_out = tmem;
+    memcpy(oparams_out, r->oparams, sizeof(int) * (5 * n + 1));
+    *noct_out = n;
+    return d.num_pts;
+}
+REF_API int ref_akazer_fastDetectAndCompute(void* hnd, unsigned char* d_img, int w, int h, int p, int desc, void* d_pts, void* h_pts, int cap)
+{
+    RefAkazer* r = (RefAkazer*)hnd;
+    akaze::AkazeData d; d.num_pts = 0; d.max_pts = cap;
+    d.d_data = (akaze::AkazePoint*)d_pts; d.h_data = (akaze::AkazePoint*)h_pts;
+    r->az.fastDetectAndCompute(d_img, d, make_int3(w, h, p), desc != 0);
+    return d.num_pts;
+}
+REF_API void ref_fast_hRefine(void* d_pts, int n, int cap, void* tmem, int noct, int S)
+{ akaze::AkazeData d = mkdata(d_pts, n, cap); if (n > 0) fastakaze::hRefine(d, tmem, noct, S); }
+REF_API void ref_fast_hCalcOrient(void* d_pts, int n, int cap, void* tmem, int noct, int S)
+{ akaze::AkazeData d = mkdata(d_pts, n, cap); if (n > 0) fastakaze::hCalcOrient(d, tmem, noct, S); }
+REF_API void ref_fast_hDescribe(void* d_pts, int n, int cap, void* tmem, int noct, int S, int pat)
+{ akaze::AkazeData d = mkdata(d_pts, n, cap); if (n > 0) fastakaze::hDescribe(d, tmem, noct, S, pat); }
 REF_API void ref_cuda_free(void* p) { cudaFree(p); }
 
 REF_API void ref_cuMatch(void* d_q, void* h_q, int nq, void* d_t, int nt)

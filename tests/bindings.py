@@ -202,6 +202,23 @@ def ref():
     L.ref_akazer_detectAndCompute.argtypes = [vp, vp, i, i, i, i, vp, vp, i]
     L.ref_akazer_detect_keep.argtypes = [vp, vp, i, i, i, i, vp, i, C.POINTER(vp), C.POINTER(i), C.POINTER(i)]
     L.ref_cuda_free.argtypes = [vp]
+    # integer pipeline
+    L.ref_fast_set_kcontrast_mode.argtypes = [i, i]
+    L.ref_fast_hConv2dR2_u8.argtypes = [vp, vp, i, i, i, f]
+    L.ref_fast_hConv2dR2_i.argtypes = [vp, vp, i, i, i, f]
+    L.ref_fast_hLowPass.argtypes = [vp, vp, i, i, i, f, i]
+    L.ref_fast_hDownWithSmooth.argtypes = [vp, vp, vp, i, i, i, i, i, i]
+    L.ref_fast_hScharrContrast.argtypes = [vp, vp, f, i, i, i]
+    L.ref_fast_hFlow.argtypes = [vp, vp, i, i, i, i, i]
+    L.ref_fast_hNldStep.argtypes = [vp, vp, vp, f, i, i, i]
+    L.ref_fast_hHessianDeterminant.argtypes = [vp, vp, vp, i, i, i, i]
+    L.ref_fast_hCalcExtremaMap.argtypes = [vp, vp, vp, vp, C.POINTER(f), i, i, i, i, i, i, i]
+    L.ref_fast_hNmsR.argtypes = [vp, vp, vp, vp, i, i, i, i, i]
+    L.ref_fast_hRefine.argtypes = [vp, i, i, vp, i, i]
+    L.ref_fast_hCalcOrient.argtypes = [vp, i, i, vp, i, i]
+    L.ref_fast_hDescribe.argtypes = [vp, i, i, vp, i, i, i]
+    L.ref_akazer_fast_detect_keep.argtypes = [vp, vp, i, i, i, i, vp, i, C.POINTER(vp), C.POINTER(i), C.POINTER(i)]
+    L.ref_akazer_fastDetectAndCompute.argtypes = [vp, vp, i, i, i, i, vp, vp, i]
     L.ref_cuMatch.argtypes = [vp, vp, i, vp, i]
     _ref = L
     return L
@@ -374,6 +391,76 @@ class RefAkazer:
         del mem, f32
         L.ref_cuda_free(tmem)
         return out, planes, float(L.ref_last_kcontrast())
+
+    def fast_detect_serialized(self, img_t, max_pts=100000, desc=True, ik_inject=0):
+        """Integer pipeline (Akazer::fastDetect, akaze.cpp:506-743) with the sublevel merge serialised, as detect_serialized
+        does for the float one.  img_t: (h, pitch) uint8 device tensor.  Returns (points, int planes, integer kcontrast)."""
+        import torch
+        L = self.L
+        dev = img_t.device
+        pts = torch.zeros(max_pts * 104, dtype=torch.uint8, device=dev)
+        tmem = C.c_void_p()
+        oparams = (C.c_int * 64)()
+        noct = C.c_int()
+        L.ref_fast_set_kcontrast_mode(1 if ik_inject > 0 else 0, int(ik_inject))
+        torch.cuda.synchronize()
+        L.ref_akazer_fast_detect_keep(self.hnd, C.c_void_p(img_t.data_ptr()), self.w, self.h, self.pitch, 0,
+                                      C.c_void_p(pts.data_ptr()), max_pts, C.byref(tmem), oparams, C.byref(noct))
+        torch.cuda.synchronize()
+        L.ref_fast_set_kcontrast_mode(0, 0)
+        no, S = noct.value, self.S
+        osizes = list(oparams[0:no])
+        offsets = list(oparams[no:2 * no + 1])
+        owhps = [tuple(oparams[2 * no + 1 + 3 * k: 2 * no + 4 + 3 * k]) for k in range(no)]
+        total = offsets[no]
+        mem = _wrap_device(tmem.value, total * 4).view(torch.int32)
+        W, H, P0 = owhps[0]
+        msz = H * P0
+        mem[0:msz] = int(np.array([0xC0C0C0C0], dtype=np.uint32).view(np.int32)[0])       # akaze.cpp:521 (memset byte of -1E6)
+        mem[msz:2 * msz] = 0                                                                   # akaze.cpp:522 (low byte of the bits of -1e6f)
+        mem[2 * msz:3 * msz] = -1
+        sched = ref_schedule(no, S)
+        psz, neigh = 10000.0, 0
+        for o in range(no):
+            w, h, p = owhps[o]
+            sizes, ss, borders = sched[o]
+            params = np.concatenate([borders, sizes]).astype(np.float32)
+            psz = min(psz, float(borders[0]) * (1 << o))
+            neigh = max(neigh, max(ss))
+            dets = mem[offsets[o] + S * osizes[o]: offsets[o] + 2 * S * osizes[o]]
+            for j in range(S):
+                scratch = torch.zeros_like(dets)
+                scratch[j * osizes[o]:(j + 1) * osizes[o]] = dets[j * osizes[o]:(j + 1) * osizes[o]]
+                torch.cuda.synchronize()
+                L.ref_fast_hCalcExtremaMap(C.c_void_p(scratch.data_ptr()), C.c_void_p(tmem.value), C.c_void_p(tmem.value + 4 * msz),
+                                           C.c_void_p(tmem.value + 8 * msz), params.ctypes.data_as(C.POINTER(C.c_float)),
+                                           o, S, 65, w, h, p, P0)
+        pts.zero_()
+        L.ref_setMaxNumPoints(max_pts)
+        L.ref_resetPointCounter()
+        L.ref_fast_hNmsR(C.c_void_p(pts.data_ptr()), C.c_void_p(tmem.value), C.c_void_p(tmem.value + 4 * msz), C.c_void_p(tmem.value + 8 * msz),
+                         int(psz), neigh, W, H, P0)
+        n = min(int(L.ref_readPointCounter()), max_pts)
+        L.ref_fast_hRefine(C.c_void_p(pts.data_ptr()), n, max_pts, C.c_void_p(tmem.value), no, S)
+        if desc:
+            L.ref_fast_hCalcOrient(C.c_void_p(pts.data_ptr()), n, max_pts, C.c_void_p(tmem.value), no, S)
+            L.ref_fast_hDescribe(C.c_void_p(pts.data_ptr()), n, max_pts, C.c_void_p(tmem.value), no, S, 10)
+        torch.cuda.synchronize()
+        host = mem.cpu().numpy()
+        planes = []
+        for o in range(no):
+            w, h, p = owhps[o]
+            for sidx in range(S):
+                grp = []
+                for which in range(4):
+                    off = offsets[o] + (which * S + sidx) * osizes[o]
+                    grp.append(host[off:off + osizes[o]].reshape(h, p)[:, :w].copy())
+                planes.append(grp)
+        out = pts.cpu().numpy().view(REF_POINT)[:n].copy()
+        k = int(L.ref_fast_last_kcontrast())
+        del mem
+        L.ref_cuda_free(tmem)
+        return out, planes, k
 
 
 # ---- seeded inputs ------------------------------------------------------------------------------------------
