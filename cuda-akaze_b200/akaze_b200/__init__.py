@@ -38,7 +38,7 @@ EXPORTS = [
     "akz_fed_cycle", "akz_hessian", "akz_match", "akz_match_merge", "akz_match_host", "akz_pack_points",
     "akz_unpack_desc", "akz_scatter_matches", "akz_orient", "akz_describe", "akz_detect_keypoints",
     "akz_profile_enable", "akz_profile_read", "akz_profile_class_name", "akz_keypoints_to_opencv", "akz_matches_to_opencv",
-    "akz_fast_detect_and_compute", "akz_fast_build_scale_space", "akz_fast_get_kcontrast", "akz_fast_lowpass",
+    "akz_fast_detect_and_compute", "akz_fast_detect_and_compute_host", "akz_fast_build_scale_space", "akz_fast_get_kcontrast", "akz_fast_lowpass",
     "akz_fast_down_with_smooth", "akz_fast_scharr_contrast", "akz_fast_flow", "akz_fast_nld_step", "akz_fast_hessian",
 ]
 NUM_KCLASS = 13
@@ -94,6 +94,7 @@ def lib():
     L.akz_unpack_desc.argtypes = [vp, vp, i, vp]
     L.akz_scatter_matches.argtypes = [vp, vp, i, vp, vp]
     L.akz_fast_detect_and_compute.argtypes = [vp, vp, i, i, i, i, ll, i, vp, vp, vp]
+    L.akz_fast_detect_and_compute_host.argtypes = [vp, vp, i, i, i, i, ll, i, vp, vp, vp]
     L.akz_fast_build_scale_space.argtypes = [vp, vp, i, i, i, i, ll]
     L.akz_fast_get_kcontrast.argtypes = [vp, C.POINTER(C.c_int), i]
     L.akz_fast_lowpass.argtypes = [vp, vp, i, vp, vp, i, i, i, ll, i, f, i]
@@ -289,8 +290,9 @@ class Context:
         """A plane of the integer pipeline as int32 (the buffers are shared with the float pipeline)."""
         return self.plane(level, which, frame).view(np.int32)
 
-    def detect_and_compute_host(self, images, describe=True, out=None, width=None):
-        """images: (n, h, pitch) numpy array (or pinned torch CPU tensor).  Returns numpy arrays."""
+    def detect_and_compute_host(self, images, describe=True, out=None, width=None, fast=False):
+        """images: (n, h, pitch) numpy array (or pinned torch CPU tensor).  Returns numpy arrays.
+        fast=True: the integer pipeline (uint8 frames only)."""
         arr = images
         n, h, pitch = arr.shape
         is_u8 = str(arr.dtype).endswith("uint8")
@@ -304,9 +306,12 @@ class Context:
         else:
             counts, kpts, desc = out
         ip = arr.data_ptr() if hasattr(arr, "data_ptr") else arr.ctypes.data
-        _check(lib().akz_detect_and_compute_host(self.h, C.c_void_p(ip), dtype, n, w, h, pitch, pitch * h, int(describe),
-                                                 C.c_void_p(_host_ptr(counts)), C.c_void_p(_host_ptr(kpts)),
-                                                 C.c_void_p(_host_ptr(desc)) if desc is not None else C.c_void_p(0)))
+        outp = (C.c_void_p(_host_ptr(counts)), C.c_void_p(_host_ptr(kpts)), C.c_void_p(_host_ptr(desc)) if desc is not None else C.c_void_p(0))
+        if fast:
+            assert is_u8
+            _check(lib().akz_fast_detect_and_compute_host(self.h, C.c_void_p(ip), n, w, h, pitch, pitch * h, int(describe), *outp))
+        else:
+            _check(lib().akz_detect_and_compute_host(self.h, C.c_void_p(ip), dtype, n, w, h, pitch, pitch * h, int(describe), *outp))
         return counts, kpts, desc
 
     # ---- stage seams -----------------------------------------------------------------------------

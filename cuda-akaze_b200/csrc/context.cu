@@ -610,8 +610,8 @@ int akz_fast_detect_and_compute(akz_ctx* c, const uint8_t* d_images, int nframes
     return AKZ_OK;
 }
 
-int akz_detect_and_compute_host(akz_ctx* c, const void* h_images, int dtype, int nframes, int w, int h, int pitch, long long stride,
-                                int describe, int* h_counts, akz_keypoint* h_kpts, uint8_t* h_desc)
+static int detect_and_compute_host(akz_ctx* c, const void* h_images, int dtype, int nframes, int w, int h, int pitch, long long stride,
+                                   int describe, int* h_counts, akz_keypoint* h_kpts, uint8_t* h_desc, int fast)
 {
     int rc = check_frame_args(c, h_images, dtype, nframes, w, h, pitch);
     if (rc != AKZ_OK) return rc;
@@ -664,9 +664,11 @@ int akz_detect_and_compute_host(akz_ctx* c, const void* h_images, int dtype, int
         const int s = i & 1, nf = chunk_frames(i);
         AKZ_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_h2d[s], 0));
         if (i >= 2) AKZ_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_d2h[s], 0));          // result set s is free again
-        if ((rc = scale_space_chunk(c, c->img_stage[s], dtype, nf, pitch, stride)) != AKZ_OK) return rc;
+        if (fast) rc = fast_scale_space_chunk(c, (const unsigned char*)c->img_stage[s], nf, pitch, stride);
+        else rc = scale_space_chunk(c, c->img_stage[s], dtype, nf, pitch, stride);
+        if (rc != AKZ_OK) return rc;
         if ((rc = detect_chunk(c, nf, describe, c->counts_own + (size_t)s * B, c->kpts_own + (size_t)s * B * MP,
-                               c->desc_own + (size_t)s * B * MP * 64)) != AKZ_OK) return rc;
+                               c->desc_own + (size_t)s * B * MP * 64, fast)) != AKZ_OK) return rc;
         AKZ_CUDA_TRY(cudaEventRecord(c->ev_comp[s], st));
         // staging[(i+1)&1] was last read by the kernels of chunk i-1, which precede ev_comp of chunk i-1
         if (i + 1 < nchunks) {
@@ -684,6 +686,18 @@ int akz_detect_and_compute_host(akz_ctx* c, const void* h_images, int dtype, int
     AKZ_CUDA_TRY(cudaStreamSynchronize(st));
     AKZ_CUDA_TRY(cudaGetLastError());
     return AKZ_OK;
+}
+
+int akz_detect_and_compute_host(akz_ctx* c, const void* h_images, int dtype, int nframes, int w, int h, int pitch, long long stride,
+                                int describe, int* h_counts, akz_keypoint* h_kpts, uint8_t* h_desc)
+{
+    return detect_and_compute_host(c, h_images, dtype, nframes, w, h, pitch, stride, describe, h_counts, h_kpts, h_desc, 0);
+}
+
+int akz_fast_detect_and_compute_host(akz_ctx* c, const uint8_t* h_images, int nframes, int w, int h, int pitch, long long stride,
+                                     int describe, int* h_counts, akz_keypoint* h_kpts, uint8_t* h_desc)
+{
+    return detect_and_compute_host(c, h_images, AKZ_U8, nframes, w, h, pitch, stride, describe, h_counts, h_kpts, h_desc, 1);
 }
 
 // ---- stage seams ------------------------------------------------------------------------------------------

@@ -143,6 +143,9 @@ AKZ_API int akz_detect_and_compute_host(akz_ctx* c, const void* h_images, int dt
  * the layout of akz_detect_and_compute; `response` holds the integer determinant converted to float. */
 AKZ_API int akz_fast_detect_and_compute(akz_ctx* c, const uint8_t* d_images, int nframes, int width, int height, int pitch,
                                         long long frame_stride, int describe, int* d_counts, akz_keypoint* d_kpts, uint8_t* d_desc);
+/* host buffers in / out, pipelined like akz_detect_and_compute_host */
+AKZ_API int akz_fast_detect_and_compute_host(akz_ctx* c, const uint8_t* h_images, int nframes, int width, int height, int pitch,
+                                             long long frame_stride, int describe, int* h_counts, akz_keypoint* h_kpts, uint8_t* h_desc);
 AKZ_API int akz_fast_build_scale_space(akz_ctx* c, const uint8_t* d_images, int nframes, int width, int height, int pitch, long long frame_stride);
 AKZ_API int akz_fast_get_kcontrast(akz_ctx* c, int* h_k, int nframes);
 /* stage seams of the integer pipeline (akazed.h:88-110), batched like the float ones; tmp: scratch plane batch */

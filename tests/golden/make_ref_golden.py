@@ -42,6 +42,24 @@ def main(out):
     np.savez_compressed(out, **g)
     print(f"wrote {out}: {len(pts)} keypoints, k = {k:.6f}, {len(planes)} levels")
     ref.close()
+    # integer pipeline (Akazer::fastDetect): int planes, keypoints of the serialised detector, integer contrast factor
+    img8 = B.synth_shapes_u8(w, h, seed=seed)
+    b8 = np.zeros((h, pitch), dtype=np.uint8)
+    b8[:, :w] = img8
+    ref = B.RefAkazer(w, h, pitch, noctaves=2)
+    pts, planes, ik = ref.fast_detect_serialized(torch.from_numpy(b8).cuda(), max_pts=20000, desc=True)
+    g = {"seed": seed, "img_sha256": hashlib.sha256(img8.tobytes()).hexdigest(), "kcontrast": np.int32(ik), "nlevels": len(planes)}
+    for l, grp in enumerate(planes):
+        for which, nm in enumerate(("lt", "det", "lx", "ly")):
+            a = np.ascontiguousarray(grp[which]).astype(np.int32)
+            g[f"sha_{l}_{nm}"] = hashlib.sha256(a.tobytes()).hexdigest()
+            g[f"sub_{l}_{nm}"] = a[::8, ::8].copy()
+    g["kp_x"], g["kp_y"], g["kp_layer"], g["kp_size"] = pts["x"].copy(), pts["y"].copy(), pts["octave"].copy(), pts["size"].copy()
+    g["kp_angle"], g["kp_desc"] = pts["angle"].copy(), pts["features"].copy()
+    out2 = out.replace("ref_320x240", "ref_fast_320x240")
+    np.savez_compressed(out2, **g)
+    print(f"wrote {out2}: {len(pts)} keypoints, integer k = {ik}, {len(planes)} levels")
+    ref.close()
 
 
 if __name__ == "__main__":

@@ -308,6 +308,33 @@ def test_oracle_against_reference_golden_fixture():
     P.close()
 
 
+GOLD_FAST = os.path.join(ROOT, "tests", "golden", "ref_fast_320x240.npz")
+
+
+@pytest.mark.skipif(not os.path.exists(GOLD_FAST), reason="integer-pipeline golden fixture not generated yet (tests/golden/make_ref_golden.py)")
+def test_fast_oracle_against_reference_golden_fixture():
+    """oracle/fast_oracle.py (numpy restatement of Akazer::fastDetect) against the compiled reference: every int plane by
+    hash, the integer contrast-factor rule, and the keypoint set with its refined positions."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fast_oracle as FO
+    g = np.load(GOLD_FAST)
+    img8 = B.synth_shapes_u8(320, 240, seed=int(g["seed"]))
+    assert hashlib.sha256(img8.tobytes()).hexdigest() == str(g["img_sha256"])
+    lv, k0 = FO.build(img8, noctaves=2, k_override=int(g["kcontrast"]))
+    assert len(lv) == int(g["nlevels"])
+    for l, L in enumerate(lv):
+        for nm, key in (("lt", "Lt"), ("det", "det"), ("lx", "Lx"), ("ly", "Ly")):
+            a = np.ascontiguousarray(L[key]).astype(np.int32)
+            assert np.array_equal(a[::8, ::8], g[f"sub_{l}_{nm}"]), f"level {l} {nm}"
+            assert hashlib.sha256(a.tobytes()).hexdigest() == str(g[f"sha_{l}_{nm}"]), f"level {l} {nm}"
+    kp = FO.detect(lv)
+    ref = sorted(zip(g["kp_layer"].tolist(), g["kp_y"].view(np.uint32).tolist(), g["kp_x"].view(np.uint32).tolist()))
+    mine = sorted(zip(kp["layer"].tolist(), kp["y"].view(np.uint32).tolist(), kp["x"].view(np.uint32).tolist()))
+    assert mine == ref and len(ref) > 50
+    # the true-maximum contrast factor is an integer within a few units of the reference's racy one
+    assert abs(FO.contrast(FO.conv(img8, 1.0, 2)) - int(g["kcontrast"])) <= max(2, int(g["kcontrast"]) // 8)
+
+
 # ---- multi-rank host logic (gloo, world_size 2) -------------------------------------------------------------------------
 def _np_partial(q, t, base, mode):
     x = np.unpackbits(q[:, None, :] ^ t[None, :, :], axis=2).sum(axis=2).astype(np.int32)    # (nq, nt)

@@ -174,3 +174,54 @@ def test_fast_pipeline_vs_serialized_reference(ref_fast_left):
     assert n == len(rp) and same.all()
     assert (da <= 1e-4).mean() >= 0.995
     assert nbad == 0 and exact.mean() >= 0.75
+
+
+def test_fast_host_api_batching_and_determinism():
+    w, h = 640, 480
+    frames = np.stack([B.synth_shapes_u8(w, h, seed=s) for s in range(5)])
+    c = ab().Context(w, h, max_batch=2, max_pts=8000)
+    c1, k1, d1 = c.fast_detect_and_compute(d(frames))
+    c.sync()
+    assert int(c1.min()) > 20
+    hc, hk, hd = c.detect_and_compute_host(frames, fast=True)                      # pipelined host path, chunks of 2
+    assert np.array_equal(hc, c1.cpu().numpy())
+    for f in range(5):
+        n = int(hc[f])
+        assert np.array_equal(hk[f, :n].view(np.int32).reshape(n, 8), k1[f, :n].cpu().numpy())
+        assert np.array_equal(hd[f, :n], d1[f, :n].cpu().numpy())
+    for _ in range(3):                                                             # run-to-run identical
+        c2, k2, d2 = c.fast_detect_and_compute(d(frames))
+        c.sync()
+        assert torch.equal(c1, c2) and torch.equal(k1, k2) and torch.equal(d1, d2)
+    cs, ks, ds = c.fast_detect_and_compute(d(frames[3:4]))                         # one frame alone == in the batch
+    c.sync()
+    n = int(cs[0])
+    assert n == int(c1[3]) and torch.equal(ks[0, :n], k1[3, :n]) and torch.equal(ds[0, :n], d1[3, :n])
+    c.close()
+
+
+def test_fast_pipeline_equals_numpy_oracle_at_odd_sizes():
+    """Sizes at which the reference's blur kernels read uninitialised halo rows (App. B-7) are checked against the numpy
+    restatement (oracle/fast_oracle.py, pinned by the reference golden fixture) instead: planes and refined keypoints."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fast_oracle as FO
+    for (w, h, seed) in [(333, 250, 5), (641, 479, 6)]:
+        img8 = B.synth_shapes_u8(w, h, seed=seed)
+        c = ab().Context(w, h, max_batch=1, max_pts=20000)
+        counts, kpts, _ = c.fast_detect_and_compute(d(img8[None]), describe=False)
+        c.sync()
+        lv, k0 = FO.build(img8)
+        assert int(c.fast_kcontrast(1)[0]) == k0
+        assert c.num_levels == len(lv)
+        for l, L in enumerate(lv):
+            for which, key in enumerate(("Lt", "det", "Lx", "Ly")):
+                eq(c.plane_int(l, which), L[key].astype(np.int32), f"{w}x{h} level {l} {key}")
+        n = int(counts[0])
+        mine = ab().keypoints_from_words(kpts[0, :n].cpu().numpy())
+        ok = FO.detect(lv)
+        assert n == len(ok) and n > 20
+        for fld in ("ix", "iy", "layer"):
+            assert np.array_equal(mine[fld], ok[fld]), fld
+        for fld in ("x", "y", "size"):
+            assert np.array_equal(mine[fld].view(np.uint32), ok[fld].view(np.uint32)), fld
+        c.close()
