@@ -26,10 +26,10 @@ using namespace akz;
 
 namespace {
 
-constexpr int P2_W = 64, P2_H = 64;          // output tile
+constexpr int P2_W = 64, P2_H = 48;          // output tile
 constexpr int P2_OX = 12;                    // shared-memory column of output column 0 (multiple of 4, >= 2*4 + 2)
 constexpr int P2_SP = P2_W + 2 * P2_OX;      // 88 floats per shared-memory row
-constexpr int P2_NT = 512;
+constexpr int P2_NT = 384;
 enum { PM_BASE = 0, PM_BLUR = 1, PM_DOWN = 2 };
 
 struct Prep2Args {
@@ -109,7 +109,7 @@ __device__ __forceinline__ void ghost_fix(float* T, int r0, int r1, int X0, int 
 }
 
 template <int S, int MODE>
-__global__ void __launch_bounds__(P2_NT, 2) k_prep2(const __grid_constant__ Prep2Args a)
+__global__ void __launch_bounds__(P2_NT, 3) k_prep2(const __grid_constant__ Prep2Args a)
 {
     constexpr int OY = 2 * S + 2;                     // shared-memory row of output row 0
     constexpr int AR = P2_H + 2 * OY;                 // rows of the input tile
