@@ -442,8 +442,25 @@ def run_reference(args):
     ms_e2e = timed(step_host, args.steps, stream, world, device)
     clocks = sampler.stop() if rank == 0 else None
     v = F * world * args.steps / (ms * 1e-3)
+    # metric 2 with the reference's own matcher (gHammingMatch through hMatch): 10k x 10k AkazePoint records.  The train
+    # count must be a multiple of 16: the kernel deadlocks on sm_100a otherwise (akazed.cu:2176-2187, App. B-15).
+    match = None
+    if not args.no_match:
+        q = B.random_descriptors(10000, 0); t = B.random_descriptors(10000, 1)
+        pq = np.zeros(10000, dtype=B.REF_POINT); pt = np.zeros(10000, dtype=B.REF_POINT)
+        pq["features"], pt["features"] = q[:, :61], t[:, :61]
+        dq = torch.from_numpy(pq.view(np.uint8).reshape(-1)).to(device); dt = torch.from_numpy(pt.view(np.uint8).reshape(-1)).to(device)
+        torch.cuda.synchronize()
+        for _ in range(2):
+            L.ref_hMatch(C.c_void_p(dq.data_ptr()), 10000, C.c_void_p(dt.data_ptr()), 10000)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            L.ref_hMatch(C.c_void_p(dq.data_ptr()), 10000, C.c_void_p(dt.data_ptr()), 10000)
+        e1.record(); e1.synchronize()
+        match = {"compat_10kx10k_ms": round(e0.elapsed_time(e1) / 5, 4), "how": "akaze::hMatch (gHammingMatch, 16 threads per query), 1-NN with the uniqueness gate"}
     line = {
-        "impl": "reference", "metric": "1080p detect+describe images/sec", "value": round(v, 2), "unit": "images/s",
+        "impl": "reference", "match": match, "metric": "1080p detect+describe images/sec", "value": round(v, 2), "unit": "images/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"configs[2]: synthetic 1920x1080 grayscale, {F} frames per GPU per step ({args.content}), "

@@ -833,7 +833,7 @@ int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt
     if (nq < 0 || nt < 0 || !d_out) return akz_set_error(AKZ_E_INVALID, "bad matcher arguments");
     if (nq == 0) return AKZ_OK;
     int qblocks = (nq + 255) / 256;                 // match.cu: 256 queries per block
-    int nsplit = std::max(1, std::min((2 * 148 + qblocks - 1) / qblocks, (nt + 127) / 128));
+    int nsplit = std::max(1, std::min((8 * 148 + qblocks - 1) / qblocks, (nt + 127) / 128));      // ~8 blocks per SM: a 2.2-blocks-per-SM grid left the ALU-bound kernel 28 % imbalanced
     size_t need = (size_t)nsplit * nq;
     if (c->match_parts_n < need) {
         if (c->match_parts) { cudaStreamSynchronize(c->stream); cudaFree(c->match_parts); }

@@ -42,32 +42,26 @@ __device__ __forceinline__ unsigned maj3(unsigned a, unsigned b, unsigned c)
 #define AKZ_CSA(h, l, a, b, c) { unsigned a_ = (a), b_ = (b), c_ = (c); (h) = maj3(a_, b_, c_); (l) = xor3(a_, b_, c_); }
 #define AKZ_HA(h, l, a, b)     { unsigned a_ = (a), b_ = (b); (h) = a_ & b_; (l) = a_ ^ b_; }
 
-// Hamming distance of two 512-bit strings as a Harley-Seal carry-save tree: 16 XOR + 30 LOP3 + 5 POPC instead of
-// 16 XOR + 16 POPC + 15 IADD.  POPC issues at 4 lanes/clk/SMSP (the plain form is POPC bound: 128 of 216 SMSP cycles per
-// warp-pair, ncu r01c), LOP3 at 16 lanes/clk/SMSP.
+// Hamming distance of two 512-bit strings: one carry-save level, then POPC.
+//   plain      : 16 XOR + 16 POPC + adds   POPC issues at 4 lanes/clk/SMSP: 128 SMSP cycles per warp-pair, POPC bound
+//   full tree  : 16 XOR + 30 LOP3 + 5 POPC  ALU pipe (16 lanes/clk/SMSP) bound: ~116 cycles (ncu r01g: ALU 84.5 % busy)
+//   this form  : 16 XOR + 10 LOP3 + 11 POPC the two pipes are balanced: 2 x 36 ALU instructions vs 8 x 11 POPC cycles
+// five 3:2 compressors turn 15 words into 5 sums (weight 1) and 5 carries (weight 2); word 15 is counted directly.
 __device__ __forceinline__ int hamming512(const unsigned (&q)[16], const uint4& t0, const uint4& t1, const uint4& t2, const uint4& t3)
 {
     const unsigned x0 = q[0] ^ t0.x, x1 = q[1] ^ t0.y, x2 = q[2] ^ t0.z, x3 = q[3] ^ t0.w;
     const unsigned x4 = q[4] ^ t1.x, x5 = q[5] ^ t1.y, x6 = q[6] ^ t1.z, x7 = q[7] ^ t1.w;
     const unsigned x8 = q[8] ^ t2.x, x9 = q[9] ^ t2.y, x10 = q[10] ^ t2.z, x11 = q[11] ^ t2.w;
     const unsigned x12 = q[12] ^ t3.x, x13 = q[13] ^ t3.y, x14 = q[14] ^ t3.z, x15 = q[15] ^ t3.w;
-    unsigned ones, twos, fours, eights, sixteens, tA, tB, fA, fB, eA, eB;
-    AKZ_CSA(tA, ones, x0, x1, x2)
-    AKZ_CSA(tB, ones, ones, x3, x4)
-    AKZ_HA(fA, twos, tA, tB)
-    AKZ_CSA(tA, ones, ones, x5, x6)
-    AKZ_CSA(tB, ones, ones, x7, x8)
-    AKZ_CSA(fB, twos, twos, tA, tB)
-    AKZ_HA(eA, fours, fA, fB)
-    AKZ_CSA(tA, ones, ones, x9, x10)
-    AKZ_CSA(tB, ones, ones, x11, x12)
-    AKZ_CSA(fA, twos, twos, tA, tB)
-    AKZ_CSA(tA, ones, ones, x13, x14)
-    AKZ_HA(tB, ones, ones, x15)
-    AKZ_CSA(fB, twos, twos, tA, tB)
-    AKZ_CSA(eB, fours, fours, fA, fB)
-    AKZ_HA(sixteens, eights, eA, eB)
-    return __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights) + 16 * __popc(sixteens);
+    unsigned s0, s1, s2, s3, s4, c0, c1, c2, c3, c4;
+    AKZ_CSA(c0, s0, x0, x1, x2)
+    AKZ_CSA(c1, s1, x3, x4, x5)
+    AKZ_CSA(c2, s2, x6, x7, x8)
+    AKZ_CSA(c3, s3, x9, x10, x11)
+    AKZ_CSA(c4, s4, x12, x13, x14)
+    const int ones = __popc(s0) + __popc(s1) + __popc(s2) + __popc(s3) + __popc(s4) + __popc(x15);
+    const int twos = __popc(c0) + __popc(c1) + __popc(c2) + __popc(c3) + __popc(c4);
+    return ones + 2 * twos;
 }
 
 // Running best of a query.  A candidate is ordered by key = distance << 22 | (index relative to the block's train
