@@ -48,6 +48,23 @@ def test_no_cpu_fallback_without_device():
         ab().Context(640, 480)
 
 
+def test_option_validation_and_error_text():
+    """akz_create rejects bad options with AKZ_E_INVALID before it touches the device; akz_last_error carries the reason.
+    The reference has no such checks: it print-and-exits from inside CUDA calls (cuda_utils.h:18-37)."""
+    L = ab().lib()
+    for kw, needle in ((dict(width=640, height=480, max_scale=6), "octaves/sublevels"), (dict(width=640, height=480, noctaves=0), "octaves/sublevels"),
+                       (dict(width=8, height=8), "frame size"), (dict(width=640, height=480, dthreshold=-1.0), "dthreshold"),
+                       (dict(width=640, height=480, max_pts=0), "max_pts")):
+        o = ab().default_options(**kw)
+        h = C.c_void_p()
+        rc = L.akz_create(C.byref(o), C.byref(h))
+        assert rc == -1 and needle in L.akz_last_error().decode(), (kw, rc, L.akz_last_error())
+    assert L.akz_create(None, None) == -1
+    d = ab().default_options()
+    assert (d.noctaves, d.max_scale, d.reordering, d.diffusivity, d.descriptor_pattern_size, d.max_pts) == (4, 4, 1, 1, 10, 10000)   # akaze.h:34-54, main.cpp:157
+    assert abs(d.per - 0.7) < 1e-7 and abs(d.soffset - 1.6) < 1e-7 and abs(d.derivative_factor - 1.5) < 1e-7 and abs(d.dthreshold - 0.001) < 1e-9
+
+
 def test_product_does_not_touch_the_oracle():
     """The oracle is test infrastructure: nothing under cuda-akaze_b200/ may reference it."""
     for base, _, files in os.walk(os.path.join(ROOT, "cuda-akaze_b200")):

@@ -416,6 +416,45 @@ def test_detector_vs_serialized_reference():
         assert nbad == 0 and exact.mean() >= 0.75          # the rest differ in the last bits of the angle (App. B-4)
 
 
+@needs_ref
+def test_1080p_vs_reference_outside_the_uninitialised_band():
+    """The benchmark size.  At 1920x1080 the reference's blur kernels read uninitialised shared-memory rows in the last tile
+    row of octaves 0 and 2 (App. B-7); the garbage spreads upwards by a few pixels per level.  Everything above that band
+    must be bit-identical: planes on the top 80 % of the rows, keypoints / descriptors with y < 0.75 H."""
+    w, h = 1920, 1080
+    img = B.u8_to_unit(B.synth_shapes_u8(w, h, seed=51))
+    pitch = 1920
+    r = B.RefAkazer(w, h, pitch)
+    rp, planes, k = r.detect_serialized(dev(img)[0], max_pts=60000)
+    r.close()
+    ctx = ab().Context(w, h, max_batch=1, max_pts=60000, kcontrast_override=k)
+    counts, kpts, desc = ctx.detect_and_compute(dev(img))
+    ctx.sync()
+    names = ["Lt", "det", "Lx", "Ly"]
+    first_bad = {}
+    for l in range(ctx.num_levels):
+        for which in range(4):
+            a, b = bits(ctx.plane(l, which)), bits(planes[l][which])
+            top = int(a.shape[0] * 0.8)
+            assert np.array_equal(a[:top], b[:top]), f"level {l} {names[which]}: differs above the band"
+            rows = np.nonzero((a != b).any(axis=1))[0]
+            if len(rows):
+                first_bad[(l, names[which])] = (int(rows[0]), a.shape[0])
+    print(f"\n[1080p] first differing row per plane (reference's uninitialised band): {sorted(first_bad.items())[:6]} ... {len(first_bad)} planes touched")
+    mine = _kp_array(counts, kpts)
+    dm = desc[0].cpu().numpy()
+    ctx.close()
+    msel, rsel = mine["y"] < 0.75 * h, rp["y"] < 0.75 * h
+    ours = {(int(q["layer"]), q["y"].view(np.uint32).item(), q["x"].view(np.uint32).item()) for q in mine[msel]}
+    theirs = {(int(q["octave"]), q["y"].view(np.uint32).item(), q["x"].view(np.uint32).item()) for q in rp[rsel]}
+    print(f"[1080p] keypoints above 0.75 H: ours={len(ours)} reference={len(theirs)} common={len(ours & theirs)}")
+    assert ours == theirs and len(ours) > 300
+    from scipy.spatial import cKDTree
+    d, j = cKDTree(np.stack([mine["x"], mine["y"]], 1)).query(np.stack([rp["x"], rp["y"]], 1))
+    exact = rsel & (d == 0) & (mine["angle"][j].view(np.uint32) == rp["angle"].view(np.uint32))
+    assert exact.sum() > 200 and not (dm[j[exact]][:, :61] != rp["features"][exact]).any()
+
+
 def test_orientation_and_descriptor_given_reference_keypoints(ref_left):
     """SURVEY App. F rows 'Orientation' and 'M-LDB': feed the reference's keypoints (and, for the descriptor, the
     reference's angle) through our kernels on bit-identical planes: descriptors must agree for 100 % of keypoints."""
