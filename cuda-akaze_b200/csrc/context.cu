@@ -826,14 +826,19 @@ int akz_detect_keypoints(akz_ctx* c, int n, int* d_counts, akz_keypoint* d_kpts)
 }
 
 // ---- matcher ----------------------------------------------------------------------------------------------
+static int g_match_kernel = 0;          // 0 = by problem size, 1 = POPC/LOP3 kernel, 2 = tensor-core kernel
+void akz_set_match_kernel(int which) { g_match_kernel = which; }
+
 int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int t_index_base, int mode, int finalize, akz_match_t* d_out)
 {
     STAGE_PROLOGUE();
     if (mode != AKZ_MATCH_COMPAT && mode != AKZ_MATCH_KNN2 && mode != AKZ_MATCH_UNIQUE2) return akz_set_error(AKZ_E_INVALID, "bad matcher mode");
     if (nq < 0 || nt < 0 || !d_out) return akz_set_error(AKZ_E_INVALID, "bad matcher arguments");
     if (nq == 0) return AKZ_OK;
-    int qblocks = (nq + 255) / 256;                 // match.cu: 256 queries per block
-    int nsplit = std::max(1, std::min((8 * 148 + qblocks - 1) / qblocks, (nt + 127) / 128));      // ~8 blocks per SM: a 2.2-blocks-per-SM grid left the ALU-bound kernel 28 % imbalanced
+    // large problems go to the tensor-core kernel (128 queries per block, one block per SM); AKZ_MATCH_KERNEL=popc|mma overrides
+    const int use_mma = g_match_kernel == 2 ? 1 : g_match_kernel == 1 ? 0 : ((long long)nq * nt >= (1ll << 20) && nq >= 256);
+    int qblocks = use_mma ? (nq + 127) / 128 : (nq + 255) / 256;                 // match.cu: queries per block
+    int nsplit = std::max(1, std::min((8 * 148 + qblocks - 1) / qblocks, (nt + 127) / 128));
     size_t need = (size_t)nsplit * nq;
     if (c->match_parts_n < need) {
         if (c->match_parts) { cudaStreamSynchronize(c->stream); cudaFree(c->match_parts); }
@@ -841,7 +846,7 @@ int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt
         AKZ_CUDA_TRY(cudaMalloc((void**)&c->match_parts, need * sizeof(akz_match_t)));
         c->match_parts_n = need;
     }
-    LAUNCHED(AKZ_K_MATCH, akzk::match_partial(c->stream, d_q, nq, d_t, nt, t_index_base, mode, nsplit, c->match_parts));
+    LAUNCHED(AKZ_K_MATCH, akzk::match_partial(c->stream, d_q, nq, d_t, nt, t_index_base, mode, nsplit, c->match_parts, use_mma));
     LAUNCHED(AKZ_K_MATCH, akzk::match_merge(c->stream, c->match_parts, nsplit, nq, mode, finalize, d_out));
     STAGE_EPILOGUE();
 }

@@ -140,6 +140,168 @@ __global__ void __launch_bounds__(NTH) k_match(const uint4* __restrict__ q, int 
     }
 }
 
+// =====================================================================================================================
+// Tensor-core variant for large problems.  popc(q ^ t) = popc(q) + popc(t) - 2 * <q, t> with the descriptors read as
+// 512-long 0/1 vectors, so the pairwise part is an integer GEMM: mma.sync.m16n8k32 (u8 x u8 -> s32, SASS IMMA.16832).
+// The 64-byte descriptors are expanded to one byte per bit in shared memory on the fly (nibble * 0x00204081 & 0x01010101
+// spreads 4 bits over 4 bytes); expanding in global memory instead would multiply the L2/HBM traffic by 8.
+//   block = 8 warps, 128 queries x a range of train descriptors in tiles of 128
+//   warp  = 16 queries: its A fragments (16 x 512 bytes) stay in 64 registers for the whole kernel
+//   per tile: 16 column blocks of 8 train descriptors x 16 k-steps -> 256 IMMA per warp for 2048 pairs (0.125 per pair),
+//             against ~36 ALU + 11 POPC instructions per pair in k_match
+// The epilogue keeps the same keyed top-2 / class-mask state as k_match (two query rows per thread), merged across the
+// four threads that share a row with shuffles at the end.  Results are bit-identical to k_match (integers).
+// =====================================================================================================================
+constexpr int MQ = 128, MT = 128, MROW = 528;                    // row pitch in bytes: 512 + 16 (conflict-free fragment loads)
+constexpr int MM_SMEM = (MQ + MT) * MROW + (MQ + MT) * 4;
+
+__device__ __forceinline__ void mma_u8(int (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// 128 packed descriptors = 2048 words = 8 per thread: item i = tid + 256 * k -> descriptor i >> 4, word i & 15
+__device__ __forceinline__ void mm_load(const unsigned* __restrict__ src, int cnt, unsigned (&w)[8], int tid)
+{
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int i = tid + 256 * k, d = i >> 4;
+        w[k] = d < cnt ? __ldg(src + (long long)d * 16 + (i & 15)) : 0u;
+    }
+}
+// expand to one byte per bit: rows[d][32 * word + bit], popcounts -> pc[d]
+__device__ __forceinline__ void mm_store(const unsigned (&wv)[8], unsigned char* rows, int* pc, int tid)
+{
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int i = tid + 256 * k, d = i >> 4, wi = i & 15;
+        unsigned w = wv[k];
+        uint4 lo, hi;
+        lo.x = ((w & 0xFu) * 0x00204081u) & 0x01010101u;         lo.y = (((w >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+        lo.z = (((w >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;  lo.w = (((w >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
+        hi.x = (((w >> 16) & 0xFu) * 0x00204081u) & 0x01010101u; hi.y = (((w >> 20) & 0xFu) * 0x00204081u) & 0x01010101u;
+        hi.z = (((w >> 24) & 0xFu) * 0x00204081u) & 0x01010101u; hi.w = ((w >> 28) * 0x00204081u) & 0x01010101u;
+        uint4* dst = reinterpret_cast<uint4*>(rows + d * MROW + wi * 32);
+        dst[0] = lo; dst[1] = hi;
+        int p = __popc(w);                                        // 16 consecutive lanes hold one descriptor
+        p += __shfl_xor_sync(0xffffffffu, p, 1); p += __shfl_xor_sync(0xffffffffu, p, 2);
+        p += __shfl_xor_sync(0xffffffffu, p, 4); p += __shfl_xor_sync(0xffffffffu, p, 8);
+        if (wi == 0) pc[d] = p;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) k_match_mma(const unsigned* __restrict__ q, int nq, const unsigned* __restrict__ t, int nt, int tbase,
+                                                      int per_split, akz_match_t* __restrict__ parts)
+{
+    extern __shared__ __align__(16) unsigned char msm[];
+    unsigned char* Qs = msm;
+    unsigned char* Ts = msm + MQ * MROW;
+    int* pqs = reinterpret_cast<int*>(msm + (MQ + MT) * MROW);
+    int* pts = pqs + MQ;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, gid = lane >> 2, tig = lane & 3;
+    const int q0 = blockIdx.x * MQ;
+    unsigned wv[8];
+    mm_load(q + (long long)q0 * 16, min(MQ, nq - q0), wv, tid);
+    mm_store(wv, Qs, pqs, tid);
+    __syncthreads();
+    unsigned a[16][4];
+    {
+        const unsigned char* r0 = Qs + (wid * 16 + gid) * MROW + tig * 4;
+        const unsigned char* r1 = r0 + 8 * MROW;
+#pragma unroll
+        for (int ks = 0; ks < 16; ks++) {
+            a[ks][0] = *reinterpret_cast<const unsigned*>(r0 + ks * 32);
+            a[ks][1] = *reinterpret_cast<const unsigned*>(r1 + ks * 32);
+            a[ks][2] = *reinterpret_cast<const unsigned*>(r0 + ks * 32 + 16);
+            a[ks][3] = *reinterpret_cast<const unsigned*>(r1 + ks * 32 + 16);
+        }
+    }
+    const int pq0 = pqs[wid * 16 + gid], pq1 = pqs[wid * 16 + gid + 8];
+    Best b0, b1;
+    b0.k1 = b1.k1 = KEY_NONE; b0.k2 = b1.k2 = (MODE == AKZ_MATCH_KNN2) ? KEY_NONE : 0u;
+    const int t0 = blockIdx.y * per_split, t1 = min(nt, t0 + per_split);
+    if (t0 < t1) mm_load(t + (long long)t0 * 16, min(MT, t1 - t0), wv, tid);
+    for (int base = t0; base < t1; base += MT) {
+        const int cnt = min(MT, t1 - base);
+        __syncthreads();                                          // the previous tile has been consumed
+        mm_store(wv, Ts, pts, tid);
+        __syncthreads();
+        if (base + MT < t1) mm_load(t + (long long)(base + MT) * 16, min(MT, t1 - base - MT), wv, tid);     // in flight during the MMAs
+        // four column blocks (4 x 8 train descriptors) at a time: four independent accumulator chains per warp
+        for (int nb = 0; nb < MT / 8; nb += 4) {
+            if (nb * 8 >= cnt) break;
+            int c[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { c[u][0] = 0; c[u][1] = 0; c[u][2] = 0; c[u][3] = 0; }
+            const unsigned char* br = Ts + (nb * 8 + gid) * MROW + tig * 4;
+#pragma unroll
+            for (int ks = 0; ks < 16; ks++) {
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    mma_u8(c[u], a[ks], *reinterpret_cast<const unsigned*>(br + u * 8 * MROW + ks * 32),
+                           *reinterpret_cast<const unsigned*>(br + u * 8 * MROW + ks * 32 + 16));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = (nb + u) * 8 + tig * 2;             // columns j, j+1 of the tile
+                const int pt0 = pts[j], pt1 = pts[j + 1];
+                const int jrel = base - t0 + j;
+                const unsigned cb0 = 1u << ((tbase + base + j) & 15), cb1 = 1u << ((tbase + base + j + 1) & 15);
+                if (j < cnt) {
+                    consider<MODE>(b0, pq0 + pt0 - 2 * c[u][0], jrel, cb0);
+                    consider<MODE>(b1, pq1 + pt0 - 2 * c[u][2], jrel, cb0);
+                }
+                if (j + 1 < cnt) {
+                    consider<MODE>(b0, pq0 + pt1 - 2 * c[u][1], jrel + 1, cb1);
+                    consider<MODE>(b1, pq1 + pt1 - 2 * c[u][3], jrel + 1, cb1);
+                }
+            }
+        }
+    }
+    // merge the four threads that share a query row
+#pragma unroll
+    for (int d = 1; d <= 2; d <<= 1) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            Best& b = r ? b1 : b0;
+            unsigned o1 = __shfl_xor_sync(0xffffffffu, b.k1, d), o2 = __shfl_xor_sync(0xffffffffu, b.k2, d);
+            if (MODE == AKZ_MATCH_KNN2) {
+                unsigned hi = max(b.k1, o1);
+                b.k1 = min(b.k1, o1);
+                b.k2 = min(min(b.k2, o2), hi);
+            } else {
+                unsigned da = b.k1 >> KEY_IDX_BITS, db = o1 >> KEY_IDX_BITS;
+                b.k2 = da < db ? b.k2 : (da == db ? (b.k2 | o2) : o2);
+                b.k1 = min(b.k1, o1);
+            }
+        }
+    }
+    if (tig == 0) {
+        const unsigned imask = (1u << KEY_IDX_BITS) - 1;
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const Best& b = r ? b1 : b0;
+            int qi = q0 + wid * 16 + gid + 8 * r;
+            if (qi < nq) {
+                akz_match_t m;
+                const bool has1 = b.k1 != KEY_NONE;
+                m.idx1 = has1 ? tbase + t0 + (int)(b.k1 & imask) : -1;
+                m.dist1 = has1 ? (int)(b.k1 >> KEY_IDX_BITS) : -1;
+                if (MODE == AKZ_MATCH_KNN2) {
+                    const bool has2 = b.k2 != KEY_NONE;
+                    m.idx2 = has2 ? tbase + t0 + (int)(b.k2 & imask) : -1;
+                    m.dist2 = has2 ? (int)(b.k2 >> KEY_IDX_BITS) : -1;
+                } else {
+                    m.idx2 = (int)b.k2; m.dist2 = 0;
+                }
+                parts[(long long)blockIdx.y * nq + qi] = m;
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ bool lex_less(int d, int i, int d2, int i2) { return d < d2 || (d == d2 && i < i2); }
 
 __global__ void k_match_merge(const akz_match_t* __restrict__ parts, int nparts, int nq, int mode, int finalize, akz_match_t* __restrict__ out)
@@ -185,14 +347,29 @@ __global__ void k_match_merge(const akz_match_t* __restrict__ parts, int nparts,
 
 namespace akzk {
 
+// use_mma != 0: tensor-core kernel (large problems); the split is in units of 128 train descriptors either way
 int match_partial(cudaStream_t st, const unsigned char* q, int nq, const unsigned char* t, int nt, int tbase, int mode,
-                  int nsplit, akz_match_t* parts)
+                  int nsplit, akz_match_t* parts, int use_mma)
 {
     if (nq <= 0) return 0;
     int per = (nt + nsplit - 1) / nsplit;
     per = ((per + TILE - 1) / TILE) * TILE;
     if (per <= 0) per = TILE;
     if (per >= (1 << KEY_IDX_BITS)) return akz_set_error(AKZ_E_UNSUPPORTED, "train range per block exceeds 2^22 descriptors: shard the train set");
+    if (use_mma) {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(k_match_mma<AKZ_MATCH_KNN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM);
+            cudaFuncSetAttribute(k_match_mma<AKZ_MATCH_COMPAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM);
+            attr = true;
+        }
+        dim3 g((nq + MQ - 1) / MQ, nsplit);
+        if (mode != AKZ_MATCH_COMPAT)
+            k_match_mma<AKZ_MATCH_KNN2><<<g, 256, MM_SMEM, st>>>((const unsigned*)q, nq, (const unsigned*)t, nt, tbase, per, parts);
+        else
+            k_match_mma<AKZ_MATCH_COMPAT><<<g, 256, MM_SMEM, st>>>((const unsigned*)q, nq, (const unsigned*)t, nt, tbase, per, parts);
+        return 1;
+    }
     dim3 g((nq + QPB - 1) / QPB, nsplit);
     if (mode != AKZ_MATCH_COMPAT)
         k_match<AKZ_MATCH_KNN2><<<g, NTH, 0, st>>>((const uint4*)q, nq, (const uint4*)t, nt, tbase, per, parts);

@@ -1,11 +1,13 @@
 #!/usr/bin/env python
-"""10k x 10k brute-force matching a few times (the command ncu wraps for the matcher capture)."""
+"""10k x 10k brute-force matching a few times (the command ncu wraps for the matcher captures).
+usage: match_probe.py [kernel]   kernel: 0 = by size, 1 = LOP3/POPC, 2 = tensor core"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "cuda-akaze_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 import akaze_b200 as ab
 import bindings as B
+ab.lib().akz_set_match_kernel(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 ctx = ab.Context(0, 0)
 q = torch.from_numpy(B.random_descriptors(10000, 0)).cuda()
 t = torch.from_numpy(B.random_descriptors(10000, 1)).cuda()

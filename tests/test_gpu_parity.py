@@ -729,6 +729,34 @@ def test_matcher_vs_cpu_oracle(nq, nt):
     ctx.close()
 
 
+@pytest.mark.parametrize("nq,nt", [(1000, 1500), (300, 129), (2049, 4097), (5, 77)])
+def test_matcher_tensor_core_kernel_equals_popc_kernel(nq, nt):
+    """k_match_mma (IMMA on bit-expanded descriptors) and k_match (LOP3/POPC) give identical results in every mode,
+    including ragged tiles, planted ties and a sharded train set."""
+    q, t = _planted(nq, nt, seed=3 * nq + nt)
+    ctx = ab().Context(0, 0)
+    qt, tt = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+    L = ab().lib()
+    try:
+        for mode in (ab().MATCH_COMPAT, ab().MATCH_KNN2, ab().MATCH_UNIQUE2):
+            out = {}
+            for kern in (1, 2):
+                L.akz_set_match_kernel(kern)
+                r = ctx.match(qt, tt, mode)
+                cut = nt // 2
+                parts = torch.stack([ctx.match(qt, tt[:cut].contiguous(), mode, t_index_base=0, finalize=False),
+                                     ctx.match(qt, tt[cut:].contiguous(), mode, t_index_base=cut, finalize=False)])
+                ctx.sync()
+                m = ctx.match_merge(parts, mode, finalize=True)
+                ctx.sync()
+                out[kern] = (r.cpu().numpy(), m.cpu().numpy())
+            assert np.array_equal(out[1][0], out[2][0]), (mode, np.argwhere(out[1][0] != out[2][0])[:4])
+            assert np.array_equal(out[1][1], out[2][1]) and np.array_equal(out[1][0], out[1][1])
+    finally:
+        L.akz_set_match_kernel(0)
+    ctx.close()
+
+
 @needs_ref
 def test_matcher_vs_reference():
     # nt must be a multiple of 16: gHammingMatch calls __syncthreads() inside a loop whose trip count differs per
