@@ -836,9 +836,21 @@ int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt
     if (nq < 0 || nt < 0 || !d_out) return akz_set_error(AKZ_E_INVALID, "bad matcher arguments");
     if (nq == 0) return AKZ_OK;
     // large problems go to the tensor-core kernel (128 queries per block, one block per SM); AKZ_MATCH_KERNEL=popc|mma overrides
-    const int use_mma = g_match_kernel == 2 ? 1 : g_match_kernel == 1 ? 0 : ((long long)nq * nt >= (1ll << 20) && nq >= 256);
-    int qblocks = use_mma ? (nq + 127) / 128 : (nq + 255) / 256;                 // match.cu: queries per block
+    const int use_mma = g_match_kernel == 2 ? 1 : g_match_kernel == 1 ? 0 : ((long long)nq * nt >= (1ll << 24) && nq >= 1024);     // below that the LOP3/POPC kernel wins (2000 x 2300: 29 vs 55 us)
+    int qblocks = (nq + 255) / 256;                 // match.cu: queries per block
     int nsplit = std::max(1, std::min((8 * 148 + qblocks - 1) / qblocks, (nt + 127) / 128));
+    if (use_mma) {
+        // one 512-thread block per SM: pick the split whose block count fills whole waves of 148 best, with at least ~4
+        // train tiles per block so the query-tile expansion is amortised
+        const int max_split = std::max(1, std::min((nt + 127) / 128 / 4, 64));
+        double best = -1.0;
+        for (int sp = 1; sp <= max_split; sp++) {
+            long long blocks = (long long)qblocks * sp;
+            double eff = (double)blocks / (double)(((blocks + 147) / 148) * 148);
+            if (blocks < 148) eff *= 0.5;
+            if (eff > best + 1e-9) { best = eff; nsplit = sp; }
+        }
+    }
     size_t need = (size_t)nsplit * nq;
     if (c->match_parts_n < need) {
         if (c->match_parts) { cudaStreamSynchronize(c->stream); cudaFree(c->match_parts); }

@@ -2,13 +2,15 @@
 // Reference: gHammingMatch (akazed.cu:2144-2241, the live 1-NN with the 16-stride uniqueness gate
 // and the <96 gate) and gMatch (akazed.cu:2028-2122, the top-2 variant).
 //
-// Layout: each thread keeps TWO query descriptors in 32 registers; the block stages tiles of train
-// descriptors in shared memory and every thread walks the tile with broadcast LDS.128 reads (one read serves
-// both queries), so the inner loop touches no global memory.  The 512-bit distance is a carry-save
-// (Harley-Seal) tree: 16 XOR + 30 LOP3 + 5 POPC per pair instead of 16 XOR + 16 POPC + 15 IADD.  The train
-// range is split across blockIdx.y so the grid covers all 148 SMs even for a few thousand queries; partial
-// results are merged by k_match_merge with an associative rule, which is also what the train-sharded
-// multi-GPU path applies to the per-shard results after the NCCL gather.
+// Two kernels with identical (integer) results; akz_match picks by problem size:
+//   k_match      LOP3/POPC: each thread keeps TWO query descriptors in 32 registers; the block stages tiles of train
+//                descriptors in shared memory and every thread walks the tile with broadcast LDS.128 reads.  The 512-bit
+//                distance is one carry-save level + 11 POPC, balanced between the ALU pipe and the POPC unit.
+//   k_match_mma  tensor cores: popc(q ^ t) = popc(q) + popc(t) - 2 <q, t> as an int8 GEMM (mma.sync m16n8k32, IMMA) on
+//                descriptors expanded to one byte per bit in shared memory.  10k x 10k: 0.203 ms against 0.318 ms.
+// The train range is split across blockIdx.y so the grid fills whole waves of the 148 SMs; partial results are merged
+// by k_match_merge with an associative rule, which is also what the train-sharded multi-GPU path applies to the
+// per-shard results after the NCCL gather.
 //
 // Partial-result encoding (akz_match_t):
 //   KNN2   (idx1,dist1) best, (idx2,dist2) second best; lexicographic (distance, index) order
@@ -145,14 +147,14 @@ __global__ void __launch_bounds__(NTH) k_match(const uint4* __restrict__ q, int 
 // 512-long 0/1 vectors, so the pairwise part is an integer GEMM: mma.sync.m16n8k32 (u8 x u8 -> s32, SASS IMMA.16832).
 // The 64-byte descriptors are expanded to one byte per bit in shared memory on the fly (nibble * 0x00204081 & 0x01010101
 // spreads 4 bits over 4 bytes); expanding in global memory instead would multiply the L2/HBM traffic by 8.
-//   block = 8 warps, 128 queries x a range of train descriptors in tiles of 128
+//   block = 16 warps, 256 queries x a range of train descriptors in tiles of 128
 //   warp  = 16 queries: its A fragments (16 x 512 bytes) stay in 64 registers for the whole kernel
 //   per tile: 16 column blocks of 8 train descriptors x 16 k-steps -> 256 IMMA per warp for 2048 pairs (0.125 per pair),
 //             against ~36 ALU + 11 POPC instructions per pair in k_match
 // The epilogue keeps the same keyed top-2 / class-mask state as k_match (two query rows per thread), merged across the
 // four threads that share a row with shuffles at the end.  Results are bit-identical to k_match (integers).
 // =====================================================================================================================
-constexpr int MQ = 128, MT = 128, MROW = 528;                    // row pitch in bytes: 512 + 16 (conflict-free fragment loads)
+constexpr int MQ = 256, MT = 128, MROW = 528, MNT = 2 * MQ;    // 16 warps x 16 query rows                    // row pitch in bytes: 512 + 16 (conflict-free fragment loads)
 constexpr int MM_SMEM = (MQ + MT) * MROW + (MQ + MT) * 4;
 
 __device__ __forceinline__ void mma_u8(int (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1)
@@ -161,21 +163,23 @@ __device__ __forceinline__ void mma_u8(int (&c)[4], const unsigned (&a)[4], unsi
                  : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// 128 packed descriptors = 2048 words = 8 per thread: item i = tid + 256 * k -> descriptor i >> 4, word i & 15
-__device__ __forceinline__ void mm_load(const unsigned* __restrict__ src, int cnt, unsigned (&w)[8], int tid)
+// NR packed descriptors = 16 NR words, NR / 32 per thread (512 threads): item i = tid + 512 * k -> descriptor i >> 4, word i & 15
+template <int NR>
+__device__ __forceinline__ void mm_load(const unsigned* __restrict__ src, int cnt, unsigned (&w)[NR / 32], int tid)
 {
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        int i = tid + 256 * k, d = i >> 4;
+    for (int k = 0; k < NR / 32; k++) {
+        int i = tid + MNT * k, d = i >> 4;
         w[k] = d < cnt ? __ldg(src + (long long)d * 16 + (i & 15)) : 0u;
     }
 }
 // expand to one byte per bit: rows[d][32 * word + bit], popcounts -> pc[d]
-__device__ __forceinline__ void mm_store(const unsigned (&wv)[8], unsigned char* rows, int* pc, int tid)
+template <int NR>
+__device__ __forceinline__ void mm_store(const unsigned (&wv)[NR / 32], unsigned char* rows, int* pc, int tid)
 {
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        int i = tid + 256 * k, d = i >> 4, wi = i & 15;
+    for (int k = 0; k < NR / 32; k++) {
+        int i = tid + MNT * k, d = i >> 4, wi = i & 15;
         unsigned w = wv[k];
         uint4 lo, hi;
         lo.x = ((w & 0xFu) * 0x00204081u) & 0x01010101u;         lo.y = (((w >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
@@ -192,7 +196,7 @@ __device__ __forceinline__ void mm_store(const unsigned (&wv)[8], unsigned char*
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 1) k_match_mma(const unsigned* __restrict__ q, int nq, const unsigned* __restrict__ t, int nt, int tbase,
+__global__ void __launch_bounds__(MNT, 1) k_match_mma(const unsigned* __restrict__ q, int nq, const unsigned* __restrict__ t, int nt, int tbase,
                                                       int per_split, akz_match_t* __restrict__ parts)
 {
     extern __shared__ __align__(16) unsigned char msm[];
@@ -202,9 +206,12 @@ __global__ void __launch_bounds__(256, 1) k_match_mma(const unsigned* __restrict
     int* pts = pqs + MQ;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, gid = lane >> 2, tig = lane & 3;
     const int q0 = blockIdx.x * MQ;
-    unsigned wv[8];
-    mm_load(q + (long long)q0 * 16, min(MQ, nq - q0), wv, tid);
-    mm_store(wv, Qs, pqs, tid);
+    {
+        unsigned wq[MQ / 32];
+        mm_load<MQ>(q + (long long)q0 * 16, min(MQ, nq - q0), wq, tid);
+        mm_store<MQ>(wq, Qs, pqs, tid);
+    }
+    unsigned wv[MT / 32];
     __syncthreads();
     unsigned a[16][4];
     {
@@ -222,20 +229,28 @@ __global__ void __launch_bounds__(256, 1) k_match_mma(const unsigned* __restrict
     Best b0, b1;
     b0.k1 = b1.k1 = KEY_NONE; b0.k2 = b1.k2 = (MODE == AKZ_MATCH_KNN2) ? KEY_NONE : 0u;
     const int t0 = blockIdx.y * per_split, t1 = min(nt, t0 + per_split);
-    if (t0 < t1) mm_load(t + (long long)t0 * 16, min(MT, t1 - t0), wv, tid);
-    for (int base = t0; base < t1; base += MT) {
+    // Two tile buffers: the query tile's bytes are dead once the A fragments sit in registers, so its region becomes the
+    // second buffer.  A warp that has finished the MMAs of tile i expands tile i+1 into the other buffer straight away
+    // (its words were prefetched during the MMAs), so expansion overlaps the other warps' tensor work: one barrier per tile.
+    __syncthreads();                                              // every warp holds its A fragments and row popcounts
+    if (t0 < t1) {
+        mm_load<MT>(t + (long long)t0 * 16, min(MT, t1 - t0), wv, tid);
+        mm_store<MT>(wv, Ts, pts, tid);
+        if (t0 + MT < t1) mm_load<MT>(t + (long long)(t0 + MT) * 16, min(MT, t1 - t0 - MT), wv, tid);
+    }
+    __syncthreads();
+    int p = 0;
+    for (int base = t0; base < t1; base += MT, p ^= 1) {
         const int cnt = min(MT, t1 - base);
-        __syncthreads();                                          // the previous tile has been consumed
-        mm_store(wv, Ts, pts, tid);
-        __syncthreads();
-        if (base + MT < t1) mm_load(t + (long long)(base + MT) * 16, min(MT, t1 - base - MT), wv, tid);     // in flight during the MMAs
+        const unsigned char* Tcur = p ? Qs : Ts;
+        const int* ptc = p ? pqs : pts;
         // four column blocks (4 x 8 train descriptors) at a time: four independent accumulator chains per warp
         for (int nb = 0; nb < MT / 8; nb += 4) {
             if (nb * 8 >= cnt) break;
             int c[4][4];
 #pragma unroll
             for (int u = 0; u < 4; u++) { c[u][0] = 0; c[u][1] = 0; c[u][2] = 0; c[u][3] = 0; }
-            const unsigned char* br = Ts + (nb * 8 + gid) * MROW + tig * 4;
+            const unsigned char* br = Tcur + (nb * 8 + gid) * MROW + tig * 4;
 #pragma unroll
             for (int ks = 0; ks < 16; ks++) {
 #pragma unroll
@@ -246,7 +261,7 @@ __global__ void __launch_bounds__(256, 1) k_match_mma(const unsigned* __restrict
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int j = (nb + u) * 8 + tig * 2;             // columns j, j+1 of the tile
-                const int pt0 = pts[j], pt1 = pts[j + 1];
+                const int pt0 = ptc[j], pt1 = ptc[j + 1];
                 const int jrel = base - t0 + j;
                 const unsigned cb0 = 1u << ((tbase + base + j) & 15), cb1 = 1u << ((tbase + base + j + 1) & 15);
                 if (j < cnt) {
@@ -259,6 +274,11 @@ __global__ void __launch_bounds__(256, 1) k_match_mma(const unsigned* __restrict
                 }
             }
         }
+        if (base + MT < t1) {
+            mm_store<MT>(wv, p ? Ts : Qs, p ? pts : pqs, tid);
+            if (base + 2 * MT < t1) mm_load<MT>(t + (long long)(base + 2 * MT) * 16, min(MT, t1 - base - 2 * MT), wv, tid);
+        }
+        __syncthreads();
     }
     // merge the four threads that share a query row
 #pragma unroll
@@ -365,9 +385,9 @@ int match_partial(cudaStream_t st, const unsigned char* q, int nq, const unsigne
         }
         dim3 g((nq + MQ - 1) / MQ, nsplit);
         if (mode != AKZ_MATCH_COMPAT)
-            k_match_mma<AKZ_MATCH_KNN2><<<g, 256, MM_SMEM, st>>>((const unsigned*)q, nq, (const unsigned*)t, nt, tbase, per, parts);
+            k_match_mma<AKZ_MATCH_KNN2><<<g, MNT, MM_SMEM, st>>>((const unsigned*)q, nq, (const unsigned*)t, nt, tbase, per, parts);
         else
-            k_match_mma<AKZ_MATCH_COMPAT><<<g, 256, MM_SMEM, st>>>((const unsigned*)q, nq, (const unsigned*)t, nt, tbase, per, parts);
+            k_match_mma<AKZ_MATCH_COMPAT><<<g, MNT, MM_SMEM, st>>>((const unsigned*)q, nq, (const unsigned*)t, nt, tbase, per, parts);
         return 1;
     }
     dim3 g((nq + QPB - 1) / QPB, nsplit);
