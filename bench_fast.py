@@ -39,7 +39,7 @@ def main():
     n = res[0].cpu().numpy()
     print(json.dumps({"metric": "1080p integer-pipeline detect+describe images/sec", "impl": "ours", "value": round(F * args.steps / (ms * 1e-3), 2),
                       "unit": "images/s", "ms_per_step": round(ms / args.steps, 3), "frames": F, "keypoints_per_frame_mean": round(float(n.mean()), 1),
-                      "note": "one kernel per reference stage, batched, no host round trips (not yet fused)"}), flush=True)
+                      "note": "one kernel per reference stage except the diffusion cycles (temporally blocked k_fed3<int>), batched, no host round trips"}), flush=True)
     ctx.close()
     if B.have_ref():
         pitch = (W + 127) // 128 * 128

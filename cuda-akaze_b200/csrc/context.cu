@@ -496,10 +496,15 @@ static int fast_scale_space_chunk(akz_ctx* c, const unsigned char* img, int nf, 
             cur = (const int*)P.lt;
         }
         LAUNCHED(AKZ_K_FLOW, akzk::fast_flow(st, smooth, flow, o.diffusivity, ikc, L.octave, w, h, p, L.plane, nf));
-        for (int k = 0; k < L.nsteps; k++) {
-            int* out = ((L.nsteps - 1 - k) % 2 == 0) ? (int*)L.lt : tA;
-            LAUNCHED(AKZ_K_FED, akzk::fast_nld_step(st, cur, flow, out, tau[k], w, h, p, L.plane, nf));
-            cur = out;
+        if (o.fused == 1) {
+            // the temporally blocked, register-resident FED kernel of the float pipeline, instantiated for int32 planes
+            LAUNCHED(AKZ_K_FED, akzk::fed_cycle(st, (const float*)cur, (const float*)flow, L.lt, (float*)tA, tau, L.nsteps, w, h, p, L.plane, nf, 1, 1));
+        } else {
+            for (int k = 0; k < L.nsteps; k++) {
+                int* out = ((L.nsteps - 1 - k) % 2 == 0) ? (int*)L.lt : tA;
+                LAUNCHED(AKZ_K_FED, akzk::fast_nld_step(st, cur, flow, out, tau[k], w, h, p, L.plane, nf));
+                cur = out;
+            }
         }
         LAUNCHED(AKZ_K_HESSIAN, akzk::fast_hessian(st, smooth, (int*)L.lx, (int*)L.ly, (int*)L.det, L.sigma_size, w, h, p, L.plane, nf));
     }

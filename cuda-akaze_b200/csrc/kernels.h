@@ -65,7 +65,7 @@ int level_prep2(cudaStream_t st, int mode, const float* src, int sw, int sh, int
                 const float* kc, float kscale, int nmul, int step, int w, int h, int pitch, long long plane, int n);
 // all n FED steps of a level (frozen conductance), temporally blocked in shared memory
 int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst, float* tmp, const float* tau, int nsteps,
-              int w, int h, int pitch, long long plane, int n, int fused);
+              int w, int h, int pitch, long long plane, int n, int fused, int int_planes = 0);
 
 // ---- fast_pipeline.cu: integer ("fast") scale-space stages, reference namespace fastakaze (akazed.cu:2781-4366) ----------
 int fast_lowpass(cudaStream_t st, const void* src, int src_u8, int* dst, int* tmp, int w, int h, int sp, long long sstride,

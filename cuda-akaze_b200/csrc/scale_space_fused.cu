@@ -19,6 +19,7 @@
 // coordinates.
 #include "common.cuh"
 #include "kernels.h"
+#include <cstring>
 
 using namespace akz;
 
@@ -578,6 +579,25 @@ __device__ __forceinline__ void f3_stage(const Fed3Args& a, const F3Tile& T, flo
     asm volatile("cp.async.commit_group;\n" ::: "memory");
 }
 
+// INT = true: the integer pipeline's step (gNldStepNaive akazed.cu:3449-3473) on int32 planes; the values travel through
+// the same float registers / shared-memory buffers as bit patterns (only moves, loads and stores touch them).
+template <bool INT>
+__device__ __forceinline__ float f3_sum(float a, float b)
+{
+    if (INT) return __int_as_float(__float_as_int(a) + __float_as_int(b));
+    return __fadd_rn(a, b);
+}
+template <bool INT>
+__device__ __forceinline__ float f3_upd(float L0, float sL, float LL, float sR, float LR, float sD, float LD, float sU, float LU, float sf)
+{
+    if (!INT) return nld_update_s(L0, sL, LL, sR, LR, sD, LD, sU, LU, sf);
+    const int l0 = __float_as_int(L0);
+    const int step = (__float_as_int(sR) * (__float_as_int(LR) - l0) + __float_as_int(sL) * (__float_as_int(LL) - l0) +
+                      __float_as_int(sD) * (__float_as_int(LD) - l0) + __float_as_int(sU) * (__float_as_int(LU) - l0)) >> 16;
+    return __int_as_float(((__float_as_int(sf) * step) >> 16) + l0);
+}
+
+template <bool INT>
 __global__ void __launch_bounds__(F2_BX * F2_BY, 2) k_fed3(const __grid_constant__ Fed3Args a)
 {
     extern __shared__ __align__(16) float sm[];
@@ -623,11 +643,11 @@ __global__ void __launch_bounds__(F2_BX * F2_BY, 2) k_fed3(const __grid_constant
 #pragma unroll
             for (int r = 0; r < 2; r++)
 #pragma unroll
-                for (int j = 0; j < 5; j++) sh[r][j] = __fadd_rn(g[r + 1][j + 1], g[r + 1][j]);
+                for (int j = 0; j < 5; j++) sh[r][j] = f3_sum<INT>(g[r + 1][j + 1], g[r + 1][j]);
 #pragma unroll
             for (int k = 0; k < 3; k++)
 #pragma unroll
-                for (int c = 0; c < 4; c++) sv[k][c] = __fadd_rn(g[k + 1][c + 1], g[k][c + 1]);
+                for (int c = 0; c < 4; c++) sv[k][c] = f3_sum<INT>(g[k + 1][c + 1], g[k][c + 1]);
         }
         // publish the rim of the block in buffer 0 (its last readers finished before the barrier above)
         *(float4*)(T0 + o_row0) = make_float4(L[0][0], L[0][1], L[0][2], L[0][3]);
@@ -667,7 +687,7 @@ __global__ void __launch_bounds__(F2_BX * F2_BY, 2) k_fed3(const __grid_constant
                         float LR = (c == 3) ? rt[r] : L[r][c + 1];
                         float LU = (r == 0) ? up[c] : L[0][c];
                         float LD = (r == 1) ? dn[c] : L[1][c];
-                        N[r][c] = nld_update_s(L[r][c], sh[r][c], LL, sh[r][c + 1], LR, sv[r + 1][c], LD, sv[r][c], LU, sf);
+                        N[r][c] = f3_upd<INT>(L[r][c], sh[r][c], LL, sh[r][c + 1], LR, sv[r + 1][c], LD, sv[r][c], LU, sf);
                     }
             } else {
 #pragma unroll
@@ -682,7 +702,7 @@ __global__ void __launch_bounds__(F2_BX * F2_BY, 2) k_fed3(const __grid_constant
                         if (c == ir) LR = LL;                      // x = w-1: right neighbour is x = w-2
                         if (r == 0 && bt) LU = LD;                 // y = 0
                         if (r == jb) LD = LU;                      // y = h-1
-                        N[r][c] = nld_update_s(L[r][c], sh[r][c], LL, sh[r][c + 1], LR, sv[r + 1][c], LD, sv[r][c], LU, sf);
+                        N[r][c] = f3_upd<INT>(L[r][c], sh[r][c], LL, sh[r][c + 1], LR, sv[r + 1][c], LD, sv[r][c], LU, sf);
                     }
             }
 #pragma unroll
@@ -729,7 +749,8 @@ static void set_attrs()
     if (g_attr_done) return;
     cudaFuncSetAttribute(k_fed, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * FE_W * FE_H * (int)sizeof(float));
     cudaFuncSetAttribute(k_fed2, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM);
-    cudaFuncSetAttribute(k_fed3, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
+    cudaFuncSetAttribute(k_fed3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
+    cudaFuncSetAttribute(k_fed3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
     cudaFuncSetAttribute(k_level_prep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_level_prep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     g_attr_done = true;
@@ -775,7 +796,7 @@ int level_prep_down(cudaStream_t st, const float* ltsrc, int sw, int sh, int sp,
 // fused == 0: n single-step launches; fused == 1: ceil(n/8) launches of the persistent, prefetching k_fed3;
 // fused == 2: the same split with the shared-memory-resident k_fed, fused == 3: with k_fed2 (kept as cross-checks).
 int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst, float* tmp, const float* tau, int nsteps,
-              int w, int h, int pitch, long long plane, int n, int fused)
+              int w, int h, int pitch, long long plane, int n, int fused, int int_planes)
 {
     if (nsteps <= 0) return 0;
     set_attrs();
@@ -798,7 +819,10 @@ int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst,
         FedArgs a = {};
         a.src = cur; a.flow = flowp; a.dst = ((m - 1 - i) % 2 == 0) ? dst : tmp;
         a.plane = plane; a.w = w; a.h = h; a.pitch = pitch; a.n = cnt;
-        for (int k = 0; k < cnt; k++) a.stepfac[k] = 0.5f * tau[done + k];      // akazed.cu:2515
+        for (int k = 0; k < cnt; k++) {
+            if (int_planes) { int sfi = (int)(0.5f * tau[done + k] * 65536 + 0.5f); memcpy(&a.stepfac[k], &sfi, 4); }      // akazed.cu:4240
+            else a.stepfac[k] = 0.5f * tau[done + k];                                                                  // akazed.cu:2515
+        }
         if (fused == 2) {
             int TWo = FE_W - 2 * cnt, THo = FE_H - 2 * cnt;
             dim3 g((w + TWo - 1) / TWo, (h + THo - 1) / THo, n), b(FE_W, FE_TY);
@@ -815,7 +839,8 @@ int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst,
                 a3.inv_per = (1ull << 40) / (unsigned long long)(g.x * g.y) + 1; a3.inv_gx = (1ull << 40) / (unsigned long long)g.x + 1;
                 if (a3.ntiles >= (1 << 24) || g.x * g.y >= (1u << 16)) return akz_set_error(AKZ_E_UNSUPPORTED, "FED tile count out of range");
                 int nb = a3.ntiles < 2 * 148 ? a3.ntiles : 2 * 148;
-                k_fed3<<<nb, b, F3_SMEM, st>>>(a3);
+                if (int_planes) k_fed3<true><<<nb, b, F3_SMEM, st>>>(a3);
+                else k_fed3<false><<<nb, b, F3_SMEM, st>>>(a3);
             }
         }
         cur = a.dst;
