@@ -831,7 +831,7 @@ int akz_detect_keypoints(akz_ctx* c, int n, int* d_counts, akz_keypoint* d_kpts)
 }
 
 // ---- matcher ----------------------------------------------------------------------------------------------
-static int g_match_kernel = 0;          // 0 = by problem size, 1 = POPC/LOP3 kernel, 2 = tensor-core kernel
+static int g_match_kernel = 0;          // 0 = by problem size, 1 = POPC/LOP3 kernel, 2 = mma.sync kernel, 3 = tcgen05 kernel
 void akz_set_match_kernel(int which) { g_match_kernel = which; }
 
 int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int t_index_base, int mode, int finalize, akz_match_t* d_out)
@@ -840,13 +840,17 @@ int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt
     if (mode != AKZ_MATCH_COMPAT && mode != AKZ_MATCH_KNN2 && mode != AKZ_MATCH_UNIQUE2) return akz_set_error(AKZ_E_INVALID, "bad matcher mode");
     if (nq < 0 || nt < 0 || !d_out) return akz_set_error(AKZ_E_INVALID, "bad matcher arguments");
     if (nq == 0) return AKZ_OK;
-    // large problems go to the tensor-core kernel (128 queries per block, one block per SM); AKZ_MATCH_KERNEL=popc|mma overrides
-    const int use_mma = g_match_kernel == 2 ? 1 : g_match_kernel == 1 ? 0 : ((long long)nq * nt >= (1ll << 24) && nq >= 1024);     // below that the LOP3/POPC kernel wins (2000 x 2300: 29 vs 55 us)
-    int qblocks = (nq + 255) / 256;                 // match.cu: queries per block
+    // Kernel choice (akz_set_match_kernel overrides): small problems -> LOP3/POPC kernel (2000 x 2300: 29 us against 55 us for
+    // the tensor-core kernels); large ones -> tcgen05 kernel (match_tc5.cu); 2 selects the legacy mma.sync kernel.
+    const bool large = (long long)nq * nt >= (1ll << 24) && nq >= 1024;
+    const int kern = g_match_kernel == 0 ? (large ? 3 : 1) : g_match_kernel;
+    const int use_mma = kern == 2;
+    const int qtile = kern == 3 ? 128 : 256;         // queries per block of the kernel
+    int qblocks = (nq + qtile - 1) / qtile;
     int nsplit = std::max(1, std::min((8 * 148 + qblocks - 1) / qblocks, (nt + 127) / 128));
-    if (use_mma) {
-        // one 512-thread block per SM: pick the split whose block count fills whole waves of 148 best, with at least ~4
-        // train tiles per block so the query-tile expansion is amortised
+    if (kern >= 2) {
+        // one block per SM: pick the split whose block count fills whole waves of 148 best, with at least ~4 train tiles
+        // per block so the query-tile expansion is amortised
         const int max_split = std::max(1, std::min((nt + 127) / 128 / 4, 64));
         double best = -1.0;
         for (int sp = 1; sp <= max_split; sp++) {
@@ -854,6 +858,10 @@ int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt
             double eff = (double)blocks / (double)(((blocks + 147) / 148) * 148);
             if (blocks < 148) eff *= 0.5;
             if (eff > best + 1e-9) { best = eff; nsplit = sp; }
+        }
+        if (kern == 3) {
+            // key layout of k_match_tc5: 20 index bits per block range
+            while ((nt + nsplit - 1) / nsplit + 128 >= (1 << 20)) nsplit++;
         }
     }
     size_t need = (size_t)nsplit * nq;
@@ -863,7 +871,8 @@ int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt
         AKZ_CUDA_TRY(cudaMalloc((void**)&c->match_parts, need * sizeof(akz_match_t)));
         c->match_parts_n = need;
     }
-    LAUNCHED(AKZ_K_MATCH, akzk::match_partial(c->stream, d_q, nq, d_t, nt, t_index_base, mode, nsplit, c->match_parts, use_mma));
+    if (kern == 3) { LAUNCHED(AKZ_K_MATCH, akzk::match_partial_tc5(c->stream, d_q, nq, d_t, nt, t_index_base, mode, nsplit, c->match_parts)); }
+    else { LAUNCHED(AKZ_K_MATCH, akzk::match_partial(c->stream, d_q, nq, d_t, nt, t_index_base, mode, nsplit, c->match_parts, use_mma)); }
     LAUNCHED(AKZ_K_MATCH, akzk::match_merge(c->stream, c->match_parts, nsplit, nq, mode, finalize, d_out));
     STAGE_EPILOGUE();
 }

@@ -98,6 +98,9 @@ int scatter_matches(cudaStream_t st, const akz_match_t* m, int nq, void* pq, con
 // ---- match.cu ----------------------------------------------------------------------------------------
 int match_partial(cudaStream_t st, const unsigned char* q, int nq, const unsigned char* t, int nt, int tbase, int mode,
                   int nsplit, akz_match_t* parts, int use_mma = 0);
+// match_tc5.cu: tcgen05 / tensor-memory matcher (same partial-result contract)
+int match_partial_tc5(cudaStream_t st, const unsigned char* q, int nq, const unsigned char* t, int nt, int tbase, int mode,
+                      int nsplit, akz_match_t* parts);
 int match_merge(cudaStream_t st, const akz_match_t* parts, int nparts, int nq, int mode, int finalize, akz_match_t* out);
 
 }  // namespace akzk

@@ -202,7 +202,8 @@ AKZ_API int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t
  * finalize != 0 applies the acceptance rule of the mode (COMPAT: unique class and < 96) */
 AKZ_API int akz_match_merge(akz_ctx* c, const akz_match_t* d_parts, int nparts, int nq, int mode,
                             int finalize, akz_match_t* d_out);
-/* kernel selection of akz_match: 0 = by problem size (default), 1 = LOP3/POPC kernel, 2 = tensor-core (IMMA) kernel.
+/* kernel selection of akz_match: 0 = by problem size (default), 1 = LOP3/POPC kernel, 2 = mma.sync (IMMA) kernel,
+ * 3 = tcgen05 kernel (tensor-memory accumulators).
  * Both produce identical results; the switch exists for tests and measurements. */
 AKZ_API void akz_set_match_kernel(int which);
 AKZ_API int akz_match_host(akz_ctx* c, const uint8_t* h_q, int nq, const uint8_t* h_t, int nt,

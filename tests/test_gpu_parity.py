@@ -731,8 +731,8 @@ def test_matcher_vs_cpu_oracle(nq, nt):
 
 @pytest.mark.parametrize("nq,nt", [(1000, 1500), (300, 129), (2049, 4097), (5, 77)])
 def test_matcher_tensor_core_kernel_equals_popc_kernel(nq, nt):
-    """k_match_mma (IMMA on bit-expanded descriptors) and k_match (LOP3/POPC) give identical results in every mode,
-    including ragged tiles, planted ties and a sharded train set."""
+    """k_match_tc5 (tcgen05.mma kind::i8, accumulators in tensor memory), k_match_mma (mma.sync IMMA) and k_match (LOP3/POPC)
+    give identical results in every mode, including ragged tiles, planted ties and a sharded train set."""
     q, t = _planted(nq, nt, seed=3 * nq + nt)
     ctx = ab().Context(0, 0)
     qt, tt = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
@@ -740,7 +740,7 @@ def test_matcher_tensor_core_kernel_equals_popc_kernel(nq, nt):
     try:
         for mode in (ab().MATCH_COMPAT, ab().MATCH_KNN2, ab().MATCH_UNIQUE2):
             out = {}
-            for kern in (1, 2):
+            for kern in (1, 2, 3):
                 L.akz_set_match_kernel(kern)
                 r = ctx.match(qt, tt, mode)
                 cut = nt // 2
@@ -750,8 +750,10 @@ def test_matcher_tensor_core_kernel_equals_popc_kernel(nq, nt):
                 m = ctx.match_merge(parts, mode, finalize=True)
                 ctx.sync()
                 out[kern] = (r.cpu().numpy(), m.cpu().numpy())
-            assert np.array_equal(out[1][0], out[2][0]), (mode, np.argwhere(out[1][0] != out[2][0])[:4])
-            assert np.array_equal(out[1][1], out[2][1]) and np.array_equal(out[1][0], out[1][1])
+            for kern in (2, 3):
+                assert np.array_equal(out[1][0], out[kern][0]), (mode, kern, np.argwhere(out[1][0] != out[kern][0])[:4])
+                assert np.array_equal(out[1][1], out[kern][1])
+            assert np.array_equal(out[1][0], out[1][1])
     finally:
         L.akz_set_match_kernel(0)
     ctx.close()
