@@ -845,7 +845,7 @@ int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt
     const bool large = (long long)nq * nt >= (1ll << 24) && nq >= 1024;
     const int kern = g_match_kernel == 0 ? (large ? 3 : 1) : g_match_kernel;
     const int use_mma = kern == 2;
-    const int qtile = kern == 3 ? 128 : 256;         // queries per block of the kernel
+    const int qtile = 256;                           // queries per block of every kernel
     int qblocks = (nq + qtile - 1) / qtile;
     int nsplit = std::max(1, std::min((8 * 148 + qblocks - 1) / qblocks, (nt + 127) / 128));
     if (kern >= 2) {

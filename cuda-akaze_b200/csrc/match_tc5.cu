@@ -4,22 +4,25 @@
 //
 //   popc(q ^ t) = popc(q) + popc(t) - 2 <q, t>      with the descriptors read as 512-long 0/1 vectors
 //
-// so the pairwise part is a u8 x u8 -> s32 GEMM with K = 512.  One CTA per SM owns 128 queries (MMA M) and walks a range
-// of train descriptors in tiles of 128 (MMA N); a tile is 16 tcgen05.mma of 128 x 128 x 32.
+// so the pairwise part is a u8 x u8 -> s32 GEMM with K = 512.  One CTA per SM owns 256 queries (two operand-A tiles of
+// MMA M = 128) and walks a range of train descriptors in tiles of 128 (MMA N); a train tile is 2 x 16 tcgen05.mma of
+// 128 x 128 x 32 into two accumulators.
 //
 // Warp roles (13 warps, no block-wide barrier inside the main loop; everything is handed over through mbarriers):
-//   warps 5-12  expanders: read packed descriptors (64 B) and write them one byte per bit into shared memory in the
+//   warps 9-12  expanders: read packed descriptors (64 B) and write them one byte per bit into shared memory in the
 //               K-major SWIZZLE_128B operand layout the tensor core reads (expanding in global memory would multiply
 //               the L2/HBM traffic by 8).  The unit is a K-block: 128 rows x 128 bytes = bits [128 kb, 128 kb + 128) of
-//               every descriptor of the tile, 16 KB; eight K-block slots form a ring (two tiles of look-ahead).
-//   warp 4      one thread issues the MMAs: per K-block four tcgen05.mma (K = 32 bytes each), tcgen05.commit releases
-//               the slot; after the fourth K-block a second commit publishes the accumulator.
-//   warps 0-3   epilogue: thread = query row = TMEM lane.  tcgen05.ld brings 32 accumulator columns at a time; the
+//               every descriptor of the tile, 16 KB; four K-block slots form a ring (one tile of look-ahead).  A slot
+//               feeds both query tiles, which halves the expansion work and the shared-memory stores per MMA.
+//   warp 8      one thread issues the MMAs: per K-block 2 x 4 tcgen05.mma (K = 32 bytes each), tcgen05.commit releases
+//               the slot; after the fourth K-block a second commit publishes the accumulator pair.
+//   warps 0-7   epilogue: thread = query row; warp w reads TMEM lanes 32 (w % 4) ... of accumulator w / 4.  tcgen05.ld
+//               brings 32 accumulator columns at a time (the next load is in flight while a chunk is processed); the
 //               running top-2 (or minimum + class mask) is kept on keys
 //                     key = (popc(t) + 512 - 2 dot) << 20 | (train index relative to the CTA's range)
-//               = ptk[column] - (dot << 21): one integer instruction per pair, then a 3-instruction min/max network.
-//               popc(q) is constant along a row and is added once at the end.  Four accumulator buffers (4 x 128 TMEM
-//               columns) decouple the epilogue from the MMAs.
+//               = ptk[column] - (dot << 21): one integer instruction per pair, then a 3-instruction min/max network on
+//               two independent chains (even / odd columns).  popc(q) is constant along a row and is added once at the
+//               end.  Two accumulator-pair buffers (2 x 256 TMEM columns) decouple the epilogue from the MMAs.
 // Any fixed permutation of the 512 bits gives the same dot product as long as both operands use it, so the expansion uses
 // the cheapest one: output word = (input word >> j) & 0x01010101.
 #include "common.cuh"
@@ -28,17 +31,21 @@
 namespace {
 
 constexpr int T5_M = 128, T5_N = 128;
-constexpr int T5_SLOTS = 8;                      // ring of K-block slots
-constexpr int T5_NACC = 4;                       // accumulator buffers in tensor memory
+constexpr int T5_QT = 2;                         // operand-A tiles (128 queries each) per CTA
+constexpr int T5_Q = T5_QT * T5_M;               // queries per CTA
+constexpr int T5_SLOTS = 4;                      // ring of K-block slots
+constexpr int T5_NACC = 2;                       // accumulator-pair buffers in tensor memory
 constexpr int T5_KB = 128 * 128;                 // bytes of one K-block slot
-constexpr int T5_NEPI = 128, T5_NEXP = 256;
+constexpr int T5_NEPI = T5_Q, T5_NEXP = 128;
 constexpr int T5_NT = T5_NEPI + 32 + T5_NEXP;    // 416 threads
+constexpr int T5_MMA_WARP = T5_NEPI / 32;
+static_assert(T5_SLOTS == 4, "the expander and issuer loops use slot = K-block");
 constexpr int T5_IDX_BITS = 20;
 constexpr unsigned T5_NONE = 0xFFFFFFFFu;
 constexpr int T5_DOFF = 512;                     // keeps popc(t) - 2 dot non-negative
 
 constexpr int T5_OFF_A = 0;
-constexpr int T5_OFF_RING = 4 * T5_KB;
+constexpr int T5_OFF_RING = T5_QT * 4 * T5_KB;
 constexpr int T5_OFF_PTK = T5_OFF_RING + T5_SLOTS * T5_KB;
 constexpr int T5_OFF_BAR = T5_OFF_PTK + T5_NACC * T5_N * 4;
 constexpr int T5_NBAR = 2 * T5_SLOTS + 2 * T5_NACC;
@@ -129,6 +136,21 @@ __device__ __forceinline__ void consider5(Best5& b, unsigned key, unsigned class
     }
 }
 
+// merge of two top-2 states (KNN2) or two (minimum, class mask) states (COMPAT)
+template <int MODE>
+__device__ __forceinline__ void merge5(Best5& a, const Best5& o)
+{
+    if (MODE == AKZ_MATCH_KNN2) {
+        const unsigned hi = max(a.k1, o.k1);
+        a.k1 = min(a.k1, o.k1);
+        a.k2 = min(min(a.k2, o.k2), hi);
+    } else {
+        const unsigned da = a.k1 >> T5_IDX_BITS, db = o.k1 >> T5_IDX_BITS;
+        a.k2 = da < db ? a.k2 : (da == db ? (a.k2 | o.k2) : o.k2);
+        a.k1 = min(a.k1, o.k1);
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t, int nt, int tbase,
                                                         int per_split, akz_match_t* __restrict__ parts)
@@ -146,24 +168,24 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
     auto bar_tempty = [&](int b) { return bar0 + 8u * (2 * T5_SLOTS + T5_NACC + b); };
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-    const int q0 = blockIdx.x * T5_M;
+    const int q0 = blockIdx.x * T5_Q;
     const int t0 = blockIdx.y * per_split, t1 = min(nt, t0 + per_split);
     const int ntiles = t1 > t0 ? (t1 - t0 + T5_N - 1) / T5_N : 0;
 
-    // ---- prologue: barriers, tensor memory, the query tile as operand A ---------------------------------------------
+    // ---- prologue: barriers, tensor memory, the query tiles as operand A ---------------------------------------------
     if (tid == 0) {
-        for (int s = 0; s < T5_SLOTS; s++) { mbar_init(bar_full(s), T5_NEXP / 2); mbar_init(bar_empty(s), 1); }
+        for (int s = 0; s < T5_SLOTS; s++) { mbar_init(bar_full(s), T5_NEXP); mbar_init(bar_empty(s), 1); }
         for (int b = 0; b < T5_NACC; b++) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), T5_NEPI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (wid == 4) {
+    if (wid == T5_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < 4 * T5_M; i += T5_NT) {
-        const int row = i & (T5_M - 1), kb = i >> 7;
+    for (int i = tid; i < 4 * T5_Q; i += T5_NT) {
+        const int row = i & (T5_Q - 1), kb = i / T5_Q;                 // query row of the CTA, K-block
         const uint4 x = q0 + row < nq ? __ldg(q + 4 * (long long)(q0 + row) + kb) : make_uint4(0, 0, 0, 0);
-        expand_store(As + kb * T5_KB, row, x);
+        expand_store(As + ((row >> 7) * 4 + kb) * T5_KB, row & 127, x);
     }
     fence_async_smem();
     tc_fence_before();
@@ -171,9 +193,9 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
     tc_fence_after();
     const unsigned tmem = *tmem_slot;
 
-    if (wid < 4) {
-        // ================================ epilogue: thread = query row = TMEM lane ================================
-        const int row = tid;
+    if (wid < T5_MMA_WARP) {
+        // ================================ epilogue: thread = query row ==========================================
+        const int row = tid;                                         // A tile row >> 7, TMEM lane row & 127
         int pq = 0;
         if (q0 + row < nq) {
 #pragma unroll
@@ -182,13 +204,13 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
                 pq += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
             }
         }
-        Best5 best;
-        best.k1 = T5_NONE; best.k2 = (MODE == AKZ_MATCH_KNN2) ? T5_NONE : 0u;
+        Best5 be, bo;                                                // even / odd columns: two independent chains
+        be.k1 = bo.k1 = T5_NONE; be.k2 = bo.k2 = (MODE == AKZ_MATCH_KNN2) ? T5_NONE : 0u;
         const unsigned cb0 = (unsigned)tbase & 15u;                  // t0 and the tile width are multiples of 16
         for (int j = 0; j < ntiles; j++) {
             const int b = j % T5_NACC;
-            // key base of column `tid` of this tile (every epilogue thread serves one column)
-            {
+            // key base of the tile's columns (the first 128 epilogue threads serve one column each)
+            if (tid < T5_N) {
                 const int col = t0 + j * T5_N + tid;
                 unsigned key = T5_NONE;
                 if (col < t1) {
@@ -202,16 +224,19 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
                 }
                 ptk[b * T5_N + tid] = key;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(T5_NEPI) : "memory");
             mbar_wait(bar_tfull(b), (unsigned)(j / T5_NACC) & 1u);
             tc_fence_after();
-            const unsigned tbase_addr = tmem + ((unsigned)(wid * 32) << 16) + (unsigned)(b * T5_N);
+            const unsigned taddr = tmem + ((unsigned)((wid & 3) * 32) << 16) + (unsigned)(b * T5_QT * T5_N + (wid >> 2) * T5_N);
             const uint4* pk4 = reinterpret_cast<const uint4*>(ptk + b * T5_N);
-#pragma unroll 1
+            unsigned va[32], vb[32];
+            tmem_ld32(taddr, va);
+            tmem_ld_wait();
+#pragma unroll
             for (int c = 0; c < T5_N / 32; c++) {
-                unsigned v[32];
-                tmem_ld32(tbase_addr + c * 32, v);
-                tmem_ld_wait();
+                unsigned (&v)[32] = (c & 1) ? vb : va;
+                unsigned (&vn)[32] = (c & 1) ? va : vb;
+                if (c + 1 < T5_N / 32) tmem_ld32(taddr + (c + 1) * 32, vn);        // in flight while this chunk is processed
 #pragma unroll
                 for (int g = 0; g < 8; g++) {
                     const uint4 k4 = pk4[c * 8 + g];
@@ -220,47 +245,51 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
                     for (int e = 0; e < 4; e++) {
                         const int i = 4 * g + e;
                         const unsigned key = kk[e] - (v[i] << (T5_IDX_BITS + 1));
-                        consider5<MODE>(best, key, 1u << ((cb0 + i) & 15u));
+                        consider5<MODE>((e & 1) ? bo : be, key, 1u << ((cb0 + i) & 15u));
                     }
                 }
+                if (c + 1 < T5_N / 32) tmem_ld_wait();
             }
             tc_fence_before();
             mbar_arrive(bar_tempty(b));
         }
+        merge5<MODE>(be, bo);
         if (q0 + row < nq) {
             const unsigned imask = (1u << T5_IDX_BITS) - 1;
             akz_match_t m;
-            const bool has1 = best.k1 != T5_NONE;
-            m.idx1 = has1 ? tbase + t0 + (int)(best.k1 & imask) : -1;
-            m.dist1 = has1 ? (int)(best.k1 >> T5_IDX_BITS) - T5_DOFF + pq : -1;
+            const bool has1 = be.k1 != T5_NONE;
+            m.idx1 = has1 ? tbase + t0 + (int)(be.k1 & imask) : -1;
+            m.dist1 = has1 ? (int)(be.k1 >> T5_IDX_BITS) - T5_DOFF + pq : -1;
             if (MODE == AKZ_MATCH_KNN2) {
-                const bool has2 = best.k2 != T5_NONE;
-                m.idx2 = has2 ? tbase + t0 + (int)(best.k2 & imask) : -1;
-                m.dist2 = has2 ? (int)(best.k2 >> T5_IDX_BITS) - T5_DOFF + pq : -1;
+                const bool has2 = be.k2 != T5_NONE;
+                m.idx2 = has2 ? tbase + t0 + (int)(be.k2 & imask) : -1;
+                m.dist2 = has2 ? (int)(be.k2 >> T5_IDX_BITS) - T5_DOFF + pq : -1;
             } else {
-                m.idx2 = has1 ? (int)best.k2 : 0; m.dist2 = 0;
+                m.idx2 = has1 ? (int)be.k2 : 0; m.dist2 = 0;
             }
             parts[(long long)blockIdx.y * nq + q0 + row] = m;
         }
-    } else if (wid == 4) {
+    } else if (wid == T5_MMA_WARP) {
         // ================================ MMA issue: one thread ==================================================
         if (lane == 0) {
             const unsigned long long adesc0 = umma_desc(smem_u32(As));
             const unsigned long long bdesc0 = umma_desc(smem_u32(Ring));
-            int it = 0;
             for (int j = 0; j < ntiles; j++) {
                 const int b = j % T5_NACC;
                 mbar_wait(bar_tempty(b), ((unsigned)(j / T5_NACC) & 1u) ^ 1u);
                 tc_fence_after();
-                const unsigned d_tmem = tmem + (unsigned)(b * T5_N);
-                for (int kb = 0; kb < 4; kb++, it++) {
-                    const int s = it % T5_SLOTS;
-                    mbar_wait(bar_full(s), (unsigned)(it / T5_SLOTS) & 1u);
+                for (int kb = 0; kb < 4; kb++) {
+                    const int s = kb;
+                    mbar_wait(bar_full(s), (unsigned)j & 1u);
                     tc_fence_after();
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        umma_i8(d_tmem, adesc0 + (unsigned long long)(kb * (T5_KB >> 4) + 2 * k), bdesc0 + (unsigned long long)(s * (T5_KB >> 4) + 2 * k),
-                                (kb | k) != 0 ? 1u : 0u);
+                    for (int h = 0; h < T5_QT; h++) {
+                        const unsigned d_tmem = tmem + (unsigned)(b * T5_QT * T5_N + h * T5_N);
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            umma_i8(d_tmem, adesc0 + (unsigned long long)((h * 4 + kb) * (T5_KB >> 4) + 2 * k),
+                                    bdesc0 + (unsigned long long)(s * (T5_KB >> 4) + 2 * k), (kb | k) != 0 ? 1u : 0u);
+                    }
                     umma_commit(bar_empty(s));
                 }
                 umma_commit(bar_tfull(b));
@@ -268,38 +297,31 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
         }
         __syncwarp();
     } else {
-        // ================================ expanders: two groups of 128 threads, group g serves K-blocks g and g + 2 =====
-        const int e = tid - (T5_NEPI + 32);
-        const int g = e >> 7, row = e & 127;
-        uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0;
-        if (ntiles > 0 && t0 + row < t1) {
-            x0 = __ldg(t + 4 * (long long)(t0 + row) + g);
-            x1 = __ldg(t + 4 * (long long)(t0 + row) + g + 2);
-        }
+        // ================================ expanders: thread = row of the train tile, all four K-blocks ===============
+        const int row = tid - (T5_NEPI + 32);
+        uint4 x[4], nx[4];
+#pragma unroll
+        for (int kb = 0; kb < 4; kb++) x[kb] = (ntiles > 0 && t0 + row < t1) ? __ldg(t + 4 * (long long)(t0 + row) + kb) : make_uint4(0, 0, 0, 0);
         for (int j = 0; j < ntiles; j++) {
-            uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
             const int nrow = t0 + (j + 1) * T5_N + row;
-            if (j + 1 < ntiles && nrow < t1) {
-                n0 = __ldg(t + 4 * (long long)nrow + g);
-                n1 = __ldg(t + 4 * (long long)nrow + g + 2);
+#pragma unroll
+            for (int kb = 0; kb < 4; kb++) nx[kb] = (j + 1 < ntiles && nrow < t1) ? __ldg(t + 4 * (long long)nrow + kb) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int kb = 0; kb < 4; kb++) {
+                mbar_wait(bar_empty(kb), ((unsigned)j & 1u) ^ 1u);                  // T5_SLOTS == 4: slot = K-block
+                expand_store(Ring + kb * T5_KB, row, x[kb]);
+                fence_async_smem();
+                mbar_arrive(bar_full(kb));
             }
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int it = 4 * j + g + 2 * h;
-                const int s = it % T5_SLOTS;
-                mbar_wait(bar_empty(s), ((unsigned)(it / T5_SLOTS) & 1u) ^ 1u);
-                expand_store(Ring + s * T5_KB, row, h ? x1 : x0);
-                fence_async_smem();
-                mbar_arrive(bar_full(s));
-            }
-            x0 = n0; x1 = n1;
+            for (int kb = 0; kb < 4; kb++) x[kb] = nx[kb];
         }
     }
 
     // ---- teardown ---------------------------------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (wid == 4) {
+    if (wid == T5_MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
     }
@@ -324,7 +346,7 @@ int match_partial_tc5(cudaStream_t st, const unsigned char* q, int nq, const uns
         cudaFuncSetAttribute(k_match_tc5<AKZ_MATCH_COMPAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM);
         attr = true;
     }
-    dim3 g((nq + T5_M - 1) / T5_M, nsplit);
+    dim3 g((nq + T5_Q - 1) / T5_Q, nsplit);
     if (mode != AKZ_MATCH_COMPAT)
         k_match_tc5<AKZ_MATCH_KNN2><<<g, T5_NT, T5_SMEM, st>>>((const uint4*)q, nq, (const uint4*)t, nt, tbase, per, parts);
     else
