@@ -843,7 +843,9 @@ int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt
     // Kernel choice (akz_set_match_kernel overrides): small problems -> LOP3/POPC kernel (2000 x 2300: 29 us against 55 us for
     // the tensor-core kernels); large ones -> tcgen05 kernel (match_tc5.cu); 2 selects the legacy mma.sync kernel.
     const bool large = (long long)nq * nt >= (1ll << 24) && nq >= 1024;
-    const int kern = g_match_kernel == 0 ? (large ? 3 : 1) : g_match_kernel;
+    int kern = g_match_kernel == 0 ? (large ? 3 : 1) : g_match_kernel;
+    akzk::match_tc5_set_filter(kern == 4 ? 1 : kern == 5 ? 0 : -1);          // 4 / 5: tcgen05 kernel with the chunk filter forced on / off (tests)
+    if (kern > 3) kern = 3;
     const int use_mma = kern == 2;
     const int qtile = 256;                           // queries per block of every kernel
     int qblocks = (nq + qtile - 1) / qtile;
@@ -860,8 +862,20 @@ int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt
             if (eff > best + 1e-9) { best = eff; nsplit = sp; }
         }
         if (kern == 3) {
-            // key layout of k_match_tc5: 20 index bits per block range
-            while ((nt + nsplit - 1) / nsplit + 128 >= (1 << 20)) nsplit++;
+            // k_match_tc5 walks ranges that are multiples of 1024 train descriptors (at most 2^19): score the splits by the
+            // work they really launch, rounded to whole waves
+            best = -1.0;
+            const int max_sp = std::max(1, std::min((nt + 1023) / 1024, 256));
+            for (int sp = 1; sp <= max_sp; sp++) {
+                long long per = (((long long)nt + sp - 1) / sp + 1023) / 1024 * 1024;
+                if (per > (1 << 19)) continue;
+                long long live = ((long long)nt + per - 1) / per;                  // splits that hold descriptors
+                long long blocks = (long long)qblocks * live;
+                long long waves = (blocks + 147) / 148;
+                double cost = (double)waves * (double)(per / 128 + 3);               // + ~3 tiles of prologue per block
+                double eff = ((double)qblocks * nt / 128.0) / (cost * 148.0);
+                if (eff > best + 1e-9) { best = eff; nsplit = sp; }
+            }
         }
     }
     size_t need = (size_t)nsplit * nq;

@@ -23,8 +23,11 @@
 //               = ptk[column] - (dot << 21): one integer instruction per pair, then a 3-instruction min/max network on
 //               two independent chains (even / odd columns).  popc(q) is constant along a row and is added once at the
 //               end.  Two accumulator-pair buffers (2 x 256 TMEM columns) decouple the epilogue from the MMAs.
-// Any fixed permutation of the 512 bits gives the same dot product as long as both operands use it, so the expansion uses
-// the cheapest one: output word = (input word >> j) & 0x01010101.
+// Any fixed permutation of the 512 bits gives the same dot product as long as both operands use it, and the operand bytes
+// need not be 0 / 1 as long as every product of two set bits is the same constant: see expand_store.
+// For long train ranges (FILTER) the epilogue first takes the minimum key of a 32-column chunk with a VIMNMX3 tree and
+// runs the exact update only when that minimum can change the state (a new top-2 entry is rare once a few thousand
+// candidates have been seen): 0.5 instead of 2.5 ALU instructions per pair.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -40,14 +43,12 @@ constexpr int T5_NEPI = T5_Q, T5_NEXP = 128;
 constexpr int T5_NT = T5_NEPI + 32 + T5_NEXP;    // 416 threads
 constexpr int T5_MMA_WARP = T5_NEPI / 32;
 static_assert(T5_SLOTS == 4, "the expander and issuer loops use slot = K-block");
-constexpr int T5_IDX_BITS = 20;
-constexpr unsigned T5_NONE = 0xFFFFFFFFu;
-constexpr int T5_DOFF = 512;                     // keeps popc(t) - 2 dot non-negative
+constexpr int T5_RANGE_UNIT = 1024;              // the train range of a CTA is a multiple of this (16 half tiles: see the class bits)
+constexpr int T5_MAX_RANGE = 8192 * 64;          // 13-bit half-tile ordinal
 
 constexpr int T5_OFF_A = 0;
 constexpr int T5_OFF_RING = T5_QT * 4 * T5_KB;
-constexpr int T5_OFF_PTK = T5_OFF_RING + T5_SLOTS * T5_KB;
-constexpr int T5_OFF_BAR = T5_OFF_PTK + T5_NACC * T5_N * 4;
+constexpr int T5_OFF_BAR = T5_OFF_RING + T5_SLOTS * T5_KB;
 constexpr int T5_NBAR = 2 * T5_SLOTS + 2 * T5_NACC;
 constexpr int T5_OFF_TMEM = T5_OFF_BAR + T5_NBAR * 8;
 constexpr int T5_SMEM = T5_OFF_TMEM + 16 + 1024;             // + slack for the 1024-byte alignment of the operand tiles
@@ -105,20 +106,49 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&v)[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// 128 bits of descriptor `row` -> 128 bytes (0 / 1) of row `row` of a K-block, SWIZZLE_128B: the 16-byte chunk j of a row sits
-// at chunk position j ^ (row & 7).  Chunk j = { (x.x >> j) & M, (x.y >> j) & M, (x.z >> j) & M, (x.w >> j) & M }.
-__device__ __forceinline__ void expand_store(unsigned char* kblock, int row, uint4 x)
+// 128 bits of descriptor `row` -> 128 bytes of row `row` of a K-block, SWIZZLE_128B: the 16-byte chunk j of a row sits at chunk
+// position j ^ (row & 7).  Chunk j carries bit (8 b + j) of each of the four words in byte b.  The operands are weighted so
+// that the train side needs no shift: a train byte is 0 or 2^j (a plain AND with a mask), a query byte is 0 or 2^(7-j), and a
+// product is 0 or 128: the accumulator receives 128 <q, t>.
+// `extra` (last K-block only) is OR-ed into the bytes of the four padding bits 486..489, see the key layout below.
+template <bool TRAIN>
+__device__ __forceinline__ void expand_store(unsigned char* kblock, int row, uint4 x, bool last, unsigned e6, unsigned e7, unsigned e0, unsigned e1)
 {
     unsigned char* rp = kblock + row * 128;
     const int sw = row & 7;
+    if (last) x.w &= 0x3Fu;                                       // bits 486..511 are padding (zero by contract): ignored
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         uint4 o;
-        o.x = (x.x >> j) & 0x01010101u; o.y = (x.y >> j) & 0x01010101u;
-        o.z = (x.z >> j) & 0x01010101u; o.w = (x.w >> j) & 0x01010101u;
+        if (TRAIN) {
+            const unsigned m = 0x01010101u << j;
+            o.x = x.x & m; o.y = x.y & m; o.z = x.z & m; o.w = x.w & m;
+        } else {
+            const unsigned m = 0x01010101u << (7 - j);            // bit j of a byte moves to bit 7 - j of the same byte
+            if (7 - 2 * j >= 0) { o.x = (x.x << (7 - 2 * j)) & m; o.y = (x.y << (7 - 2 * j)) & m; o.z = (x.z << (7 - 2 * j)) & m; o.w = (x.w << (7 - 2 * j)) & m; }
+            else { o.x = (x.x >> (2 * j - 7)) & m; o.y = (x.y >> (2 * j - 7)) & m; o.z = (x.z >> (2 * j - 7)) & m; o.w = (x.w >> (2 * j - 7)) & m; }
+        }
+        if (last) {
+            if (j == 6) o.w |= e6;
+            if (j == 7) o.w |= e7;
+            if (j == 0) o.w |= e0 << 8;
+            if (j == 1) o.w |= e1 << 8;
+        }
         *reinterpret_cast<uint4*>(rp + ((j ^ sw) << 4)) = o;
     }
 }
+
+// ---- keys ----------------------------------------------------------------------------------------------------------------
+// The four padding positions carry, on the query side, the constants 64, 64, 64, 1 and, on the train side, three bytes that sum
+// to 512 - popc(t) and the byte 63 - c (c = column within its half tile of 64), so the tensor core itself delivers
+//        acc = 128 dot + 64 (512 - popc(t)) + (63 - c) = 64 E + (63 - c),     E = 512 - (popc(t) - 2 dot)  in [26, 1024]
+// and the epilogue needs ONE integer multiply-add per pair and no shared-memory traffic:
+//        key = acc << 13 | (8191 - ordinal of the half tile)            bits [19,30) E, [13,19) 63 - c, [0,13) 8191 - ordinal
+// The train index inside the CTA's range is  rel = c * H + ordinal  (H = number of half tiles of the range): the column is the
+// MOST significant part, so the unsigned order of the keys is exactly (smaller distance, then smaller train index) and the
+// running top-2 is a max network.  A row of zeros (beyond the range) gives key < 8192 = "none".
+// Hamming distance = popc(q) + 512 - E.
+constexpr unsigned T5_EMASK = (1u << 19) - 1;
 
 struct Best5 { unsigned k1, k2; };
 
@@ -126,32 +156,44 @@ template <int MODE>
 __device__ __forceinline__ void consider5(Best5& b, unsigned key, unsigned classbit)
 {
     if (MODE == AKZ_MATCH_KNN2) {
-        const unsigned hi = max(b.k1, key);
-        b.k1 = min(b.k1, key);
-        b.k2 = min(b.k2, hi);
+        const unsigned lo = min(b.k1, key);
+        b.k1 = max(b.k1, key);
+        b.k2 = max(b.k2, lo);
     } else {
-        const unsigned d = key >> T5_IDX_BITS, dcur = b.k1 >> T5_IDX_BITS;
-        b.k2 = d < dcur ? classbit : (d == dcur ? (b.k2 | classbit) : b.k2);
-        b.k1 = min(b.k1, key);
+        // E(key) > E(k1)  <=>  key > (k1 | EMASK);   E(key) >= E(k1)  <=>  key >= (k1 & ~EMASK)
+        const bool gt = key > (b.k1 | T5_EMASK), ge = key >= (b.k1 & ~T5_EMASK);
+        b.k2 = gt ? 0u : b.k2;
+        if (ge) b.k2 |= classbit;
+        b.k1 = max(b.k1, key);
     }
 }
+// two candidates at once (KNN2): five instructions with the three-input maximum
+__device__ __forceinline__ void consider5_pair(Best5& b, unsigned ka, unsigned kb)
+{
+    const unsigned lo = min(ka, kb), hi = max(ka, kb);
+    const unsigned t = min(b.k1, hi);
+    b.k1 = max(b.k1, hi);
+    b.k2 = __vimax3_u32(b.k2, t, lo);
+}
 
-// merge of two top-2 states (KNN2) or two (minimum, class mask) states (COMPAT)
+// merge of two top-2 states (KNN2) or two (best, class mask) states (COMPAT)
 template <int MODE>
 __device__ __forceinline__ void merge5(Best5& a, const Best5& o)
 {
     if (MODE == AKZ_MATCH_KNN2) {
-        const unsigned hi = max(a.k1, o.k1);
-        a.k1 = min(a.k1, o.k1);
-        a.k2 = min(min(a.k2, o.k2), hi);
+        const unsigned lo = min(a.k1, o.k1);
+        a.k1 = max(a.k1, o.k1);
+        a.k2 = max(max(a.k2, o.k2), lo);
     } else {
-        const unsigned da = a.k1 >> T5_IDX_BITS, db = o.k1 >> T5_IDX_BITS;
-        a.k2 = da < db ? a.k2 : (da == db ? (a.k2 | o.k2) : o.k2);
-        a.k1 = min(a.k1, o.k1);
+        const unsigned ea = a.k1 >> 19, eb = o.k1 >> 19;
+        a.k2 = ea > eb ? a.k2 : (ea == eb ? (a.k2 | o.k2) : o.k2);
+        a.k1 = max(a.k1, o.k1);
     }
 }
 
-template <int MODE>
+__device__ __forceinline__ int popc128(const uint4& w) { return __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w); }
+
+template <int MODE, bool FILTER>
 __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t, int nt, int tbase,
                                                         int per_split, akz_match_t* __restrict__ parts)
 {
@@ -159,7 +201,6 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
     unsigned char* sm = t5raw + ((1024u - (smem_u32(t5raw) & 1023u)) & 1023u);
     unsigned char* As = sm + T5_OFF_A;
     unsigned char* Ring = sm + T5_OFF_RING;
-    unsigned* ptk = reinterpret_cast<unsigned*>(sm + T5_OFF_PTK);
     const unsigned bar0 = smem_u32(sm + T5_OFF_BAR);
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(sm + T5_OFF_TMEM);
     auto bar_full = [&](int s) { return bar0 + 8u * s; };
@@ -170,7 +211,8 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * T5_Q;
     const int t0 = blockIdx.y * per_split, t1 = min(nt, t0 + per_split);
-    const int ntiles = t1 > t0 ? (t1 - t0 + T5_N - 1) / T5_N : 0;
+    const int ntiles = t1 > t0 ? per_split / T5_N : 0;              // every tile holds rows of the whole range (rel = c * H + ordinal)
+    const int H = 2 * (per_split / T5_N);
 
     // ---- prologue: barriers, tensor memory, the query tiles as operand A ---------------------------------------------
     if (tid == 0) {
@@ -185,7 +227,7 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
     for (int i = tid; i < 4 * T5_Q; i += T5_NT) {
         const int row = i & (T5_Q - 1), kb = i / T5_Q;                 // query row of the CTA, K-block
         const uint4 x = q0 + row < nq ? __ldg(q + 4 * (long long)(q0 + row) + kb) : make_uint4(0, 0, 0, 0);
-        expand_store(As + ((row >> 7) * 4 + kb) * T5_KB, row & 127, x);
+        expand_store<false>(As + ((row >> 7) * 4 + kb) * T5_KB, row & 127, x, kb == 3, 64u, 64u, 64u, 1u);
     }
     fence_async_smem();
     tc_fence_before();
@@ -200,35 +242,18 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
         if (q0 + row < nq) {
 #pragma unroll
             for (int v = 0; v < 4; v++) {
-                const uint4 w = __ldg(q + 4 * (long long)(q0 + row) + v);
-                pq += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+                uint4 w = __ldg(q + 4 * (long long)(q0 + row) + v);
+                if (v == 3) w.w &= 0x3Fu;
+                pq += popc128(w);
             }
         }
-        Best5 be, bo;                                                // even / odd columns: two independent chains
-        be.k1 = bo.k1 = T5_NONE; be.k2 = bo.k2 = (MODE == AKZ_MATCH_KNN2) ? T5_NONE : 0u;
-        const unsigned cb0 = (unsigned)tbase & 15u;                  // t0 and the tile width are multiples of 16
+        Best5 be, bo;                                                // two independent chains
+        be.k1 = bo.k1 = 0u; be.k2 = bo.k2 = 0u;
         for (int j = 0; j < ntiles; j++) {
             const int b = j % T5_NACC;
-            // key base of the tile's columns (the first 128 epilogue threads serve one column each)
-            if (tid < T5_N) {
-                const int col = t0 + j * T5_N + tid;
-                unsigned key = T5_NONE;
-                if (col < t1) {
-                    int pt = 0;
-#pragma unroll
-                    for (int v = 0; v < 4; v++) {
-                        const uint4 w = __ldg(t + 4 * (long long)col + v);
-                        pt += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
-                    }
-                    key = ((unsigned)(pt + T5_DOFF) << T5_IDX_BITS) | (unsigned)(j * T5_N + tid);
-                }
-                ptk[b * T5_N + tid] = key;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(T5_NEPI) : "memory");
             mbar_wait(bar_tfull(b), (unsigned)(j / T5_NACC) & 1u);
             tc_fence_after();
             const unsigned taddr = tmem + ((unsigned)((wid & 3) * 32) << 16) + (unsigned)(b * T5_QT * T5_N + (wid >> 2) * T5_N);
-            const uint4* pk4 = reinterpret_cast<const uint4*>(ptk + b * T5_N);
             unsigned va[32], vb[32];
             tmem_ld32(taddr, va);
             tmem_ld_wait();
@@ -237,15 +262,27 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
                 unsigned (&v)[32] = (c & 1) ? vb : va;
                 unsigned (&vn)[32] = (c & 1) ? va : vb;
                 if (c + 1 < T5_N / 32) tmem_ld32(taddr + (c + 1) * 32, vn);        // in flight while this chunk is processed
+                const int ordinal = 2 * j + (c >> 1);
+                const unsigned ordinv = 8191u - (unsigned)ordinal;
 #pragma unroll
-                for (int g = 0; g < 8; g++) {
-                    const uint4 k4 = pk4[c * 8 + g];
-                    const unsigned kk[4] = { k4.x, k4.y, k4.z, k4.w };
+                for (int i = 0; i < 32; i++) v[i] = v[i] * 8192u + ordinv;
+                bool update = true;
+                if (FILTER) {
+                    unsigned m = __vimax3_u32(v[0], v[1], v[2]);
 #pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const int i = 4 * g + e;
-                        const unsigned key = kk[e] - (v[i] << (T5_IDX_BITS + 1));
-                        consider5<MODE>((e & 1) ? bo : be, key, 1u << ((cb0 + i) & 15u));
+                    for (int i = 3; i + 1 < 32; i += 2) m = __vimax3_u32(m, v[i], v[i + 1]);
+                    m = max(m, v[31]);
+                    update = (MODE == AKZ_MATCH_KNN2) ? (m > max(be.k2, bo.k2)) : (m >= (max(be.k1, bo.k1) & ~T5_EMASK));
+                }
+                if (update) {
+                    if (MODE == AKZ_MATCH_KNN2) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) { consider5_pair(be, v[i], v[i + 1]); consider5_pair(bo, v[i + 2], v[i + 3]); }
+                    } else {
+                        // H is a multiple of 16, so the 64 columns of a half tile share their index class
+                        const unsigned classbit = 1u << ((unsigned)(tbase + ordinal) & 15u);
+#pragma unroll
+                        for (int i = 0; i < 32; i++) consider5<MODE>((i & 1) ? bo : be, v[i], classbit);
                     }
                 }
                 if (c + 1 < T5_N / 32) tmem_ld_wait();
@@ -255,15 +292,16 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
         }
         merge5<MODE>(be, bo);
         if (q0 + row < nq) {
-            const unsigned imask = (1u << T5_IDX_BITS) - 1;
             akz_match_t m;
-            const bool has1 = be.k1 != T5_NONE;
-            m.idx1 = has1 ? tbase + t0 + (int)(be.k1 & imask) : -1;
-            m.dist1 = has1 ? (int)(be.k1 >> T5_IDX_BITS) - T5_DOFF + pq : -1;
+            auto rel = [&](unsigned k) { return (int)(63u - ((k >> 13) & 63u)) * H + (int)(8191u - (k & 8191u)); };
+            auto dist = [&](unsigned k) { return pq + 512 - (int)(k >> 19); };
+            const bool has1 = be.k1 >= 8192u;
+            m.idx1 = has1 ? tbase + t0 + rel(be.k1) : -1;
+            m.dist1 = has1 ? dist(be.k1) : -1;
             if (MODE == AKZ_MATCH_KNN2) {
-                const bool has2 = be.k2 != T5_NONE;
-                m.idx2 = has2 ? tbase + t0 + (int)(be.k2 & imask) : -1;
-                m.dist2 = has2 ? (int)(be.k2 >> T5_IDX_BITS) - T5_DOFF + pq : -1;
+                const bool has2 = be.k2 >= 8192u;
+                m.idx2 = has2 ? tbase + t0 + rel(be.k2) : -1;
+                m.dist2 = has2 ? dist(be.k2) : -1;
             } else {
                 m.idx2 = has1 ? (int)be.k2 : 0; m.dist2 = 0;
             }
@@ -299,22 +337,36 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
     } else {
         // ================================ expanders: thread = row of the train tile, all four K-blocks ===============
         const int row = tid - (T5_NEPI + 32);
+        const int c64 = row & 63, half = row >> 6;
+        const long long tlim = (long long)t1 - t0;
+        auto load_row = [&](int j, uint4 (&x)[4]) {
+            const long long r = (long long)c64 * H + 2 * j + half;        // index inside the range: the column is the major part
+            const bool ok = j < ntiles && r < tlim;
+#pragma unroll
+            for (int kb = 0; kb < 4; kb++) x[kb] = ok ? __ldg(t + 4 * (t0 + r) + kb) : make_uint4(0, 0, 0, 0);
+            return ok;
+        };
         uint4 x[4], nx[4];
-#pragma unroll
-        for (int kb = 0; kb < 4; kb++) x[kb] = (ntiles > 0 && t0 + row < t1) ? __ldg(t + 4 * (long long)(t0 + row) + kb) : make_uint4(0, 0, 0, 0);
+        bool ok = load_row(0, x);
         for (int j = 0; j < ntiles; j++) {
-            const int nrow = t0 + (j + 1) * T5_N + row;
-#pragma unroll
-            for (int kb = 0; kb < 4; kb++) nx[kb] = (j + 1 < ntiles && nrow < t1) ? __ldg(t + 4 * (long long)nrow + kb) : make_uint4(0, 0, 0, 0);
+            const bool nok = load_row(j + 1, nx);
+            // padding bytes of the row: three bytes summing to 512 - popc(t), and 63 - column
+            x[3].w &= 0x3Fu;
+            const int rest = 512 - (popc128(x[0]) + popc128(x[1]) + popc128(x[2]) + popc128(x[3]));
+            const unsigned e6 = ok ? (unsigned)min(rest, 255) : 0u;
+            const unsigned e7 = ok ? (unsigned)min(rest - (int)e6, 255) : 0u;
+            const unsigned e0 = ok ? (unsigned)(rest - (int)e6 - (int)e7) : 0u;
+            const unsigned e1 = ok ? (unsigned)(63 - c64) : 0u;
 #pragma unroll
             for (int kb = 0; kb < 4; kb++) {
                 mbar_wait(bar_empty(kb), ((unsigned)j & 1u) ^ 1u);                  // T5_SLOTS == 4: slot = K-block
-                expand_store(Ring + kb * T5_KB, row, x[kb]);
+                expand_store<true>(Ring + kb * T5_KB, row, x[kb], kb == 3, e6, e7, e0, e1);
                 fence_async_smem();
                 mbar_arrive(bar_full(kb));
             }
 #pragma unroll
             for (int kb = 0; kb < 4; kb++) x[kb] = nx[kb];
+            ok = nok;
         }
     }
 
@@ -331,26 +383,36 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
 
 namespace akzk {
 
+static int g_tc5_filter = -1;                    // -1 = by range length, 0 / 1 = forced (tests)
+void match_tc5_set_filter(int v) { g_tc5_filter = v; }
+
 // Tensor-memory matcher; `per` (train descriptors per blockIdx.y) is a multiple of 128 chosen by the caller.
 int match_partial_tc5(cudaStream_t st, const unsigned char* q, int nq, const unsigned char* t, int nt, int tbase, int mode,
                       int nsplit, akz_match_t* parts)
 {
     if (nq <= 0) return 0;
     int per = (nt + nsplit - 1) / nsplit;
-    per = ((per + T5_N - 1) / T5_N) * T5_N;
-    if (per <= 0) per = T5_N;
-    if (per >= (1 << T5_IDX_BITS)) return akz_set_error(AKZ_E_UNSUPPORTED, "train range per block exceeds 2^20 descriptors: raise the split or shard the train set");
+    per = ((per + T5_RANGE_UNIT - 1) / T5_RANGE_UNIT) * T5_RANGE_UNIT;
+    if (per <= 0) per = T5_RANGE_UNIT;
+    if (per > T5_MAX_RANGE) return akz_set_error(AKZ_E_UNSUPPORTED, "train range per block exceeds 2^19 descriptors: raise the split or shard the train set");
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k_match_tc5<AKZ_MATCH_KNN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM);
-        cudaFuncSetAttribute(k_match_tc5<AKZ_MATCH_COMPAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM);
+        cudaFuncSetAttribute(k_match_tc5<AKZ_MATCH_KNN2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM);
+        cudaFuncSetAttribute(k_match_tc5<AKZ_MATCH_COMPAT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM);
+        cudaFuncSetAttribute(k_match_tc5<AKZ_MATCH_KNN2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM);
+        cudaFuncSetAttribute(k_match_tc5<AKZ_MATCH_COMPAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM);
         attr = true;
     }
     dim3 g((nq + T5_Q - 1) / T5_Q, nsplit);
-    if (mode != AKZ_MATCH_COMPAT)
-        k_match_tc5<AKZ_MATCH_KNN2><<<g, T5_NT, T5_SMEM, st>>>((const uint4*)q, nq, (const uint4*)t, nt, tbase, per, parts);
-    else
-        k_match_tc5<AKZ_MATCH_COMPAT><<<g, T5_NT, T5_SMEM, st>>>((const uint4*)q, nq, (const uint4*)t, nt, tbase, per, parts);
+    const bool filter = g_tc5_filter < 0 ? per >= 2048 : g_tc5_filter != 0;     // a chunk rarely holds a new top-2 entry after ~2000 candidates
+    const uint4 *q4 = (const uint4*)q, *t4 = (const uint4*)t;
+    if (mode != AKZ_MATCH_COMPAT) {
+        if (filter) k_match_tc5<AKZ_MATCH_KNN2, true><<<g, T5_NT, T5_SMEM, st>>>(q4, nq, t4, nt, tbase, per, parts);
+        else k_match_tc5<AKZ_MATCH_KNN2, false><<<g, T5_NT, T5_SMEM, st>>>(q4, nq, t4, nt, tbase, per, parts);
+    } else {
+        if (filter) k_match_tc5<AKZ_MATCH_COMPAT, true><<<g, T5_NT, T5_SMEM, st>>>(q4, nq, t4, nt, tbase, per, parts);
+        else k_match_tc5<AKZ_MATCH_COMPAT, false><<<g, T5_NT, T5_SMEM, st>>>(q4, nq, t4, nt, tbase, per, parts);
+    }
     return 1;
 }
 

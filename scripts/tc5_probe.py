@@ -15,22 +15,22 @@ for nq, nt in ((128, 128), (100, 300), (1000, 1500), (300, 129), (2049, 4097), (
     qt, tt = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
     for mode in (ab.MATCH_COMPAT, ab.MATCH_KNN2):
         out = {}
-        for kern in (1, 3):
+        for kern in (1, 3, 4, 5):
             L.akz_set_match_kernel(kern)
             r = ctx.match(qt, tt, mode); ctx.sync()
             out[kern] = r.cpu().numpy()
-        same = np.array_equal(out[1], out[3])
+        same = all(np.array_equal(out[1], out[k]) for k in (3, 4, 5))
         ok_all &= same
-        bad = np.argwhere((out[1] != out[3]).any(axis=1))[:, 0]
+        bad = np.argwhere(np.logical_or.reduce([(out[1] != out[k]).any(axis=1) for k in (3, 4, 5)]))[:, 0]
         print(f"{nq}x{nt} mode {mode}: equal={same} mismatching rows={len(bad)}", flush=True)
         if len(bad):
-            for i in bad[:4]: print("   row", i, out[1][i], out[3][i])
+            for i in bad[:4]: print("   row", i, out[1][i], out[3][i], out[4][i], out[5][i])
 print("ALL EQUAL" if ok_all else "MISMATCH", flush=True)
 
 for nq, nt in ((10000, 10000), (10000, 100000)):
     q = B.random_descriptors(nq, 0); t = B.random_descriptors(nt, 1)
     qt, tt = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
-    for kern in (1, 2, 3):
+    for kern in (1, 2, 3, 4, 5):
         L.akz_set_match_kernel(kern)
         for _ in range(3): ctx.match(qt, tt, ab.MATCH_KNN2)
         ctx.sync()
