@@ -331,23 +331,33 @@ __global__ void k_match_merge(const akz_match_t* __restrict__ parts, int nparts,
     akz_match_t r;
     const bool top2 = mode != AKZ_MATCH_COMPAT;                // KNN2 and UNIQUE2 share the partial form
     r.idx1 = -1; r.dist1 = -1; r.idx2 = top2 ? -1 : 0; r.dist2 = top2 ? -1 : 0;
-    for (int p = 0; p < nparts; p++) {
-        akz_match_t m = parts[(long long)p * nq + qi];
-        if (m.idx1 < 0) continue;
-        if (top2) {
-            // merge two sorted pairs, lowest (distance, index) first
-            int cd[4] = { r.dist1, r.dist2, m.dist1, m.dist2 };
-            int ci[4] = { r.idx1, r.idx2, m.idx1, m.idx2 };
-            int bd1 = 1 << 20, bi1 = -1, bd2 = 1 << 20, bi2 = -1;
-            for (int k = 0; k < 4; k++) {
-                if (ci[k] < 0) continue;
-                if (bi1 < 0 || lex_less(cd[k], ci[k], bd1, bi1)) { bd2 = bd1; bi2 = bi1; bd1 = cd[k]; bi1 = ci[k]; }
-                else if (bi2 < 0 || lex_less(cd[k], ci[k], bd2, bi2)) { bd2 = cd[k]; bi2 = ci[k]; }
+    // the partial results of a query are 16-byte records nq apart: fetch them eight at a time (independent 128-bit loads in
+    // flight) before the serial merge -- one load per iteration left the kernel latency bound (9.7 us for 10 x 10k records)
+    const int4* p4 = reinterpret_cast<const int4*>(parts);
+    for (int p0 = 0; p0 < nparts; p0 += 8) {
+        int4 buf[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) buf[k] = p0 + k < nparts ? __ldg(p4 + (long long)(p0 + k) * nq + qi) : make_int4(-1, -1, -1, -1);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            akz_match_t m;
+            m.idx1 = buf[k].x; m.dist1 = buf[k].y; m.idx2 = buf[k].z; m.dist2 = buf[k].w;
+            if (m.idx1 < 0) continue;
+            if (top2) {
+                // merge two sorted pairs, lowest (distance, index) first
+                int cd[4] = { r.dist1, r.dist2, m.dist1, m.dist2 };
+                int ci[4] = { r.idx1, r.idx2, m.idx1, m.idx2 };
+                int bd1 = 1 << 20, bi1 = -1, bd2 = 1 << 20, bi2 = -1;
+                for (int c = 0; c < 4; c++) {
+                    if (ci[c] < 0) continue;
+                    if (bi1 < 0 || lex_less(cd[c], ci[c], bd1, bi1)) { bd2 = bd1; bi2 = bi1; bd1 = cd[c]; bi1 = ci[c]; }
+                    else if (bi2 < 0 || lex_less(cd[c], ci[c], bd2, bi2)) { bd2 = cd[c]; bi2 = ci[c]; }
+                }
+                r.idx1 = bi1; r.dist1 = bi1 < 0 ? -1 : bd1; r.idx2 = bi2; r.dist2 = bi2 < 0 ? -1 : bd2;
+            } else {
+                if (r.idx1 < 0 || m.dist1 < r.dist1) r = m;
+                else if (m.dist1 == r.dist1) { r.idx1 = min(r.idx1, m.idx1); r.idx2 |= m.idx2; }
             }
-            r.idx1 = bi1; r.dist1 = bi1 < 0 ? -1 : bd1; r.idx2 = bi2; r.dist2 = bi2 < 0 ? -1 : bd2;
-        } else {
-            if (r.idx1 < 0 || m.dist1 < r.dist1) r = m;
-            else if (m.dist1 == r.dist1) { r.idx1 = min(r.idx1, m.idx1); r.idx2 |= m.idx2; }
         }
     }
     if (finalize && mode == AKZ_MATCH_UNIQUE2) {

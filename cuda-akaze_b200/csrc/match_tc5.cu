@@ -49,7 +49,7 @@ constexpr int T5_MAX_RANGE = 8192 * 64;          // 13-bit half-tile ordinal
 constexpr int T5_OFF_A = 0;
 constexpr int T5_OFF_RING = T5_QT * 4 * T5_KB;
 constexpr int T5_OFF_BAR = T5_OFF_RING + T5_SLOTS * T5_KB;
-constexpr int T5_NBAR = 2 * T5_SLOTS + 2 * T5_NACC;
+constexpr int T5_NBAR = 2 * T5_SLOTS + 2 * T5_NACC + 1;
 constexpr int T5_OFF_TMEM = T5_OFF_BAR + T5_NBAR * 8;
 constexpr int T5_SMEM = T5_OFF_TMEM + 16 + 1024;             // + slack for the 1024-byte alignment of the operand tiles
 
@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
     auto bar_empty = [&](int s) { return bar0 + 8u * (T5_SLOTS + s); };
     auto bar_tfull = [&](int b) { return bar0 + 8u * (2 * T5_SLOTS + b); };
     auto bar_tempty = [&](int b) { return bar0 + 8u * (2 * T5_SLOTS + T5_NACC + b); };
+    const unsigned bar_afull = bar0 + 8u * (2 * T5_SLOTS + 2 * T5_NACC);
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * T5_Q;
@@ -214,22 +215,17 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
     const int ntiles = t1 > t0 ? per_split / T5_N : 0;              // every tile holds rows of the whole range (rel = c * H + ordinal)
     const int H = 2 * (per_split / T5_N);
 
-    // ---- prologue: barriers, tensor memory, the query tiles as operand A ---------------------------------------------
+    // ---- prologue: barriers and tensor memory; the roles start right after one block barrier ---------------------------
     if (tid == 0) {
         for (int s = 0; s < T5_SLOTS; s++) { mbar_init(bar_full(s), T5_NEXP); mbar_init(bar_empty(s), 1); }
         for (int b = 0; b < T5_NACC; b++) { mbar_init(bar_tfull(b), 1); mbar_init(bar_tempty(b), T5_NEPI); }
+        mbar_init(bar_afull, T5_NEPI);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (wid == T5_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < 4 * T5_Q; i += T5_NT) {
-        const int row = i & (T5_Q - 1), kb = i / T5_Q;                 // query row of the CTA, K-block
-        const uint4 x = q0 + row < nq ? __ldg(q + 4 * (long long)(q0 + row) + kb) : make_uint4(0, 0, 0, 0);
-        expand_store<false>(As + ((row >> 7) * 4 + kb) * T5_KB, row & 127, x, kb == 3, 64u, 64u, 64u, 1u);
-    }
-    fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -239,13 +235,17 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
         // ================================ epilogue: thread = query row ==========================================
         const int row = tid;                                         // A tile row >> 7, TMEM lane row & 127
         int pq = 0;
-        if (q0 + row < nq) {
+        {
+            // operand A: every epilogue thread expands its own query (the expanders are already at work on the first train tile)
+            uint4 x[4];
 #pragma unroll
-            for (int v = 0; v < 4; v++) {
-                uint4 w = __ldg(q + 4 * (long long)(q0 + row) + v);
-                if (v == 3) w.w &= 0x3Fu;
-                pq += popc128(w);
-            }
+            for (int kb = 0; kb < 4; kb++) x[kb] = q0 + row < nq ? __ldg(q + 4 * (long long)(q0 + row) + kb) : make_uint4(0, 0, 0, 0);
+            x[3].w &= 0x3Fu;
+            pq = popc128(x[0]) + popc128(x[1]) + popc128(x[2]) + popc128(x[3]);
+#pragma unroll
+            for (int kb = 0; kb < 4; kb++) expand_store<false>(As + ((row >> 7) * 4 + kb) * T5_KB, row & 127, x[kb], kb == 3, 64u, 64u, 64u, 1u);
+            fence_async_smem();
+            mbar_arrive(bar_afull);
         }
         Best5 be, bo;                                                // two independent chains
         be.k1 = bo.k1 = 0u; be.k2 = bo.k2 = 0u;
@@ -312,6 +312,7 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
         if (lane == 0) {
             const unsigned long long adesc0 = umma_desc(smem_u32(As));
             const unsigned long long bdesc0 = umma_desc(smem_u32(Ring));
+            if (ntiles > 0) mbar_wait(bar_afull, 0u);
             for (int j = 0; j < ntiles; j++) {
                 const int b = j % T5_NACC;
                 mbar_wait(bar_tempty(b), ((unsigned)(j / T5_NACC) & 1u) ^ 1u);
