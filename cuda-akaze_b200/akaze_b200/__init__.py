@@ -22,7 +22,7 @@ class Options(C.Structure):
                 ("derivative_factor", C.c_float), ("dthreshold", C.c_float), ("diffusivity", C.c_int),
                 ("descriptor_pattern_size", C.c_int), ("max_pts", C.c_int), ("max_batch", C.c_int),
                 ("device", C.c_int), ("kcontrast_override", C.c_float), ("fused", C.c_int),
-                ("fast_kcontrast_override", C.c_int)]
+                ("fast_kcontrast_override", C.c_int), ("lanes", C.c_int)]
 
 
 KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("response", "<f4"), ("size", "<f4"), ("angle", "<f4"),

@@ -39,7 +39,7 @@ void akz_default_options(akz_options* o)
     o->width = 0; o->height = 0;
     o->noctaves = 4; o->max_scale = 4; o->per = 0.7f; o->kcontrast = 0.03f; o->soffset = 1.6f; o->reordering = 1;
     o->derivative_factor = 1.5f; o->dthreshold = 0.001f; o->diffusivity = 1; o->descriptor_pattern_size = 10;
-    o->max_pts = 10000; o->max_batch = 8; o->device = -1; o->kcontrast_override = 0.f; o->fused = 1; o->fast_kcontrast_override = 0;
+    o->max_pts = 10000; o->max_batch = 8; o->device = -1; o->kcontrast_override = 0.f; o->fused = 1; o->fast_kcontrast_override = 0; o->lanes = 1;
 }
 
 // ---- host math ----------------------------------------------------------------------------------------
@@ -113,6 +113,8 @@ void akz_compare_indices(int* c1, int* c2)
 }  // extern "C"
 
 // ---- context -----------------------------------------------------------------------------------------
+constexpr int AKZ_NSET = 4;                 // staging buffers / result sets of the host pipeline
+
 struct akz_ctx {
     akz_options opt;
     int device;
@@ -127,16 +129,20 @@ struct akz_ctx {
     float *smooth, *flow, *tmpA, *tmpB;
     unsigned long long* map;
     unsigned* rowmask;
-    int *rowcount, *prefix, *hist, *counts_own;      // counts_own / kpts_own / desc_own: two result sets (host API pipeline)
+    int *rowcount, *prefix, *hist, *counts_own;      // counts_own / kpts_own / desc_own: AKZ_NSET result sets (host API pipeline)
     unsigned* hmax;
     float* kc;
     akz_keypoint* kpts_own;
     unsigned char* desc_own;
-    void* img_stage[2];
+    void* img_stage[AKZ_NSET];
     size_t img_stage_bytes;
     cudaStream_t h2d_stream, d2h_stream;
-    cudaEvent_t ev_h2d[2], ev_comp[2], ev_cnt[2], ev_d2h[2];
-    int* h_cnt_pinned;                               // [2][max_batch] pinned landing zone of the per-chunk counts
+    cudaEvent_t ev_h2d[AKZ_NSET], ev_comp[AKZ_NSET], ev_cnt[AKZ_NSET], ev_d2h[AKZ_NSET];
+    int* h_cnt_pinned;                               // [AKZ_NSET][max_batch] pinned landing zone of the per-chunk counts
+    // second lane (akz_options::lanes == 2): a child context with its own pyramid, scratch planes and stream; chunks
+    // alternate between the lanes so that two chunks are in flight (kernels bound by different pipes overlap)
+    akz_ctx* lane1;
+    cudaEvent_t ev_fork, ev_join;
     akz_match_t* match_parts;
     size_t match_parts_n;
     void* match_stage; size_t match_stage_bytes;
@@ -239,9 +245,11 @@ int akz_create(const akz_options* o, akz_ctx** out)
     c->opt = *o;
     c->launches = 0; c->last_frames = 0; c->prof_on = false;
     memset(c->prof_ms, 0, sizeof(c->prof_ms)); memset(c->prof_launches, 0, sizeof(c->prof_launches));
-    c->img_stage[0] = c->img_stage[1] = nullptr; c->img_stage_bytes = 0; c->match_parts = nullptr; c->match_parts_n = 0;
+    for (int i = 0; i < AKZ_NSET; i++) c->img_stage[i] = nullptr;
+    c->lane1 = nullptr; c->ev_fork = c->ev_join = nullptr;
+    c->img_stage_bytes = 0; c->match_parts = nullptr; c->match_parts_n = 0;
     c->h2d_stream = c->d2h_stream = nullptr; c->h_cnt_pinned = nullptr;
-    for (int i = 0; i < 2; i++) { c->ev_h2d[i] = c->ev_comp[i] = c->ev_cnt[i] = c->ev_d2h[i] = nullptr; }
+    for (int i = 0; i < AKZ_NSET; i++) { c->ev_h2d[i] = c->ev_comp[i] = c->ev_cnt[i] = c->ev_d2h[i] = nullptr; }
     c->match_stage = nullptr; c->match_stage_bytes = 0;
     int rc = AKZ_OK;
     do {
@@ -276,16 +284,16 @@ int akz_create(const akz_options* o, akz_ctx** out)
         int mwords = (o->width + 31) / 32;
         if ((rc = dalloc(c, &c->rowmask, (size_t)mwords * o->height * B)) != AKZ_OK) break;
         if ((rc = dalloc(c, &c->rowcount, (size_t)o->height * B)) != AKZ_OK) break;
-        if ((rc = dalloc(c, &c->counts_own, (size_t)2 * B)) != AKZ_OK) break;
-        if ((rc = dalloc(c, &c->kpts_own, (size_t)2 * o->max_pts * B)) != AKZ_OK) break;
-        if ((rc = dalloc(c, &c->desc_own, (size_t)2 * o->max_pts * B * 64)) != AKZ_OK) break;
+        if ((rc = dalloc(c, &c->counts_own, (size_t)AKZ_NSET * B)) != AKZ_OK) break;
+        if ((rc = dalloc(c, &c->kpts_own, (size_t)AKZ_NSET * o->max_pts * B)) != AKZ_OK) break;
+        if ((rc = dalloc(c, &c->desc_own, (size_t)AKZ_NSET * o->max_pts * B * 64)) != AKZ_OK) break;
         if (cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = akz_set_error(AKZ_E_CUDA, "stream creation failed"); break; }
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < AKZ_NSET; i++) {
             cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming);
             cudaEventCreateWithFlags(&c->ev_cnt[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming);
         }
-        if (cudaMallocHost((void**)&c->h_cnt_pinned, sizeof(int) * 2 * B) != cudaSuccess) { rc = akz_set_error(AKZ_E_NOMEM, "pinned allocation failed"); break; }
+        if (cudaMallocHost((void**)&c->h_cnt_pinned, sizeof(int) * AKZ_NSET * B) != cudaSuccess) { rc = akz_set_error(AKZ_E_NOMEM, "pinned allocation failed"); break; }
         cudaMemsetAsync(c->rowcount, 0, sizeof(int) * (size_t)o->height * B, c->stream);
         cudaMemsetAsync(c->rowmask, 0, sizeof(unsigned) * (size_t)mwords * o->height * B, c->stream);
         // level table for the keypoint kernels
@@ -300,6 +308,15 @@ int akz_create(const akz_options* o, akz_ctx** out)
         akzk::orient_table_init(c->stream);
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = akz_set_cuda_error(cudaGetLastError(), "context init", __FILE__, __LINE__); break; }
     } while (0);
+    if (rc == AKZ_OK && !matcher_only && o->lanes >= 2) {
+        akz_options o1 = *o;
+        o1.lanes = 1;
+        rc = akz_create(&o1, &c->lane1);
+        if (rc == AKZ_OK) {
+            cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+        }
+    }
     if (rc != AKZ_OK) { akz_destroy(c); return rc; }
     *out = c;
     return AKZ_OK;
@@ -308,10 +325,13 @@ int akz_create(const akz_options* o, akz_ctx** out)
 void akz_destroy(akz_ctx* c)
 {
     if (!c) return;
+    if (c->lane1) akz_destroy(c->lane1);
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (void* p : c->allocs) cudaFree(p);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < AKZ_NSET; i++) {
         if (c->img_stage[i]) cudaFree(c->img_stage[i]);
         if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
         if (c->ev_comp[i]) cudaEventDestroy(c->ev_comp[i]);
@@ -331,13 +351,14 @@ void akz_destroy(akz_ctx* c)
 
 int akz_sync(akz_ctx* c)
 {
+    if (c && c->lane1) AKZ_CUDA_TRY(cudaStreamSynchronize(c->lane1->stream));
     AKZ_CUDA_TRY(cudaStreamSynchronize(c->stream));
     AKZ_CUDA_TRY(cudaGetLastError());
     return AKZ_OK;
 }
 void* akz_stream(akz_ctx* c) { return (void*)c->stream; }
 int akz_num_levels(const akz_ctx* c) { return c->nlev; }
-int akz_launch_count(const akz_ctx* c) { return (int)c->launches; }
+int akz_launch_count(const akz_ctx* c) { return (int)(c->launches + (c->lane1 ? c->lane1->launches : 0)); }
 
 int akz_level_info(const akz_ctx* c, int l, int* w, int* h, int* pitch, int* nsteps, float* size, int* sigma_size, float* tau, int cap)
 {
@@ -569,12 +590,24 @@ int akz_detect_and_compute(akz_ctx* c, const void* d_images, int dtype, int nfra
     AKZ_CUDA_TRY(cudaSetDevice(c->device));
     const int B = c->opt.max_batch;
     const size_t esz = dtype == AKZ_U8 ? 1 : 4;
-    for (int f0 = 0; f0 < nframes; f0 += B) {
+    // two lanes: chunks alternate between the parent and the child context, each on its own stream
+    const bool two = c->lane1 != nullptr && nframes > B;
+    if (two) {
+        AKZ_CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
+        AKZ_CUDA_TRY(cudaStreamWaitEvent(c->lane1->stream, c->ev_fork, 0));
+    }
+    int k = 0;
+    for (int f0 = 0; f0 < nframes; f0 += B, k++) {
         int nf = std::min(B, nframes - f0);
+        akz_ctx* L = (two && (k & 1)) ? c->lane1 : c;
         const char* img = (const char*)d_images + (size_t)f0 * stride * esz;
-        if ((rc = scale_space_chunk(c, img, dtype, nf, pitch, stride)) != AKZ_OK) return rc;
-        if ((rc = detect_chunk(c, nf, describe, d_counts + f0, d_kpts + (size_t)f0 * c->opt.max_pts,
+        if ((rc = scale_space_chunk(L, img, dtype, nf, pitch, stride)) != AKZ_OK) return rc;
+        if ((rc = detect_chunk(L, nf, describe, d_counts + f0, d_kpts + (size_t)f0 * c->opt.max_pts,
                                d_desc ? d_desc + (size_t)f0 * c->opt.max_pts * 64 : nullptr)) != AKZ_OK) return rc;
+    }
+    if (two) {
+        AKZ_CUDA_TRY(cudaEventRecord(c->ev_join, c->lane1->stream));
+        AKZ_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     }
     AKZ_CUDA_TRY(cudaGetLastError());
     return AKZ_OK;
@@ -605,11 +638,22 @@ int akz_fast_detect_and_compute(akz_ctx* c, const uint8_t* d_images, int nframes
     if (!d_counts || !d_kpts || (describe && !d_desc)) return akz_set_error(AKZ_E_INVALID, "null result buffer");
     AKZ_CUDA_TRY(cudaSetDevice(c->device));
     const int B = c->opt.max_batch;
-    for (int f0 = 0; f0 < nframes; f0 += B) {
+    const bool two = c->lane1 != nullptr && nframes > B;
+    if (two) {
+        AKZ_CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
+        AKZ_CUDA_TRY(cudaStreamWaitEvent(c->lane1->stream, c->ev_fork, 0));
+    }
+    int k = 0;
+    for (int f0 = 0; f0 < nframes; f0 += B, k++) {
         int nf = std::min(B, nframes - f0);
-        if ((rc = fast_scale_space_chunk(c, d_images + (size_t)f0 * stride, nf, pitch, stride)) != AKZ_OK) return rc;
-        if ((rc = detect_chunk(c, nf, describe, d_counts + f0, d_kpts + (size_t)f0 * c->opt.max_pts,
+        akz_ctx* L = (two && (k & 1)) ? c->lane1 : c;
+        if ((rc = fast_scale_space_chunk(L, d_images + (size_t)f0 * stride, nf, pitch, stride)) != AKZ_OK) return rc;
+        if ((rc = detect_chunk(L, nf, describe, d_counts + f0, d_kpts + (size_t)f0 * c->opt.max_pts,
                                d_desc ? d_desc + (size_t)f0 * c->opt.max_pts * 64 : nullptr, 1)) != AKZ_OK) return rc;
+    }
+    if (two) {
+        AKZ_CUDA_TRY(cudaEventRecord(c->ev_join, c->lane1->stream));
+        AKZ_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     }
     AKZ_CUDA_TRY(cudaGetLastError());
     return AKZ_OK;
@@ -626,31 +670,35 @@ static int detect_and_compute_host(akz_ctx* c, const void* h_images, int dtype, 
     const size_t esz = dtype == AKZ_U8 ? 1 : 4;
     const size_t need = (size_t)B * stride * esz;
     if (c->img_stage_bytes < need) {
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < AKZ_NSET; i++) {
             if (c->img_stage[i]) cudaFree(c->img_stage[i]);
             c->img_stage[i] = nullptr;
         }
         c->img_stage_bytes = 0;
-        AKZ_CUDA_TRY(cudaMalloc(&c->img_stage[0], need));
-        AKZ_CUDA_TRY(cudaMalloc(&c->img_stage[1], need));
+        for (int i = 0; i < AKZ_NSET; i++) AKZ_CUDA_TRY(cudaMalloc(&c->img_stage[i], need));
         c->img_stage_bytes = need;
     }
-    // Three-stage pipeline over chunks of max_batch frames, two buffer sets:
-    //   h2d stream : frames of chunk i+1 -> staging[(i+1)&1]      (overlaps the kernels of chunk i)
-    //   main stream: scale space + detector + descriptors of chunk i -> result set i&1
-    //   d2h stream : counts of chunk i, then (once the host knows them) one strided copy of keypoints and one of
-    //                descriptors, width = the largest count of the chunk (overlaps the kernels of chunk i+1)
-    cudaStream_t st = c->stream;
+    // Pipeline over chunks of max_batch frames with AKZ_NSET staging buffers / result sets (chunk i uses set i % AKZ_NSET):
+    //   h2d stream   : frames of chunk i+LAG -> staging                  (overlaps the kernels of the chunks before it)
+    //   lane streams : scale space + detector + descriptors of chunk i -> result set; with two lanes (akz_options::lanes)
+    //                  consecutive chunks run on different streams with their own pyramids, so two are in flight
+    //   d2h stream   : counts of chunk i, then (once the host knows them) one strided copy of keypoints and one of
+    //                  descriptors, width = the largest count of the chunk
+    // The host drains chunk i-LAG after enqueueing chunk i, so LAG chunks are always queued ahead of the GPU.
+    const int NL = c->lane1 ? 2 : 1, LAG = NL;
     const int nchunks = (nframes + B - 1) / B;
     auto chunk_frames = [&](int i) { return std::min(B, nframes - i * B); };
     auto issue_h2d = [&](int i) -> int {
+        const int s = i % AKZ_NSET;
+        // staging[s] was last read by the kernels of chunk i - AKZ_NSET
+        if (i >= AKZ_NSET) AKZ_CUDA_TRY(cudaStreamWaitEvent(c->h2d_stream, c->ev_comp[s], 0));
         const char* src = (const char*)h_images + (size_t)i * B * stride * esz;
-        AKZ_CUDA_TRY(cudaMemcpyAsync(c->img_stage[i & 1], src, (size_t)chunk_frames(i) * stride * esz, cudaMemcpyHostToDevice, c->h2d_stream));
-        AKZ_CUDA_TRY(cudaEventRecord(c->ev_h2d[i & 1], c->h2d_stream));
+        AKZ_CUDA_TRY(cudaMemcpyAsync(c->img_stage[s], src, (size_t)chunk_frames(i) * stride * esz, cudaMemcpyHostToDevice, c->h2d_stream));
+        AKZ_CUDA_TRY(cudaEventRecord(c->ev_h2d[s], c->h2d_stream));
         return AKZ_OK;
     };
     auto drain = [&](int i) -> int {          // host side of the result download of chunk i
-        const int s = i & 1, nf = chunk_frames(i), f0 = i * B;
+        const int s = i % AKZ_NSET, nf = chunk_frames(i), f0 = i * B;
         AKZ_CUDA_TRY(cudaEventSynchronize(c->ev_cnt[s]));
         int maxc = 0;
         for (int f = 0; f < nf; f++) { h_counts[f0 + f] = c->h_cnt_pinned[s * B + f]; maxc = std::max(maxc, h_counts[f0 + f]); }
@@ -664,31 +712,32 @@ static int detect_and_compute_host(akz_ctx* c, const void* h_images, int dtype, 
         AKZ_CUDA_TRY(cudaEventRecord(c->ev_d2h[s], c->d2h_stream));
         return AKZ_OK;
     };
-    if (nchunks > 0 && (rc = issue_h2d(0)) != AKZ_OK) return rc;
+    for (int i = 0; i < std::min(LAG, nchunks); i++)
+        if ((rc = issue_h2d(i)) != AKZ_OK) return rc;
     for (int i = 0; i < nchunks; i++) {
-        const int s = i & 1, nf = chunk_frames(i);
+        const int s = i % AKZ_NSET, nf = chunk_frames(i);
+        akz_ctx* L = (NL == 2 && (i & 1)) ? c->lane1 : c;
+        cudaStream_t st = L->stream;
         AKZ_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_h2d[s], 0));
-        if (i >= 2) AKZ_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_d2h[s], 0));          // result set s is free again
-        if (fast) rc = fast_scale_space_chunk(c, (const unsigned char*)c->img_stage[s], nf, pitch, stride);
-        else rc = scale_space_chunk(c, c->img_stage[s], dtype, nf, pitch, stride);
+        if (i >= AKZ_NSET) AKZ_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_d2h[s], 0));   // result set s is free again
+        if (fast) rc = fast_scale_space_chunk(L, (const unsigned char*)c->img_stage[s], nf, pitch, stride);
+        else rc = scale_space_chunk(L, c->img_stage[s], dtype, nf, pitch, stride);
         if (rc != AKZ_OK) return rc;
-        if ((rc = detect_chunk(c, nf, describe, c->counts_own + (size_t)s * B, c->kpts_own + (size_t)s * B * MP,
+        if ((rc = detect_chunk(L, nf, describe, c->counts_own + (size_t)s * B, c->kpts_own + (size_t)s * B * MP,
                                c->desc_own + (size_t)s * B * MP * 64, fast)) != AKZ_OK) return rc;
         AKZ_CUDA_TRY(cudaEventRecord(c->ev_comp[s], st));
-        // staging[(i+1)&1] was last read by the kernels of chunk i-1, which precede ev_comp of chunk i-1
-        if (i + 1 < nchunks) {
-            if (i >= 1) AKZ_CUDA_TRY(cudaStreamWaitEvent(c->h2d_stream, c->ev_comp[(i + 1) & 1], 0));
-            if ((rc = issue_h2d(i + 1)) != AKZ_OK) return rc;
-        }
-        // results of chunk i-1 first (the GPU is already busy with chunk i), so that they do not queue behind the wait below
-        if (i >= 1 && (rc = drain(i - 1)) != AKZ_OK) return rc;
+        if (i + LAG < nchunks && (rc = issue_h2d(i + LAG)) != AKZ_OK) return rc;
+        // results of an earlier chunk first (the GPU is busy with later ones), so that they do not queue behind the wait below
+        if (i >= LAG && (rc = drain(i - LAG)) != AKZ_OK) return rc;
         AKZ_CUDA_TRY(cudaStreamWaitEvent(c->d2h_stream, c->ev_comp[s], 0));
         AKZ_CUDA_TRY(cudaMemcpyAsync(c->h_cnt_pinned + s * B, c->counts_own + (size_t)s * B, sizeof(int) * nf, cudaMemcpyDeviceToHost, c->d2h_stream));
         AKZ_CUDA_TRY(cudaEventRecord(c->ev_cnt[s], c->d2h_stream));
     }
-    if (nchunks > 0 && (rc = drain(nchunks - 1)) != AKZ_OK) return rc;
+    for (int i = std::max(0, nchunks - LAG); i < nchunks; i++)
+        if ((rc = drain(i)) != AKZ_OK) return rc;
     AKZ_CUDA_TRY(cudaStreamSynchronize(c->d2h_stream));
-    AKZ_CUDA_TRY(cudaStreamSynchronize(st));
+    AKZ_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->lane1) AKZ_CUDA_TRY(cudaStreamSynchronize(c->lane1->stream));
     AKZ_CUDA_TRY(cudaGetLastError());
     return AKZ_OK;
 }
@@ -929,6 +978,7 @@ int akz_profile_enable(akz_ctx* c, int on)
 {
     if (!c) return akz_set_error(AKZ_E_INVALID, "null context");
     c->prof_on = on != 0;
+    if (c->lane1) c->lane1->prof_on = on != 0;
     return AKZ_OK;
 }
 
@@ -946,6 +996,13 @@ int akz_profile_read(akz_ctx* c, int ncls, double* ms, long long* launches)
     c->prof_pairs.clear();
     for (int i = 0; i < ncls && i < AKZ_NUM_KCLASS; i++) { ms[i] = c->prof_ms[i]; launches[i] = c->prof_launches[i]; }
     memset(c->prof_ms, 0, sizeof(c->prof_ms)); memset(c->prof_launches, 0, sizeof(c->prof_launches));
+    if (c->lane1) {
+        // with two lanes the per-class times are summed over both streams (they overlap in wall-clock time)
+        double ms1[AKZ_NUM_KCLASS]; long long l1[AKZ_NUM_KCLASS];
+        int rc = akz_profile_read(c->lane1, AKZ_NUM_KCLASS, ms1, l1);
+        if (rc != AKZ_OK) return rc;
+        for (int i = 0; i < ncls && i < AKZ_NUM_KCLASS; i++) { ms[i] += ms1[i]; launches[i] += l1[i]; }
+    }
     return AKZ_OK;
 }
 

@@ -63,6 +63,8 @@ typedef struct akz_options {
     int   fused;                    /* 1 = fused production kernels, 0 = one kernel per reference     */
                                     /*     stage (same results; used as a cross-check)                */
     int   fast_kcontrast_override;  /* > 0: integer pipeline only, use this integer contrast factor   */
+    int   lanes;                    /* 1 (default) or 2: with 2, batches larger than max_batch keep two */
+                                    /*     chunks in flight on two streams with their own pyramids    */
 } akz_options;
 
 /* One detected keypoint (32 bytes, device or host). */

@@ -581,6 +581,48 @@ def test_u8_ingest_batching_host_api_and_determinism():
     ctx.close()
 
 
+def test_two_lanes_equal_one_lane():
+    """akz_options.lanes = 2 (chunks alternate between two streams with their own pyramids, AKZ_NSET staging buffers and
+    result sets in the host pipeline) returns exactly what the single-lane context returns: device API, host API with
+    float and u8 frames, the integer pipeline, and a batch that is not a multiple of the chunk size."""
+    w, h = 640, 480
+    nfr = 11
+    frames8 = np.stack([B.synth_shapes_u8(w, h, seed=40 + s) for s in range(nfr)])
+    framesf = B.u8_to_unit(frames8)
+    one = ab().Context(w, h, max_batch=2, max_pts=6000, lanes=1)
+    two = ab().Context(w, h, max_batch=2, max_pts=6000, lanes=2)
+    dev = torch.from_numpy(framesf).cuda()
+    c1, k1, d1 = one.detect_and_compute(dev)
+    one.sync()
+    for _ in range(3):
+        c2, k2, d2 = two.detect_and_compute(dev)
+        two.sync()
+        assert torch.equal(c1, c2) and int(c1.min()) > 20
+        for f in range(nfr):
+            n = int(c1[f])
+            assert torch.equal(k1[f, :n], k2[f, :n]) and torch.equal(d1[f, :n], d2[f, :n])
+    for frames in (framesf, frames8):
+        hc, hk, hd = two.detect_and_compute_host(frames)
+        assert np.array_equal(hc, c1.cpu().numpy())
+        for f in range(nfr):
+            n = int(hc[f])
+            assert np.array_equal(hk[f, :n].view(np.int32).reshape(n, 8), k1[f, :n].cpu().numpy())
+            assert np.array_equal(hd[f, :n], d1[f, :n].cpu().numpy())
+    dev8 = torch.from_numpy(frames8).cuda()
+    f1 = one.fast_detect_and_compute(dev8)
+    one.sync()
+    f2 = two.fast_detect_and_compute(dev8)
+    two.sync()
+    assert torch.equal(f1[0], f2[0])
+    for f in range(nfr):
+        n = int(f1[0][f])
+        assert torch.equal(f1[1][f, :n], f2[1][f, :n]) and torch.equal(f1[2][f, :n], f2[2][f, :n])
+    hf = two.detect_and_compute_host(frames8, fast=True)
+    assert np.array_equal(hf[0], f1[0].cpu().numpy())
+    assert two.launches > 0
+    one.close(); two.close()
+
+
 def test_small_image_drops_octaves_and_empty_image():
     # 200x150: octave 1 is 100x75 (h < 80) -> one octave only (akaze.cpp:215-219, App. B-12)
     ctx = ab().Context(200, 150, max_batch=1, max_pts=1000)
