@@ -199,13 +199,20 @@ def match_metric(ab, device, rank, world, clock_mhz):
 
     for mode, name in ((ab.MATCH_KNN2, "knn2"), (ab.MATCH_COMPAT, "compat")):
         out[f"{name}_10kx10k_ms"] = round(time_it(lambda: ctx.match(q, t, mode, out=res), 20), 4)
-    # SURVEY 8d counts 16 XOR + 16 POPC per pair (the plain formulation, POPC bound at 16 POPC/clk/SM); the kernel evaluates a
-    # carry-save tree (46 LOP3 + 5 POPC per pair), so the figure below is pairs/s against the plain formulation's POPC bound
+    # SURVEY 8d counts 16 XOR + 16 POPC per pair (the plain formulation, POPC bound at 16 POPC/clk/SM).  Large problems run on
+    # the tcgen05 kernel (u8 GEMM on bit-expanded descriptors, 512 MACs per pair), so two fractions are reported: pairs/s
+    # against the plain formulation's POPC bound (can exceed 1: the tensor cores are not bound by it) and MACs/s against the
+    # dense int8 tensor rate of the tcgen05 floor (128 x 128 x 32 MACs per 64 clocks per SM, B300_MICROARCH.md "tcgen05 floor").
     pairs = 10000 * 10000 / (out["knn2_10kx10k_ms"] * 1e-3)
-    peak_pairs = 148 * 16 * (clock_mhz or 1965.0) * 1e6 / 16
+    clk = (clock_mhz or 1965.0) * 1e6
+    peak_pairs = 148 * 16 * clk / 16
+    peak_macs = 148 * 8192 * clk
+    out["kernel"] = "k_match_tc5 (tcgen05.mma kind::i8, TMEM accumulators) + k_match_merge"
     out["pairs_per_s"] = float(f"{pairs:.4g}")
     out["frac_of_plain_popc_bound"] = round(pairs / peak_pairs, 3)
     out["plain_popc_bound"] = "148 SMs x 16 POPC.32/clk x SM clock / 16 POPC per pair"
+    out["frac_of_i8_tensor_peak"] = round(pairs * 512 / peak_macs, 3)
+    out["i8_tensor_peak"] = "148 SMs x 8192 MAC/clk x SM clock (tcgen05 kind::i8, M = 128)"
     # 10k x 1M, train sharded over the ranks (config 4)
     nt_total = 1_000_000
     lo, hi = D.shard_bounds(nt_total, world, rank)
@@ -233,6 +240,7 @@ def match_metric(ab, device, rank, world, clock_mhz):
     out["knn2_10kx1M_ms"] = round(ms, 3)
     out["knn2_10kx1M_shards"] = world
     out["knn2_10kx1M_frac_of_plain_popc_bound"] = round(10000 * nt_total / (ms * 1e-3) / (peak_pairs * world), 3)
+    out["knn2_10kx1M_frac_of_i8_tensor_peak"] = round(10000 * nt_total * 512 / (ms * 1e-3) / (peak_macs * world), 3)
     ctx.close()
     return out
 
