@@ -686,19 +686,31 @@ static int detect_and_compute_host(akz_ctx* c, const void* h_images, int dtype, 
     //                  descriptors, width = the largest count of the chunk
     // The host drains chunk i-LAG after enqueueing chunk i, so LAG chunks are always queued ahead of the GPU.
     const int NL = c->lane1 ? 2 : 1, LAG = NL;
-    const int nchunks = (nframes + B - 1) / B;
-    auto chunk_frames = [&](int i) { return std::min(B, nframes - i * B); };
+    // Chunk plan: the upload of the first chunk is not hidden behind anything, so the first chunks are small (B/8, B/4, B/2)
+    // and the pipeline ramps up to full chunks of B frames (a full first chunk of 32 float frames is 265 MB = 5 ms exposed).
+    std::vector<int> cstart, csize;
+    {
+        int f = 0, sz = std::max(1, B / 8);
+        while (f < nframes) {
+            int n = std::min(sz, nframes - f);
+            cstart.push_back(f); csize.push_back(n);
+            f += n;
+            sz = std::min(B, sz * 2);
+        }
+    }
+    const int nchunks = (int)cstart.size();
+    auto chunk_frames = [&](int i) { return csize[i]; };
     auto issue_h2d = [&](int i) -> int {
         const int s = i % AKZ_NSET;
         // staging[s] was last read by the kernels of chunk i - AKZ_NSET
         if (i >= AKZ_NSET) AKZ_CUDA_TRY(cudaStreamWaitEvent(c->h2d_stream, c->ev_comp[s], 0));
-        const char* src = (const char*)h_images + (size_t)i * B * stride * esz;
+        const char* src = (const char*)h_images + (size_t)cstart[i] * stride * esz;
         AKZ_CUDA_TRY(cudaMemcpyAsync(c->img_stage[s], src, (size_t)chunk_frames(i) * stride * esz, cudaMemcpyHostToDevice, c->h2d_stream));
         AKZ_CUDA_TRY(cudaEventRecord(c->ev_h2d[s], c->h2d_stream));
         return AKZ_OK;
     };
     auto drain = [&](int i) -> int {          // host side of the result download of chunk i
-        const int s = i % AKZ_NSET, nf = chunk_frames(i), f0 = i * B;
+        const int s = i % AKZ_NSET, nf = chunk_frames(i), f0 = cstart[i];
         AKZ_CUDA_TRY(cudaEventSynchronize(c->ev_cnt[s]));
         int maxc = 0;
         for (int f = 0; f < nf; f++) { h_counts[f0 + f] = c->h_cnt_pinned[s * B + f]; maxc = std::max(maxc, h_counts[f0 + f]); }
