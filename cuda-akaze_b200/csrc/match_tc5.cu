@@ -405,7 +405,9 @@ int match_partial_tc5(cudaStream_t st, const unsigned char* q, int nq, const uns
         attr = true;
     }
     dim3 g((nq + T5_Q - 1) / T5_Q, nsplit);
-    const bool filter = g_tc5_filter < 0 ? per >= 2048 : g_tc5_filter != 0;     // a chunk rarely holds a new top-2 entry after ~2000 candidates
+    // a chunk rarely holds a new top-2 entry after ~2000 candidates; the reference-compatible state changes only on a new best
+    // distance or a tie with it, which is rarer still: its filter pays off at every range length
+    const bool filter = g_tc5_filter < 0 ? (per >= 2048 || mode == AKZ_MATCH_COMPAT) : g_tc5_filter != 0;
     const uint4 *q4 = (const uint4*)q, *t4 = (const uint4*)t;
     if (mode != AKZ_MATCH_COMPAT) {
         if (filter) k_match_tc5<AKZ_MATCH_KNN2, true><<<g, T5_NT, T5_SMEM, st>>>(q4, nq, t4, nt, tbase, per, parts);

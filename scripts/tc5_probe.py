@@ -41,3 +41,16 @@ for nq, nt in ((10000, 10000), (10000, 100000)):
         e1.record(s); e1.synchronize()
         print(f"{nq}x{nt} kernel {kern}: {e0.elapsed_time(e1) / 10:.4f} ms", flush=True)
 L.akz_set_match_kernel(0)
+q = B.random_descriptors(10000, 0); t = B.random_descriptors(10000, 1)
+qt, tt = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+for kern in (3, 4, 5):
+    L.akz_set_match_kernel(kern)
+    for _ in range(3): ctx.match(qt, tt, ab.MATCH_COMPAT)
+    ctx.sync()
+    s = ctx.torch_stream()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(s)
+    for _ in range(10): ctx.match(qt, tt, ab.MATCH_COMPAT)
+    e1.record(s); e1.synchronize()
+    print(f"compat 10000x10000 kernel {kern}: {e0.elapsed_time(e1) / 10:.4f} ms", flush=True)
+L.akz_set_match_kernel(0)
