@@ -801,6 +801,68 @@ def test_matcher_tensor_core_kernel_equals_popc_kernel(nq, nt):
     ctx.close()
 
 
+@pytest.mark.parametrize("nq,nt", [(1, 100), (257, 16), (33, 4099), (3000, 5000), (700, 1024), (256, 1025)])
+def test_tcgen05_matcher_vs_cpu_oracle(nq, nt):
+    """k_match_tc5 forced (kernel 3 = filter by range length, 4 = chunk filter on, 5 = off) against the CPU oracle in both
+    modes: single query, fewer train descriptors than a tile, ragged last tiles, planted ties inside and across the
+    16-strides, ranges that are exact multiples of the 1024-descriptor unit, and a sharded train set whose shard bases are
+    not multiples of 16 (the class of a train index is (base + index) mod 16)."""
+    q, t = _planted(nq, nt, seed=7 * nq + nt)
+    o = B.oracle_match(q, t, "compat")
+    o2 = B.oracle_match(q, t, "knn2")
+    ctx = ab().Context(0, 0)
+    qt, tt = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+    L = ab().lib()
+    try:
+        for kern in (3, 4, 5):
+            L.akz_set_match_kernel(kern)
+            r = ctx.match(qt, tt, ab().MATCH_COMPAT)
+            ctx.sync()
+            assert np.array_equal(r.cpu().numpy()[:, :2], o), (kern, np.argwhere(r.cpu().numpy()[:, :2] != o)[:5])
+            r2 = ctx.match(qt, tt, ab().MATCH_KNN2)
+            ctx.sync()
+            assert np.array_equal(r2.cpu().numpy(), o2), (kern, np.argwhere(r2.cpu().numpy() != o2)[:5])
+            if nt >= 40:
+                cuts = [0, nt // 3 + 5, (2 * nt) // 3 + 3, nt]
+                for mode, ref_out in ((ab().MATCH_COMPAT, o), (ab().MATCH_KNN2, o2)):
+                    parts = torch.stack([ctx.match(qt, tt[cuts[i]:cuts[i + 1]].contiguous(), mode, t_index_base=cuts[i], finalize=False)
+                                         for i in range(3)])
+                    ctx.sync()
+                    m = ctx.match_merge(parts, mode, finalize=True)
+                    ctx.sync()
+                    assert np.array_equal(m.cpu().numpy()[:, :ref_out.shape[1]], ref_out), (kern, mode)
+    finally:
+        L.akz_set_match_kernel(0)
+    ctx.close()
+
+
+def test_tcgen05_matcher_long_range_is_split():
+    """A train set longer than the 2^19-descriptor range one block can index is split by akz_match; results equal the
+    LOP3/POPC kernel's (which has no such limit below 2^22)."""
+    nq, nt = 300, 600_000
+    q = B.random_descriptors(nq, 11)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(77)
+    tt = torch.randint(0, 256, (nt, 64), dtype=torch.uint8, device="cuda", generator=g)
+    tt[:, 61:] = 0
+    tt[:, 60] &= 0x3F
+    qt = torch.from_numpy(q).cuda()
+    tt[599_999] = qt[7]                         # best match in the very last row
+    tt[524_288] = qt[8]                         # and at the first index beyond one block's range
+    ctx = ab().Context(0, 0)
+    L = ab().lib()
+    try:
+        out = {}
+        for kern in (1, 3):
+            L.akz_set_match_kernel(kern)
+            out[kern] = (ctx.match(qt, tt, ab().MATCH_KNN2).cpu().numpy(), ctx.match(qt, tt, ab().MATCH_COMPAT).cpu().numpy())
+        assert np.array_equal(out[1][0], out[3][0]) and np.array_equal(out[1][1], out[3][1])
+        assert out[3][0][7, 0] == 599_999 and out[3][0][7, 1] == 0 and out[3][0][8, 0] == 524_288
+    finally:
+        L.akz_set_match_kernel(0)
+    ctx.close()
+
+
 @needs_ref
 def test_matcher_vs_reference():
     # nt must be a multiple of 16: gHammingMatch calls __syncthreads() inside a loop whose trip count differs per
