@@ -452,16 +452,17 @@ def test_1080p_vs_reference_outside_the_uninitialised_band():
     # fresh GPU they can be huge or NaN, and octave-3 candidates inside the band then suppress true keypoints of the finer
     # octaves around them through the radius NMS (seen once as a failure of a 99.5 % bar on y < 0.7 H in the first process
     # of a fresh box).  The set must be IDENTICAL where no level is contaminated and no contaminated candidate is within
-    # NMS reach: level 15 is clean above row 27 of 135 (y < 216 at full resolution), so compare y < 0.1 H; the larger
+    # NMS reach: level 15 is clean above row 27 of 135 (y < 216 at full resolution) and an octave-3 keypoint suppresses within
+    # ~32 full-resolution pixels, so compare y < 0.15 H; the larger
     # region is reported, not asserted.
     def keyset(a, layer_field, ymax, lmax):
         sel = (a["y"] < ymax) & (a[layer_field] < lmax)
         return {(int(q[layer_field]), q["y"].view(np.uint32).item(), q["x"].view(np.uint32).item()) for q in a[sel]}
     ours, theirs = keyset(mine, "layer", 0.7 * h, 12), keyset(rp, "octave", 0.7 * h, 12)
     print(f"[1080p] keypoints (octaves 0-2, y < 0.7 H): ours={len(ours)} reference={len(theirs)} common={len(ours & theirs)}")
-    ours, theirs = keyset(mine, "layer", 0.1 * h, 16), keyset(rp, "octave", 0.1 * h, 16)
-    print(f"[1080p] keypoints (all octaves, y < 0.1 H): ours={len(ours)} reference={len(theirs)} common={len(ours & theirs)}")
-    assert len(ours) > 50 and ours == theirs
+    ours, theirs = keyset(mine, "layer", 0.15 * h, 16), keyset(rp, "octave", 0.15 * h, 16)
+    print(f"[1080p] keypoints (all octaves, y < 0.15 H): ours={len(ours)} reference={len(theirs)} common={len(ours & theirs)}")
+    assert len(ours) > 30 and ours == theirs
     from scipy.spatial import cKDTree
     d, j = cKDTree(np.stack([mine["x"], mine["y"]], 1)).query(np.stack([rp["x"], rp["y"]], 1))
     exact = (rp["y"] < 0.55 * h) & (rp["octave"] < 8) & (d == 0) & (mine["angle"][j].view(np.uint32) == rp["angle"].view(np.uint32))
