@@ -320,11 +320,11 @@ constexpr int F2_BUF = F2_T * F2_T + 2 * F2_BX * F2_CP;      // floats per excha
 constexpr int F2_SMEM = 2 * F2_BUF * (int)sizeof(float);
 
 struct Fed2Geom { int nhx, nhy, two, tho; };
-__host__ __device__ inline Fed2Geom fed2_geom(int n)
+__host__ __device__ inline Fed2Geom fed2_geom(int n, int rb = 2)
 {
-    Fed2Geom g;
-    g.nhx = (n + 3) & ~3; g.nhy = (n + 1) & ~1;
-    g.two = (F2_T - g.nhx - n) & ~3; g.tho = (F2_T - g.nhy - n) & ~1;
+    Fed2Geom g;                                  // rb = rows of a thread's block: the tile origin is aligned to it
+    g.nhx = (n + 3) & ~3; g.nhy = (n + rb - 1) & ~(rb - 1);
+    g.two = (F2_T - g.nhx - n) & ~3; g.tho = (F2_T - g.nhy - n) & ~(rb - 1);
     return g;
 }
 
@@ -543,12 +543,13 @@ __device__ __forceinline__ F3Tile f3_decode(const Fed3Args& a, int t)
 }
 
 // fill the staging area with the Lt and g tiles of T (asynchronously for interior tiles)
+template <int NT>
 __device__ __forceinline__ void f3_stage(const Fed3Args& a, const F3Tile& T, float* St, int tid)
 {
     const float* __restrict__ src = a.f.src + T.base;
     const float* __restrict__ flw = a.f.flow + T.base;
     if (!T.border) {
-        for (int i = tid; i < F2_T * (F2_T / 4); i += F2_BX * F2_BY) {
+        for (int i = tid; i < F2_T * (F2_T / 4); i += NT) {
             int r = i >> 4, c4 = (i & 15) * 4;
             long long o = (long long)(T.GY0 + r) * a.f.pitch + T.GX0 + c4;
             f3_cp_async16(St + r * F2_T + c4, src + o);
@@ -557,7 +558,7 @@ __device__ __forceinline__ void f3_stage(const Fed3Args& a, const F3Tile& T, flo
     } else {
         // border tile: rows by reflected index; a group of 4 columns inside the image is one float4 load per plane
         const int w = a.f.w, h = a.f.h;
-        for (int i = tid; i < F2_T * (F2_T / 4); i += F2_BX * F2_BY) {
+        for (int i = tid; i < F2_T * (F2_T / 4); i += NT) {
             int r = i >> 4, c4 = (i & 15) * 4;
             int sy = min(max(refl(T.GY0 + r, h), 0), h - 1), gx = T.GX0 + c4;
             long long ro = (long long)sy * a.f.pitch;
@@ -597,9 +598,13 @@ __device__ __forceinline__ float f3_upd(float L0, float sL, float LL, float sR, 
     return __int_as_float(((__float_as_int(sf) * step) >> 16) + l0);
 }
 
-template <bool INT>
-__global__ void __launch_bounds__(F2_BX * F2_BY, 2) k_fed3(const __grid_constant__ Fed3Args a)
+// RB = rows of the block a thread owns (4 x RB pixels).  RB = 4 halves the number of threads per tile: the per-thread fixed
+// work of a tile (decode, addresses, border flags, rim exchange: two thirds of the executed instructions at 3-4 steps, ncu
+// r01i per-line table) is paid once per 16 pixels instead of once per 8.
+template <bool INT, int RB>
+__global__ void __launch_bounds__(F2_BX * (F2_T / RB), 2) k_fed3(const __grid_constant__ Fed3Args a)
 {
+    constexpr int NT = F2_BX * (F2_T / RB);
     extern __shared__ __align__(16) float sm[];
     float* T0 = sm;
     float* T1 = sm + F2_BUF;
@@ -607,55 +612,63 @@ __global__ void __launch_bounds__(F2_BX * F2_BY, 2) k_fed3(const __grid_constant
     float* Gs = St + F2_T * F2_T;
     const int n = a.f.n, w = a.f.w, h = a.f.h;
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * F2_BX + tx;
-    const int bx = 4 * tx, by = 2 * ty;
+    const int bx = 4 * tx, by = RB * ty;
 
     const int txl = max(tx - 1, 0), txr = min(tx + 1, F2_BX - 1);
-    const int ru = max(by - 1, 0), rd = min(by + 2, F2_T - 1);
+    const int ru = max(by - 1, 0), rd = min(by + RB, F2_T - 1);
     const int o_row0 = by * F2_T + bx, o_up = ru * F2_T + bx, o_dn = rd * F2_T + bx;
     const int o_cl = F2_T * F2_T + tx * F2_CP + by, o_cr = o_cl + F2_BX * F2_CP;
     const int o_lf = F2_T * F2_T + F2_BX * F2_CP + txl * F2_CP + by;      // CR of the left neighbour
     const int o_rt = F2_T * F2_T + txr * F2_CP + by;                      // CL of the right neighbour
 
+    // rim of the block: first and last row as float4, first and last column as RB / 2 float2
+    auto publish = [&](float* buf, const float (&L)[RB][4]) {
+        *(float4*)(buf + o_row0) = make_float4(L[0][0], L[0][1], L[0][2], L[0][3]);
+        *(float4*)(buf + o_row0 + (RB - 1) * F2_T) = make_float4(L[RB - 1][0], L[RB - 1][1], L[RB - 1][2], L[RB - 1][3]);
+#pragma unroll
+        for (int r = 0; r < RB; r += 2) {
+            *(float2*)(buf + o_cl + r) = make_float2(L[r][0], L[r + 1][0]);
+            *(float2*)(buf + o_cr + r) = make_float2(L[r][3], L[r + 1][3]);
+        }
+    };
+
     int t = blockIdx.x;
-    if (t < a.ntiles) { F3Tile Tn = f3_decode(a, t); f3_stage(a, Tn, St, tid); }
+    if (t < a.ntiles) { F3Tile Tn = f3_decode(a, t); f3_stage<NT>(a, Tn, St, tid); }
     for (; t < a.ntiles; t += gridDim.x) {
         const F3Tile T = f3_decode(a, t);
         const int gx0 = T.GX0 + bx, gy0 = T.GY0 + by;
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         __syncthreads();                                                   // stage(t) complete and visible
 
-        float L[2][4];
+        float L[RB][4];
 #pragma unroll
-        for (int r = 0; r < 2; r++) {
+        for (int r = 0; r < RB; r++) {
             float4 v = *(const float4*)(St + (by + r) * F2_T + bx);
             L[r][0] = v.x; L[r][1] = v.y; L[r][2] = v.z; L[r][3] = v.w;
         }
-        float sh[2][5], sv[3][4];
+        float sh[RB][5], sv[RB + 1][4];
         {
-            float g[4][6];
+            float g[RB + 2][6];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < RB + 2; k++) {
                 int rr = min(max(by - 1 + k, 0), F2_T - 1);
                 const float* gr = Gs + rr * F2_T;
                 float4 v = *(const float4*)(gr + bx);
                 g[k][0] = gr[max(bx - 1, 0)]; g[k][1] = v.x; g[k][2] = v.y; g[k][3] = v.z; g[k][4] = v.w; g[k][5] = gr[min(bx + 4, F2_T - 1)];
             }
 #pragma unroll
-            for (int r = 0; r < 2; r++)
+            for (int r = 0; r < RB; r++)
 #pragma unroll
                 for (int j = 0; j < 5; j++) sh[r][j] = f3_sum<INT>(g[r + 1][j + 1], g[r + 1][j]);
 #pragma unroll
-            for (int k = 0; k < 3; k++)
+            for (int k = 0; k < RB + 1; k++)
 #pragma unroll
                 for (int c = 0; c < 4; c++) sv[k][c] = f3_sum<INT>(g[k + 1][c + 1], g[k][c + 1]);
         }
         // publish the rim of the block in buffer 0 (its last readers finished before the barrier above)
-        *(float4*)(T0 + o_row0) = make_float4(L[0][0], L[0][1], L[0][2], L[0][3]);
-        *(float4*)(T0 + o_row0 + F2_T) = make_float4(L[1][0], L[1][1], L[1][2], L[1][3]);
-        *(float2*)(T0 + o_cl) = make_float2(L[0][0], L[1][0]);
-        *(float2*)(T0 + o_cr) = make_float2(L[0][3], L[1][3]);
+        publish(T0, L);
         __syncthreads();                                                   // stage fully consumed, rim visible
-        if (t + (int)gridDim.x < a.ntiles) { F3Tile Tn = f3_decode(a, t + gridDim.x); f3_stage(a, Tn, St, tid); }
+        if (t + (int)gridDim.x < a.ntiles) { F3Tile Tn = f3_decode(a, t + gridDim.x); f3_stage<NT>(a, Tn, St, tid); }
 
         // image-border bookkeeping (only tiles that touch the border pay for it)
         const bool border = T.GX0 <= 0 || T.GY0 <= 0 || T.GX0 + F2_T >= w || T.GY0 + F2_T >= h;
@@ -664,7 +677,7 @@ __global__ void __launch_bounds__(F2_BX * F2_BY, 2) k_fed3(const __grid_constant
         if (border) {
             bl = (gx0 == 0); bt = (gy0 == 0);
             ir = (w - 1) - gx0; if (ir < 0 || ir > 3) ir = -1;
-            jb = (h - 1) - gy0; if (jb < 0 || jb > 1) jb = -1;
+            jb = (h - 1) - gy0; if (jb < 0 || jb > RB - 1) jb = -1;
         }
 
         float* cur = T0;
@@ -673,31 +686,34 @@ __global__ void __launch_bounds__(F2_BX * F2_BY, 2) k_fed3(const __grid_constant
             const float sf = a.f.stepfac[st];
             const float4 up4 = *(const float4*)(cur + o_up);
             const float4 dn4 = *(const float4*)(cur + o_dn);
-            const float2 lf2 = *(const float2*)(cur + o_lf);
-            const float2 rt2 = *(const float2*)(cur + o_rt);
+            float lf[RB], rt[RB];
+#pragma unroll
+            for (int r = 0; r < RB; r += 2) {
+                const float2 l2 = *(const float2*)(cur + o_lf + r), r2 = *(const float2*)(cur + o_rt + r);
+                lf[r] = l2.x; lf[r + 1] = l2.y; rt[r] = r2.x; rt[r + 1] = r2.y;
+            }
             const float up[4] = { up4.x, up4.y, up4.z, up4.w }, dn[4] = { dn4.x, dn4.y, dn4.z, dn4.w };
-            const float lf[2] = { lf2.x, lf2.y }, rt[2] = { rt2.x, rt2.y };
-            float N[2][4];
+            float N[RB][4];
             if (!border) {
 #pragma unroll
-                for (int r = 0; r < 2; r++)
+                for (int r = 0; r < RB; r++)
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
                         float LL = (c == 0) ? lf[r] : L[r][c - 1];
                         float LR = (c == 3) ? rt[r] : L[r][c + 1];
-                        float LU = (r == 0) ? up[c] : L[0][c];
-                        float LD = (r == 1) ? dn[c] : L[1][c];
+                        float LU = (r == 0) ? up[c] : L[r - 1 < 0 ? 0 : r - 1][c];
+                        float LD = (r == RB - 1) ? dn[c] : L[r + 1 > RB - 1 ? RB - 1 : r + 1][c];
                         N[r][c] = f3_upd<INT>(L[r][c], sh[r][c], LL, sh[r][c + 1], LR, sv[r + 1][c], LD, sv[r][c], LU, sf);
                     }
             } else {
 #pragma unroll
-                for (int r = 0; r < 2; r++)
+                for (int r = 0; r < RB; r++)
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
                         float LL = (c == 0) ? lf[r] : L[r][c - 1];
                         float LR = (c == 3) ? rt[r] : L[r][c + 1];
-                        float LU = (r == 0) ? up[c] : L[0][c];
-                        float LD = (r == 1) ? dn[c] : L[1][c];
+                        float LU = (r == 0) ? up[c] : L[r - 1 < 0 ? 0 : r - 1][c];
+                        float LD = (r == RB - 1) ? dn[c] : L[r + 1 > RB - 1 ? RB - 1 : r + 1][c];
                         if (c == 0 && bl) LL = LR;                 // x = 0: left neighbour is x = 1
                         if (c == ir) LR = LL;                      // x = w-1: right neighbour is x = w-2
                         if (r == 0 && bt) LU = LD;                 // y = 0
@@ -706,14 +722,11 @@ __global__ void __launch_bounds__(F2_BX * F2_BY, 2) k_fed3(const __grid_constant
                     }
             }
 #pragma unroll
-            for (int r = 0; r < 2; r++)
+            for (int r = 0; r < RB; r++)
 #pragma unroll
                 for (int c = 0; c < 4; c++) L[r][c] = N[r][c];
             if (st + 1 < n) {
-                *(float4*)(nxt + o_row0) = make_float4(L[0][0], L[0][1], L[0][2], L[0][3]);
-                *(float4*)(nxt + o_row0 + F2_T) = make_float4(L[1][0], L[1][1], L[1][2], L[1][3]);
-                *(float2*)(nxt + o_cl) = make_float2(L[0][0], L[1][0]);
-                *(float2*)(nxt + o_cr) = make_float2(L[0][3], L[1][3]);
+                publish(nxt, L);
                 __syncthreads();
                 float* tt = cur; cur = nxt; nxt = tt;
             }
@@ -723,7 +736,7 @@ __global__ void __launch_bounds__(F2_BX * F2_BY, 2) k_fed3(const __grid_constant
         if (gx0 >= T.X0 && gx0 < T.X0 + a.two && gx0 < w) {
             float* dst = a.f.dst + T.base;
 #pragma unroll
-            for (int r = 0; r < 2; r++) {
+            for (int r = 0; r < RB; r++) {
                 int gy = gy0 + r;
                 if (gy >= T.Y0 && gy < T.Y0 + a.tho && gy < h) {
                     float* d = dst + (long long)gy * a.f.pitch + gx0;
@@ -739,6 +752,7 @@ __global__ void __launch_bounds__(F2_BX * F2_BY, 2) k_fed3(const __grid_constant
 }
 
 bool g_attr_done = false;
+int g_fed_rb = 4;                            // rows per thread block of k_fed3 (AKZ_FED_RB=2 selects the 4 x 2 variant)
 
 }  // namespace
 
@@ -747,10 +761,13 @@ namespace akzk {
 static void set_attrs()
 {
     if (g_attr_done) return;
+    if (const char* e = getenv("AKZ_FED_RB")) g_fed_rb = atoi(e) == 2 ? 2 : 4;
     cudaFuncSetAttribute(k_fed, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * FE_W * FE_H * (int)sizeof(float));
     cudaFuncSetAttribute(k_fed2, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM);
-    cudaFuncSetAttribute(k_fed3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
-    cudaFuncSetAttribute(k_fed3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
+    cudaFuncSetAttribute(k_fed3<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
+    cudaFuncSetAttribute(k_fed3<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
+    cudaFuncSetAttribute(k_fed3<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
+    cudaFuncSetAttribute(k_fed3<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
     cudaFuncSetAttribute(k_level_prep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_level_prep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     g_attr_done = true;
@@ -828,8 +845,9 @@ int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst,
             dim3 g((w + TWo - 1) / TWo, (h + THo - 1) / THo, n), b(FE_W, FE_TY);
             k_fed<<<g, b, 3 * FE_W * FE_H * sizeof(float), st>>>(a);
         } else {
-            Fed2Geom ge = fed2_geom(cnt);
-            dim3 g((w + ge.two - 1) / ge.two, (h + ge.tho - 1) / ge.tho, n), b(F2_BX, F2_BY);
+            const int rb = (fused == 3 || g_fed_rb == 2) ? 2 : 4;
+            Fed2Geom ge = fed2_geom(cnt, rb);
+            dim3 g((w + ge.two - 1) / ge.two, (h + ge.tho - 1) / ge.tho, n), b(F2_BX, F2_T / rb);
             int vec_ok = (pitch % 4 == 0) && (plane % 4 == 0) && (((uintptr_t)a.src | (uintptr_t)flowp | (uintptr_t)a.dst) % 16 == 0);
             if (fused == 3) k_fed2<<<g, b, F2_SMEM, st>>>(a, vec_ok);
             else {
@@ -839,8 +857,13 @@ int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst,
                 a3.inv_per = (1ull << 40) / (unsigned long long)(g.x * g.y) + 1; a3.inv_gx = (1ull << 40) / (unsigned long long)g.x + 1;
                 if (a3.ntiles >= (1 << 24) || g.x * g.y >= (1u << 16)) return akz_set_error(AKZ_E_UNSUPPORTED, "FED tile count out of range");
                 int nb = a3.ntiles < 2 * 148 ? a3.ntiles : 2 * 148;
-                if (int_planes) k_fed3<true><<<nb, b, F3_SMEM, st>>>(a3);
-                else k_fed3<false><<<nb, b, F3_SMEM, st>>>(a3);
+                if (rb == 4) {
+                    if (int_planes) k_fed3<true, 4><<<nb, b, F3_SMEM, st>>>(a3);
+                    else k_fed3<false, 4><<<nb, b, F3_SMEM, st>>>(a3);
+                } else {
+                    if (int_planes) k_fed3<true, 2><<<nb, b, F3_SMEM, st>>>(a3);
+                    else k_fed3<false, 2><<<nb, b, F3_SMEM, st>>>(a3);
+                }
             }
         }
         cur = a.dst;
