@@ -45,7 +45,7 @@ def main():
     frames = np.stack([base[16 * f:16 * f + H, 16 * f:16 * f + W] for f in idx])      # content moves by (-16, -16) per frame
     dev = torch.from_numpy(frames).to(device)
     nfr = len(idx)
-    ctx = ab.Context(W, H, noctaves=5, max_batch=args.chunk, max_pts=args.max_pts, device=local)
+    ctx = ab.Context(W, H, noctaves=5, max_batch=args.chunk, max_pts=args.max_pts, device=local, lanes=2)
     mctx = ab.Context(0, 0, device=local)
     res = ctx.alloc_results(nfr, True)
     mres = torch.zeros(nfr, args.max_pts, 4, dtype=torch.int32, device=device)
