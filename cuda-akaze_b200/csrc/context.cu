@@ -937,22 +937,12 @@ int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt
             if (blocks < 148) eff *= 0.5;
             if (eff > best + 1e-9) { best = eff; nsplit = sp; }
         }
-        if (kern == 3) {
-            // k_match_tc5 walks ranges that are multiples of 1024 train descriptors (at most 2^19): score the splits by the
-            // work they really launch, rounded to whole waves
-            best = -1.0;
-            const int max_sp = std::max(1, std::min((nt + 1023) / 1024, 256));
-            for (int sp = 1; sp <= max_sp; sp++) {
-                long long per = (((long long)nt + sp - 1) / sp + 1023) / 1024 * 1024;
-                if (per > (1 << 19)) continue;
-                long long live = ((long long)nt + per - 1) / per;                  // splits that hold descriptors
-                long long blocks = (long long)qblocks * live;
-                long long waves = (blocks + 147) / 148;
-                double cost = (double)waves * (double)(per / 128 + 3);               // + ~3 tiles of prologue per block
-                double eff = ((double)qblocks * nt / 128.0) / (cost * 148.0);
-                if (eff > best + 1e-9) { best = eff; nsplit = sp; }
-            }
-        }
+    }
+    if (kern == 3) {
+        // k_match_tc5 balances the tiles over one CTA per SM itself; it reports how many partial results per query it writes
+        int sp, T, S, grid;
+        nsplit = akzk::match_tc5_plan(nq, nt, &sp, &T, &S, &grid);
+        if (nsplit < 0) return nsplit;
     }
     size_t need = (size_t)nsplit * nq;
     if (c->match_parts_n < need) {
@@ -961,7 +951,7 @@ int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt
         AKZ_CUDA_TRY(cudaMalloc((void**)&c->match_parts, need * sizeof(akz_match_t)));
         c->match_parts_n = need;
     }
-    if (kern == 3) { LAUNCHED(AKZ_K_MATCH, akzk::match_partial_tc5(c->stream, d_q, nq, d_t, nt, t_index_base, mode, nsplit, c->match_parts)); }
+    if (kern == 3) { LAUNCHED(AKZ_K_MATCH, akzk::match_partial_tc5(c->stream, d_q, nq, d_t, nt, t_index_base, mode, c->match_parts)); }
     else { LAUNCHED(AKZ_K_MATCH, akzk::match_partial(c->stream, d_q, nq, d_t, nt, t_index_base, mode, nsplit, c->match_parts, use_mma)); }
     LAUNCHED(AKZ_K_MATCH, akzk::match_merge(c->stream, c->match_parts, nsplit, nq, mode, finalize, d_out));
     STAGE_EPILOGUE();

@@ -30,6 +30,7 @@
 // candidates have been seen): 0.5 instead of 2.5 ALU instructions per pair.
 #include "common.cuh"
 #include "kernels.h"
+#include <algorithm>
 
 namespace {
 
@@ -75,6 +76,22 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
         if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
+// spinning wait (test_wait never suspends the thread): for the MMA issuer and the expanders, whose wake-up latency is on the
+// critical path of the slot ring (a slot is refilled while the three other K-blocks of the tile are multiplied)
+__device__ __forceinline__ unsigned mbar_test(unsigned bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_spin(unsigned bar, unsigned parity)
+{
+    if (mbar_test(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_test(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -84,18 +101,35 @@ __device__ __forceinline__ unsigned long long umma_desc(unsigned saddr)
 {
     return (unsigned long long)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// Issued by a whole, converged warp: one elected lane executes the instruction.  With warp-uniform control flow and operands
+// the compiler keeps descriptors and addresses in uniform registers; issued from inside `if (lane == 0)` every MMA cost four
+// R2UR moves and a waterfall loop (ELECT / R2UR.BROADCAST / BRA.U.ANY), about as long as the 64 clocks the MMA itself takes.
 __device__ __forceinline__ void umma_i8(unsigned d_tmem, unsigned long long adesc, unsigned long long bdesc, unsigned accumulate)
 {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+    asm volatile("{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t@e tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(T5_IDESC), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(unsigned bar)
 {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&v)[32])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+}
+// the same load with two adjacent columns packed into one register (their low 16 bits): the accumulators are at most
+// 64 * 998 + 63 < 2^16, and the TMEM -> register traffic shares the SM's 128 B/clk memory datapath with the operand reads of the
+// tensor core and the expanders' stores (ncu r01j: the three add up to the kernel's duration), so half the bytes is time won
+__device__ __forceinline__ void tmem_ld32_pack16(unsigned taddr, unsigned (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                  "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
@@ -193,9 +227,24 @@ __device__ __forceinline__ void merge5(Best5& a, const Best5& o)
 
 __device__ __forceinline__ int popc128(const uint4& w) { return __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w); }
 
+// Work decomposition.  An ITEM is (query block of 256, split of the train set): T tiles of 128 train descriptors whose index
+// inside the item's range is c * H + ordinal (H = 2 T half tiles, see above).  The tiles of all items form one linear space
+// (item-major); the grid is one CTA per SM and CTA g walks the tiles [g S, (g + 1) S): every SM gets the same number of tiles
+// whatever the problem size, and a CTA pays its prologue once.  A CTA that crosses into the next item writes the partial
+// result of the item it leaves (slot = its rank among the CTAs that cover that item), re-expands operand A and goes on; the
+// expanders and the MMA issuer run ahead across the boundary.  k_match_merge folds the slots.
+struct T5Args {
+    const uint4* q; const uint4* t; akz_match_t* parts;
+    int nq, nt, tbase;
+    int T;                  // tiles per item (multiple of 8: the 64 columns of a half tile share their index class)
+    int nsplit;             // items per query block
+    int S;                  // tiles per CTA
+    int total;              // tiles in the linear space
+    int maxslots;           // partial results per item
+};
+
 template <int MODE, bool FILTER>
-__global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t, int nt, int tbase,
-                                                        int per_split, akz_match_t* __restrict__ parts)
+__global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const __grid_constant__ T5Args a)
 {
     extern __shared__ unsigned char t5raw[];
     unsigned char* sm = t5raw + ((1024u - (smem_u32(t5raw) & 1023u)) & 1023u);
@@ -210,10 +259,10 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
     const unsigned bar_afull = bar0 + 8u * (2 * T5_SLOTS + 2 * T5_NACC);
 
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-    const int q0 = blockIdx.x * T5_Q;
-    const int t0 = blockIdx.y * per_split, t1 = min(nt, t0 + per_split);
-    const int ntiles = t1 > t0 ? per_split / T5_N : 0;              // every tile holds rows of the whole range (rel = c * H + ordinal)
-    const int H = 2 * (per_split / T5_N);
+    const uint4* __restrict__ q = a.q;
+    const uint4* __restrict__ t = a.t;
+    const int nq = a.nq, nt = a.nt, T = a.T, H = 2 * a.T;
+    const int lin0 = blockIdx.x * a.S, lin1 = min(a.total, lin0 + a.S);
 
     // ---- prologue: barriers and tensor memory; the roles start right after one block barrier ---------------------------
     if (tid == 0) {
@@ -234,123 +283,153 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
     if (wid < T5_MMA_WARP) {
         // ================================ epilogue: thread = query row ==========================================
         const int row = tid;                                         // A tile row >> 7, TMEM lane row & 127
-        int pq = 0;
-        {
-            // operand A: every epilogue thread expands its own query (the expanders are already at work on the first train tile)
-            uint4 x[4];
+        const unsigned taddr0 = tmem + ((unsigned)((wid & 3) * 32) << 16) + (unsigned)((wid >> 2) * T5_N);
+        int gt = 0;                                                  // tiles this CTA has consumed (barrier phases)
+        for (int lin = lin0; lin < lin1;) {
+            const int item = lin / T, j0 = lin - item * T, j1 = min(T, j0 + (lin1 - lin));
+            const int q0 = (item / a.nsplit) * T5_Q, t0 = (item % a.nsplit) * T * T5_N;
+            // operand A of this item: every epilogue thread expands its own query.  The MMAs of the previous item are complete
+            // (this thread has consumed the accumulator of its last tile), the expanders are already at work on the train tiles.
+            int pq = 0;
+            {
+                uint4 x[4];
 #pragma unroll
-            for (int kb = 0; kb < 4; kb++) x[kb] = q0 + row < nq ? __ldg(q + 4 * (long long)(q0 + row) + kb) : make_uint4(0, 0, 0, 0);
-            x[3].w &= 0x3Fu;
-            pq = popc128(x[0]) + popc128(x[1]) + popc128(x[2]) + popc128(x[3]);
+                for (int kb = 0; kb < 4; kb++) x[kb] = q0 + row < nq ? __ldg(q + 4 * (long long)(q0 + row) + kb) : make_uint4(0, 0, 0, 0);
+                x[3].w &= 0x3Fu;
+                pq = popc128(x[0]) + popc128(x[1]) + popc128(x[2]) + popc128(x[3]);
 #pragma unroll
-            for (int kb = 0; kb < 4; kb++) expand_store<false>(As + ((row >> 7) * 4 + kb) * T5_KB, row & 127, x[kb], kb == 3, 64u, 64u, 64u, 1u);
-            fence_async_smem();
-            mbar_arrive(bar_afull);
-        }
-        Best5 be, bo;                                                // two independent chains
-        be.k1 = bo.k1 = 0u; be.k2 = bo.k2 = 0u;
-        for (int j = 0; j < ntiles; j++) {
-            const int b = j % T5_NACC;
-            mbar_wait(bar_tfull(b), (unsigned)(j / T5_NACC) & 1u);
-            tc_fence_after();
-            const unsigned taddr = tmem + ((unsigned)((wid & 3) * 32) << 16) + (unsigned)(b * T5_QT * T5_N + (wid >> 2) * T5_N);
-            unsigned va[32], vb[32];
-            tmem_ld32(taddr, va);
-            tmem_ld_wait();
+                for (int kb = 0; kb < 4; kb++) expand_store<false>(As + ((row >> 7) * 4 + kb) * T5_KB, row & 127, x[kb], kb == 3, 64u, 64u, 64u, 1u);
+                fence_async_smem();
+                mbar_arrive(bar_afull);
+            }
+            Best5 be, bo;                                            // two independent chains
+            be.k1 = bo.k1 = 0u; be.k2 = bo.k2 = 0u;
+            for (int j = j0; j < j1; j++, gt++) {
+                const int b = gt % T5_NACC;
+                mbar_wait(bar_tfull(b), (unsigned)(gt / T5_NACC) & 1u);
+                tc_fence_after();
+                const unsigned taddr = taddr0 + (unsigned)(b * T5_QT * T5_N);
+                unsigned va[32], vb[32];
+                tmem_ld32_pack16(taddr, va);                          // 64 columns = one half tile, two per register
+                tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < T5_N / 32; c++) {
-                unsigned (&v)[32] = (c & 1) ? vb : va;
-                unsigned (&vn)[32] = (c & 1) ? va : vb;
-                if (c + 1 < T5_N / 32) tmem_ld32(taddr + (c + 1) * 32, vn);        // in flight while this chunk is processed
-                const int ordinal = 2 * j + (c >> 1);
-                const unsigned ordinv = 8191u - (unsigned)ordinal;
+                for (int c = 0; c < 2; c++) {
+                    unsigned (&v)[32] = c ? vb : va;
+                    if (c == 0) tmem_ld32_pack16(taddr + 64, vb);      // in flight while the first half is processed
+                    const int ordinal = 2 * j + c;
+                    const unsigned ordinv = 8191u - (unsigned)ordinal;
+                    bool update = true;
+                    if (FILTER) {
+                        // packed maximum of the 64 accumulators; a key is acc << 13 | ordinv, so (max << 13) | 8191 bounds the keys
+                        unsigned m = __vimax3_u16x2(v[0], v[1], v[2]);
 #pragma unroll
-                for (int i = 0; i < 32; i++) v[i] = v[i] * 8192u + ordinv;
-                bool update = true;
-                if (FILTER) {
-                    unsigned m = __vimax3_u32(v[0], v[1], v[2]);
-#pragma unroll
-                    for (int i = 3; i + 1 < 32; i += 2) m = __vimax3_u32(m, v[i], v[i + 1]);
-                    m = max(m, v[31]);
-                    update = (MODE == AKZ_MATCH_KNN2) ? (m > max(be.k2, bo.k2)) : (m >= (max(be.k1, bo.k1) & ~T5_EMASK));
-                }
-                if (update) {
-                    if (MODE == AKZ_MATCH_KNN2) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) { consider5_pair(be, v[i], v[i + 1]); consider5_pair(bo, v[i + 2], v[i + 3]); }
-                    } else {
-                        // H is a multiple of 16, so the 64 columns of a half tile share their index class
-                        const unsigned classbit = 1u << ((unsigned)(tbase + ordinal) & 15u);
-#pragma unroll
-                        for (int i = 0; i < 32; i++) consider5<MODE>((i & 1) ? bo : be, v[i], classbit);
+                        for (int i = 3; i + 1 < 32; i += 2) m = __vimax3_u16x2(m, v[i], v[i + 1]);
+                        m = __vmaxu2(m, v[31]);
+                        const unsigned bound = (max(m & 0xFFFFu, m >> 16) << 13) | 8191u;
+                        update = (MODE == AKZ_MATCH_KNN2) ? (bound > max(be.k2, bo.k2)) : (bound >= (max(be.k1, bo.k1) & ~T5_EMASK));
                     }
+                    if (update) {
+                        const unsigned classbit = 1u << ((unsigned)(a.tbase + ordinal) & 15u);   // H is a multiple of 16: one class per half tile
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const unsigned k0 = (v[i] & 0xFFFFu) * 8192u + ordinv, k1 = (v[i] >> 16) * 8192u + ordinv;
+                            const unsigned k2 = (v[i + 1] & 0xFFFFu) * 8192u + ordinv, k3 = (v[i + 1] >> 16) * 8192u + ordinv;
+                            if (MODE == AKZ_MATCH_KNN2) { consider5_pair(be, k0, k1); consider5_pair(bo, k2, k3); }
+                            else { consider5<MODE>(be, k0, classbit); consider5<MODE>(bo, k1, classbit); consider5<MODE>(be, k2, classbit); consider5<MODE>(bo, k3, classbit); }
+                        }
+                    }
+                    if (c == 0) tmem_ld_wait();
                 }
-                if (c + 1 < T5_N / 32) tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(bar_tempty(b));
             }
-            tc_fence_before();
-            mbar_arrive(bar_tempty(b));
-        }
-        merge5<MODE>(be, bo);
-        if (q0 + row < nq) {
-            akz_match_t m;
-            auto rel = [&](unsigned k) { return (int)(63u - ((k >> 13) & 63u)) * H + (int)(8191u - (k & 8191u)); };
-            auto dist = [&](unsigned k) { return pq + 512 - (int)(k >> 19); };
-            const bool has1 = be.k1 >= 8192u;
-            m.idx1 = has1 ? tbase + t0 + rel(be.k1) : -1;
-            m.dist1 = has1 ? dist(be.k1) : -1;
-            if (MODE == AKZ_MATCH_KNN2) {
-                const bool has2 = be.k2 >= 8192u;
-                m.idx2 = has2 ? tbase + t0 + rel(be.k2) : -1;
-                m.dist2 = has2 ? dist(be.k2) : -1;
-            } else {
-                m.idx2 = has1 ? (int)be.k2 : 0; m.dist2 = 0;
+            merge5<MODE>(be, bo);
+            if (q0 + row < nq) {
+                akz_match_t m;
+                auto rel = [&](unsigned k) { return (int)(63u - ((k >> 13) & 63u)) * H + (int)(8191u - (k & 8191u)); };
+                auto dist = [&](unsigned k) { return pq + 512 - (int)(k >> 19); };
+                const bool has1 = be.k1 >= 8192u;
+                m.idx1 = has1 ? a.tbase + t0 + rel(be.k1) : -1;
+                m.dist1 = has1 ? dist(be.k1) : -1;
+                if (MODE == AKZ_MATCH_KNN2) {
+                    const bool has2 = be.k2 >= 8192u;
+                    m.idx2 = has2 ? a.tbase + t0 + rel(be.k2) : -1;
+                    m.dist2 = has2 ? dist(be.k2) : -1;
+                } else {
+                    m.idx2 = has1 ? (int)be.k2 : 0; m.dist2 = 0;
+                }
+                // slot = rank of this CTA among the CTAs that cover the item; the first of them also voids the unused slots
+                const int gfirst = (item * T) / a.S, glast = ((item + 1) * T - 1) / a.S;
+                akz_match_t* dst = a.parts + (long long)(item % a.nsplit) * a.maxslots * nq + q0 + row;
+                dst[(long long)((int)blockIdx.x - gfirst) * nq] = m;
+                if ((int)blockIdx.x == gfirst) {
+                    akz_match_t none; none.idx1 = -1; none.dist1 = -1; none.idx2 = (MODE == AKZ_MATCH_KNN2) ? -1 : 0; none.dist2 = (MODE == AKZ_MATCH_KNN2) ? -1 : 0;
+                    for (int sl = glast - gfirst + 1; sl < a.maxslots; sl++) dst[(long long)sl * nq] = none;
+                }
             }
-            parts[(long long)blockIdx.y * nq + q0 + row] = m;
+            lin += j1 - j0;
         }
     } else if (wid == T5_MMA_WARP) {
-        // ================================ MMA issue: one thread ==================================================
-        if (lane == 0) {
+        // ================================ MMA issue: one warp, one elected lane per instruction =====================
+        {
+            const unsigned tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
             const unsigned long long adesc0 = umma_desc(smem_u32(As));
             const unsigned long long bdesc0 = umma_desc(smem_u32(Ring));
-            if (ntiles > 0) mbar_wait(bar_afull, 0u);
-            for (int j = 0; j < ntiles; j++) {
-                const int b = j % T5_NACC;
-                mbar_wait(bar_tempty(b), ((unsigned)(j / T5_NACC) & 1u) ^ 1u);
+            int gt = 0, seg = 0, cur_item = -1;
+            int item = lin0 / T, j = lin0 - item * T;
+            for (int lin = lin0; lin < lin1; lin++, gt++) {
+                if (item != cur_item) {                                   // operand A of the new item
+                    mbar_spin(bar_afull, (unsigned)seg & 1u);
+                    cur_item = item; seg++;
+                }
+                const int b = gt % T5_NACC;
+                mbar_spin(bar_tempty(b), ((unsigned)(gt / T5_NACC) & 1u) ^ 1u);
                 tc_fence_after();
+#pragma unroll
                 for (int kb = 0; kb < 4; kb++) {
-                    const int s = kb;
-                    mbar_wait(bar_full(s), (unsigned)j & 1u);
+                    mbar_spin(bar_full(kb), (unsigned)gt & 1u);
                     tc_fence_after();
 #pragma unroll
                     for (int h = 0; h < T5_QT; h++) {
-                        const unsigned d_tmem = tmem + (unsigned)(b * T5_QT * T5_N + h * T5_N);
+                        const unsigned d_tmem = tmem_u + (unsigned)(b * T5_QT * T5_N + h * T5_N);
 #pragma unroll
                         for (int k = 0; k < 4; k++)
                             umma_i8(d_tmem, adesc0 + (unsigned long long)((h * 4 + kb) * (T5_KB >> 4) + 2 * k),
-                                    bdesc0 + (unsigned long long)(s * (T5_KB >> 4) + 2 * k), (kb | k) != 0 ? 1u : 0u);
+                                    bdesc0 + (unsigned long long)(kb * (T5_KB >> 4) + 2 * k), (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(bar_empty(s));
+                    umma_commit(bar_empty(kb));
                 }
                 umma_commit(bar_tfull(b));
+                if (++j == T) { j = 0; item++; }
             }
         }
         __syncwarp();
     } else {
         // ================================ expanders: thread = row of the train tile, all four K-blocks ===============
+        // The serial instruction chain of an expander thread per tile (wait, expand, store, fence, arrive: four times) paces the
+        // whole kernel (measured: a division per tile in this loop cost 13 %; moving the popcount behind its own loads 20 %), so
+        // the loop is kept minimal: the next tile's row is prefetched, its position advances incrementally.
         const int row = tid - (T5_NEPI + 32);
         const int c64 = row & 63, half = row >> 6;
-        const long long tlim = (long long)t1 - t0;
-        auto load_row = [&](int j, uint4 (&x)[4]) {
-            const long long r = (long long)c64 * H + 2 * j + half;        // index inside the range: the column is the major part
-            const bool ok = j < ntiles && r < tlim;
+        const unsigned rowoff = (unsigned)c64 * (unsigned)H + (unsigned)half;      // index of the row inside the item's range, tile 0
+        int nitem = lin0 / T, nj = lin0 - nitem * T;                               // position of the NEXT row to load
+        long long ibase = (long long)(nitem % a.nsplit) * T * T5_N;
+        auto load_next = [&](uint4 (&x)[4], bool live) {
+            const long long g = ibase + rowoff + 2u * (unsigned)nj;               // the column is the major part of the index
+            const bool ok = live && g < nt;
 #pragma unroll
-            for (int kb = 0; kb < 4; kb++) x[kb] = ok ? __ldg(t + 4 * (t0 + r) + kb) : make_uint4(0, 0, 0, 0);
+            for (int kb = 0; kb < 4; kb++) x[kb] = ok ? __ldg(t + 4 * g + kb) : make_uint4(0, 0, 0, 0);
+            if (++nj == T) { nj = 0; nitem++; ibase = (long long)(nitem % a.nsplit) * T * T5_N; }
             return ok;
         };
-        uint4 x[4], nx[4];
-        bool ok = load_row(0, x);
-        for (int j = 0; j < ntiles; j++) {
-            const bool nok = load_row(j + 1, nx);
+        // two tiles of look-ahead: the rows of a tile lie H descriptors apart (up to 500 KB), one tile time does not cover
+        // the latency of such a scattered read
+        uint4 x[4], nx[4], nnx[4];
+        bool ok = load_next(x, lin0 < lin1);
+        bool nok = load_next(nx, lin0 + 1 < lin1);
+        int gt = 0;
+        for (int lin = lin0; lin < lin1; lin++, gt++) {
+            const bool nnok = load_next(nnx, lin + 2 < lin1);
             // padding bytes of the row: three bytes summing to 512 - popc(t), and 63 - column
             x[3].w &= 0x3Fu;
             const int rest = 512 - (popc128(x[0]) + popc128(x[1]) + popc128(x[2]) + popc128(x[3]));
@@ -358,16 +437,17 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
             const unsigned e7 = ok ? (unsigned)min(rest - (int)e6, 255) : 0u;
             const unsigned e0 = ok ? (unsigned)(rest - (int)e6 - (int)e7) : 0u;
             const unsigned e1 = ok ? (unsigned)(63 - c64) : 0u;
+            const unsigned par = ((unsigned)gt & 1u) ^ 1u;
 #pragma unroll
             for (int kb = 0; kb < 4; kb++) {
-                mbar_wait(bar_empty(kb), ((unsigned)j & 1u) ^ 1u);                  // T5_SLOTS == 4: slot = K-block
+                mbar_spin(bar_empty(kb), par);                                      // T5_SLOTS == 4: slot = K-block
                 expand_store<true>(Ring + kb * T5_KB, row, x[kb], kb == 3, e6, e7, e0, e1);
                 fence_async_smem();
                 mbar_arrive(bar_full(kb));
             }
 #pragma unroll
-            for (int kb = 0; kb < 4; kb++) x[kb] = nx[kb];
-            ok = nok;
+            for (int kb = 0; kb < 4; kb++) { x[kb] = nx[kb]; nx[kb] = nnx[kb]; }
+            ok = nok; nok = nnok;
         }
     }
 
@@ -384,18 +464,40 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const uint4* __restrict_
 
 namespace akzk {
 
+static int g_tc5_max_tiles = 4096;
 static int g_tc5_filter = -1;                    // -1 = by range length, 0 / 1 = forced (tests)
 void match_tc5_set_filter(int v) { g_tc5_filter = v; }
 
-// Tensor-memory matcher; `per` (train descriptors per blockIdx.y) is a multiple of 128 chosen by the caller.
-int match_partial_tc5(cudaStream_t st, const unsigned char* q, int nq, const unsigned char* t, int nt, int tbase, int mode,
-                      int nsplit, akz_match_t* parts)
+// Tensor-memory matcher.  Writes plan->nparts partial results per query to `parts` (see the work decomposition above);
+// match_tc5_plan gives the number of slots so that the caller can size the buffer first.
+int match_tc5_plan(int nq, int nt, int* nsplit_out, int* tiles_out, int* per_cta_out, int* grid_out)
+{
+    static int nsm = 0;
+    if (const char* e = getenv("AKZ_TC5_MAX_TILES")) g_tc5_max_tiles = std::max(8, atoi(e) / 8 * 8);
+    if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); if (nsm <= 0) nsm = 148; }
+    const int nqb = (nq + T5_Q - 1) / T5_Q;
+    // items of at most g_tc5_max_tiles tiles: the rows of a tile are H = 2 T descriptors apart, and long ranges spread the 128 rows
+    // of every tile over the whole train set
+    const long long max_range = std::min<long long>(T5_MAX_RANGE, (long long)g_tc5_max_tiles * T5_N);
+    int nsplit = (int)(((long long)nt + max_range - 1) / max_range);
+    if (nsplit < 1) nsplit = 1;
+    int T = (int)((((long long)nt + nsplit - 1) / nsplit + T5_RANGE_UNIT - 1) / T5_RANGE_UNIT) * (T5_RANGE_UNIT / T5_N);
+    if (T < T5_RANGE_UNIT / T5_N) T = T5_RANGE_UNIT / T5_N;
+    const long long total = (long long)nqb * nsplit * T;
+    if (total >= (1ll << 30)) return akz_set_error(AKZ_E_UNSUPPORTED, "matching problem too large for one launch: shard the train set");
+    const int grid = (int)std::min<long long>(nsm, total);
+    const int S = (int)((total + grid - 1) / grid);
+    const int maxslots = (T + S - 1) / S + 1;
+    *nsplit_out = nsplit; *tiles_out = T; *per_cta_out = S; *grid_out = (int)((total + S - 1) / S);
+    return nsplit * maxslots;
+}
+
+int match_partial_tc5(cudaStream_t st, const unsigned char* q, int nq, const unsigned char* t, int nt, int tbase, int mode, akz_match_t* parts)
 {
     if (nq <= 0) return 0;
-    int per = (nt + nsplit - 1) / nsplit;
-    per = ((per + T5_RANGE_UNIT - 1) / T5_RANGE_UNIT) * T5_RANGE_UNIT;
-    if (per <= 0) per = T5_RANGE_UNIT;
-    if (per > T5_MAX_RANGE) return akz_set_error(AKZ_E_UNSUPPORTED, "train range per block exceeds 2^19 descriptors: raise the split or shard the train set");
+    int nsplit, T, S, grid;
+    const int nparts = match_tc5_plan(nq, nt, &nsplit, &T, &S, &grid);
+    if (nparts < 0) return nparts;
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_match_tc5<AKZ_MATCH_KNN2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM);
@@ -404,17 +506,18 @@ int match_partial_tc5(cudaStream_t st, const unsigned char* q, int nq, const uns
         cudaFuncSetAttribute(k_match_tc5<AKZ_MATCH_COMPAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM);
         attr = true;
     }
-    dim3 g((nq + T5_Q - 1) / T5_Q, nsplit);
+    T5Args a;
+    a.q = (const uint4*)q; a.t = (const uint4*)t; a.parts = parts; a.nq = nq; a.nt = nt; a.tbase = tbase;
+    a.T = T; a.nsplit = nsplit; a.S = S; a.total = ((nq + T5_Q - 1) / T5_Q) * nsplit * T; a.maxslots = nparts / nsplit;
     // a chunk rarely holds a new top-2 entry after ~2000 candidates; the reference-compatible state changes only on a new best
     // distance or a tie with it, which is rarer still: its filter pays off at every range length
-    const bool filter = g_tc5_filter < 0 ? (per >= 2048 || mode == AKZ_MATCH_COMPAT) : g_tc5_filter != 0;
-    const uint4 *q4 = (const uint4*)q, *t4 = (const uint4*)t;
+    const bool filter = g_tc5_filter < 0 ? (T * T5_N >= 2048 || mode == AKZ_MATCH_COMPAT) : g_tc5_filter != 0;
     if (mode != AKZ_MATCH_COMPAT) {
-        if (filter) k_match_tc5<AKZ_MATCH_KNN2, true><<<g, T5_NT, T5_SMEM, st>>>(q4, nq, t4, nt, tbase, per, parts);
-        else k_match_tc5<AKZ_MATCH_KNN2, false><<<g, T5_NT, T5_SMEM, st>>>(q4, nq, t4, nt, tbase, per, parts);
+        if (filter) k_match_tc5<AKZ_MATCH_KNN2, true><<<grid, T5_NT, T5_SMEM, st>>>(a);
+        else k_match_tc5<AKZ_MATCH_KNN2, false><<<grid, T5_NT, T5_SMEM, st>>>(a);
     } else {
-        if (filter) k_match_tc5<AKZ_MATCH_COMPAT, true><<<g, T5_NT, T5_SMEM, st>>>(q4, nq, t4, nt, tbase, per, parts);
-        else k_match_tc5<AKZ_MATCH_COMPAT, false><<<g, T5_NT, T5_SMEM, st>>>(q4, nq, t4, nt, tbase, per, parts);
+        if (filter) k_match_tc5<AKZ_MATCH_COMPAT, true><<<grid, T5_NT, T5_SMEM, st>>>(a);
+        else k_match_tc5<AKZ_MATCH_COMPAT, false><<<grid, T5_NT, T5_SMEM, st>>>(a);
     }
     return 1;
 }
