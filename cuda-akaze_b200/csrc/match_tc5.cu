@@ -318,24 +318,32 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const __grid_constant__ 
                     if (c == 0) tmem_ld32_pack16(taddr + 64, vb);      // in flight while the first half is processed
                     const int ordinal = 2 * j + c;
                     const unsigned ordinv = 8191u - (unsigned)ordinal;
-                    bool update = true;
-                    if (FILTER) {
-                        // packed maximum of the 64 accumulators; a key is acc << 13 | ordinv, so (max << 13) | 8191 bounds the keys
-                        unsigned m = __vimax3_u16x2(v[0], v[1], v[2]);
+                    // packed maximum of the 64 accumulators (even columns in the low halves, odd ones in the high halves)
+                    unsigned m = 0;
+                    if (FILTER || MODE != AKZ_MATCH_KNN2) {
+                        m = __vimax3_u16x2(v[0], v[1], v[2]);
 #pragma unroll
                         for (int i = 3; i + 1 < 32; i += 2) m = __vimax3_u16x2(m, v[i], v[i + 1]);
                         m = __vmaxu2(m, v[31]);
-                        const unsigned bound = (max(m & 0xFFFFu, m >> 16) << 13) | 8191u;
-                        update = (MODE == AKZ_MATCH_KNN2) ? (bound > max(be.k2, bo.k2)) : (bound >= (max(be.k1, bo.k1) & ~T5_EMASK));
+                        m = max(m & 0xFFFFu, m >> 16);
                     }
-                    if (update) {
-                        const unsigned classbit = 1u << ((unsigned)(a.tbase + ordinal) & 15u);   // H is a multiple of 16: one class per half tile
+                    if (MODE != AKZ_MATCH_KNN2) {
+                        // reference-compatible state = (best key, classes that attain the best distance).  H is a multiple of 16,
+                        // so the 64 columns of a half tile share their index class: only the best key of the chunk can change
+                        // the state, and one update per chunk is exact.
+                        consider5<MODE>(be, m * 8192u + ordinv, 1u << ((unsigned)(a.tbase + ordinal) & 15u));
+                    } else {
+                        // a key is acc << 13 | ordinv, so (max << 13) | 8191 bounds the keys of the chunk
+                        const bool update = !FILTER || ((m << 13) | 8191u) > max(be.k2, bo.k2);
+                        if (update) {
+                            // (a per-register test against the current second best was tried here: 32 divergent branches cost
+                            // more than the five-instruction pair updates they skip, 0.054 -> 0.069 ms at 10k x 10k)
 #pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            const unsigned k0 = (v[i] & 0xFFFFu) * 8192u + ordinv, k1 = (v[i] >> 16) * 8192u + ordinv;
-                            const unsigned k2 = (v[i + 1] & 0xFFFFu) * 8192u + ordinv, k3 = (v[i + 1] >> 16) * 8192u + ordinv;
-                            if (MODE == AKZ_MATCH_KNN2) { consider5_pair(be, k0, k1); consider5_pair(bo, k2, k3); }
-                            else { consider5<MODE>(be, k0, classbit); consider5<MODE>(bo, k1, classbit); consider5<MODE>(be, k2, classbit); consider5<MODE>(bo, k3, classbit); }
+                            for (int i = 0; i < 32; i += 2) {
+                                const unsigned k0 = (v[i] & 0xFFFFu) * 8192u + ordinv, k1 = (v[i] >> 16) * 8192u + ordinv;
+                                const unsigned k2 = (v[i + 1] & 0xFFFFu) * 8192u + ordinv, k3 = (v[i + 1] >> 16) * 8192u + ordinv;
+                                consider5_pair(be, k0, k1); consider5_pair(bo, k2, k3);
+                            }
                         }
                     }
                     if (c == 0) tmem_ld_wait();
