@@ -336,14 +336,26 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const __grid_constant__ 
                         // a key is acc << 13 | ordinv, so (max << 13) | 8191 bounds the keys of the chunk
                         const bool update = !FILTER || ((m << 13) | 8191u) > max(be.k2, bo.k2);
                         if (update) {
-                            // (a per-register test against the current second best was tried here: 32 divergent branches cost
-                            // more than the five-instruction pair updates they skip, 0.054 -> 0.069 ms at 10k x 10k)
+                            // top-2 of the chunk on packed 16-bit pairs (even columns in the low halves, odd ones in the high
+                            // halves; the accumulators of a chunk are distinct, they carry their column): 16 sorted pairs, then a
+                            // merge tree of three packed instructions per node -- 1.2 ALU instructions per column instead of 4.5
+                            // for unpacking every accumulator into a key.  Only the four winners become keys.
+                            // (a per-register test against the current second best was tried first: 32 divergent branches cost
+                            // more than the updates they skip.)
+                            unsigned hi[16], lo[16];
 #pragma unroll
-                            for (int i = 0; i < 32; i += 2) {
-                                const unsigned k0 = (v[i] & 0xFFFFu) * 8192u + ordinv, k1 = (v[i] >> 16) * 8192u + ordinv;
-                                const unsigned k2 = (v[i + 1] & 0xFFFFu) * 8192u + ordinv, k3 = (v[i + 1] >> 16) * 8192u + ordinv;
-                                consider5_pair(be, k0, k1); consider5_pair(bo, k2, k3);
+                            for (int i = 0; i < 16; i++) { hi[i] = __vmaxu2(v[2 * i], v[2 * i + 1]); lo[i] = __vminu2(v[2 * i], v[2 * i + 1]); }
+#pragma unroll
+                            for (int n = 16; n > 1; n >>= 1) {
+#pragma unroll
+                                for (int i = 0; i < n / 2; i++) {
+                                    const unsigned a1 = hi[2 * i], a2 = lo[2 * i], b1 = hi[2 * i + 1], b2 = lo[2 * i + 1];
+                                    hi[i] = __vmaxu2(a1, b1);
+                                    lo[i] = __vimax3_u16x2(__vminu2(a1, b1), a2, b2);
+                                }
                             }
+                            consider5_pair(be, (hi[0] & 0xFFFFu) * 8192u + ordinv, (lo[0] & 0xFFFFu) * 8192u + ordinv);
+                            consider5_pair(bo, (hi[0] >> 16) * 8192u + ordinv, (lo[0] >> 16) * 8192u + ordinv);
                         }
                     }
                     if (c == 0) tmem_ld_wait();
