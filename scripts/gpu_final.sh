@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 timeout 400 python bench.py > gpurun_out/bench_default_ours.json 2> gpurun_out/bench_default_ours.err; tail -c 400 gpurun_out/bench_default_ours.json; tail -3 gpurun_out/bench_default_ours.err
 timeout 400 python bench.py --impl reference > gpurun_out/bench_default_ref.json 2> gpurun_out/bench_default_ref.err; tail -c 300 gpurun_out/bench_default_ref.json; tail -3 gpurun_out/bench_default_ref.err
 timeout 700 bash scripts/gpu_ncu.sh $1 k_prep2 k_fed3
-for K in 1 3; do
+for K in 3; do
   python scripts/match_probe.py $K && ncu --set full --clock-control none --import-source on -k regex:k_match -c 1 -f -o gpurun_out/prof_$1_k_match_kernel$K python scripts/match_probe.py $K > gpurun_out/ncu_match_$1_$K.log 2>&1
   echo "match ncu $K rc=$?"
 done
