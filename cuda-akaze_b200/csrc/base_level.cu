@@ -272,11 +272,10 @@ int base_level2(cudaStream_t st, const void* img, int dtype, int w, int h, int i
                 float* lt, int pitch, long long plane, float* mag, unsigned* hmax_bits, int* hist, float var0, int ksz0, int n)
 {
     if (radius_from_ksz(ksz0) != 4 || w < 16 || h < 16) return 0;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;
+    if (akz_once_per_device(attr)) {
         cudaFuncSetAttribute(k_base2<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
         cudaFuncSetAttribute(k_base2<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
-        attr = true;
     }
     Base2Args a = {};
     a.img = img; a.lt = lt; a.mag = mag; a.hmax_bits = hmax_bits; a.istride = istride; a.plane = plane;

@@ -107,5 +107,16 @@ struct AkzLevelDev {
         if (e_ != cudaSuccess) return akz_set_cuda_error(e_, #expr, __FILE__, __LINE__); \
     } while (0)
 
+// cudaFuncSetAttribute is per device: true the first time it is asked on the current device (one process may drive several GPUs)
+inline bool akz_once_per_device(unsigned long long& mask)
+{
+    int d = 0;
+    cudaGetDevice(&d);
+    const unsigned long long bit = 1ull << (d & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
+
 int akz_set_cuda_error(cudaError_t e, const char* what, const char* file, int line);
 int akz_set_error(int code, const char* fmt, ...);

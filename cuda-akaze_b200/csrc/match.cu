@@ -387,11 +387,10 @@ int match_partial(cudaStream_t st, const unsigned char* q, int nq, const unsigne
     if (per <= 0) per = TILE;
     if (per >= (1 << KEY_IDX_BITS)) return akz_set_error(AKZ_E_UNSUPPORTED, "train range per block exceeds 2^22 descriptors: shard the train set");
     if (use_mma) {
-        static bool attr = false;
-        if (!attr) {
+        static unsigned long long attr = 0;
+        if (akz_once_per_device(attr)) {
             cudaFuncSetAttribute(k_match_mma<AKZ_MATCH_KNN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM);
             cudaFuncSetAttribute(k_match_mma<AKZ_MATCH_COMPAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM);
-            attr = true;
         }
         dim3 g((nq + MQ - 1) / MQ, nsplit);
         if (mode != AKZ_MATCH_COMPAT)

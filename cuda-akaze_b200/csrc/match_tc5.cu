@@ -518,13 +518,12 @@ int match_partial_tc5(cudaStream_t st, const unsigned char* q, int nq, const uns
     int nsplit, T, S, grid;
     const int nparts = match_tc5_plan(nq, nt, &nsplit, &T, &S, &grid);
     if (nparts < 0) return nparts;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;
+    if (akz_once_per_device(attr)) {
         cudaFuncSetAttribute(k_match_tc5<AKZ_MATCH_KNN2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM);
         cudaFuncSetAttribute(k_match_tc5<AKZ_MATCH_COMPAT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM);
         cudaFuncSetAttribute(k_match_tc5<AKZ_MATCH_KNN2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM);
         cudaFuncSetAttribute(k_match_tc5<AKZ_MATCH_COMPAT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM);
-        attr = true;
     }
     T5Args a;
     a.q = (const uint4*)q; a.t = (const uint4*)t; a.parts = parts; a.nq = nq; a.nt = nt; a.tbase = tbase;
