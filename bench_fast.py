@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--frames", type=int, default=64)
+    ap.add_argument("--frames", type=int, default=128)
     ap.add_argument("--chunk", type=int, default=32)
     ap.add_argument("--steps", type=int, default=3)
     args = ap.parse_args()
@@ -28,7 +28,7 @@ def main():
     F, W, H = args.frames, BN.W, BN.H
     frames8 = BN.make_frames(F, "shapes")
     dev = torch.from_numpy(frames8).cuda()
-    ctx = ab.Context(W, H, max_batch=args.chunk, max_pts=20000)
+    ctx = ab.Context(W, H, max_batch=args.chunk, max_pts=20000, lanes=2)
     res = ctx.alloc_results(F, True)
     stream = ctx.torch_stream()
     step = lambda: ctx.fast_detect_and_compute(dev, True, out=res)
@@ -37,7 +37,13 @@ def main():
     ctx.sync()
     ms = BN.timed(step, args.steps, stream, 1, dev.device)
     n = res[0].cpu().numpy()
-    print(json.dumps({"metric": "1080p integer-pipeline detect+describe images/sec", "impl": "ours", "value": round(F * args.steps / (ms * 1e-3), 2),
+    ctx.profile(True)
+    for f0 in range(0, F, args.chunk):
+        ctx.fast_detect_and_compute(dev[f0:f0 + args.chunk], True, out=tuple(r[f0:f0 + args.chunk] for r in res))
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    classes = {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0]) if v[0] > 0}
+    print(json.dumps({"metric": "1080p integer-pipeline detect+describe images/sec", "impl": "ours", "classes_ms_per_step": classes, "value": round(F * args.steps / (ms * 1e-3), 2),
                       "unit": "images/s", "ms_per_step": round(ms / args.steps, 3), "frames": F, "keypoints_per_frame_mean": round(float(n.mean()), 1),
                       "note": "one kernel per reference stage except the diffusion cycles (temporally blocked k_fed3<int>), batched, no host round trips"}), flush=True)
     ctx.close()

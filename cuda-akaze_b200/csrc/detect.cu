@@ -68,14 +68,13 @@ __global__ void __launch_bounds__(256) k_extrema(const __grid_constant__ AkzExtr
 // one block per (row, frame): radius NMS decision per pixel -> bit mask + row count
 __global__ void __launch_bounds__(256) k_nms_mark(const unsigned long long* __restrict__ map, int mpitch, long long mplane,
                                                   int W, int H, int psz, const __grid_constant__ AkzLevelTable tab,
-                                                  unsigned* __restrict__ rowmask, int mwords, int* __restrict__ rowcount)
+                                                  unsigned* __restrict__ rowmask, int mwords)
 {
     int iy = blockIdx.x + psz, frame = blockIdx.y;
     const unsigned long long* m = map + (long long)frame * mplane;
-    __shared__ int s_cnt;
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
-    int cnt = 0;
+    // (no block barrier: the row count is taken from the bit masks by k_row_scan.  With a shared counter and two
+    // __syncthreads every warp waited for the one warp of the row that walks an NMS neighbourhood: ncu r01j, 13 warps per
+    // issue stalled at the barrier)
     int xend = W - psz;                                   // ix + psz < W
     for (int x0 = 0; x0 < mwords * 32; x0 += 256) {
         int ix = x0 + threadIdx.x;
@@ -107,17 +106,13 @@ __global__ void __launch_bounds__(256) k_nms_mark(const unsigned long long* __re
         if ((threadIdx.x & 31) == 0) {
             int word = (x0 + threadIdx.x) >> 5;
             if (word < mwords) rowmask[((long long)frame * H + iy) * mwords + word] = b;
-            cnt += __popc(b);
         }
     }
-    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
-    __syncthreads();
-    if (threadIdx.x == 0) rowcount[(long long)frame * H + iy] = s_cnt;
 }
 
 // one block per frame: exclusive scan of the row counts (in place) -> per-frame total
-__global__ void __launch_bounds__(1024) k_row_scan(int* __restrict__ rowcount, int H, int psz, int* __restrict__ counts,
-                                                   int* __restrict__ totals, int max_pts)
+__global__ void __launch_bounds__(1024) k_row_scan(int* __restrict__ rowcount, const unsigned* __restrict__ rowmask, int mwords, int H, int psz,
+                                                   int* __restrict__ counts, int* __restrict__ totals, int max_pts)
 {
     __shared__ int warp_sums[32];
     __shared__ int carry;
@@ -128,7 +123,17 @@ __global__ void __launch_bounds__(1024) k_row_scan(int* __restrict__ rowcount, i
     int lo = psz, hi = H - psz;
     for (int base = lo; base < hi; base += 1024) {
         int y = base + threadIdx.x;
-        int v = (y < hi) ? rc[y] : 0;
+        int v = 0;
+        if (y < hi) {                                     // survivors of row y = set bits of its mask words
+            const unsigned* mw = rowmask + ((long long)frame * H + y) * mwords;
+            if ((mwords & 3) == 0) {                      // rows of 16-byte multiples: 128-bit loads, four in flight
+                const uint4* m4 = reinterpret_cast<const uint4*>(mw);
+#pragma unroll 4
+                for (int k = 0; k < mwords / 4; k++) { const uint4 q = __ldg(m4 + k); v += __popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w); }
+            } else {
+                for (int k = 0; k < mwords; k++) v += __popc(__ldg(mw + k));
+            }
+        }
         int incl = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -282,10 +287,10 @@ int nms_emit(cudaStream_t st, const unsigned long long* map, int mpitch, long lo
     int rows = H - 2 * psz;
     int launches = 0;
     if (rows > 0) {
-        k_nms_mark<<<dim3(rows, n), 256, 0, st>>>(map, mpitch, mplane, W, H, psz, tab, rowmask, mwords, rowcount);
+        k_nms_mark<<<dim3(rows, n), 256, 0, st>>>(map, mpitch, mplane, W, H, psz, tab, rowmask, mwords);
         launches++;
     }
-    k_row_scan<<<n, 1024, 0, st>>>(rowcount, H, rows > 0 ? psz : H, counts, prefix + n + 1, max_pts);
+    k_row_scan<<<n, 1024, 0, st>>>(rowcount, rowmask, mwords, H, rows > 0 ? psz : H, counts, prefix + n + 1, max_pts);
     k_frame_prefix<<<1, 32, 0, st>>>(counts, prefix, n);
     launches += 2;
     if (rows > 0) {
