@@ -45,7 +45,7 @@ def main():
     classes = {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0]) if v[0] > 0}
     print(json.dumps({"metric": "1080p integer-pipeline detect+describe images/sec", "impl": "ours", "classes_ms_per_step": classes, "value": round(F * args.steps / (ms * 1e-3), 2),
                       "unit": "images/s", "ms_per_step": round(ms / args.steps, 3), "frames": F, "keypoints_per_frame_mean": round(float(n.mean()), 1),
-                      "note": "one kernel per reference stage except the diffusion cycles (temporally blocked k_fed3<int>), batched, no host round trips"}), flush=True)
+                      "note": "fused level kernel k_prep2<.., INT> and temporally blocked k_fed3<int> of the float pipeline instantiated for int32 planes, two lanes, batched, no host round trips"}), flush=True)
     ctx.close()
     if B.have_ref():
         pitch = (W + 127) // 128 * 128

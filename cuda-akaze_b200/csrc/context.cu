@@ -501,22 +501,36 @@ static int fast_scale_space_chunk(akz_ctx* c, const unsigned char* img, int nf, 
     LAUNCHED(AKZ_K_BASE, akzk::fast_lowpass(st, img, 1, smooth, tA, w0, h0, ipitch, istride, p0, L0.plane, nf, 1.f, 5));
     LAUNCHED(AKZ_K_CONTRAST, akzk::fast_contrast(st, smooth, tB, ihmax, c->hist, ikc, o.per, o.fast_kcontrast_override, w0, h0, p0, L0.plane, nf));
     LAUNCHED(AKZ_K_BASE, akzk::fast_lowpass(st, img, 1, (int*)L0.lt, tA, w0, h0, ipitch, istride, p0, L0.plane, nf, var0, ksz0));
-    LAUNCHED(AKZ_K_HESSIAN, akzk::fast_hessian(st, (const int*)L0.lt, (int*)L0.lx, (int*)L0.ly, (int*)L0.det, L0.sigma_size, w0, h0, p0, L0.plane, nf));
+    // fused == 1: blur / octave transition + conductance + derivatives + determinant of a level in ONE kernel, the float
+    // pipeline's k_prep2 instantiated for the integer arithmetic (level_prep.cu); 0 = one kernel per reference stage
+    auto iprep = [&](int mode, const int* src, int sw, int sh, int sp, long long splane, int* ltdst, int* flowp, AkzLevel& L, int nmul) -> int {
+        if (o.fused != 1) return 0;
+        return akzk::level_prep2(st, mode, (const float*)src, sw, sh, sp, splane, (float*)ltdst, (float*)flowp, L.lx, L.ly, L.det, o.diffusivity,
+                                 c->kc, 0.75f, nmul, L.sigma_size, L.w, L.h, L.pitch, L.plane, nf, 1);
+    };
+    {
+        int r = 0;
+        LAUNCHED(AKZ_K_PREP, (r = iprep(0, (const int*)L0.lt, w0, h0, p0, L0.plane, nullptr, nullptr, L0, 0)));
+        if (r == 0) LAUNCHED(AKZ_K_HESSIAN, akzk::fast_hessian(st, (const int*)L0.lt, (int*)L0.lx, (int*)L0.ly, (int*)L0.det, L0.sigma_size, w0, h0, p0, L0.plane, nf));
+    }
     for (int l = 1; l < c->nlev; l++) {
         AkzLevel& L = c->lev[l];
         const float* tau = c->tau + L.tau_off;
         const int w = L.w, h = L.h, p = L.pitch;
         const int* cur;
+        int r = 0;
         if (L.sub == 0) {
             AkzLevel& P = c->lev[l - S];                                   // sublevel 0 of the previous octave (akaze.cpp:650)
-            LAUNCHED(AKZ_K_BLUR, akzk::fast_down(st, (const int*)P.lt, tB, smooth, P.w, P.h, P.pitch, P.plane, w, h, p, L.plane, nf));
+            LAUNCHED(AKZ_K_PREP, (r = iprep(2, (const int*)P.lt, P.w, P.h, P.pitch, P.plane, tB, flow, L, L.octave)));
+            if (r == 0) LAUNCHED(AKZ_K_BLUR, akzk::fast_down(st, (const int*)P.lt, tB, smooth, P.w, P.h, P.pitch, P.plane, w, h, p, L.plane, nf));
             cur = tB;
         } else {
             AkzLevel& P = c->lev[l - 1];
-            LAUNCHED(AKZ_K_BLUR, akzk::fast_lowpass(st, P.lt, 0, smooth, tA, w, h, p, L.plane, p, L.plane, nf, 1.f, 5));
+            LAUNCHED(AKZ_K_PREP, (r = iprep(1, (const int*)P.lt, w, h, p, L.plane, nullptr, flow, L, L.octave)));
+            if (r == 0) LAUNCHED(AKZ_K_BLUR, akzk::fast_lowpass(st, P.lt, 0, smooth, tA, w, h, p, L.plane, p, L.plane, nf, 1.f, 5));
             cur = (const int*)P.lt;
         }
-        LAUNCHED(AKZ_K_FLOW, akzk::fast_flow(st, smooth, flow, o.diffusivity, ikc, L.octave, w, h, p, L.plane, nf));
+        if (r == 0) LAUNCHED(AKZ_K_FLOW, akzk::fast_flow(st, smooth, flow, o.diffusivity, ikc, L.octave, w, h, p, L.plane, nf));
         if (o.fused == 1) {
             // the temporally blocked, register-resident FED kernel of the float pipeline, instantiated for int32 planes
             LAUNCHED(AKZ_K_FED, akzk::fed_cycle(st, (const float*)cur, (const float*)flow, L.lt, (float*)tA, tau, L.nsteps, w, h, p, L.plane, nf, 1, 1));
@@ -527,7 +541,7 @@ static int fast_scale_space_chunk(akz_ctx* c, const unsigned char* img, int nf, 
                 cur = out;
             }
         }
-        LAUNCHED(AKZ_K_HESSIAN, akzk::fast_hessian(st, smooth, (int*)L.lx, (int*)L.ly, (int*)L.det, L.sigma_size, w, h, p, L.plane, nf));
+        if (r == 0) LAUNCHED(AKZ_K_HESSIAN, akzk::fast_hessian(st, smooth, (int*)L.lx, (int*)L.ly, (int*)L.det, L.sigma_size, w, h, p, L.plane, nf));
     }
     c->last_frames = nf;
     return AKZ_OK;

@@ -62,7 +62,7 @@ int contrast_scan(cudaStream_t st, const unsigned* hmax_bits, const int* hist, f
 // (step, size) combination is not covered and the caller must use level_prep / level_prep_down.
 int level_prep2(cudaStream_t st, int mode, const float* src, int sw, int sh, int sp, long long splane,
                 float* ltdst, float* flowp, float* lx, float* ly, float* det, int type,
-                const float* kc, float kscale, int nmul, int step, int w, int h, int pitch, long long plane, int n);
+                const float* kc, float kscale, int nmul, int step, int w, int h, int pitch, long long plane, int n, int int_planes = 0);
 // all n FED steps of a level (frozen conductance), temporally blocked in shared memory
 int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst, float* tmp, const float* tau, int nsteps,
               int w, int h, int pitch, long long plane, int n, int fused, int int_planes = 0);

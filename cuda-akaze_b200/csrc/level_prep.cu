@@ -39,6 +39,7 @@ struct Prep2Args {
     const float* kc;                     // per-frame contrast factor
     long long splane, plane;
     float kscale, fac1, fac2, k0, k1, k2;
+    int ik0, ik1, ik2, ifac1, ifac2;     // INT: 16.16 fixed-point taps and derivative factors (akazed.cu:3896, :4184)
     int nmul, type, vec_ok;
     int sw, sh, sp;                      // source dims (== w, h, pitch unless PM_DOWN)
     int w, h, pitch;
@@ -64,6 +65,69 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_sr
 __device__ __forceinline__ void cp_async_wait_all()
 {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// ---- arithmetic of the two pipelines ---------------------------------------------------------------------------------------
+// INT = false: the float pipeline, pinned operation order of common.cuh.  INT = true: the integer pipeline (namespace fastakaze,
+// akazed.cu:2781-4366): planes are int32 whose bit patterns travel through the same float registers / shared-memory tiles;
+// every product sum is shifted right by 16, integer addition is associative, so only the truncation points matter.
+__device__ __forceinline__ int fi(float v) { return __float_as_int(v); }
+__device__ __forceinline__ float fb(int v) { return __int_as_float(v); }
+
+template <bool INT>
+__device__ __forceinline__ float p2_gauss(float m2, float m1, float c, float p1, float p2, const Prep2Args& a)
+{
+    if (!INT) return gauss_r2(m2, m1, c, p1, p2, a.k0, a.k1, a.k2);
+    return fb((a.ik0 * fi(c) + a.ik1 * (fi(m1) + fi(p1)) + a.ik2 * (fi(m2) + fi(p2))) >> 16);        // akazed.cu:2786-3076
+}
+// conductance of one pixel from its 3 x 3 neighbourhood of the smoothed level; ikc = 1 / k^2
+template <bool INT>
+__device__ __forceinline__ float p2_flow(float ul, float uc, float ur, float cl, float cr, float ll, float lc, float lr, int type, float ikc)
+{
+    if (!INT) {
+        float dx = scharr_dx(ul, ur, cl, cr, ll, lr);
+        float dy = scharr_dy(ul, uc, ur, ll, lc, lr);
+        return conductance(type, __fmul_rn(grad_sq(dx, dy), ikc));
+    }
+    // gFlowNaive akazed.cu:3406-3446, written in the reference's form (same contraction by nvcc as k_fflow)
+    const int dx = 10 * (fi(cr) - fi(cl)) + 3 * (fi(ur) + fi(lr) - fi(ul) - fi(ll));
+    const int dy = 10 * (fi(lc) - fi(uc)) + 3 * (fi(ll) + fi(lr) - fi(ul) - fi(ur));
+    const float dif2 = (dx * dx + dy * dy) * ikc;
+    int g;
+    if (type == 0) g = (int)(__expf(-dif2) * 65536 + 0.5f);
+    else if (type == 1) g = (int)(1.f / (1.f + dif2) * 65536 + 0.5f);
+    else if (type == 2) g = (int)((1.f - __expf(-3.315f / __powf(dif2, 4))) * 65536 + 0.5f);
+    else g = (int)(1.f / __fsqrt_rn(1.f + dif2) * 65536 + 0.5f);
+    return fb(g);
+}
+// first derivatives (x: sum_x / cr - cl, y: sum_y / lc - uc)
+template <bool INT>
+__device__ __forceinline__ void p2_deriv1(float ul, float uc, float ur, float cl, float cr, float ll, float lc, float lr, const Prep2Args& a, float& vx, float& vy)
+{
+    if (!INT) {
+        vx = deriv1(sum_x(ul, ur, ll, lr), __fsub_rn(cr, cl), a.fac1, a.fac2);
+        vy = deriv1(sum_y(ul, ur, ll, lr), __fsub_rn(lc, uc), a.fac1, a.fac2);
+    } else {                                                                                         // gDerivate akazed.cu:3339-3368
+        vx = fb((a.ifac1 * (fi(ur) + fi(lr) - fi(ul) - fi(ll)) + a.ifac2 * (fi(cr) - fi(cl))) >> 16);
+        vy = fb((a.ifac1 * (fi(lr) + fi(ll) - fi(ur) - fi(ul)) + a.ifac2 * (fi(lc) - fi(uc))) >> 16);
+    }
+}
+// determinant of the Hessian from the neighbourhoods of Lx (xu*, xc*, xl*) and Ly (yu*, yl*)
+template <bool INT>
+__device__ __forceinline__ float p2_det(float xul, float xuc, float xur, float xcl, float xcr, float xll, float xlc, float xlr,
+                                        float yul, float yuc, float yur, float yll, float ylc, float ylr, const Prep2Args& a)
+{
+    if (!INT) {
+        float dxx = deriv2(sum_x(xul, xur, xll, xlr), __fsub_rn(xcr, xcl), a.fac1, a.fac2);
+        float dxy = deriv2(sum_y(xul, xur, xll, xlr), __fsub_rn(xlc, xuc), a.fac1, a.fac2);
+        float dyy = deriv2(sum_y(yul, yur, yll, ylr), __fsub_rn(ylc, yuc), a.fac1, a.fac2);
+        return hess_det(dxx, dyy, dxy);
+    }
+    // gHessianDeterminant akazed.cu:3371-3403
+    const int dxx = (a.ifac1 * (fi(xur) + fi(xlr) - fi(xul) - fi(xll)) + a.ifac2 * (fi(xcr) - fi(xcl))) >> 16;
+    const int dxy = (a.ifac1 * (fi(xlr) + fi(xll) - fi(xur) - fi(xul)) + a.ifac2 * (fi(xlc) - fi(xuc))) >> 16;
+    const int dyy = (a.ifac1 * (fi(ylr) + fi(yll) - fi(yur) - fi(yul)) + a.ifac2 * (fi(ylc) - fi(yuc))) >> 16;
+    return fb(dxx * dyy - dxy * dxy);
 }
 
 // source-coordinate reflect of a coarse index (gDownWithSmooth reflects 2x+-2, 2x+-4 in the SOURCE image)
@@ -108,7 +172,7 @@ __device__ __forceinline__ void ghost_fix(float* T, int r0, int r1, int X0, int 
     }
 }
 
-template <int S, int MODE>
+template <int S, int MODE, bool INT>
 __global__ void __launch_bounds__(P2_NT, 3) k_prep2(const __grid_constant__ Prep2Args a)
 {
     constexpr int OY = 2 * S + 2;                     // shared-memory row of output row 0
@@ -172,7 +236,6 @@ __global__ void __launch_bounds__(P2_NT, 3) k_prep2(const __grid_constant__ Prep
     }
 
     if (MODE != PM_BASE) {
-        const float k0 = a.k0, k1 = a.k1, k2 = a.k2;
         // ---- 2. row pass: Bf[r][4..84) from A[r][2..86) -----------------------------------------------
         // (24 lanes per row, 20 active: a quarter-warp never straddles two rows, which would be a 2-way bank conflict)
         for (int i = tid; i < AR * 24; i += P2_NT) {
@@ -181,8 +244,8 @@ __global__ void __launch_bounds__(P2_NT, 3) k_prep2(const __grid_constant__ Prep
             const float* p = A + r * SP + 4 + 4 * g;
             float4 v0 = lds4(p - 4), v1 = lds4(p), v2 = lds4(p + 4);
             sts4(Bf + r * SP + 4 + 4 * g,
-                 gauss_r2(v0.z, v0.w, v1.x, v1.y, v1.z, k0, k1, k2), gauss_r2(v0.w, v1.x, v1.y, v1.z, v1.w, k0, k1, k2),
-                 gauss_r2(v1.x, v1.y, v1.z, v1.w, v2.x, k0, k1, k2), gauss_r2(v1.y, v1.z, v1.w, v2.x, v2.y, k0, k1, k2));
+                 p2_gauss<INT>(v0.z, v0.w, v1.x, v1.y, v1.z, a), p2_gauss<INT>(v0.w, v1.x, v1.y, v1.z, v1.w, a),
+                 p2_gauss<INT>(v1.x, v1.y, v1.z, v1.w, v2.x, a), p2_gauss<INT>(v1.y, v1.z, v1.w, v2.x, v2.y, a));
         }
         __syncthreads();
         // ---- 3. column pass: Sm rows [2, AR-2), two rows per item --------------------------------------
@@ -193,10 +256,10 @@ __global__ void __launch_bounds__(P2_NT, 3) k_prep2(const __grid_constant__ Prep
             const float* p = Bf + (r - 2) * SP + 4 + 4 * g;
             float4 b0 = lds4(p), b1 = lds4(p + SP), b2 = lds4(p + 2 * SP), b3 = lds4(p + 3 * SP), b4 = lds4(p + 4 * SP), b5 = lds4(p + 5 * SP);
             float* q = Sm + r * SP + 4 + 4 * g;
-            sts4(q, gauss_r2(b0.x, b1.x, b2.x, b3.x, b4.x, k0, k1, k2), gauss_r2(b0.y, b1.y, b2.y, b3.y, b4.y, k0, k1, k2),
-                 gauss_r2(b0.z, b1.z, b2.z, b3.z, b4.z, k0, k1, k2), gauss_r2(b0.w, b1.w, b2.w, b3.w, b4.w, k0, k1, k2));
-            sts4(q + SP, gauss_r2(b1.x, b2.x, b3.x, b4.x, b5.x, k0, k1, k2), gauss_r2(b1.y, b2.y, b3.y, b4.y, b5.y, k0, k1, k2),
-                 gauss_r2(b1.z, b2.z, b3.z, b4.z, b5.z, k0, k1, k2), gauss_r2(b1.w, b2.w, b3.w, b4.w, b5.w, k0, k1, k2));
+            sts4(q, p2_gauss<INT>(b0.x, b1.x, b2.x, b3.x, b4.x, a), p2_gauss<INT>(b0.y, b1.y, b2.y, b3.y, b4.y, a),
+                 p2_gauss<INT>(b0.z, b1.z, b2.z, b3.z, b4.z, a), p2_gauss<INT>(b0.w, b1.w, b2.w, b3.w, b4.w, a));
+            sts4(q + SP, p2_gauss<INT>(b1.x, b2.x, b3.x, b4.x, b5.x, a), p2_gauss<INT>(b1.y, b2.y, b3.y, b4.y, b5.y, a),
+                 p2_gauss<INT>(b1.z, b2.z, b3.z, b4.z, b5.z, a), p2_gauss<INT>(b1.w, b2.w, b3.w, b4.w, b5.w, a));
         }
         __syncthreads();
     }
@@ -207,9 +270,17 @@ __global__ void __launch_bounds__(P2_NT, 3) k_prep2(const __grid_constant__ Prep
 
     // ---- 4. conductance of the output pixels ----------------------------------------------------------
     if (a.flow) {
-        float k = a.kc[frame];
-        for (int i = 0; i < a.nmul; i++) k = __fmul_rn(k, a.kscale);
-        const float ikc = __fdiv_rn(1.f, __fmul_rn(k, k));
+        float ikc;
+        if (!INT) {
+            float k = a.kc[frame];
+            for (int i = 0; i < a.nmul; i++) k = __fmul_rn(k, a.kscale);
+            ikc = __fdiv_rn(1.f, __fmul_rn(k, k));
+        } else {
+            // integer contrast factor, scaled per octave as akaze.cpp:649 does on the host: k = (int)(k * 0.75f + 0.5f)
+            int k = reinterpret_cast<const int*>(a.kc)[frame];
+            for (int i = 0; i < a.nmul; i++) k = (int)__fadd_rn(__fmul_rn((float)k, 0.75f), 0.5f);
+            ikc = __fdiv_rn(1.f, (float)(k * k));                       // akazed.cu:4218 (host)
+        }
         float* fl = a.flow + (long long)frame * a.plane;
         for (int i = tid; i < P2_H * 16; i += P2_NT) {
             int r = i >> 4, g = i & 15;
@@ -232,9 +303,7 @@ __global__ void __launch_bounds__(P2_NT, 3) k_prep2(const __grid_constant__ Prep
             float o[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                float dx = scharr_dx(u[j], u[j + 2], c[j], c[j + 2], l[j], l[j + 2]);
-                float dy = scharr_dy(u[j], u[j + 1], u[j + 2], l[j], l[j + 1], l[j + 2]);
-                o[j] = conductance(a.type, __fmul_rn(grad_sq(dx, dy), ikc));
+                o[j] = p2_flow<INT>(u[j], u[j + 1], u[j + 2], c[j], c[j + 2], l[j], l[j + 1], l[j + 2], a.type, ikc);
             }
             int y = Y0 + r, x = X0 + 4 * g;
             float* d = fl + (long long)y * a.pitch + x;
@@ -248,7 +317,6 @@ __global__ void __launch_bounds__(P2_NT, 3) k_prep2(const __grid_constant__ Prep
 
     // ---- 5. first derivatives on the tile extended by S: rows [OY-S, OY+64+S), columns [8, 80) ----------
     {
-        const float fac1 = a.fac1, fac2 = a.fac2;
         float* lxg = a.lx + (long long)frame * a.plane;
         float* lyg = a.ly + (long long)frame * a.plane;
         for (int i = tid; i < (P2_H + 2 * S) * 24; i += P2_NT) {
@@ -269,8 +337,7 @@ __global__ void __launch_bounds__(P2_NT, 3) k_prep2(const __grid_constant__ Prep
             for (int j = 0; j < 4; j++) {
                 const int m = 4 + j;
                 float ul = u[m - S], uc = u[m], ur = u[m + S], cl = c[m - S], cr = c[m + S], ll = l[m - S], lc = l[m], lr = l[m + S];
-                vx[j] = deriv1(sum_x(ul, ur, ll, lr), __fsub_rn(cr, cl), fac1, fac2);
-                vy[j] = deriv1(sum_y(ul, ur, ll, lr), __fsub_rn(lc, uc), fac1, fac2);
+                p2_deriv1<INT>(ul, uc, ur, cl, cr, ll, lc, lr, a, vx[j], vy[j]);
             }
             sts4(LX + sr * SP + c4, vx[0], vx[1], vx[2], vx[3]);
             sts4(LY + sr * SP + c4, vy[0], vy[1], vy[2], vy[3]);
@@ -296,7 +363,6 @@ __global__ void __launch_bounds__(P2_NT, 3) k_prep2(const __grid_constant__ Prep
 
     // ---- 6. second derivatives and determinant ----------------------------------------------------------
     {
-        const float fac1 = a.fac1, fac2 = a.fac2;
         float* dg = a.det + (long long)frame * a.plane;
         for (int i = tid; i < P2_H * 16; i += P2_NT) {
             int r = i >> 4, g = i & 15;
@@ -316,10 +382,8 @@ __global__ void __launch_bounds__(P2_NT, 3) k_prep2(const __grid_constant__ Prep
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int m = 4 + j;
-                float dxx = deriv2(sum_x(xu[m - S], xu[m + S], xl[m - S], xl[m + S]), __fsub_rn(xc[m + S], xc[m - S]), fac1, fac2);
-                float dxy = deriv2(sum_y(xu[m - S], xu[m + S], xl[m - S], xl[m + S]), __fsub_rn(xl[m], xu[m]), fac1, fac2);
-                float dyy = deriv2(sum_y(yu[m - S], yu[m + S], yl[m - S], yl[m + S]), __fsub_rn(yl[m], yu[m]), fac1, fac2);
-                o[j] = hess_det(dxx, dyy, dxy);
+                o[j] = p2_det<INT>(xu[m - S], xu[m], xu[m + S], xc[m - S], xc[m + S], xl[m - S], xl[m], xl[m + S],
+                                   yu[m - S], yu[m], yu[m + S], yl[m - S], yl[m], yl[m + S], a);
             }
             int y = Y0 + r, x = X0 + 4 * g;
             float* d = dg + (long long)y * a.pitch + x;
@@ -335,22 +399,22 @@ __global__ void __launch_bounds__(P2_NT, 3) k_prep2(const __grid_constant__ Prep
 template <int S>
 constexpr int prep2_smem() { return 3 * (P2_H + 2 * (2 * S + 2)) * P2_SP * (int)sizeof(float); }
 
-template <int S, int MODE>
+template <int S, int MODE, bool INT>
 void prep2_launch(cudaStream_t st, const Prep2Args& a, int n)
 {
     static unsigned long long attr = 0;
-    if (akz_once_per_device(attr)) cudaFuncSetAttribute(k_prep2<S, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, prep2_smem<S>());
+    if (akz_once_per_device(attr)) cudaFuncSetAttribute(k_prep2<S, MODE, INT>, cudaFuncAttributeMaxDynamicSharedMemorySize, prep2_smem<S>());
     dim3 g((a.w + P2_W - 1) / P2_W, (a.h + P2_H - 1) / P2_H, n);
-    k_prep2<S, MODE><<<g, P2_NT, prep2_smem<S>(), st>>>(a);
+    k_prep2<S, MODE, INT><<<g, P2_NT, prep2_smem<S>(), st>>>(a);
 }
 
-template <int MODE>
+template <int MODE, bool INT>
 bool prep2_dispatch(cudaStream_t st, const Prep2Args& a, int step, int n)
 {
     switch (step) {
-    case 2: prep2_launch<2, MODE>(st, a, n); return true;
-    case 3: prep2_launch<3, MODE>(st, a, n); return true;
-    case 4: prep2_launch<4, MODE>(st, a, n); return true;
+    case 2: prep2_launch<2, MODE, INT>(st, a, n); return true;
+    case 3: prep2_launch<3, MODE, INT>(st, a, n); return true;
+    case 4: prep2_launch<4, MODE, INT>(st, a, n); return true;
     default: return false;
     }
 }
@@ -363,7 +427,7 @@ namespace akzk {
 // Returns 1 when launched, 0 when this (step, size) combination is not covered (caller falls back to k_level_prep).
 int level_prep2(cudaStream_t st, int mode, const float* src, int sw, int sh, int sp, long long splane,
                 float* ltdst, float* flowp, float* lx, float* ly, float* det, int type,
-                const float* kc, float kscale, int nmul, int step, int w, int h, int pitch, long long plane, int n)
+                const float* kc, float kscale, int nmul, int step, int w, int h, int pitch, long long plane, int n, int int_planes)
 {
     if (step < 2 || step > 4 || w < 24 || h < 24) return 0;       // reflections must stay single (halo <= 10 + 2)
     Prep2Args a = {};
@@ -377,8 +441,15 @@ int level_prep2(cudaStream_t st, int mode, const float* src, int sw, int sh, int
     auto al16 = [](const void* p) { return p == nullptr || ((uintptr_t)p % 16) == 0; };
     a.vec_ok = (pitch % 4 == 0) && (plane % 4 == 0) && (sp % 4 == 0) && (splane % 4 == 0) &&
                al16(src) && al16(flowp) && al16(lx) && al16(ly) && al16(det);
-    bool ok = mode == 0 ? prep2_dispatch<PM_BASE>(st, a, step, n) : mode == 1 ? prep2_dispatch<PM_BLUR>(st, a, step, n)
-                                                                              : prep2_dispatch<PM_DOWN>(st, a, step, n);
+    a.ik0 = (int)(k[0] * 65536 + 0.5f); a.ik1 = (int)(k[1] * 65536 + 0.5f); a.ik2 = (int)(k[2] * 65536 + 0.5f);      // akazed.cu:3896
+    a.ifac1 = (int)(a.fac1 * 65536 + 0.5f); a.ifac2 = (int)(a.fac2 * 65536 + 0.5f);                                  // akazed.cu:4184-4185
+    bool ok;
+    if (int_planes)
+        ok = mode == 0 ? prep2_dispatch<PM_BASE, true>(st, a, step, n) : mode == 1 ? prep2_dispatch<PM_BLUR, true>(st, a, step, n)
+                                                                                 : prep2_dispatch<PM_DOWN, true>(st, a, step, n);
+    else
+        ok = mode == 0 ? prep2_dispatch<PM_BASE, false>(st, a, step, n) : mode == 1 ? prep2_dispatch<PM_BLUR, false>(st, a, step, n)
+                                                                                  : prep2_dispatch<PM_DOWN, false>(st, a, step, n);
     return ok ? 1 : 0;
 }
 
