@@ -29,6 +29,7 @@ struct Base2Args {
     int w, h, ipitch, pitch, vec_ok;
     float a0, a1, a2, a3, a4;      // sigma0 taps (radius 4)
     float k0, k1, k2;              // sigma = 1 taps (radius 2)
+    int ia[5], ik[3];              // INT: the same taps in 16.16 fixed point (akazed.cu:3896)
 };
 
 __device__ __forceinline__ float4 lds4(const float* p)
@@ -60,7 +61,38 @@ __device__ __forceinline__ float gauss_r4(float m4, float m3, float m2, float m1
 __device__ __forceinline__ float to_unit(float v) { return v; }
 __device__ __forceinline__ float to_unit(unsigned char v) { return u8_to_unit(v); }
 
-template <typename Tin>
+// INT = true: the integer pipeline's base level (fastakaze, akaze.cpp:593-617): pixels stay 0..255 integers whose bit patterns
+// travel through the float tiles; a blur pass is (k0 x0 + sum ki (x-i + x+i)) >> 16 (gConv2d akazed.cu:2786-3076), the gradient
+// magnitude (int)(sqrt(dx^2 + dy^2) + 0.5f) (gScharrContrastNaive akazed.cu:3208-3231).  Integer sums are associative.
+__device__ __forceinline__ int b2i(float v) { return __float_as_int(v); }
+template <bool INT, typename T> __device__ __forceinline__ float b2_px(T v) { return INT ? __int_as_float((int)v) : to_unit(v); }
+template <bool INT>
+__device__ __forceinline__ float b2_gauss2(float m2, float m1, float c, float p1, float p2, const Base2Args& a)
+{
+    if (!INT) return gauss_r2(m2, m1, c, p1, p2, a.k0, a.k1, a.k2);
+    return __int_as_float((a.ik[0] * b2i(c) + a.ik[1] * (b2i(m1) + b2i(p1)) + a.ik[2] * (b2i(m2) + b2i(p2))) >> 16);
+}
+template <bool INT>
+__device__ __forceinline__ float b2_gauss4(float m4, float m3, float m2, float m1, float c, float p1, float p2, float p3, float p4, const Base2Args& a)
+{
+    if (!INT) return gauss_r4(m4, m3, m2, m1, c, p1, p2, p3, p4, a.a0, a.a1, a.a2, a.a3, a.a4);
+    return __int_as_float((a.ia[0] * b2i(c) + a.ia[1] * (b2i(m1) + b2i(p1)) + a.ia[2] * (b2i(m2) + b2i(p2)) + a.ia[3] * (b2i(m3) + b2i(p3)) +
+                           a.ia[4] * (b2i(m4) + b2i(p4))) >> 16);
+}
+template <bool INT>
+__device__ __forceinline__ float b2_mag(float ul, float uc, float ur, float cl, float cr, float ll, float lc, float lr)
+{
+    if (!INT) {
+        float dx = scharr_dx(ul, ur, cl, cr, ll, lr);
+        float dy = scharr_dy(ul, uc, ur, ll, lc, lr);
+        return __fsqrt_rn(grad_sq(dx, dy));
+    }
+    const int dx = 10 * (b2i(cr) - b2i(cl)) + 3 * (b2i(ur) + b2i(lr) - b2i(ul) - b2i(ll));
+    const int dy = 10 * (b2i(lc) - b2i(uc)) + 3 * (b2i(ll) + b2i(lr) - b2i(ul) - b2i(ur));
+    return __int_as_float((int)(__fsqrt_rn(dx * dx + dy * dy) + 0.5f));
+}
+
+template <typename Tin, bool INT>
 __global__ void __launch_bounds__(B2_NT, 2) k_base2(const __grid_constant__ Base2Args a)
 {
     constexpr int SP = B2_SP;
@@ -87,14 +119,14 @@ __global__ void __launch_bounds__(B2_NT, 2) k_base2(const __grid_constant__ Base
             int r = i / (SP / 8), g = i - r * (SP / 8);
             uint2 v = __ldg(reinterpret_cast<const uint2*>((const unsigned char*)src + (long long)(Y0 - 4 + r) * a.ipitch + (X0 - B2_O + 8 * g)));
             float* d = In + r * SP + 8 * g;
-            sts4(d, u8_to_unit((unsigned char)(v.x)), u8_to_unit((unsigned char)(v.x >> 8)), u8_to_unit((unsigned char)(v.x >> 16)), u8_to_unit((unsigned char)(v.x >> 24)));
-            sts4(d + 4, u8_to_unit((unsigned char)(v.y)), u8_to_unit((unsigned char)(v.y >> 8)), u8_to_unit((unsigned char)(v.y >> 16)), u8_to_unit((unsigned char)(v.y >> 24)));
+            sts4(d, b2_px<INT>((unsigned char)(v.x)), b2_px<INT>((unsigned char)(v.x >> 8)), b2_px<INT>((unsigned char)(v.x >> 16)), b2_px<INT>((unsigned char)(v.x >> 24)));
+            sts4(d + 4, b2_px<INT>((unsigned char)(v.y)), b2_px<INT>((unsigned char)(v.y >> 8)), b2_px<INT>((unsigned char)(v.y >> 16)), b2_px<INT>((unsigned char)(v.y >> 24)));
         }
     } else {
         for (int i = tid; i < B2_R * SP; i += B2_NT) {
             int r = i / SP, c = i - r * SP;
             int sy = min(max(refl(Y0 - 4 + r, h), 0), h - 1), sx = min(max(refl(X0 - B2_O + c, w), 0), w - 1);
-            In[i] = to_unit(__ldg(src + (long long)sy * a.ipitch + sx));
+            In[i] = b2_px<INT>(__ldg(src + (long long)sy * a.ipitch + sx));
         }
     }
     __syncthreads();
@@ -108,13 +140,13 @@ __global__ void __launch_bounds__(B2_NT, 2) k_base2(const __grid_constant__ Base
         const float e[12] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w };
         float o1[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) o1[j] = gauss_r2(e[2 + j], e[3 + j], e[4 + j], e[5 + j], e[6 + j], a.k0, a.k1, a.k2);
+        for (int j = 0; j < 4; j++) o1[j] = b2_gauss2<INT>(e[2 + j], e[3 + j], e[4 + j], e[5 + j], e[6 + j], a);
         sts4(R1 + r * SP + 4 + 4 * g, o1[0], o1[1], o1[2], o1[3]);
         if (g >= 1 && g <= 16) {
             float o0[4];
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                o0[j] = gauss_r4(e[j], e[1 + j], e[2 + j], e[3 + j], e[4 + j], e[5 + j], e[6 + j], e[7 + j], e[8 + j], a.a0, a.a1, a.a2, a.a3, a.a4);
+                o0[j] = b2_gauss4<INT>(e[j], e[1 + j], e[2 + j], e[3 + j], e[4 + j], e[5 + j], e[6 + j], e[7 + j], e[8 + j], a);
             sts4(R0 + r * SP + 4 + 4 * g, o0[0], o0[1], o0[2], o0[3]);
         }
     }
@@ -133,10 +165,10 @@ __global__ void __launch_bounds__(B2_NT, 2) k_base2(const __grid_constant__ Base
             float o[2][4];
 #pragma unroll
             for (int t = 0; t < 2; t++) {
-                o[t][0] = gauss_r4(q[t].x, q[t + 1].x, q[t + 2].x, q[t + 3].x, q[t + 4].x, q[t + 5].x, q[t + 6].x, q[t + 7].x, q[t + 8].x, a.a0, a.a1, a.a2, a.a3, a.a4);
-                o[t][1] = gauss_r4(q[t].y, q[t + 1].y, q[t + 2].y, q[t + 3].y, q[t + 4].y, q[t + 5].y, q[t + 6].y, q[t + 7].y, q[t + 8].y, a.a0, a.a1, a.a2, a.a3, a.a4);
-                o[t][2] = gauss_r4(q[t].z, q[t + 1].z, q[t + 2].z, q[t + 3].z, q[t + 4].z, q[t + 5].z, q[t + 6].z, q[t + 7].z, q[t + 8].z, a.a0, a.a1, a.a2, a.a3, a.a4);
-                o[t][3] = gauss_r4(q[t].w, q[t + 1].w, q[t + 2].w, q[t + 3].w, q[t + 4].w, q[t + 5].w, q[t + 6].w, q[t + 7].w, q[t + 8].w, a.a0, a.a1, a.a2, a.a3, a.a4);
+                o[t][0] = b2_gauss4<INT>(q[t].x, q[t + 1].x, q[t + 2].x, q[t + 3].x, q[t + 4].x, q[t + 5].x, q[t + 6].x, q[t + 7].x, q[t + 8].x, a);
+                o[t][1] = b2_gauss4<INT>(q[t].y, q[t + 1].y, q[t + 2].y, q[t + 3].y, q[t + 4].y, q[t + 5].y, q[t + 6].y, q[t + 7].y, q[t + 8].y, a);
+                o[t][2] = b2_gauss4<INT>(q[t].z, q[t + 1].z, q[t + 2].z, q[t + 3].z, q[t + 4].z, q[t + 5].z, q[t + 6].z, q[t + 7].z, q[t + 8].z, a);
+                o[t][3] = b2_gauss4<INT>(q[t].w, q[t + 1].w, q[t + 2].w, q[t + 3].w, q[t + 4].w, q[t + 5].w, q[t + 6].w, q[t + 7].w, q[t + 8].w, a);
             }
 #pragma unroll
             for (int t = 0; t < 2; t++) {
@@ -160,10 +192,10 @@ __global__ void __launch_bounds__(B2_NT, 2) k_base2(const __grid_constant__ Base
         const float* p = R1 + (r - 2) * SP + 4 + 4 * g;
         float4 b0 = lds4(p), b1 = lds4(p + SP), b2 = lds4(p + 2 * SP), b3 = lds4(p + 3 * SP), b4 = lds4(p + 4 * SP), b5 = lds4(p + 5 * SP);
         float* q = In + r * SP + 4 + 4 * g;
-        sts4(q, gauss_r2(b0.x, b1.x, b2.x, b3.x, b4.x, a.k0, a.k1, a.k2), gauss_r2(b0.y, b1.y, b2.y, b3.y, b4.y, a.k0, a.k1, a.k2),
-             gauss_r2(b0.z, b1.z, b2.z, b3.z, b4.z, a.k0, a.k1, a.k2), gauss_r2(b0.w, b1.w, b2.w, b3.w, b4.w, a.k0, a.k1, a.k2));
-        sts4(q + SP, gauss_r2(b1.x, b2.x, b3.x, b4.x, b5.x, a.k0, a.k1, a.k2), gauss_r2(b1.y, b2.y, b3.y, b4.y, b5.y, a.k0, a.k1, a.k2),
-             gauss_r2(b1.z, b2.z, b3.z, b4.z, b5.z, a.k0, a.k1, a.k2), gauss_r2(b1.w, b2.w, b3.w, b4.w, b5.w, a.k0, a.k1, a.k2));
+        sts4(q, b2_gauss2<INT>(b0.x, b1.x, b2.x, b3.x, b4.x, a), b2_gauss2<INT>(b0.y, b1.y, b2.y, b3.y, b4.y, a),
+             b2_gauss2<INT>(b0.z, b1.z, b2.z, b3.z, b4.z, a), b2_gauss2<INT>(b0.w, b1.w, b2.w, b3.w, b4.w, a));
+        sts4(q + SP, b2_gauss2<INT>(b1.x, b2.x, b3.x, b4.x, b5.x, a), b2_gauss2<INT>(b1.y, b2.y, b3.y, b4.y, b5.y, a),
+             b2_gauss2<INT>(b1.z, b2.z, b3.z, b4.z, b5.z, a), b2_gauss2<INT>(b1.w, b2.w, b3.w, b4.w, b5.w, a));
     }
     __syncthreads();
 
@@ -191,9 +223,7 @@ __global__ void __launch_bounds__(B2_NT, 2) k_base2(const __grid_constant__ Base
             int y = Y0 + r, x = X0 + 4 * g;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                float dx = scharr_dx(u[j], u[j + 2], c[j], c[j + 2], l[j], l[j + 2]);
-                float dy = scharr_dy(u[j], u[j + 1], u[j + 2], l[j], l[j + 1], l[j + 2]);
-                o[j] = __fsqrt_rn(grad_sq(dx, dy));
+                o[j] = b2_mag<INT>(u[j], u[j + 1], u[j + 2], c[j], c[j + 2], l[j], l[j + 1], l[j + 2]);
                 if (y < h && x + j < w) best = max(best, __float_as_uint(o[j]));      // o >= 0: bit patterns order like the floats
             }
             float* d = mg + (long long)y * a.pitch + x;
@@ -269,13 +299,15 @@ namespace akzk {
 // Fused base level: Lt(0,0) and (unless mag == nullptr) the gradient-magnitude plane + per-frame maximum + histogram.
 // Covers sigma0 kernels of radius 4 (ksz0 = 9, the reference default soffset = 1.6); returns 0 when not applicable.
 int base_level2(cudaStream_t st, const void* img, int dtype, int w, int h, int ipitch, long long istride,
-                float* lt, int pitch, long long plane, float* mag, unsigned* hmax_bits, int* hist, float var0, int ksz0, int n)
+                float* lt, int pitch, long long plane, float* mag, unsigned* hmax_bits, int* hist, float var0, int ksz0, int n, int int_planes)
 {
     if (radius_from_ksz(ksz0) != 4 || w < 16 || h < 16) return 0;
+    if (int_planes && dtype != AKZ_U8) return 0;
     static unsigned long long attr = 0;
     if (akz_once_per_device(attr)) {
-        cudaFuncSetAttribute(k_base2<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
-        cudaFuncSetAttribute(k_base2<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
+        cudaFuncSetAttribute(k_base2<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
+        cudaFuncSetAttribute(k_base2<unsigned char, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
+        cudaFuncSetAttribute(k_base2<unsigned char, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
     }
     Base2Args a = {};
     a.img = img; a.lt = lt; a.mag = mag; a.hmax_bits = hmax_bits; a.istride = istride; a.plane = plane;
@@ -285,14 +317,21 @@ int base_level2(cudaStream_t st, const void* img, int dtype, int w, int h, int i
     akz_gauss_taps(1.f, 2, t1);
     a.a0 = t0[0]; a.a1 = t0[1]; a.a2 = t0[2]; a.a3 = t0[3]; a.a4 = t0[4];
     a.k0 = t1[0]; a.k1 = t1[1]; a.k2 = t1[2];
+    for (int i = 0; i < 5; i++) a.ia[i] = (int)(t0[i] * 65536 + 0.5f);           // akazed.cu:3896 (kernel * 65536 is exact)
+    for (int i = 0; i < 3; i++) a.ik[i] = (int)(t1[i] * 65536 + 0.5f);
     const size_t esz = dtype == AKZ_U8 ? 1 : 4;
     a.vec_ok = (pitch % 4 == 0) && (plane % 4 == 0) && ((uintptr_t)lt % 16 == 0) && (mag == nullptr || (uintptr_t)mag % 16 == 0) &&
                ((uintptr_t)img % 16 == 0) && (((size_t)ipitch * esz) % 16 == 0) && (((size_t)istride * esz) % 16 == 0);
     int launches = 0;
-    if (mag) { int tot = n * AKZ_NBINS; k_contrast_init2<<<(tot + 255) / 256, 256, 0, st>>>(hmax_bits, hist, n); launches++; }
     dim3 g((w + B2_T - 1) / B2_T, (h + B2_T - 1) / B2_T, n);
-    if (dtype == AKZ_U8) k_base2<unsigned char><<<g, B2_NT, B2_SMEM, st>>>(a);
-    else k_base2<float><<<g, B2_NT, B2_SMEM, st>>>(a);
+    if (int_planes) {
+        // integer pipeline: the caller zeroes the maximum / histogram before and runs the integer histogram + scan after
+        k_base2<unsigned char, true><<<g, B2_NT, B2_SMEM, st>>>(a);
+        return 1;
+    }
+    if (mag) { int tot = n * AKZ_NBINS; k_contrast_init2<<<(tot + 255) / 256, 256, 0, st>>>(hmax_bits, hist, n); launches++; }
+    if (dtype == AKZ_U8) k_base2<unsigned char, false><<<g, B2_NT, B2_SMEM, st>>>(a);
+    else k_base2<float, false><<<g, B2_NT, B2_SMEM, st>>>(a);
     launches++;
     if (mag) {
         k_hist2<<<dim3((h + 7) / 8, n), 256, 0, st>>>(mag, hmax_bits, hist, w, h, pitch, plane, a.vec_ok);

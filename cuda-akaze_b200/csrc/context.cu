@@ -498,9 +498,24 @@ static int fast_scale_space_chunk(akz_ctx* c, const unsigned char* img, int nf, 
     const float var0 = o.soffset * o.soffset;
     const int ksz0 = (int)(2 * ceilf((o.soffset - 0.8f) / 0.3f) + 3);
     // level (0,0): akaze.cpp:593-617
-    LAUNCHED(AKZ_K_BASE, akzk::fast_lowpass(st, img, 1, smooth, tA, w0, h0, ipitch, istride, p0, L0.plane, nf, 1.f, 5));
-    LAUNCHED(AKZ_K_CONTRAST, akzk::fast_contrast(st, smooth, tB, ihmax, c->hist, ikc, o.per, o.fast_kcontrast_override, w0, h0, p0, L0.plane, nf));
-    LAUNCHED(AKZ_K_BASE, akzk::fast_lowpass(st, img, 1, (int*)L0.lt, tA, w0, h0, ipitch, istride, p0, L0.plane, nf, var0, ksz0));
+    bool base_done = false;
+    if (o.fused == 1) {
+        // one pass over the input (the float pipeline's k_base2 instantiated for the integer arithmetic): Lt(0,0), the gradient
+        // magnitude plane of the sigma = 1 blur and its maximum; then the integer histogram and the percentile scan
+        int r = 0;
+        LAUNCHED(AKZ_K_CONTRAST, akzk::fast_contrast_init(st, ihmax, c->hist, nf));
+        LAUNCHED(AKZ_K_BASE, (r = akzk::base_level2(st, img, AKZ_U8, w0, h0, ipitch, istride, L0.lt, p0, L0.plane,
+                                                    o.fast_kcontrast_override > 0 ? nullptr : (float*)tB, (unsigned*)ihmax, c->hist, var0, ksz0, nf, 1)));
+        if (r > 0) {
+            base_done = true;
+            LAUNCHED(AKZ_K_CONTRAST, akzk::fast_contrast_tail(st, tB, ihmax, c->hist, ikc, o.per, o.fast_kcontrast_override, w0, h0, p0, L0.plane, nf));
+        }
+    }
+    if (!base_done) {
+        LAUNCHED(AKZ_K_BASE, akzk::fast_lowpass(st, img, 1, smooth, tA, w0, h0, ipitch, istride, p0, L0.plane, nf, 1.f, 5));
+        LAUNCHED(AKZ_K_CONTRAST, akzk::fast_contrast(st, smooth, tB, ihmax, c->hist, ikc, o.per, o.fast_kcontrast_override, w0, h0, p0, L0.plane, nf));
+        LAUNCHED(AKZ_K_BASE, akzk::fast_lowpass(st, img, 1, (int*)L0.lt, tA, w0, h0, ipitch, istride, p0, L0.plane, nf, var0, ksz0));
+    }
     // fused == 1: blur / octave transition + conductance + derivatives + determinant of a level in ONE kernel, the float
     // pipeline's k_prep2 instantiated for the integer arithmetic (level_prep.cu); 0 = one kernel per reference stage
     auto iprep = [&](int mode, const int* src, int sw, int sh, int sp, long long splane, int* ltdst, int* flowp, AkzLevel& L, int nmul) -> int {

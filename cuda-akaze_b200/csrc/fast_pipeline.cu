@@ -280,6 +280,25 @@ int fast_contrast(cudaStream_t st, const int* src, int* mag, int* hmax, int* his
     return launches;
 }
 
+int fast_contrast_init(cudaStream_t st, int* hmax, int* hist, int n)
+{
+    int tot = n * AKZ_NBINS;
+    k_finit<<<(tot + 255) / 256, 256, 0, st>>>(hmax, hist, n);
+    return 1;
+}
+
+int fast_contrast_tail(cudaStream_t st, const int* mag, const int* hmax, int* hist, int* kout, float per, int override_k,
+                       int w, int h, int pitch, long long stride, int n)
+{
+    int launches = 1;
+    if (override_k <= 0) {
+        k_fhist<<<dim3((w + FBX - 1) / FBX, (h + 4 * FBY - 1) / (4 * FBY), n), dim3(FBX, FBY), 0, st>>>(mag, hmax, hist, w, h, pitch, stride);
+        launches++;
+    }
+    k_fscan<<<(n + 63) / 64, 64, 0, st>>>(hist, hmax, kout, per, w, h, n, override_k);
+    return launches;
+}
+
 int fast_flow(cudaStream_t st, const int* src, int* flow, int type, const int* kc, int nmul, int w, int h, int pitch, long long stride, int n)
 {
     k_fflow<<<fgrid(w, h, n), dim3(FBX, FBY), 0, st>>>(src, flow, type, kc, nmul, w, h, pitch, stride);

@@ -55,7 +55,7 @@ int level_prep_down(cudaStream_t st, const float* ltsrc, int sw, int sh, int sp,
 // base_level.cu: Lt(0,0), gradient-magnitude plane, its maximum and histogram in one pass over the input (+ one over the
 // magnitude plane).  Returns the number of launches, 0 when the sigma0 radius is not 4 (caller uses the staged kernels).
 int base_level2(cudaStream_t st, const void* img, int dtype, int w, int h, int ipitch, long long istride,
-                float* lt, int pitch, long long plane, float* mag, unsigned* hmax_bits, int* hist, float var0, int ksz0, int n);
+                float* lt, int pitch, long long plane, float* mag, unsigned* hmax_bits, int* hist, float var0, int ksz0, int n, int int_planes = 0);
 int contrast_scan(cudaStream_t st, const unsigned* hmax_bits, const int* hist, float* kout, float per, float override_k, int w, int h, int n);
 // level_prep.cu: second-generation level kernel (templated on the derivative step, 64x64 tiles, vector shared-memory
 // traffic).  mode 0 = base level (no blur), 1 = blur, 2 = octave transition.  Returns 1 if launched, 0 if the
@@ -72,6 +72,10 @@ int fast_lowpass(cudaStream_t st, const void* src, int src_u8, int* dst, int* tm
                  int dp, long long dstride, int n, float var, int ksz);
 int fast_down(cudaStream_t st, const int* src, int* dst, int* smooth, int sw, int sh, int sp, long long sstride,
               int dw, int dh, int dp, long long dstride, int n);
+// fast_contrast split for the fused integer base level: zero the maximum / histogram; histogram of a magnitude plane + scan
+int fast_contrast_init(cudaStream_t st, int* hmax, int* hist, int n);
+int fast_contrast_tail(cudaStream_t st, const int* mag, const int* hmax, int* hist, int* kout, float per, int override_k,
+                       int w, int h, int pitch, long long stride, int n);
 int fast_contrast(cudaStream_t st, const int* src, int* mag, int* hmax, int* hist, int* kout, float per, int override_k,
                   int w, int h, int pitch, long long stride, int n);
 int fast_flow(cudaStream_t st, const int* src, int* flow, int type, const int* kc, int nmul, int w, int h, int pitch, long long stride, int n);
