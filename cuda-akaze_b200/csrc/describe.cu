@@ -244,7 +244,19 @@ __global__ void __launch_bounds__(64) k_describe(const __grid_constant__ AkzLeve
 //   * the reduction is transposed: thread v owns output value v and evaluates the reference's tree itself,
 //     a_t = acc_t + acc_{t+32}, then the shuffle-down pairing ((a0+a1)+(a2+a3))+... serially from shared memory
 //     (row stride 65: conflict-free both for the per-thread accumulation columns and for the transposed reads).
-template <int PAT>
+template <bool INT> __device__ __forceinline__ float dsum(float a, float b)
+{
+    return INT ? __int_as_float(__float_as_int(a) + __float_as_int(b)) : __fadd_rn(a, b);
+}
+template <bool INT> __device__ __forceinline__ bool dgreater(float a, float b)
+{
+    return INT ? __float_as_int(a) > __float_as_int(b) : a > b;
+}
+
+// INT = true: the integer pipeline's M-LDB (gDescribe2 akazed.cu:3723-3855): int planes (bit patterns in the float registers and
+// accumulators), sample positions and rotated derivatives in the reference's own float expressions truncated to int, int
+// cell sums (associative: any reduction order), int comparisons.
+template <int PAT, bool INT>
 __global__ void __launch_bounds__(64) k_describe_t(const __grid_constant__ AkzLevelTable tab, const int* __restrict__ prefix, int nframes,
                                                    const akz_keypoint* __restrict__ kpts, unsigned char* __restrict__ desc, int max_pts)
 {
@@ -278,7 +290,8 @@ __global__ void __launch_bounds__(64) k_describe_t(const __grid_constant__ AkzLe
         const int o = L.octave, p = L.pitch;
         const float iratio = 1.f / (1 << o);
         const float fscale = (float)(int)__fadd_rn(kp->size, 0.5f);
-        const float xf = __fmul_rn(kp->x, iratio), yf = __fmul_rn(kp->y, iratio);
+        const int iscale = (int)(kp->size + 0.5f);
+        const float xf = INT ? kp->x * iratio : __fmul_rn(kp->x, iratio), yf = INT ? kp->y * iratio : __fmul_rn(kp->y, iratio);
         const float ang = kp->angle;
         const float co = __cosf(ang), si = __sinf(ang);
         K.co = co; K.si = si;
@@ -292,8 +305,15 @@ __global__ void __launch_bounds__(64) k_describe_t(const __grid_constant__ AkzLe
             if (i < NS) {
                 int y = i / WIN, x = i - WIN * y;
                 float l = (float)(x - S2), kk = (float)(y - S2);
-                int xp = (int)__fadd_rn(__fmaf_rn(fscale, __fmaf_rn(co, kk, -__fmul_rn(si, l)), xf), 0.5f);
-                int yp = (int)__fadd_rn(__fmaf_rn(fscale, __fmaf_rn(si, kk, __fmul_rn(co, l)), yf), 0.5f);
+                int xp, yp;
+                if (!INT) {
+                    xp = (int)__fadd_rn(__fmaf_rn(fscale, __fmaf_rn(co, kk, -__fmul_rn(si, l)), xf), 0.5f);
+                    yp = (int)__fadd_rn(__fmaf_rn(fscale, __fmaf_rn(si, kk, __fmul_rn(co, l)), yf), 0.5f);
+                } else {                                                   // the reference's expressions, as k_describe_int writes them
+                    const int li = x - S2, ki = y - S2;
+                    xp = (int)(xf + iscale * (ki * co - li * si) + 0.5f);
+                    yp = (int)(yf + iscale * (ki * si + li * co) + 0.5f);
+                }
                 xp = min(max(xp, 0), L.w - 1); yp = min(max(yp, 0), L.h - 1);       // no-op for in-range patches (border test)
                 long long pos = (long long)yp * p + xp;
                 im[k] = __ldg(imd + pos); dx[k] = __ldg(dxd + pos); dy[k] = __ldg(dyd + pos);
@@ -320,8 +340,15 @@ __global__ void __launch_bounds__(64) k_describe_t(const __grid_constant__ AkzLe
             int i = tix + 64 * k;
             if (i < NS) {
                 int y = i / WIN, x = i - WIN * y, m = max(x, y);
-                float rx = __fmaf_rn(co, dy[k], -__fmul_rn(si, dx[k]));
-                float ry = __fmaf_rn(co, dx[k], __fmul_rn(si, dy[k]));
+                float rx, ry;
+                if (!INT) {
+                    rx = __fmaf_rn(co, dy[k], -__fmul_rn(si, dx[k]));
+                    ry = __fmaf_rn(co, dx[k], __fmul_rn(si, dy[k]));
+                } else {
+                    const int dxi = __float_as_int(dx[k]), dyi = __float_as_int(dy[k]);
+                    const int rxi = -dxi * si + dyi * co, ryi = dxi * co + dyi * si;          // float expressions truncated to int
+                    rx = __int_as_float(rxi); ry = __int_as_float(ryi);
+                }
                 // The cells of the three grids live in disjoint rows of acc, but the compiler cannot know that and would
                 // serialise the three read-modify-write groups of a sample (load after the previous group's store: ncu r01j,
                 // 6.3 warps per issue on the short scoreboard).  All nine loads first, then the adds, then the stores.
@@ -336,9 +363,9 @@ __global__ void __launch_bounds__(64) k_describe_t(const __grid_constant__ AkzLe
                 if (g2) { v2[0] = a2[0]; v2[1] = a2[RS]; v2[2] = a2[2 * RS]; }
                 if (g3) { v3[0] = a3[0]; v3[1] = a3[RS]; v3[2] = a3[2 * RS]; }
                 if (g4) { v4[0] = a4[0]; v4[1] = a4[RS]; v4[2] = a4[2 * RS]; }
-                if (g2) { a2[0] = __fadd_rn(v2[0], im[k]); a2[RS] = __fadd_rn(v2[1], rx); a2[2 * RS] = __fadd_rn(v2[2], ry); }
-                if (g3) { a3[0] = __fadd_rn(v3[0], im[k]); a3[RS] = __fadd_rn(v3[1], rx); a3[2 * RS] = __fadd_rn(v3[2], ry); }
-                if (g4) { a4[0] = __fadd_rn(v4[0], im[k]); a4[RS] = __fadd_rn(v4[1], rx); a4[2 * RS] = __fadd_rn(v4[2], ry); }
+                if (g2) { a2[0] = dsum<INT>(v2[0], im[k]); a2[RS] = dsum<INT>(v2[1], rx); a2[2 * RS] = dsum<INT>(v2[2], ry); }
+                if (g3) { a3[0] = dsum<INT>(v3[0], im[k]); a3[RS] = dsum<INT>(v3[1], rx); a3[2 * RS] = dsum<INT>(v3[2], ry); }
+                if (g4) { a4[0] = dsum<INT>(v4[0], im[k]); a4[RS] = dsum<INT>(v4[1], rx); a4[2 * RS] = dsum<INT>(v4[2], ry); }
             }
         }
         __syncthreads();
@@ -347,11 +374,11 @@ __global__ void __launch_bounds__(64) k_describe_t(const __grid_constant__ AkzLe
             const float* a = acc + v * RS;
             float r[32];
 #pragma unroll
-            for (int t = 0; t < 32; t++) r[t] = __fadd_rn(a[t], a[t + 32]);
+            for (int t = 0; t < 32; t++) r[t] = dsum<INT>(a[t], a[t + 32]);
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1)
 #pragma unroll
-                for (int t = 0; t + d < 32; t += 2 * d) r[t] = __fadd_rn(r[t], r[t + d]);
+                for (int t = 0; t + d < 32; t += 2 * d) r[t] = dsum<INT>(r[t], r[t + d]);
             val[v] = r[0];
         }
         __syncthreads();
@@ -361,7 +388,7 @@ __global__ void __launch_bounds__(64) k_describe_t(const __grid_constant__ AkzLe
             const int nb = (tix == 60 ? 6 : 8);
 #pragma unroll
             for (int i = 0; i < 8; i++)
-                if (i < nb) rbits |= (val[cmp[i] & 0xFFFFu] > val[cmp[i] >> 16] ? 1u : 0u) << i;
+                if (i < nb) rbits |= (dgreater<INT>(val[cmp[i] & 0xFFFFu], val[cmp[i] >> 16]) ? 1u : 0u) << i;
         }
         out[tix] = (unsigned char)rbits;                  // bytes 61..63 are written as zero
         __syncthreads();
@@ -524,8 +551,12 @@ int describe(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const
     int size2 = pattern;                                          // akazed.cu:2681-2683
     int size3 = (int)ceilf(2.0f * pattern / 3.0f);
     int size4 = (int)ceilf(0.5f * pattern);
-    if (fast) { k_describe_int<<<148 * 8, 64, 0, st>>>(tab, prefix, n, kpts, desc, max_pts, size2, size3, size4); return 1; }
-    if (pattern == 10 && n <= AKZ_MAX_FRAMES_SEARCH) k_describe_t<10><<<148 * 9, 64, 0, st>>>(tab, prefix, n, kpts, desc, max_pts);
+    if (fast) {
+        if (pattern == 10 && n <= AKZ_MAX_FRAMES_SEARCH) k_describe_t<10, true><<<148 * 9, 64, 0, st>>>(tab, prefix, n, kpts, desc, max_pts);
+        else k_describe_int<<<148 * 8, 64, 0, st>>>(tab, prefix, n, kpts, desc, max_pts, size2, size3, size4);
+        return 1;
+    }
+    if (pattern == 10 && n <= AKZ_MAX_FRAMES_SEARCH) k_describe_t<10, false><<<148 * 9, 64, 0, st>>>(tab, prefix, n, kpts, desc, max_pts);
     else k_describe<<<148 * 8, 64, 0, st>>>(tab, prefix, n, kpts, desc, max_pts, size2, size3, size4);
     return 1;
 }
