@@ -248,18 +248,21 @@ __global__ void __launch_bounds__(P2_NT, 3) k_prep2(const __grid_constant__ Prep
                  p2_gauss<INT>(v1.x, v1.y, v1.z, v1.w, v2.x, a), p2_gauss<INT>(v1.y, v1.z, v1.w, v2.x, v2.y, a));
         }
         __syncthreads();
-        // ---- 3. column pass: Sm rows [2, AR-2), two rows per item --------------------------------------
-        for (int i = tid; i < ((AR - 4) / 2) * 24; i += P2_NT) {
+        // ---- 3. column pass: Sm rows [2, AR-2), four rows per item (8 loads + 4 stores per 4 rows; two-row items: 2 x (6 + 2)) ----
+        static_assert((AR - 4) % 4 == 0, "column pass works in groups of four rows");
+        for (int i = tid; i < ((AR - 4) / 4) * 24; i += P2_NT) {
             int rb = i / 24, g = i - rb * 24;
             if (g >= 20) continue;
-            int r = 2 + 2 * rb;
+            int r = 2 + 4 * rb;
             const float* p = Bf + (r - 2) * SP + 4 + 4 * g;
-            float4 b0 = lds4(p), b1 = lds4(p + SP), b2 = lds4(p + 2 * SP), b3 = lds4(p + 3 * SP), b4 = lds4(p + 4 * SP), b5 = lds4(p + 5 * SP);
+            float4 b[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) b[k] = lds4(p + k * SP);
             float* q = Sm + r * SP + 4 + 4 * g;
-            sts4(q, p2_gauss<INT>(b0.x, b1.x, b2.x, b3.x, b4.x, a), p2_gauss<INT>(b0.y, b1.y, b2.y, b3.y, b4.y, a),
-                 p2_gauss<INT>(b0.z, b1.z, b2.z, b3.z, b4.z, a), p2_gauss<INT>(b0.w, b1.w, b2.w, b3.w, b4.w, a));
-            sts4(q + SP, p2_gauss<INT>(b1.x, b2.x, b3.x, b4.x, b5.x, a), p2_gauss<INT>(b1.y, b2.y, b3.y, b4.y, b5.y, a),
-                 p2_gauss<INT>(b1.z, b2.z, b3.z, b4.z, b5.z, a), p2_gauss<INT>(b1.w, b2.w, b3.w, b4.w, b5.w, a));
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+                sts4(q + t * SP, p2_gauss<INT>(b[t].x, b[t + 1].x, b[t + 2].x, b[t + 3].x, b[t + 4].x, a), p2_gauss<INT>(b[t].y, b[t + 1].y, b[t + 2].y, b[t + 3].y, b[t + 4].y, a),
+                     p2_gauss<INT>(b[t].z, b[t + 1].z, b[t + 2].z, b[t + 3].z, b[t + 4].z, a), p2_gauss<INT>(b[t].w, b[t + 1].w, b[t + 2].w, b[t + 3].w, b[t + 4].w, a));
         }
         __syncthreads();
     }
