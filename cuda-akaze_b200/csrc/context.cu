@@ -986,6 +986,25 @@ int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt
     STAGE_EPILOGUE();
 }
 
+int akz_plan_chunks(int nframes, int max_batch, int ramp_up, int* starts, int* sizes, int cap)
+{
+    if (nframes < 0 || max_batch < 1 || !starts || !sizes) return akz_set_error(AKZ_E_INVALID, "bad arguments");
+    std::vector<int> st, sz;
+    chunk_plan(nframes, max_batch, ramp_up != 0, false, st, sz);
+    for (size_t i = 0; i < st.size() && (int)i < cap; i++) { starts[i] = st[i]; sizes[i] = sz[i]; }
+    return (int)st.size();
+}
+
+int akz_plan_match(int nq, int nt, int* out5)
+{
+    if (nq < 1 || nt < 0 || !out5) return akz_set_error(AKZ_E_INVALID, "bad arguments");
+    int nsplit, T, S, grid;
+    const int nparts = akzk::match_tc5_plan(nq, nt, &nsplit, &T, &S, &grid);
+    if (nparts < 0) return nparts;
+    out5[0] = nparts; out5[1] = nsplit; out5[2] = T; out5[3] = S; out5[4] = grid;
+    return AKZ_OK;
+}
+
 int akz_match_merge(akz_ctx* c, const akz_match_t* d_parts, int nparts, int nq, int mode, int finalize, akz_match_t* d_out)
 {
     STAGE_PROLOGUE();

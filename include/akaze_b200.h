@@ -208,6 +208,13 @@ AKZ_API int akz_match_merge(akz_ctx* c, const akz_match_t* d_parts, int nparts, 
  * 3 = tcgen05 kernel (tensor-memory accumulators).
  * Both produce identical results; the switch exists for tests and measurements. */
 AKZ_API void akz_set_match_kernel(int which);
+/* Host-side planning, exposed for tests (no device work).
+ * akz_plan_chunks: the chunk plan of a batch of nframes frames (max_batch per chunk, ramp_up = the host pipeline's short first
+ *   chunks); writes starts / sizes (up to cap entries) and returns the number of chunks.
+ * akz_plan_match: work decomposition of the tcgen05 matcher for nq x nt descriptors: out = { partial results per query,
+ *   items per query block, tiles of 128 train descriptors per item, tiles per CTA, CTAs }; returns 0 or an error code. */
+AKZ_API int akz_plan_chunks(int nframes, int max_batch, int ramp_up, int* starts, int* sizes, int cap);
+AKZ_API int akz_plan_match(int nq, int nt, int* out5);
 AKZ_API int akz_match_host(akz_ctx* c, const uint8_t* h_q, int nq, const uint8_t* h_t, int nt,
                            int mode, akz_match_t* h_out);
 

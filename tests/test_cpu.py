@@ -444,3 +444,47 @@ def test_frame_and_train_sharding_bounds():
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in cuts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_chunk_plan_of_the_host_pipeline():
+    """akz_plan_chunks: the chunks of a batch are contiguous, cover it exactly and never exceed max_batch; the host pipeline
+    ramps up (B/8, B/4, B/2, B, ...) so that its first upload is short, the device path uses full chunks."""
+    L = ab().lib()
+    cap = 4096
+    starts, sizes = (C.c_int * cap)(), (C.c_int * cap)()
+    for n in (0, 1, 3, 5, 11, 64, 100, 256, 1000):
+        for B_ in (1, 2, 8, 32):
+            for ramp in (0, 1):
+                k = L.akz_plan_chunks(n, B_, ramp, starts, sizes, cap)
+                assert k >= 0
+                st, sz = list(starts[:k]), list(sizes[:k])
+                assert sum(sz) == n and all(0 < s <= B_ for s in sz)
+                assert st == [sum(sz[:i]) for i in range(k)]
+                if not ramp:
+                    assert all(s == B_ for s in sz[:-1])
+    k = L.akz_plan_chunks(256, 32, 1, starts, sizes, cap)
+    assert list(sizes[:k]) == [4, 8, 16] + [32] * 7 + [4]
+    assert L.akz_plan_chunks(-1, 8, 0, starts, sizes, cap) < 0 and L.akz_plan_chunks(8, 0, 0, starts, sizes, cap) < 0
+
+
+def test_work_decomposition_of_the_tcgen05_matcher():
+    """akz_plan_match (host arithmetic of match_tc5.cu): one CTA per SM at most, equal tile shares that cover the linear
+    tile space, item ranges that are multiples of 1024 descriptors (8 tiles: the 64 columns of a half tile share their index
+    class) and at most 2^19 (13-bit half-tile ordinal), enough slots for every CTA that touches an item."""
+    L = ab().lib()
+    out = (C.c_int * 5)()
+    for nq, nt in ((1, 1), (5, 77), (256, 1024), (257, 1025), (10000, 10000), (10000, 100000), (10000, 1000000),
+                   (300, 600000), (1 << 20, 4096), (128, 1 << 22)):
+        assert L.akz_plan_match(nq, nt, out) == 0, (nq, nt)
+        nparts, nsplit, T, S, grid = list(out)
+        nqb = (nq + 255) // 256
+        total = nqb * nsplit * T
+        assert T % 8 == 0 and T >= 8 and T * 128 <= 1 << 19
+        assert nsplit * T * 128 >= nt and (nsplit - 1) * T * 128 < max(nt, 1) + T * 128
+        assert 1 <= grid <= 148 and grid * S >= total and (grid - 1) * S < total
+        maxslots = nparts // nsplit
+        assert nparts == nsplit * maxslots
+        for item in range(0, nqb * nsplit, max(1, nqb * nsplit // 50)):
+            first, last = (item * T) // S, ((item + 1) * T - 1) // S
+            assert last - first + 1 <= maxslots
+    assert L.akz_plan_match(0, 10, out) < 0
