@@ -330,9 +330,12 @@ __global__ void __launch_bounds__(P2_NT, 3) k_prep2(const __grid_constant__ Prep
             float u[12], c[12], l[12];
 #pragma unroll
             for (int q = 0; q < 3; q++) {
-                float4 vu = lds4(p - S * SP - 4 + 4 * q), vc = lds4(p - 4 + 4 * q), vl = lds4(p + S * SP - 4 + 4 * q);
+                float4 vu = lds4(p - S * SP - 4 + 4 * q), vl = lds4(p + S * SP - 4 + 4 * q);
                 u[4 * q] = vu.x; u[4 * q + 1] = vu.y; u[4 * q + 2] = vu.z; u[4 * q + 3] = vu.w;
-                c[4 * q] = vc.x; c[4 * q + 1] = vc.y; c[4 * q + 2] = vc.z; c[4 * q + 3] = vc.w;
+                if (S < 4 || q != 1) {                       // the centre row is read at m - S and m + S only
+                    float4 vc = lds4(p - 4 + 4 * q);
+                    c[4 * q] = vc.x; c[4 * q + 1] = vc.y; c[4 * q + 2] = vc.z; c[4 * q + 3] = vc.w;
+                }
                 l[4 * q] = vl.x; l[4 * q + 1] = vl.y; l[4 * q + 2] = vl.z; l[4 * q + 3] = vl.w;
             }
             float vx[4], vy[4];
