@@ -285,35 +285,36 @@ __global__ void __launch_bounds__(P2_NT, 3) k_prep2(const __grid_constant__ Prep
             ikc = __fdiv_rn(1.f, (float)(k * k));                       // akazed.cu:4218 (host)
         }
         float* fl = a.flow + (long long)frame * a.plane;
-        for (int i = tid; i < P2_H * 16; i += P2_NT) {
-            int r = i >> 4, g = i & 15;
+        // two output rows per item: four row loads for two rows instead of six
+        static_assert(P2_H % 2 == 0, "conductance phase works on row pairs");
+        for (int i = tid; i < (P2_H / 2) * 16; i += P2_NT) {
+            int r = 2 * (i >> 4), g = i & 15;
             const float* p = Sm + (r + OY) * SP + P2_OX + 4 * g;
-            // the two values beside the float4 come from the neighbouring lanes (same row: 16 items per row, all 32
+            // the two values beside the float4 come from the neighbouring lanes (same row pair: 16 items per row, all 32
             // lanes active); only the row ends read shared memory (a 4-float-strided scalar LDS is a 4-way bank conflict)
-            float u[6], c[6], l[6];
-#define AKZ_ROW6(arr, q)                                                                         \
-            {                                                                                        \
-                float4 v = lds4(q);                                                                  \
-                float lft = __shfl_up_sync(0xffffffffu, v.w, 1), rgt = __shfl_down_sync(0xffffffffu, v.x, 1); \
-                if (g == 0) lft = (q)[-1];                                                           \
-                if (g == 15) rgt = (q)[4];                                                           \
-                arr[0] = lft; arr[1] = v.x; arr[2] = v.y; arr[3] = v.z; arr[4] = v.w; arr[5] = rgt; \
-            }
-            AKZ_ROW6(u, p - SP)
-            AKZ_ROW6(c, p)
-            AKZ_ROW6(l, p + SP)
-#undef AKZ_ROW6
-            float o[4];
+            float rw[4][6];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                o[j] = p2_flow<INT>(u[j], u[j + 1], u[j + 2], c[j], c[j + 2], l[j], l[j + 1], l[j + 2], a.type, ikc);
+            for (int k = 0; k < 4; k++) {
+                const float* q = p + (k - 1) * SP;
+                float4 v = lds4(q);
+                float lft = __shfl_up_sync(0xffffffffu, v.w, 1), rgt = __shfl_down_sync(0xffffffffu, v.x, 1);
+                if (g == 0) lft = q[-1];
+                if (g == 15) rgt = q[4];
+                rw[k][0] = lft; rw[k][1] = v.x; rw[k][2] = v.y; rw[k][3] = v.z; rw[k][4] = v.w; rw[k][5] = rgt;
             }
-            int y = Y0 + r, x = X0 + 4 * g;
-            float* d = fl + (long long)y * a.pitch + x;
-            if (fast) *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
-            else if (y < h) {
 #pragma unroll
-                for (int j = 0; j < 4; j++) if (x + j < w) d[j] = o[j];
+            for (int t = 0; t < 2; t++) {
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    o[j] = p2_flow<INT>(rw[t][j], rw[t][j + 1], rw[t][j + 2], rw[t + 1][j], rw[t + 1][j + 2], rw[t + 2][j], rw[t + 2][j + 1], rw[t + 2][j + 2], a.type, ikc);
+                int y = Y0 + r + t, x = X0 + 4 * g;
+                float* d = fl + (long long)y * a.pitch + x;
+                if (fast) *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
+                else if (y < h) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) if (x + j < w) d[j] = o[j];
+                }
             }
         }
     }
