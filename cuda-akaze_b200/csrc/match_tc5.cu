@@ -4,30 +4,29 @@
 //
 //   popc(q ^ t) = popc(q) + popc(t) - 2 <q, t>      with the descriptors read as 512-long 0/1 vectors
 //
-// so the pairwise part is a u8 x u8 -> s32 GEMM with K = 512.  One CTA per SM owns 256 queries (two operand-A tiles of
-// MMA M = 128) and walks a range of train descriptors in tiles of 128 (MMA N); a train tile is 2 x 16 tcgen05.mma of
-// 128 x 128 x 32 into two accumulators.
+// so the pairwise part is a u8 x u8 -> s32 GEMM with K = 512.  The grid is one persistent CTA per SM; a CTA works on one item
+// at a time -- 256 queries (two operand-A tiles of MMA M = 128) against a range of train descriptors in tiles of 128 (MMA N);
+// a train tile is 2 x 16 tcgen05.mma of 128 x 128 x 32 into two accumulators (see "Work decomposition" at the kernel).
 //
 // Warp roles (13 warps, no block-wide barrier inside the main loop; everything is handed over through mbarriers):
-//   warps 9-12  expanders: read packed descriptors (64 B) and write them one byte per bit into shared memory in the
-//               K-major SWIZZLE_128B operand layout the tensor core reads (expanding in global memory would multiply
-//               the L2/HBM traffic by 8).  The unit is a K-block: 128 rows x 128 bytes = bits [128 kb, 128 kb + 128) of
-//               every descriptor of the tile, 16 KB; four K-block slots form a ring (one tile of look-ahead).  A slot
-//               feeds both query tiles, which halves the expansion work and the shared-memory stores per MMA.
-//   warp 8      one thread issues the MMAs: per K-block 2 x 4 tcgen05.mma (K = 32 bytes each), tcgen05.commit releases
-//               the slot; after the fourth K-block a second commit publishes the accumulator pair.
-//   warps 0-7   epilogue: thread = query row; warp w reads TMEM lanes 32 (w % 4) ... of accumulator w / 4.  tcgen05.ld
-//               brings 32 accumulator columns at a time (the next load is in flight while a chunk is processed); the
-//               running top-2 (or minimum + class mask) is kept on keys
-//                     key = (popc(t) + 512 - 2 dot) << 20 | (train index relative to the CTA's range)
-//               = ptk[column] - (dot << 21): one integer instruction per pair, then a 3-instruction min/max network on
-//               two independent chains (even / odd columns).  popc(q) is constant along a row and is added once at the
-//               end.  Two accumulator-pair buffers (2 x 256 TMEM columns) decouple the epilogue from the MMAs.
+//   warps 9-12  expanders: read packed descriptors (64 B, two tiles of look-ahead in registers) and write them one byte per
+//               bit into shared memory in the K-major SWIZZLE_128B operand layout the tensor core reads (expanding in global
+//               memory would multiply the L2/HBM traffic by 8).  The unit is a K-block: 128 rows x 128 bytes = bits
+//               [128 kb, 128 kb + 128) of every descriptor of the tile, 16 KB; four K-block slots form a ring.  A slot feeds
+//               both query tiles, which halves the expansion work and the shared-memory stores per MMA.
+//   warp 8      issues the MMAs: per K-block 2 x 4 tcgen05.mma (K = 32 bytes each), tcgen05.commit releases the slot; after
+//               the fourth K-block a second commit publishes the accumulator pair.  The whole warp runs the loop and
+//               elect.sync picks the issuing lane inside the asm statement (see umma_i8).
+//   warps 0-7   epilogue: thread = query row; warp w reads TMEM lanes 32 (w % 4) ... of accumulator w / 4.  A packed
+//               tcgen05.ld brings 64 accumulator columns (two per register) with the next load in flight.  The padding
+//               positions of the GEMM carry popc(t) and the column index, so an accumulator IS the sortable part of a key
+//               (see "keys"): the top-2 of a chunk is taken on the packed 16-bit values and only the winners are unpacked.
+//               Two accumulator-pair buffers (2 x 256 TMEM columns) decouple the epilogue from the MMAs.
 // Any fixed permutation of the 512 bits gives the same dot product as long as both operands use it, and the operand bytes
 // need not be 0 / 1 as long as every product of two set bits is the same constant: see expand_store.
-// For long train ranges (FILTER) the epilogue first takes the minimum key of a 32-column chunk with a VIMNMX3 tree and
-// runs the exact update only when that minimum can change the state (a new top-2 entry is rare once a few thousand
-// candidates have been seen): 0.5 instead of 2.5 ALU instructions per pair.
+// For long train ranges (FILTER) the epilogue first takes the maximum of a 64-column chunk with a packed VIMNMX3 tree and runs
+// the exact top-2 only when that maximum can change the state (a new top-2 entry is rare once a few thousand candidates have
+// been seen).  The reference-compatible mode needs one update per chunk in any case.
 #include "common.cuh"
 #include "kernels.h"
 #include <algorithm>
