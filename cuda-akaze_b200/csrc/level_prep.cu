@@ -17,7 +17,11 @@
 //     first-derivative phase, overwrite the out-of-image cells of the tile with the value of their mirror
 //     cell (a copy, so operators are never evaluated on a mirrored extension: Lx/Ly are antisymmetric and
 //     the octave transition reflects in SOURCE coordinates);
-//   * 64x64 output tile (halo overhead 1.7x instead of 2.1x at S = 4), 512 threads, 2 CTAs per SM.
+//   * 64x48 output tile, 384 threads, 3 CTAs per SM (first version: 64x64, 512 threads, 2 CTAs: the six barrier-separated
+//     phases overlap better across three CTAs);
+//   * the column pass works on four-row items and the conductance phase on row pairs (fewer shared-memory loads per output:
+//     the kernel sits on the LSU wavefront pipe, 85 % busy);
+//   * INT = true instantiates the same kernel for the integer pipeline (int32 planes as bit patterns, 16.16 fixed point).
 // The arithmetic is the pinned sequence of common.cuh: results are bit-identical to the staged kernels.
 #include "common.cuh"
 #include "kernels.h"
