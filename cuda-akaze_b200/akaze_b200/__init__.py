@@ -31,7 +31,7 @@ MATCH_DTYPE = np.dtype([("idx1", "<i4"), ("dist1", "<i4"), ("idx2", "<i4"), ("di
 
 # every symbol include/akaze_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "akz_version", "akz_last_error", "akz_default_options", "akz_fed_tau", "akz_gauss_taps", "akz_compare_indices",
+    "akz_version", "akz_last_error", "akz_default_options", "akz_fed_tau", "akz_fed_tau_internal", "akz_gauss_taps", "akz_compare_indices",
     "akz_create", "akz_destroy", "akz_sync", "akz_stream", "akz_num_levels", "akz_level_info", "akz_level_plane",
     "akz_launch_count", "akz_detect_and_compute", "akz_detect_and_compute_host", "akz_build_scale_space",
     "akz_get_kcontrast", "akz_lowpass", "akz_down_with_smooth", "akz_scharr_contrast", "akz_flow", "akz_nld_step",
@@ -59,6 +59,7 @@ def lib():
     L.akz_last_error.restype = C.c_char_p
     L.akz_default_options.argtypes = [C.POINTER(Options)]
     L.akz_fed_tau.argtypes = [f, i, f, i, C.POINTER(C.c_float), i]
+    L.akz_fed_tau_internal.argtypes = [i, f, f, i, C.POINTER(C.c_float), i]
     L.akz_gauss_taps.argtypes = [f, i, C.POINTER(C.c_float)]
     L.akz_compare_indices.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.akz_create.argtypes = [C.POINTER(Options), C.POINTER(vp)]

@@ -7,6 +7,7 @@
 #include "../../include/akaze_b200.h"
 #include <cstring>
 #include <cmath>
+#include <mutex>
 
 namespace {
 
@@ -25,29 +26,46 @@ namespace {
     exit(-1);
 }
 
-// one lazily created context for the matcher and the synchronous stage functions (unfused kernels:
-// hHessianDeterminant writes the determinant over its input, which needs separate passes)
-akz_ctx* stage_ctx()
+// One lazily created context PER DEVICE for the matcher and the synchronous stage functions (unfused kernels:
+// hHessianDeterminant writes the determinant over its input, which needs separate passes).  The reference runs on
+// whatever device is current (cuda_utils.h initDevice), so the context is looked up by the current device; creation
+// is serialised, and callers that share a device share the context the way the reference's callers share the default stream.
+constexpr int kMaxDevices = 64;
+std::mutex g_stage_mutex;
+akz_ctx* g_stage_ctx[kMaxDevices] = {};
+
+int current_device()
 {
-    static akz_ctx* c = nullptr;
-    if (!c) {
-        akz_options o;
-        akz_default_options(&o);
-        o.width = 0; o.height = 0; o.fused = 0; o.max_batch = 1;
-        AKZ_DO(akz_create(&o, &c));
-    }
-    return c;
+    int d = 0;
+    CHECK(cudaGetDevice(&d));
+    return d & (kMaxDevices - 1);
 }
 
+akz_ctx* stage_ctx()
+{
+    const int d = current_device();
+    std::lock_guard<std::mutex> lock(g_stage_mutex);
+    if (!g_stage_ctx[d]) {
+        akz_options o;
+        akz_default_options(&o);
+        o.width = 0; o.height = 0; o.fused = 0; o.max_batch = 1; o.device = d;
+        AKZ_DO(akz_create(&o, &g_stage_ctx[d]));
+    }
+    return g_stage_ctx[d];
+}
+
+// scratch device buffers of the shims, one set per device (grown on demand, never shrunk)
 struct Scratch {
-    void* p = nullptr; size_t n = 0;
+    void* p[kMaxDevices] = {}; size_t n[kMaxDevices] = {};
     void* get(size_t bytes)
     {
-        if (n < bytes) { if (p) cudaFree(p); CHECK(cudaMalloc(&p, bytes)); n = bytes; }
-        return p;
+        const int d = current_device();
+        std::lock_guard<std::mutex> lock(g_stage_mutex);
+        if (n[d] < bytes) { if (p[d]) cudaFree(p[d]); CHECK(cudaMalloc(&p[d], bytes)); n[d] = bytes; }
+        return p[d];
     }
 };
-Scratch g_match_scratch, g_k_scratch;
+Scratch g_match_scratch, g_k_scratch, g_tmp_scratch;
 
 void match_points(akaze::AkazeData& r1, akaze::AkazeData& r2)
 {
@@ -82,10 +100,11 @@ int fed_tau_by_cycle_time(const float t, const float tau_max, const bool reorder
 }
 int fed_tau_internal(const int n, const float scale, const float tau_max, const bool reordering, std::vector<float>& tau)
 {
-    // invert scale = 3t / (tau_max n (n+1)) so that the cycle-time entry point reproduces (n, scale)
     if (n <= 0) return 0;
-    const float t = scale * tau_max * (float)(n * (n + 1)) / 3.0f;
-    return fed_tau_by_cycle_time(t, tau_max, reordering, tau);
+    tau.assign((size_t)n, 0.f);
+    const int m = akz_fed_tau_internal(n, scale, tau_max, reordering ? 1 : 0, tau.data(), n);
+    if (m <= 0) { tau.clear(); return 0; }
+    return m;
 }
 bool fed_is_prime_internal(const int number)
 {
@@ -292,17 +311,65 @@ namespace akaze
 
 namespace fastakaze
 {
-    void hConv2dR2(unsigned char*, int*, int, int, int, float) { not_routed("fastakaze::hConv2dR2"); }
-    void hConv2dR2(int*, int*, int, int, int, float) { not_routed("fastakaze::hConv2dR2"); }
-    void hConv2dR2(unsigned char*, int*, int*, int, int, int, float) { not_routed("fastakaze::hConv2dR2"); }
-    void hConv2dR2(int*, int*, int*, int, int, int, float) { not_routed("fastakaze::hConv2dR2"); }
-    void hLowPass(unsigned char*, int*, int, int, int, float, int) { not_routed("fastakaze::hLowPass"); }
-    void hLowPass(unsigned char*, int*, int*, int, int, int, float, int) { not_routed("fastakaze::hLowPass"); }
-    void hDownWithSmooth(int*, int*, int*, int3, int3) { not_routed("fastakaze::hDownWithSmooth"); }
-    void hScharrContrast(int*, int*, int&, float, int, int, int) { not_routed("fastakaze::hScharrContrast"); }
-    void hHessianDeterminant(int*, int*, int*, int, int, int, int) { not_routed("fastakaze::hHessianDeterminant"); }
-    void hFlow(int*, int*, akaze::DiffusivityType, int, int, int, int) { not_routed("fastakaze::hFlow"); }
-    void hNldStep(int*, int*, int*, float, int, int, int) { not_routed("fastakaze::hNldStep"); }
+    // Integer stage functions (akazed.h:88-110), synchronous like the reference's wrappers.  The overloads without a
+    // `temp` argument run the same separable kernels on a scratch plane of the shim (the results are identical: integer sums).
+    static void blur(const void* src, int src_u8, int* dst, int* temp, int width, int height, int pitch, float var, int ksz)
+    {
+        akz_ctx* c = stage_ctx();
+        if (ksz > 11) { std::cerr << "Kernels larger than 11 not implemented" << std::endl; return; }   // akazed.cu:4007
+        if (!temp) temp = (int*)g_tmp_scratch.get(sizeof(int) * (size_t)pitch * height);
+        AKZ_DO(akz_fast_lowpass(c, src, src_u8, dst, temp, width, height, pitch, (long long)pitch * height, 1, var, ksz));
+        AKZ_DO(akz_sync(c));
+    }
+    void hConv2dR2(unsigned char* src, int* dst, int width, int height, int pitch, float var) { blur(src, 1, dst, nullptr, width, height, pitch, var, 5); }
+    void hConv2dR2(int* src, int* dst, int width, int height, int pitch, float var) { blur(src, 0, dst, nullptr, width, height, pitch, var, 5); }
+    void hConv2dR2(unsigned char* src, int* dst, int* temp, int width, int height, int pitch, float var) { blur(src, 1, dst, temp, width, height, pitch, var, 5); }
+    void hConv2dR2(int* src, int* dst, int* temp, int width, int height, int pitch, float var) { blur(src, 0, dst, temp, width, height, pitch, var, 5); }
+    void hLowPass(unsigned char* src, int* dst, int width, int height, int pitch, float var, int ksz) { blur(src, 1, dst, nullptr, width, height, pitch, var, ksz); }
+    void hLowPass(unsigned char* src, int* dst, int* temp, int width, int height, int pitch, float var, int ksz) { blur(src, 1, dst, temp, width, height, pitch, var, ksz); }
+
+    void hDownWithSmooth(int* src, int* dst, int* smooth, int3 swhp, int3 dwhp)
+    {
+        akz_ctx* c = stage_ctx();
+        AKZ_DO(akz_fast_down_with_smooth(c, src, dst, smooth, swhp.x, swhp.y, swhp.z, (long long)swhp.y * swhp.z,
+                                         dwhp.x, dwhp.y, dwhp.z, (long long)dwhp.y * dwhp.z, 1));
+        AKZ_DO(akz_sync(c));
+    }
+
+    // grad receives the gradient-magnitude plane, as in the reference (akazed.cu:4098)
+    void hScharrContrast(int* src, int* grad, int& kcontrast, float per, int width, int height, int pitch)
+    {
+        akz_ctx* c = stage_ctx();
+        int* dk = (int*)g_k_scratch.get(sizeof(int));
+        AKZ_DO(akz_fast_scharr_contrast(c, src, grad, dk, per, width, height, pitch, (long long)pitch * height, 1));
+        CHECK(cudaMemcpyAsync(&kcontrast, dk, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)akz_stream(c)));
+        AKZ_DO(akz_sync(c));
+    }
+
+    // like the reference, the determinant overwrites src (akazed.cu:4175-4206)
+    void hHessianDeterminant(int* src, int* dx, int* dy, int step, int width, int height, int pitch)
+    {
+        akz_ctx* c = stage_ctx();
+        AKZ_DO(akz_fast_hessian(c, src, dx, dy, src, step, width, height, pitch, (long long)pitch * height, 1));
+        AKZ_DO(akz_sync(c));
+    }
+
+    void hFlow(int* src, int* flow, akaze::DiffusivityType type, int kcontrast, int width, int height, int pitch)
+    {
+        akz_ctx* c = stage_ctx();
+        int* dk = (int*)g_k_scratch.get(sizeof(int));
+        CHECK(cudaMemcpyAsync(dk, &kcontrast, sizeof(int), cudaMemcpyHostToDevice, (cudaStream_t)akz_stream(c)));
+        AKZ_DO(akz_fast_flow(c, src, flow, (int)type, dk, width, height, pitch, (long long)pitch * height, 1));
+        AKZ_DO(akz_sync(c));
+    }
+
+    void hNldStep(int* img, int* flow, int* temp, float step_size, int width, int height, int pitch)
+    {
+        akz_ctx* c = stage_ctx();
+        AKZ_DO(akz_fast_nld_step(c, img, flow, temp, step_size, width, height, pitch, (long long)pitch * height, 1));
+        AKZ_DO(akz_sync(c));
+    }
+
     void hCalcExtremaMap(int*, int*, float*, int*, float*, int, int, int, int, int, int, int) { not_routed("fastakaze::hCalcExtremaMap"); }
     void hNmsR(akaze::AkazePoint*, int*, float*, int*, int, int, int, int, int) { not_routed("fastakaze::hNmsR"); }
     void hRefine(akaze::AkazeData&, void*, int, int) { not_routed("fastakaze::hRefine"); }

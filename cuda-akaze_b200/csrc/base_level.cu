@@ -303,8 +303,8 @@ int base_level2(cudaStream_t st, const void* img, int dtype, int w, int h, int i
 {
     if (radius_from_ksz(ksz0) != 4 || w < 16 || h < 16) return 0;
     if (int_planes && dtype != AKZ_U8) return 0;
-    static unsigned long long attr = 0;
-    if (akz_once_per_device(attr)) {
+    static akz_once_t attr;
+    if (akz_once_guard once{attr}) {
         cudaFuncSetAttribute(k_base2<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
         cudaFuncSetAttribute(k_base2<unsigned char, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
         cudaFuncSetAttribute(k_base2<unsigned char, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);

@@ -5,6 +5,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
+#include <mutex>
 
 #define AKZ_NBINS 300          // akazed.cu:8
 #define AKZ_MAX_DIST 96        // akazed.cu:11
@@ -107,16 +109,42 @@ struct AkzLevelDev {
         if (e_ != cudaSuccess) return akz_set_cuda_error(e_, #expr, __FILE__, __LINE__); \
     } while (0)
 
-// cudaFuncSetAttribute is per device: true the first time it is asked on the current device (one process may drive several GPUs)
-inline bool akz_once_per_device(unsigned long long& mask)
-{
-    int d = 0;
-    cudaGetDevice(&d);
-    const unsigned long long bit = 1ull << (d & 63);
-    if (mask & bit) return false;
-    mask |= bit;
-    return true;
-}
+// cudaFuncSetAttribute and __constant__ uploads are per device.  `if (akz_once_guard g{flag}) { ... }` runs its body exactly
+// once per device, also when several host threads create contexts at the same time: the first caller holds the flag's mutex
+// while the body runs and publishes the device bit afterwards; later callers see the bit (acquire) and skip.
+struct akz_once_t {
+    std::atomic<unsigned long long> done{0};
+    std::mutex m;
+};
+struct akz_once_guard {
+    akz_once_t& f;
+    unsigned long long bit;
+    bool first;
+    explicit akz_once_guard(akz_once_t& fl) : f(fl), bit(0), first(false)
+    {
+        int d = 0;
+        cudaGetDevice(&d);
+        bit = 1ull << (d & 63);
+        if (f.done.load(std::memory_order_acquire) & bit) return;
+        f.m.lock();
+        if (f.done.load(std::memory_order_relaxed) & bit) { f.m.unlock(); return; }
+        first = true;
+    }
+    ~akz_once_guard()
+    {
+        if (first) { f.done.fetch_or(bit, std::memory_order_release); f.m.unlock(); }
+    }
+    explicit operator bool() const { return first; }
+    akz_once_guard(const akz_once_guard&) = delete;
+    akz_once_guard& operator=(const akz_once_guard&) = delete;
+};
+
+// restores the caller's current device when an entry point returns (the library switches to the context's device)
+struct akz_device_guard {
+    int prev;
+    akz_device_guard() : prev(-1) { cudaGetDevice(&prev); }
+    ~akz_device_guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 int akz_set_cuda_error(cudaError_t e, const char* what, const char* file, int line);
 int akz_set_error(int code, const char* fmt, ...);

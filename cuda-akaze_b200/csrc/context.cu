@@ -10,6 +10,8 @@
 #include <cmath>
 #include <vector>
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 
 // ---- errors ---------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -62,8 +64,15 @@ int akz_fed_tau(float T, int M, float tau_max, int reordering, float* tau, int c
     const float t = T / (float)M;
     const int n = (int)(ceil(sqrt(3.0 * t / tau_max + 0.25f) - 0.5f - 1.0e-8f) + 0.5f);
     if (n <= 0) return 0;
-    if (n > cap) return -n;
     const float scale = (float)(3.0 * t / (tau_max * (float)(n * (n + 1))));
+    return akz_fed_tau_internal(n, scale, tau_max, reordering, tau, cap);
+}
+
+// the n time steps of one cycle for a given (n, scale): replaces fed_tau_internal (fed.cpp:64-119)
+int akz_fed_tau_internal(int n, float scale, float tau_max, int reordering, float* tau, int cap)
+{
+    if (n <= 0) return 0;
+    if (n > cap) return -n;
     const float c = 1.0f / (4.0f * (float)n + 2.0f);
     const float d = scale * tau_max / 2.0f;
     std::vector<float> plain(n);
@@ -238,6 +247,11 @@ int akz_create(const akz_options* o, akz_ctx** out)
     if (o->max_scale < 1 || o->max_scale > 5 || o->noctaves < 1 || o->noctaves > 8) return akz_set_error(AKZ_E_INVALID, "octaves/sublevels out of range");
     if (o->dthreshold < 0.f) return akz_set_error(AKZ_E_INVALID, "dthreshold must be >= 0");
     if (o->max_pts < 1 || o->max_batch < 1) return akz_set_error(AKZ_E_INVALID, "max_pts / max_batch must be positive");
+    if (!matcher_only && o->height > 4096) return akz_set_error(AKZ_E_INVALID, "frame size %dx%d unsupported", o->width, o->height);
+    if (o->lanes < 0 || o->lanes > 2) return akz_set_error(AKZ_E_INVALID, "lanes must be 1 or 2");
+    if (o->diffusivity < 0 || o->diffusivity > 3) return akz_set_error(AKZ_E_INVALID, "diffusivity must be 0..3 (akaze_structures.h:51-57)");
+    if (o->descriptor_pattern_size < 1 || o->descriptor_pattern_size > 64) return akz_set_error(AKZ_E_INVALID, "descriptor_pattern_size out of range");
+    if (!(o->per > 0.f && o->per <= 1.f) || !(o->soffset > 0.f) || !(o->derivative_factor > 0.f)) return akz_set_error(AKZ_E_INVALID, "per / soffset / derivative_factor out of range");
     int ndev = 0;
     AKZ_CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (ndev <= 0) return akz_set_error(AKZ_E_CUDA, "no CUDA device: this library has no CPU fallback");
@@ -351,7 +365,8 @@ void akz_destroy(akz_ctx* c)
 
 int akz_sync(akz_ctx* c)
 {
-    if (c && c->lane1) AKZ_CUDA_TRY(cudaStreamSynchronize(c->lane1->stream));
+    if (!c) return akz_set_error(AKZ_E_INVALID, "null context");
+    if (c->lane1) AKZ_CUDA_TRY(cudaStreamSynchronize(c->lane1->stream));
     AKZ_CUDA_TRY(cudaStreamSynchronize(c->stream));
     AKZ_CUDA_TRY(cudaGetLastError());
     return AKZ_OK;
@@ -391,13 +406,14 @@ const float* akz_level_plane(const akz_ctx* c, int l, int which, int frame)
                    c->prof_pairs.push_back({ ea_, eb_, (cls_), r_ }); }                        \
     } while (0)
 
-static int check_frame_args(akz_ctx* c, const void* img, int dtype, int nframes, int w, int h, int pitch)
+static int check_frame_args(akz_ctx* c, const void* img, int dtype, int nframes, int w, int h, int pitch, long long stride)
 {
     if (!c || !img) return akz_set_error(AKZ_E_INVALID, "null argument");
     if (dtype != AKZ_F32 && dtype != AKZ_U8) return akz_set_error(AKZ_E_INVALID, "dtype must be AKZ_F32 or AKZ_U8");
     if (c->nlev == 0) return akz_set_error(AKZ_E_INVALID, "matcher-only context");
     if (w != c->opt.width || h != c->opt.height) return akz_set_error(AKZ_E_INVALID, "frame size %dx%d differs from the context's %dx%d", w, h, c->opt.width, c->opt.height);
     if (pitch < w || nframes < 0) return akz_set_error(AKZ_E_INVALID, "bad pitch or frame count");
+    if (nframes > 1 && stride < (long long)pitch * h) return akz_set_error(AKZ_E_INVALID, "frame stride %lld smaller than pitch * height = %lld", stride, (long long)pitch * h);
     return AKZ_OK;
 }
 
@@ -594,9 +610,10 @@ extern "C" {
 
 int akz_build_scale_space(akz_ctx* c, const void* d_images, int dtype, int nframes, int w, int h, int pitch, long long stride)
 {
-    int rc = check_frame_args(c, d_images, dtype, nframes, w, h, pitch);
+    int rc = check_frame_args(c, d_images, dtype, nframes, w, h, pitch, stride);
     if (rc != AKZ_OK) return rc;
     if (nframes > c->opt.max_batch) return akz_set_error(AKZ_E_INVALID, "nframes exceeds max_batch");
+    akz_device_guard dev_guard_;
     AKZ_CUDA_TRY(cudaSetDevice(c->device));
     rc = scale_space_chunk(c, d_images, dtype, nframes, pitch, stride);
     if (rc != AKZ_OK) return rc;
@@ -634,9 +651,10 @@ static void chunk_plan(int nframes, int B, bool ramp_up, bool ramp_down, std::ve
 int akz_detect_and_compute(akz_ctx* c, const void* d_images, int dtype, int nframes, int w, int h, int pitch, long long stride,
                            int describe, int* d_counts, akz_keypoint* d_kpts, uint8_t* d_desc)
 {
-    int rc = check_frame_args(c, d_images, dtype, nframes, w, h, pitch);
+    int rc = check_frame_args(c, d_images, dtype, nframes, w, h, pitch, stride);
     if (rc != AKZ_OK) return rc;
     if (!d_counts || !d_kpts || (describe && !d_desc)) return akz_set_error(AKZ_E_INVALID, "null result buffer");
+    akz_device_guard dev_guard_;
     AKZ_CUDA_TRY(cudaSetDevice(c->device));
     const int B = c->opt.max_batch;
     const size_t esz = dtype == AKZ_U8 ? 1 : 4;
@@ -652,23 +670,25 @@ int akz_detect_and_compute(akz_ctx* c, const void* d_images, int dtype, int nfra
         const int f0 = cstart[k], nf = csize[k];
         akz_ctx* L = (two && (k & 1)) ? c->lane1 : c;
         const char* img = (const char*)d_images + (size_t)f0 * stride * esz;
-        if ((rc = scale_space_chunk(L, img, dtype, nf, pitch, stride)) != AKZ_OK) return rc;
+        if ((rc = scale_space_chunk(L, img, dtype, nf, pitch, stride)) != AKZ_OK) break;
         if ((rc = detect_chunk(L, nf, describe, d_counts + f0, d_kpts + (size_t)f0 * c->opt.max_pts,
-                               d_desc ? d_desc + (size_t)f0 * c->opt.max_pts * 64 : nullptr)) != AKZ_OK) return rc;
+                               d_desc ? d_desc + (size_t)f0 * c->opt.max_pts * 64 : nullptr)) != AKZ_OK) break;
     }
-    if (two) {
+    if (two) {                                   // also on an error: the second lane is always joined
         AKZ_CUDA_TRY(cudaEventRecord(c->ev_join, c->lane1->stream));
         AKZ_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     }
+    if (rc != AKZ_OK) return rc;
     AKZ_CUDA_TRY(cudaGetLastError());
     return AKZ_OK;
 }
 
 int akz_fast_build_scale_space(akz_ctx* c, const uint8_t* d_images, int nframes, int w, int h, int pitch, long long stride)
 {
-    int rc = check_frame_args(c, d_images, AKZ_U8, nframes, w, h, pitch);
+    int rc = check_frame_args(c, d_images, AKZ_U8, nframes, w, h, pitch, stride);
     if (rc != AKZ_OK) return rc;
     if (nframes > c->opt.max_batch) return akz_set_error(AKZ_E_INVALID, "nframes exceeds max_batch");
+    akz_device_guard dev_guard_;
     AKZ_CUDA_TRY(cudaSetDevice(c->device));
     if ((rc = fast_scale_space_chunk(c, d_images, nframes, pitch, stride)) != AKZ_OK) return rc;
     AKZ_CUDA_TRY(cudaGetLastError());
@@ -684,9 +704,10 @@ int akz_fast_get_kcontrast(akz_ctx* c, int* h_k, int nframes)
 int akz_fast_detect_and_compute(akz_ctx* c, const uint8_t* d_images, int nframes, int w, int h, int pitch, long long stride,
                                 int describe, int* d_counts, akz_keypoint* d_kpts, uint8_t* d_desc)
 {
-    int rc = check_frame_args(c, d_images, AKZ_U8, nframes, w, h, pitch);
+    int rc = check_frame_args(c, d_images, AKZ_U8, nframes, w, h, pitch, stride);
     if (rc != AKZ_OK) return rc;
     if (!d_counts || !d_kpts || (describe && !d_desc)) return akz_set_error(AKZ_E_INVALID, "null result buffer");
+    akz_device_guard dev_guard_;
     AKZ_CUDA_TRY(cudaSetDevice(c->device));
     const int B = c->opt.max_batch;
     const bool two = c->lane1 != nullptr && nframes > B;
@@ -699,24 +720,45 @@ int akz_fast_detect_and_compute(akz_ctx* c, const uint8_t* d_images, int nframes
     for (int k = 0; k < (int)cstart.size(); k++) {
         const int f0 = cstart[k], nf = csize[k];
         akz_ctx* L = (two && (k & 1)) ? c->lane1 : c;
-        if ((rc = fast_scale_space_chunk(L, d_images + (size_t)f0 * stride, nf, pitch, stride)) != AKZ_OK) return rc;
+        if ((rc = fast_scale_space_chunk(L, d_images + (size_t)f0 * stride, nf, pitch, stride)) != AKZ_OK) break;
         if ((rc = detect_chunk(L, nf, describe, d_counts + f0, d_kpts + (size_t)f0 * c->opt.max_pts,
-                               d_desc ? d_desc + (size_t)f0 * c->opt.max_pts * 64 : nullptr, 1)) != AKZ_OK) return rc;
+                               d_desc ? d_desc + (size_t)f0 * c->opt.max_pts * 64 : nullptr, 1)) != AKZ_OK) break;
     }
-    if (two) {
+    if (two) {                                   // also on an error: the second lane is always joined
         AKZ_CUDA_TRY(cudaEventRecord(c->ev_join, c->lane1->stream));
         AKZ_CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     }
+    if (rc != AKZ_OK) return rc;
     AKZ_CUDA_TRY(cudaGetLastError());
     return AKZ_OK;
 }
 
+static int detect_and_compute_host_impl(akz_ctx* c, const void* h_images, int dtype, int nframes, int w, int h, int pitch, long long stride,
+                                        int describe, int* h_counts, akz_keypoint* h_kpts, uint8_t* h_desc, int fast);
+
+// On an error in the middle of the pipeline nothing may stay in flight: copies into the caller's buffers and both lanes are
+// drained before the error is returned (the message of the first failure is kept).
 static int detect_and_compute_host(akz_ctx* c, const void* h_images, int dtype, int nframes, int w, int h, int pitch, long long stride,
                                    int describe, int* h_counts, akz_keypoint* h_kpts, uint8_t* h_desc, int fast)
 {
-    int rc = check_frame_args(c, h_images, dtype, nframes, w, h, pitch);
+    const int rc = detect_and_compute_host_impl(c, h_images, dtype, nframes, w, h, pitch, stride, describe, h_counts, h_kpts, h_desc, fast);
+    if (rc != AKZ_OK && c && c->nlev > 0) {
+        if (c->h2d_stream) cudaStreamSynchronize(c->h2d_stream);
+        cudaStreamSynchronize(c->stream);
+        if (c->lane1) cudaStreamSynchronize(c->lane1->stream);
+        if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+static int detect_and_compute_host_impl(akz_ctx* c, const void* h_images, int dtype, int nframes, int w, int h, int pitch, long long stride,
+                                        int describe, int* h_counts, akz_keypoint* h_kpts, uint8_t* h_desc, int fast)
+{
+    int rc = check_frame_args(c, h_images, dtype, nframes, w, h, pitch, stride);
     if (rc != AKZ_OK) return rc;
     if (!h_counts || !h_kpts || (describe && !h_desc)) return akz_set_error(AKZ_E_INVALID, "null result buffer");
+    akz_device_guard dev_guard_;
     AKZ_CUDA_TRY(cudaSetDevice(c->device));
     const int B = c->opt.max_batch, MP = c->opt.max_pts;
     const size_t esz = dtype == AKZ_U8 ? 1 : 4;
@@ -811,7 +853,10 @@ int akz_fast_detect_and_compute_host(akz_ctx* c, const uint8_t* h_images, int nf
 }
 
 // ---- stage seams ------------------------------------------------------------------------------------------
-#define STAGE_PROLOGUE() do { if (!c) return akz_set_error(AKZ_E_INVALID, "null context"); AKZ_CUDA_TRY(cudaSetDevice(c->device)); } while (0)
+#define STAGE_PROLOGUE()                                                    \
+    if (!c) return akz_set_error(AKZ_E_INVALID, "null context");            \
+    akz_device_guard dev_guard_;      /* the caller's current device is restored on return */ \
+    AKZ_CUDA_TRY(cudaSetDevice(c->device))
 #define STAGE_EPILOGUE() do { AKZ_CUDA_TRY(cudaGetLastError()); return AKZ_OK; } while (0)
 
 int akz_lowpass(akz_ctx* c, const float* src, float* dst, int w, int h, int pitch, long long stride, int n, float var, int ksz)
@@ -863,6 +908,8 @@ int akz_fed_cycle(akz_ctx* c, const float* src, const float* flow, float* dst, f
 int akz_hessian(akz_ctx* c, const float* smooth, float* lx, float* ly, float* det, int step, int w, int h, int pitch, long long stride, int n)
 {
     STAGE_PROLOGUE();
+    if (c->opt.fused && (det == smooth || lx == smooth || ly == smooth))
+        return akz_set_error(AKZ_E_INVALID, "the fused level kernel cannot work in place: outputs must not alias the input (use fused = 0)");
     if (c->opt.fused) LAUNCHED(AKZ_K_PREP, prep_level(c, 0, smooth, w, h, pitch, stride, nullptr, nullptr, lx, ly, det, 0, step, w, h, pitch, stride, n));
     else LAUNCHED(AKZ_K_HESSIAN, akzk::hessian(c->stream, smooth, lx, ly, det, step, w, h, pitch, stride, n));
     STAGE_EPILOGUE();
@@ -936,8 +983,8 @@ int akz_detect_keypoints(akz_ctx* c, int n, int* d_counts, akz_keypoint* d_kpts)
 }
 
 // ---- matcher ----------------------------------------------------------------------------------------------
-static int g_match_kernel = 0;          // 0 = by problem size, 1 = POPC/LOP3 kernel, 2 = mma.sync kernel, 3 = tcgen05 kernel
-void akz_set_match_kernel(int which) { g_match_kernel = which; }
+static std::atomic<int> g_match_kernel{0};   // 0 = by problem size, 1 = POPC/LOP3 kernel, 2 = mma.sync kernel, 3 = tcgen05 kernel
+void akz_set_match_kernel(int which) { g_match_kernel.store(which, std::memory_order_relaxed); }
 
 int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int t_index_base, int mode, int finalize, akz_match_t* d_out)
 {
@@ -948,8 +995,9 @@ int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt
     // Kernel choice (akz_set_match_kernel overrides): small problems -> LOP3/POPC kernel (2000 x 2300: 29 us against 55 us for
     // the tensor-core kernels); large ones -> tcgen05 kernel (match_tc5.cu); 2 selects the legacy mma.sync kernel.
     const bool large = (long long)nq * nt >= (1ll << 24) && nq >= 1024;
-    int kern = g_match_kernel == 0 ? (large ? 3 : 1) : g_match_kernel;
-    akzk::match_tc5_set_filter(kern == 4 ? 1 : kern == 5 ? 0 : -1);          // 4 / 5: tcgen05 kernel with the chunk filter forced on / off (tests)
+    const int forced = g_match_kernel.load(std::memory_order_relaxed);
+    int kern = forced == 0 ? (large ? 3 : 1) : forced;
+    const int tc5_filter = kern == 4 ? 1 : kern == 5 ? 0 : -1;               // 4 / 5: tcgen05 kernel with the chunk filter forced on / off (tests)
     if (kern > 3) kern = 3;
     const int use_mma = kern == 2;
     const int qtile = 256;                           // queries per block of every kernel
@@ -980,7 +1028,7 @@ int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt
         AKZ_CUDA_TRY(cudaMalloc((void**)&c->match_parts, need * sizeof(akz_match_t)));
         c->match_parts_n = need;
     }
-    if (kern == 3) { LAUNCHED(AKZ_K_MATCH, akzk::match_partial_tc5(c->stream, d_q, nq, d_t, nt, t_index_base, mode, c->match_parts)); }
+    if (kern == 3) { LAUNCHED(AKZ_K_MATCH, akzk::match_partial_tc5(c->stream, d_q, nq, d_t, nt, t_index_base, mode, c->match_parts, tc5_filter)); }
     else { LAUNCHED(AKZ_K_MATCH, akzk::match_partial(c->stream, d_q, nq, d_t, nt, t_index_base, mode, nsplit, c->match_parts, use_mma)); }
     LAUNCHED(AKZ_K_MATCH, akzk::match_merge(c->stream, c->match_parts, nsplit, nq, mode, finalize, d_out));
     STAGE_EPILOGUE();
@@ -1050,6 +1098,7 @@ int akz_profile_enable(akz_ctx* c, int on)
 int akz_profile_read(akz_ctx* c, int ncls, double* ms, long long* launches)
 {
     if (!c || !ms || !launches) return akz_set_error(AKZ_E_INVALID, "null argument");
+    akz_device_guard dev_guard_;
     AKZ_CUDA_TRY(cudaSetDevice(c->device));
     AKZ_CUDA_TRY(cudaStreamSynchronize(c->stream));
     for (auto& pp : c->prof_pairs) {

@@ -516,7 +516,7 @@ __global__ void k_scatter(const akz_match_t* __restrict__ m, int nq, RefPoint* _
     else { pq[i].match = -1; pq[i].distance = -1; pq[i].match_x = -1.f; pq[i].match_y = -1.f; }     // akazed.cu:2231-2237
 }
 
-unsigned long long g_cmp_uploaded = 0;       // per device: constant memory is per device
+akz_once_t g_cmp_uploaded;                // per device: constant memory is per device
 
 }  // namespace
 
@@ -525,7 +525,7 @@ namespace akzk {
 int orient_table_init(cudaStream_t st)
 {
     k_orient_table<<<1, 64, 0, st>>>();
-    if (akz_once_per_device(g_cmp_uploaded)) {
+    if (akz_once_guard once{g_cmp_uploaded}) {
         int c1[488], c2[488];
         short h[2][488];
         akz_compare_indices(c1, c2);

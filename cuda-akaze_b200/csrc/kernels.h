@@ -104,8 +104,8 @@ int match_partial(cudaStream_t st, const unsigned char* q, int nq, const unsigne
                   int nsplit, akz_match_t* parts, int use_mma = 0);
 // match_tc5.cu: tcgen05 / tensor-memory matcher (same partial-result contract)
 int match_tc5_plan(int nq, int nt, int* nsplit, int* tiles, int* per_cta, int* grid);     // returns the number of partial results per query
-int match_partial_tc5(cudaStream_t st, const unsigned char* q, int nq, const unsigned char* t, int nt, int tbase, int mode, akz_match_t* parts);
-void match_tc5_set_filter(int v);          // -1 = by range length (default), 0 / 1 = chunk filter forced off / on
+int match_partial_tc5(cudaStream_t st, const unsigned char* q, int nq, const unsigned char* t, int nt, int tbase, int mode, akz_match_t* parts,
+                      int filter_mode = -1);     // -1 = chunk filter by range length (default), 0 / 1 = forced off / on (tests)
 int match_merge(cudaStream_t st, const akz_match_t* parts, int nparts, int nq, int mode, int finalize, akz_match_t* out);
 
 }  // namespace akzk

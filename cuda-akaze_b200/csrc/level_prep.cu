@@ -413,8 +413,8 @@ constexpr int prep2_smem() { return 3 * (P2_H + 2 * (2 * S + 2)) * P2_SP * (int)
 template <int S, int MODE, bool INT>
 void prep2_launch(cudaStream_t st, const Prep2Args& a, int n)
 {
-    static unsigned long long attr = 0;
-    if (akz_once_per_device(attr)) cudaFuncSetAttribute(k_prep2<S, MODE, INT>, cudaFuncAttributeMaxDynamicSharedMemorySize, prep2_smem<S>());
+    static akz_once_t attr;
+    if (akz_once_guard once{attr}) cudaFuncSetAttribute(k_prep2<S, MODE, INT>, cudaFuncAttributeMaxDynamicSharedMemorySize, prep2_smem<S>());
     dim3 g((a.w + P2_W - 1) / P2_W, (a.h + P2_H - 1) / P2_H, n);
     k_prep2<S, MODE, INT><<<g, P2_NT, prep2_smem<S>(), st>>>(a);
 }

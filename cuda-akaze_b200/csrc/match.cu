@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(NTH) k_match(const uint4* __restrict__ q, int 
 #pragma unroll
         for (int v = 0; v < 4; v++) {
             uint4 w = qi[k] < nq ? __ldg(q + 4 * (long long)qi[k] + v) : make_uint4(0, 0, 0, 0);
+            if (v == 3) w.w &= 0x3Fu;                      // bits 486..511 are padding: every matcher kernel ignores them
             qa[k][4 * v] = w.x; qa[k][4 * v + 1] = w.y; qa[k][4 * v + 2] = w.z; qa[k][4 * v + 3] = w.w;
         }
         b[k].k1 = KEY_NONE; b[k].k2 = (MODE == AKZ_MATCH_KNN2) ? KEY_NONE : 0u;
@@ -111,7 +112,11 @@ __global__ void __launch_bounds__(NTH) k_match(const uint4* __restrict__ q, int 
     for (int base = t0; base < t1; base += TILE) {
         int cnt = min(TILE, t1 - base);
         __syncthreads();
-        for (int i = threadIdx.x; i < cnt * 4; i += NTH) tile[i] = __ldg(t + 4 * (long long)base + i);
+        for (int i = threadIdx.x; i < cnt * 4; i += NTH) {
+            uint4 w = __ldg(t + 4 * (long long)base + i);
+            if ((i & 3) == 3) w.w &= 0x3Fu;                // padding bits (as k_match_tc5)
+            tile[i] = w;
+        }
         __syncthreads();
 #pragma unroll 2
         for (int j = 0; j < cnt; j++) {
@@ -171,6 +176,7 @@ __device__ __forceinline__ void mm_load(const unsigned* __restrict__ src, int cn
     for (int k = 0; k < NR / 32; k++) {
         int i = tid + MNT * k, d = i >> 4;
         w[k] = d < cnt ? __ldg(src + (long long)d * 16 + (i & 15)) : 0u;
+        if ((i & 15) == 15) w[k] &= 0x3Fu;                 // padding bits 486..511 are ignored (as k_match_tc5)
     }
 }
 // expand to one byte per bit: rows[d][32 * word + bit], popcounts -> pc[d]
@@ -387,8 +393,8 @@ int match_partial(cudaStream_t st, const unsigned char* q, int nq, const unsigne
     if (per <= 0) per = TILE;
     if (per >= (1 << KEY_IDX_BITS)) return akz_set_error(AKZ_E_UNSUPPORTED, "train range per block exceeds 2^22 descriptors: shard the train set");
     if (use_mma) {
-        static unsigned long long attr = 0;
-        if (akz_once_per_device(attr)) {
+        static akz_once_t attr;
+        if (akz_once_guard once{attr}) {
             cudaFuncSetAttribute(k_match_mma<AKZ_MATCH_KNN2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM);
             cudaFuncSetAttribute(k_match_mma<AKZ_MATCH_COMPAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM);
         }

@@ -483,17 +483,32 @@ __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const __grid_constant__ 
 
 namespace akzk {
 
-static int g_tc5_max_tiles = 4096;
-static int g_tc5_filter = -1;                    // -1 = by range length, 0 / 1 = forced (tests)
-void match_tc5_set_filter(int v) { g_tc5_filter = v; }
+// tuning knob (environment AKZ_TC5_MAX_TILES), read once
+static int tc5_max_tiles()
+{
+    static const int v = [] { const char* e = getenv("AKZ_TC5_MAX_TILES"); return e ? std::max(8, atoi(e) / 8 * 8) : 4096; }();
+    return v;
+}
+// SM count of the current device (cached per device ordinal; a process may drive several GPUs)
+static int tc5_sm_count()
+{
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int n = cache[dev & 63].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev & 63].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
 
 // Tensor-memory matcher.  Writes plan->nparts partial results per query to `parts` (see the work decomposition above);
 // match_tc5_plan gives the number of slots so that the caller can size the buffer first.
 int match_tc5_plan(int nq, int nt, int* nsplit_out, int* tiles_out, int* per_cta_out, int* grid_out)
 {
-    static int nsm = 0;
-    if (const char* e = getenv("AKZ_TC5_MAX_TILES")) g_tc5_max_tiles = std::max(8, atoi(e) / 8 * 8);
-    if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); if (nsm <= 0) nsm = 148; }
+    const int nsm = tc5_sm_count();
+    const int g_tc5_max_tiles = tc5_max_tiles();
     const int nqb = (nq + T5_Q - 1) / T5_Q;
     // items of at most g_tc5_max_tiles tiles: the rows of a tile are H = 2 T descriptors apart, and long ranges spread the 128 rows
     // of every tile over the whole train set
@@ -511,14 +526,14 @@ int match_tc5_plan(int nq, int nt, int* nsplit_out, int* tiles_out, int* per_cta
     return nsplit * maxslots;
 }
 
-int match_partial_tc5(cudaStream_t st, const unsigned char* q, int nq, const unsigned char* t, int nt, int tbase, int mode, akz_match_t* parts)
+int match_partial_tc5(cudaStream_t st, const unsigned char* q, int nq, const unsigned char* t, int nt, int tbase, int mode, akz_match_t* parts, int filter_mode)
 {
     if (nq <= 0) return 0;
     int nsplit, T, S, grid;
     const int nparts = match_tc5_plan(nq, nt, &nsplit, &T, &S, &grid);
     if (nparts < 0) return nparts;
-    static unsigned long long attr = 0;
-    if (akz_once_per_device(attr)) {
+    static akz_once_t attr;
+    if (akz_once_guard once{attr}) {
         cudaFuncSetAttribute(k_match_tc5<AKZ_MATCH_KNN2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM);
         cudaFuncSetAttribute(k_match_tc5<AKZ_MATCH_COMPAT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM);
         cudaFuncSetAttribute(k_match_tc5<AKZ_MATCH_KNN2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM);
@@ -529,7 +544,7 @@ int match_partial_tc5(cudaStream_t st, const unsigned char* q, int nq, const uns
     a.T = T; a.nsplit = nsplit; a.S = S; a.total = ((nq + T5_Q - 1) / T5_Q) * nsplit * T; a.maxslots = nparts / nsplit;
     // a chunk rarely holds a new top-2 entry after ~2000 candidates; the reference-compatible state changes only on a new best
     // distance or a tie with it, which is rarer still: its filter pays off at every range length
-    const bool filter = g_tc5_filter < 0 ? (T * T5_N >= 2048 || mode == AKZ_MATCH_COMPAT) : g_tc5_filter != 0;
+    const bool filter = filter_mode < 0 ? (T * T5_N >= 2048 || mode == AKZ_MATCH_COMPAT) : filter_mode != 0;
     if (mode != AKZ_MATCH_COMPAT) {
         if (filter) k_match_tc5<AKZ_MATCH_KNN2, true><<<grid, T5_NT, T5_SMEM, st>>>(a);
         else k_match_tc5<AKZ_MATCH_KNN2, false><<<grid, T5_NT, T5_SMEM, st>>>(a);

@@ -751,7 +751,7 @@ __global__ void __launch_bounds__(F2_BX * (F2_T / RB), 2) k_fed3(const __grid_co
     }
 }
 
-unsigned long long g_attr_done = 0;
+akz_once_t g_attr_done;
 int g_fed_rb = 4;                            // rows per thread block of k_fed3 (AKZ_FED_RB=2 selects the 4 x 2 variant)
 
 }  // namespace
@@ -760,7 +760,8 @@ namespace akzk {
 
 static void set_attrs()
 {
-    if (!akz_once_per_device(g_attr_done)) return;
+    akz_once_guard once{g_attr_done};
+    if (!once) return;
     if (const char* e = getenv("AKZ_FED_RB")) g_fed_rb = atoi(e) == 2 ? 2 : 4;
     cudaFuncSetAttribute(k_fed, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * FE_W * FE_H * (int)sizeof(float));
     cudaFuncSetAttribute(k_fed2, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM);

@@ -5,6 +5,9 @@
 #include "akaze_structures.h"
 #include "cuda_utils.h"
 
+// the product library is built with -fvisibility=hidden: the drop-in surface is exported explicitly
+#pragma GCC visibility push(default)
+
 namespace akaze
 {
     // Allocate / release the host and device arrays of an AkazeData (reference akaze.cpp:26-52).
@@ -36,3 +39,5 @@ namespace akaze
         Akazer& operator=(const Akazer&);
     };
 }
+
+#pragma GCC visibility pop

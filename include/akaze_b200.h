@@ -95,6 +95,8 @@ AKZ_API void        akz_default_options(akz_options* o);
 /* FED time steps, host only — replaces fed_tau_by_process_time (fed.cpp:41). Returns n (or -n if
  * cap is too small). */
 AKZ_API int akz_fed_tau(float T, int M, float tau_max, int reordering, float* tau, int cap);
+/* the time steps of one cycle for a given step count and scale — replaces fed_tau_internal (fed.cpp:64) */
+AKZ_API int akz_fed_tau_internal(int n, float scale, float tau_max, int reordering, float* tau, int cap);
 /* Normalised Gaussian taps k[0..radius] — replaces createGaussKernel (akazed.cu:2298). */
 AKZ_API void akz_gauss_taps(float var, int radius, float* taps);
 /* M-LDB comparison table (486 pairs) — replaces setCompareIndices (akazed.cu:65). */

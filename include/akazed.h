@@ -9,6 +9,9 @@
 #include "akaze_structures.h"
 #include "cuda_utils.h"
 
+// the product library is built with -fvisibility=hidden: the drop-in surface is exported explicitly
+#pragma GCC visibility push(default)
+
 void setMaxNumPoints(const int num);
 void getPointCounter(void** addr);
 void getMaxContrastAddr(void** addr);
@@ -59,3 +62,5 @@ namespace fastakaze
     void hCalcOrient(akaze::AkazeData& result, void* tmem, int noctaves, int max_scale);
     void hDescribe(akaze::AkazeData& result, void* tmem, int noctaves, int max_scale, int patsize);
 }
+
+#pragma GCC visibility pop

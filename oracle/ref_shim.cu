@@ -69,6 +69,14 @@ REF_API int ref_fed_tau(float T, int M, float tau_max, int reordering, float* ou
     return n;
 }
 
+REF_API int ref_fed_tau_internal(int n, float scale, float tau_max, int reordering, float* out, int cap)
+{
+    std::vector<float> tau;
+    int m = fed_tau_internal(n, scale, tau_max, reordering != 0, tau);
+    for (int i = 0; i < m && i < cap; i++) out[i] = tau[i];
+    return m;
+}
+
 // ---- stage seams (akazed.h) -------------------------------------------------------------
 REF_API void ref_setCompareIndices() { setCompareIndices(); }
 REF_API void ref_setMaxNumPoints(int n) { setMaxNumPoints(n); }

@@ -180,6 +180,7 @@ def ref():
     L.ref_set_kcontrast_mode.argtypes = [i, f]
     L.ref_last_kcontrast.restype = f
     L.ref_fed_tau.argtypes = [f, i, f, i, C.POINTER(f), i]
+    L.ref_fed_tau_internal.argtypes = [i, f, f, i, C.POINTER(f), i]
     L.ref_setOparam.argtypes = [C.POINTER(i), i]
     L.ref_setMaxNumPoints.argtypes = [i]
     L.ref_readPointCounter.restype = C.c_uint
@@ -223,6 +224,133 @@ def ref():
     _ref = L
     return L
 
+
+
+# ---- the PRODUCT's drop-in C++ surface (include/akaze.h ...) behind tests/cpp/dropin_shim.cu -------------------------
+DROPIN_DIR = os.path.join(ROOT, "tests", "cpp", "build")
+DROPIN_SO = os.path.join(DROPIN_DIR, "libdropin_shim.so")
+DROPIN_EXE = os.path.join(DROPIN_DIR, "dropin_usage")
+_dropin = None
+
+
+def have_dropin():
+    return os.path.exists(DROPIN_SO)
+
+
+def dropin():
+    """ctypes handle of the shim that drives akaze::Akazer / initAkazeData / cuMatch / the h* stage functions of the
+    product library exactly as the reference's main.cpp does (the twin of ref())."""
+    global _dropin
+    if _dropin is not None:
+        return _dropin
+    L = C.CDLL(DROPIN_SO)
+    f, i, vp = C.c_float, C.c_int, C.c_void_p
+    L.dropin_data_create.argtypes = [i, i, i]
+    L.dropin_data_create.restype = vp
+    L.dropin_data_free.argtypes = [vp]
+    for name in ("dropin_data_num", "dropin_data_max"):
+        getattr(L, name).argtypes = [vp]
+    for name in ("dropin_data_host", "dropin_data_dev"):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = vp
+    L.dropin_data_set_num.argtypes = [vp, i]
+    L.dropin_akazer_create.argtypes = [i, i, i, i, i, f, f, f, i, f, f, i, i]
+    L.dropin_akazer_create.restype = vp
+    L.dropin_akazer_destroy.argtypes = [vp]
+    L.dropin_akazer_detectAndCompute.argtypes = [vp, vp, vp, i, i, i, i]
+    L.dropin_akazer_fastDetectAndCompute.argtypes = [vp, vp, vp, i, i, i, i]
+    L.dropin_akazer_time.argtypes = [vp, vp, vp, i, i, i, i, i, i]
+    L.dropin_akazer_time.restype = f
+    L.dropin_cuMatch.argtypes = [vp, vp]
+    L.dropin_hMatch.argtypes = [vp, vp]
+    L.dropin_fed_tau.argtypes = [f, i, f, i, C.POINTER(f), i]
+    L.dropin_fed_tau_internal.argtypes = [i, f, f, i, C.POINTER(f), i]
+    L.dropin_hLowPass.argtypes = [vp, vp, i, i, i, f, i]
+    L.dropin_hDownWithSmooth.argtypes = [vp, vp, vp, i, i, i, i, i, i]
+    L.dropin_hScharrContrast.argtypes = [vp, vp, f, i, i, i]
+    L.dropin_hScharrContrast.restype = f
+    L.dropin_hFlow.argtypes = [vp, vp, i, f, i, i, i]
+    L.dropin_hNldStep.argtypes = [vp, vp, vp, f, i, i, i]
+    L.dropin_hHessianDeterminant.argtypes = [vp, vp, vp, i, i, i, i]
+    L.dropin_fast_hConv2dR2_u8.argtypes = [vp, vp, i, i, i, f]
+    L.dropin_fast_hConv2dR2_i.argtypes = [vp, vp, i, i, i, f]
+    L.dropin_fast_hConv2dR2_u8_t.argtypes = [vp, vp, vp, i, i, i, f]
+    L.dropin_fast_hConv2dR2_i_t.argtypes = [vp, vp, vp, i, i, i, f]
+    L.dropin_fast_hLowPass.argtypes = [vp, vp, i, i, i, f, i]
+    L.dropin_fast_hLowPass_t.argtypes = [vp, vp, vp, i, i, i, f, i]
+    L.dropin_fast_hDownWithSmooth.argtypes = [vp, vp, vp, i, i, i, i, i, i]
+    L.dropin_fast_hScharrContrast.argtypes = [vp, vp, f, i, i, i]
+    L.dropin_fast_hFlow.argtypes = [vp, vp, i, i, i, i, i]
+    L.dropin_fast_hNldStep.argtypes = [vp, vp, vp, f, i, i, i]
+    L.dropin_fast_hHessianDeterminant.argtypes = [vp, vp, vp, i, i, i, i]
+    _dropin = L
+    return L
+
+
+class DropinData:
+    """akaze::AkazeData allocated by the product's initAkazeData (akaze.h:12); host / device records as REF_POINT arrays."""
+
+    def __init__(self, max_pts, host=True, dev=True):
+        self.L = dropin()
+        self.h = self.L.dropin_data_create(max_pts, int(host), int(dev))
+        self.max_pts = max_pts
+
+    @property
+    def num(self):
+        return self.L.dropin_data_num(self.h)
+
+    def host_records(self, n=None):
+        n = self.num if n is None else n
+        p = self.L.dropin_data_host(self.h)
+        if not p or n <= 0:
+            return np.zeros(0, dtype=REF_POINT)
+        buf = (C.c_uint8 * (n * 104)).from_address(p)
+        return np.frombuffer(buf, dtype=np.uint8).copy().view(REF_POINT)
+
+    def dev_records(self, n=None):
+        import torch
+        n = self.num if n is None else n
+        p = self.L.dropin_data_dev(self.h)
+        if not p or n <= 0:
+            return np.zeros(0, dtype=REF_POINT)
+        torch.cuda.synchronize()
+        return _wrap_device(p, n * 104).cpu().numpy().view(REF_POINT).copy()
+
+    @property
+    def dev_ptr(self):
+        return self.L.dropin_data_dev(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.dropin_data_free(self.h)
+            self.h = None
+
+
+class DropinAkazer:
+    """akaze::Akazer of the PRODUCT (include/akaze.h) driven like main.cpp:192-205 drives the reference's."""
+
+    def __init__(self, w, h, pitch, noctaves=4, max_scale=4, per=0.7, kcontrast=0.03, soffset=1.6, reordering=True,
+                 derivative_factor=1.5, dthreshold=0.001, diffusivity=1, pattern=10):
+        self.L = dropin()
+        self.w, self.h, self.pitch = w, h, pitch
+        self.hnd = self.L.dropin_akazer_create(w, h, pitch, noctaves, max_scale, per, kcontrast, soffset, int(reordering),
+                                               derivative_factor, dthreshold, diffusivity, pattern)
+
+    def detect_and_compute(self, img_t, data, desc=True, fast=False):
+        import torch
+        torch.cuda.synchronize()
+        fn = self.L.dropin_akazer_fastDetectAndCompute if fast else self.L.dropin_akazer_detectAndCompute
+        return fn(self.hnd, C.c_void_p(img_t.data_ptr()), data.h, self.w, self.h, self.pitch, int(desc))
+
+    def time(self, img_t, data, iters, desc=True, fast=False):
+        """ms per call of the synchronous entry point (the reference's own timed loop, main.cpp:199-205)"""
+        return float(self.L.dropin_akazer_time(self.hnd, C.c_void_p(img_t.data_ptr()), data.h, self.w, self.h, self.pitch,
+                                               int(desc), int(fast), iters))
+
+    def close(self):
+        if self.hnd:
+            self.L.dropin_akazer_destroy(self.hnd)
+            self.hnd = None
 
 
 def _wrap_device(ptr, nbytes):
