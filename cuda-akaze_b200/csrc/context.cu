@@ -417,20 +417,35 @@ static int check_frame_args(akz_ctx* c, const void* img, int dtype, int nframes,
     return AKZ_OK;
 }
 
-// fused level kernel: second generation when it covers the case (fused == 1), else the first generation
+// One level's "everything but the diffusion": the fused kernel k_prep2 when it covers the case (fused == 1, derivative step 2..4,
+// level at least 24 x 24); otherwise one kernel per reference stage (blur or octave transition, conductance, derivatives).
+// mode: 0 = base level (smooth := src), 1 = same-resolution blur, 2 = octave transition.
 static int prep_level(akz_ctx* c, int mode, const float* src, int sw, int sh, int sp, long long splane, float* ltdst, float* flowp,
                       float* lx, float* ly, float* det, int nmul, int step, int w, int h, int pitch, long long plane, int nf)
 {
     const akz_options& o = c->opt;
+    cudaStream_t st = c->stream;
     if (o.fused == 1) {
-        int r = akzk::level_prep2(c->stream, mode, src, sw, sh, sp, splane, ltdst, flowp, lx, ly, det, o.diffusivity, c->kc, 0.75f, nmul,
+        int r = akzk::level_prep2(st, mode, src, sw, sh, sp, splane, ltdst, flowp, lx, ly, det, o.diffusivity, c->kc, 0.75f, nmul,
                                   step, w, h, pitch, plane, nf);
         if (r != 0) return r;
     }
-    if (mode == 2)
-        return akzk::level_prep_down(c->stream, src, sw, sh, sp, splane, ltdst, flowp, lx, ly, det, o.diffusivity, c->kc, 0.75f, nmul,
-                                     step, w, h, pitch, plane, nf);
-    return akzk::level_prep(c->stream, src, flowp, lx, ly, det, mode, o.diffusivity, c->kc, 0.75f, nmul, step, w, h, pitch, plane, nf);
+    int launches = 0, r = 0;
+    const float* sm = src;
+    if (mode != 0) {
+        if (!c->smooth) return akz_set_error(AKZ_E_INVALID, "this context has no scratch planes for the staged level path");
+        if (mode == 2) r = akzk::down_with_smooth(st, src, ltdst, c->smooth, sw, sh, sp, splane, w, h, pitch, plane, nf);
+        else r = akzk::lowpass(st, src, c->smooth, w, h, pitch, plane, pitch, plane, nf, 1.f, 5);
+        if (r < 0) return r;
+        launches += r;
+        sm = c->smooth;
+    }
+    if (flowp) {
+        if ((r = akzk::flow(st, sm, flowp, o.diffusivity, c->kc, 0.75f, nmul, w, h, pitch, plane, nf)) < 0) return r;
+        launches += r;
+    }
+    if ((r = akzk::hessian(st, sm, lx, ly, det, step, w, h, pitch, plane, nf)) < 0) return r;
+    return launches + r;
 }
 
 static int scale_space_chunk(akz_ctx* c, const void* img, int dtype, int nf, int ipitch, long long istride)

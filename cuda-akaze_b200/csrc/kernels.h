@@ -40,18 +40,7 @@ int flow(cudaStream_t st, const float* src, float* flowp, int type, const float*
 int nld_step(cudaStream_t st, const float* src, const float* flowp, float* dst, float tau, int w, int h, int pitch, long long stride, int n);
 int hessian(cudaStream_t st, const float* smooth, float* lx, float* ly, float* det, int step, int w, int h, int pitch, long long stride, int n);
 
-// ---- scale_space_fused.cu: production kernels ------------------------------------------------------
-// base level from the input image: sigma=1 blur -> Scharr max / histogram -> k ; sigma0 blur -> Lt(0,0)
-int base_level(cudaStream_t st, const void* img, int dtype, int w, int h, int ipitch, long long istride,
-               float* lt, int pitch, long long plane, unsigned* hmax_bits, int* hist, float* kout, float per, float override_k,
-               float var0, int ksz0, int n);
-// Lt_prev -> (sigma=1 blur in smem) -> flow, Lx, Ly, det.  prev==cur plane for the base level (smooth := Lt)
-int level_prep(cudaStream_t st, const float* ltprev, float* flowp, float* lx, float* ly, float* det, int blur, int type,
-               const float* kc, float kscale, int nmul, int step, int w, int h, int pitch, long long plane, int n);
-// octave transition: Lt(o-1,0) -> Lt(o,0) (subsample) + flow, Lx, Ly, det from the coarse-lattice blur
-int level_prep_down(cudaStream_t st, const float* ltsrc, int sw, int sh, int sp, long long splane,
-                    float* ltdst, float* flowp, float* lx, float* ly, float* det, int type,
-                    const float* kc, float kscale, int nmul, int step, int w, int h, int pitch, long long plane, int n);
+// ---- fused production kernels ---------------------------------------------------------------------
 // base_level.cu: Lt(0,0), gradient-magnitude plane, its maximum and histogram in one pass over the input (+ one over the
 // magnitude plane).  Returns the number of launches, 0 when the sigma0 radius is not 4 (caller uses the staged kernels).
 int base_level2(cudaStream_t st, const void* img, int dtype, int w, int h, int ipitch, long long istride,
@@ -59,11 +48,12 @@ int base_level2(cudaStream_t st, const void* img, int dtype, int w, int h, int i
 int contrast_scan(cudaStream_t st, const unsigned* hmax_bits, const int* hist, float* kout, float per, float override_k, int w, int h, int n);
 // level_prep.cu: second-generation level kernel (templated on the derivative step, 64x64 tiles, vector shared-memory
 // traffic).  mode 0 = base level (no blur), 1 = blur, 2 = octave transition.  Returns 1 if launched, 0 if the
-// (step, size) combination is not covered and the caller must use level_prep / level_prep_down.
+// (step, size) combination is not covered and the caller must run the per-stage kernels.
 int level_prep2(cudaStream_t st, int mode, const float* src, int sw, int sh, int sp, long long splane,
                 float* ltdst, float* flowp, float* lx, float* ly, float* det, int type,
                 const float* kc, float kscale, int nmul, int step, int w, int h, int pitch, long long plane, int n, int int_planes = 0);
-// all n FED steps of a level (frozen conductance), temporally blocked in shared memory
+// fed.cu: all n FED steps of a level (frozen conductance) in ceil(n / 4) launches of the streaming warp kernel (k_fed4), or of the
+// tile kernel (k_fed3) when the rows are not 16-byte aligned
 int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst, float* tmp, const float* tau, int nsteps,
               int w, int h, int pitch, long long plane, int n, int fused, int int_planes = 0);
 

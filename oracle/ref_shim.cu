@@ -249,6 +249,27 @@ REF_API void ref_fast_hDescribe(void* d_pts, int n, int cap, void* tmem, int noc
 { akaze::AkazeData d = mkdata(d_pts, n, cap); if (n > 0) fastakaze::hDescribe(d, tmem, noct, S, pat); }
 REF_API void ref_cuda_free(void* p) { cudaFree(p); }
 
+// gHammingMatch reads 3 bytes of shared memory it never wrote: whatever earlier kernels left there is
+// added to every distance of a query.  This helper (ours, test infrastructure) fills the shared memory of every SM with
+// zeros so that a following hMatch / cuMatch is deterministic and comparable bit for bit.
+__global__ void k_scrub_shared(int words)
+{
+    extern __shared__ int scrub[];
+    for (int i = threadIdx.x; i < words; i += blockDim.x) scrub[i] = 0;
+    __syncthreads();
+    if (scrub[(threadIdx.x * 97) % words] != 0) printf("scrub\n");        // keeps the stores alive
+}
+REF_API int ref_scrub_shared_memory()
+{
+    int dev = 0, nsm = 0, maxsm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (cudaFuncSetAttribute(k_scrub_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm) != cudaSuccess) return -1;
+    k_scrub_shared<<<nsm * 8, 256, maxsm>>>(maxsm / 4);
+    return cudaDeviceSynchronize() == cudaSuccess ? 0 : -2;
+}
+
 REF_API void ref_cuMatch(void* d_q, void* h_q, int nq, void* d_t, int nt)
 {
     akaze::AkazeData a = mkdata(d_q, nq, nq), b = mkdata(d_t, nt, nt);

@@ -221,6 +221,7 @@ def ref():
     L.ref_akazer_fast_detect_keep.argtypes = [vp, vp, i, i, i, i, vp, i, C.POINTER(vp), C.POINTER(i), C.POINTER(i)]
     L.ref_akazer_fastDetectAndCompute.argtypes = [vp, vp, i, i, i, i, vp, vp, i]
     L.ref_cuMatch.argtypes = [vp, vp, i, vp, i]
+    L.ref_scrub_shared_memory.restype = i
     _ref = L
     return L
 

@@ -159,10 +159,10 @@ def test_akazer_vs_reference_akazer():
             (k["y"][j].view(np.uint32) == rp["y"].view(np.uint32))
         assert int((d[j[exact]][:, :61] != rp["features"][exact]).any(axis=1).sum()) == 0 and exact.mean() >= 0.75
         # and the drop-in run with its own k: identical to the override run wherever k agrees, else a near-identical set
-        overlap = len(set(zip(mine["octave"].tolist(), np.round(mine["x"], 2).tolist(), np.round(mine["y"], 2).tolist())) &
-                      set(zip(k["layer"].tolist(), np.round(k["x"], 2).tolist(), np.round(k["y"], 2).tolist()))) / max(len(k), 1)
-        print(f"\n[{name}] drop-in Akazer: {n} keypoints; reference (serialised): {len(rp)}; "
-              f"overlap of the drop-in set (own contrast maximum) with the reference-k set: {overlap:.4f}")
+        dd2, _ = cKDTree(np.stack([k["x"], k["y"]], 1)).query(np.stack([mine["x"], mine["y"]], 1))
+        overlap = float((dd2 <= 0.5).mean())
+        print(f"\n[{name}] drop-in Akazer (true contrast maximum): {n} keypoints; reference (serialised, its own k = {kref:.6f}): {len(rp)}; "
+              f"drop-in keypoints within 0.5 px of a reference-k keypoint: {overlap:.4f}")
         assert overlap >= 0.9
 
 
@@ -222,22 +222,29 @@ def test_cumatch_vs_reference_cumatch():
     tq = torch.from_numpy(q0.view(np.uint8).reshape(-1).copy()).cuda()
     tt = torch.from_numpy(d2.dev_records(n2).view(np.uint8).reshape(-1).copy()).cuda()
     torch.cuda.synchronize()
+    # The reference reads 64 bytes of both operands: 3 bytes beyond ofeat[61] in shared memory, never written by the kernel
+    # (whatever an earlier kernel left there), against the 3 padding bytes of the train record (zero here) -- App. B-6.  With
+    # the shared memory of every SM scrubbed first (ref_scrub_shared_memory, test infrastructure in oracle/ref_shim.cu) those
+    # bytes are zero and the two libraries must agree in every field of every record.
+    assert B.ref().ref_scrub_shared_memory() == 0
     B.ref().ref_cuMatch(C.c_void_p(tq.data_ptr()), None, n1, C.c_void_p(tt.data_ptr()), n2)
     torch.cuda.synchronize()
     rq = tq.cpu().numpy().view(B.REF_POINT)
     B.dropin().dropin_cuMatch(d1.h, d2.h)
     mq = d1.dev_records()
+    # our result is also exact by the CPU oracle's restatement of the rule (akazed.cu:2144-2241)
+    qf = np.zeros((n1, 64), np.uint8); qf[:, :61] = q0["features"]
+    tf = np.zeros((n2, 64), np.uint8); tf[:, :61] = d2.dev_records(n2)["features"]
+    o = B.oracle_match(qf, tf, "compat")
+    assert np.array_equal(mq["match"], o[:, 0]) and np.array_equal(mq["distance"], o[:, 1])
     agree = mq["match"] == rq["match"]
-    # the reference sums 3 uninitialised shared-memory bytes into every distance (App. B-6): only the <96 gate may flip
-    gate = (mq["match"] >= 0) & (mq["distance"] >= 96 - 24) & (rq["match"] < 0)
-    print(f"\n[cuMatch vs reference] {n1}x{n2}: index agreement {agree.mean():.5f}, gate flips {int((~agree & gate).sum())}, "
-          f"unexplained {int((~agree & ~gate).sum())}")
-    assert (~agree & ~gate).sum() == 0 and agree.mean() >= 0.97
     both = (mq["match"] >= 0) & (rq["match"] >= 0)
-    assert np.array_equal(mq["match_x"][both].view(np.uint32), rq["match_x"][both].view(np.uint32))
-    assert np.array_equal(mq["match_y"][both].view(np.uint32), rq["match_y"][both].view(np.uint32))
     off = rq["distance"][both] - mq["distance"][both]
-    assert off.min() >= 0 and off.max() <= 24
+    print(f"\n[cuMatch vs reference, shared memory scrubbed] {n1}x{n2}: index agreement {agree.mean():.5f}; accepted {int((mq['match'] >= 0).sum())} / "
+          f"{int((rq['match'] >= 0).sum())}; distance offsets {dict(zip(*[x.tolist() for x in np.unique(off, return_counts=True)]))}")
+    assert agree.all()
+    for f in ("distance", "match_x", "match_y"):
+        assert np.array_equal(mq[f].view(np.uint32), rq[f].view(np.uint32)), f
     d1.close(); d2.close()
 
 
@@ -386,7 +393,14 @@ def test_stage_functions_of_the_dropin_surface_vs_reference():
     ikm = D.dropin_fast_hScharrContrast(p(ismooth), p(g1), 0.7, w, h, w)
     ikr = R.ref_fast_hScharrContrast(p(ismooth), p(g2), 0.7, w, h, w)
     torch.cuda.synchronize()
-    assert torch.equal(g1, g2), "fastakaze::hScharrContrast gradient plane"
+    # (the reference's maximum search reorders values inside its gradient plane, akazed.cu:3233-3330: the planes are not comparable
+    # after the call; the magnitude itself is checked against the integer formula of gScharrContrastNaive akazed.cu:3208-3231)
+    sm = ismooth.cpu().numpy().astype(np.int64)
+    pad = np.pad(sm, 1, mode="reflect")
+    dx = 10 * (pad[1:-1, 2:] - pad[1:-1, :-2]) + 3 * (pad[:-2, 2:] + pad[2:, 2:] - pad[:-2, :-2] - pad[2:, :-2])
+    dy = 10 * (pad[2:, 1:-1] - pad[:-2, 1:-1]) + 3 * (pad[2:, :-2] + pad[2:, 2:] - pad[:-2, :-2] - pad[:-2, 2:])
+    expect = (np.sqrt((dx * dx + dy * dy).astype(np.float32)).astype(np.float32) + np.float32(0.5)).astype(np.int32)
+    assert np.array_equal(g1.cpu().numpy(), expect), "fastakaze::hScharrContrast gradient plane"
     print(f"[fastakaze::hScharrContrast] product {ikm} reference {ikr}")
     assert ikm > 0 and abs(ikm - ikr) <= max(2, 0.2 * ikr)
 

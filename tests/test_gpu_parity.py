@@ -233,10 +233,13 @@ def test_contrast_factor(stage_ctx):
 # fused kernels vs per-stage kernels
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [1, 3, 7, 8, 9, 14, 29])
-@pytest.mark.parametrize("size", [(333, 217), (1280, 96), (64, 300)])
+@pytest.mark.parametrize("size", [(333, 217, 32), (1280, 96, 32), (64, 300, 32), (121, 70, 4), (480, 270, 32), (250, 33, 1), (333, 100, 1)])
 def test_fed_cycle_fused_equals_single_steps(stage_ctx, stage_ctx_fused, n, size):
-    w, h = size
-    p = (w + 31) // 32 * 32
+    """The FED cycle kernels against n single-step launches and the CPU oracle.  Row pitches that are multiples of 4 floats run
+    the streaming warp kernel k_fed4 (widths that are not multiples of 4 its general variant; 121 = one full strip of 120
+    columns plus a strip of one column); unaligned pitches (last entries) run the tile kernel k_fed3."""
+    w, h, align = size
+    p = (w + align - 1) // align * align
     rng = np.random.default_rng(n)
     L = rng.random((2, h, p), dtype=np.float32)
     g = rng.random((2, h, p), dtype=np.float32)
