@@ -315,7 +315,8 @@ class DropinData:
         if not p or n <= 0:
             return np.zeros(0, dtype=REF_POINT)
         torch.cuda.synchronize()
-        return _wrap_device(p, n * 104).cpu().numpy().view(REF_POINT).copy()
+        # raw bytes first: a structured-array .copy() copies field by field and leaves the padding bytes (85..87) uninitialised
+        return _wrap_device(p, n * 104).cpu().numpy().copy().view(REF_POINT)
 
     @property
     def dev_ptr(self):
