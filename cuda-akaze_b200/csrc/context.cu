@@ -6,6 +6,7 @@
 #include "kernels.h"
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <vector>
@@ -417,6 +418,31 @@ static int check_frame_args(akz_ctx* c, const void* img, int dtype, int nframes,
     return AKZ_OK;
 }
 
+static bool prep_split_enabled()
+{
+    static const bool on = [] { const char* e = getenv("AKZ_PREP_SPLIT"); return !e || atoi(e) != 0; }();      // A/B knob, read once
+    return on;
+}
+
+// Split level pipeline (k_prep3 + k_deriv4).  Returns the number of launches, 0 when the level is not covered.
+static int prep_level_split(akz_ctx* c, int mode, const float* src, int sw, int sh, int sp, long long splane, float* ltdst, float* flowp,
+                            float* lx, float* ly, float* det, int nmul, int step, int w, int h, int pitch, long long plane, int nf, int int_planes)
+{
+    if (!prep_split_enabled() || step < 2 || step > 4 || w < 32 || h < 32 || (w % 4) != 0) return 0;
+    cudaStream_t st = c->stream;
+    if (mode == 0) return akzk::deriv_stream(st, src, lx, ly, det, step, w, h, pitch, plane, nf, int_planes);
+    if (!c->smooth || !flowp) return 0;
+    // both halves must take the level: probe the derivative half's conditions first (it has the stricter ones)
+    if ((pitch % 4) != 0 || (plane % 4) != 0 || (((uintptr_t)c->smooth | (uintptr_t)lx | (uintptr_t)ly | (uintptr_t)det) % 16) != 0) return 0;
+    int r1 = akzk::level_blur_flow(st, mode, src, sw, sh, sp, splane, ltdst, flowp, c->smooth, c->opt.diffusivity, c->kc, 0.75f, nmul,
+                                   w, h, pitch, plane, nf, int_planes);
+    if (r1 <= 0) return r1;
+    int r2 = akzk::deriv_stream(st, c->smooth, lx, ly, det, step, w, h, pitch, plane, nf, int_planes);
+    if (r2 < 0) return r2;
+    if (r2 == 0) return akz_set_error(AKZ_E_UNSUPPORTED, "split level pipeline: derivative half refused a level the blur half took");
+    return r1 + r2;
+}
+
 // One level's "everything but the diffusion": the fused kernel k_prep2 when it covers the case (fused == 1, derivative step 2..4,
 // level at least 24 x 24); otherwise one kernel per reference stage (blur or octave transition, conductance, derivatives).
 // mode: 0 = base level (smooth := src), 1 = same-resolution blur, 2 = octave transition.
@@ -426,8 +452,12 @@ static int prep_level(akz_ctx* c, int mode, const float* src, int sw, int sh, in
     const akz_options& o = c->opt;
     cudaStream_t st = c->stream;
     if (o.fused == 1) {
-        int r = akzk::level_prep2(st, mode, src, sw, sh, sp, splane, ltdst, flowp, lx, ly, det, o.diffusivity, c->kc, 0.75f, nmul,
-                                  step, w, h, pitch, plane, nf);
+        // split pipeline: tile kernel for the blur / octave transition + conductance (blurred plane to c->smooth), streaming warp
+        // kernel for the derivatives and the determinant; the single tile kernel k_prep2 takes what they do not cover
+        int r = prep_level_split(c, mode, src, sw, sh, sp, splane, ltdst, flowp, lx, ly, det, nmul, step, w, h, pitch, plane, nf, 0);
+        if (r != 0) return r;
+        r = akzk::level_prep2(st, mode, src, sw, sh, sp, splane, ltdst, flowp, lx, ly, det, o.diffusivity, c->kc, 0.75f, nmul,
+                              step, w, h, pitch, plane, nf);
         if (r != 0) return r;
     }
     int launches = 0, r = 0;
@@ -551,6 +581,9 @@ static int fast_scale_space_chunk(akz_ctx* c, const unsigned char* img, int nf, 
     // pipeline's k_prep2 instantiated for the integer arithmetic (level_prep.cu); 0 = one kernel per reference stage
     auto iprep = [&](int mode, const int* src, int sw, int sh, int sp, long long splane, int* ltdst, int* flowp, AkzLevel& L, int nmul) -> int {
         if (o.fused != 1) return 0;
+        int rs = prep_level_split(c, mode, (const float*)src, sw, sh, sp, splane, (float*)ltdst, (float*)flowp, L.lx, L.ly, L.det, nmul,
+                                  L.sigma_size, L.w, L.h, L.pitch, L.plane, nf, 1);
+        if (rs != 0) return rs;
         return akzk::level_prep2(st, mode, (const float*)src, sw, sh, sp, splane, (float*)ltdst, (float*)flowp, L.lx, L.ly, L.det, o.diffusivity,
                                  c->kc, 0.75f, nmul, L.sigma_size, L.w, L.h, L.pitch, L.plane, nf, 1);
     };

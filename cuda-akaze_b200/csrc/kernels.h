@@ -52,6 +52,13 @@ int contrast_scan(cudaStream_t st, const unsigned* hmax_bits, const int* hist, f
 int level_prep2(cudaStream_t st, int mode, const float* src, int sw, int sh, int sp, long long splane,
                 float* ltdst, float* flowp, float* lx, float* ly, float* det, int type,
                 const float* kc, float kscale, int nmul, int step, int w, int h, int pitch, long long plane, int n, int int_planes = 0);
+// split level pipeline: k_prep3 (level_prep.cu: blur or octave transition + conductance, blurred plane to global memory) and
+// k_deriv4 + border-ring kernels (deriv_stream.cu: Lx, Ly, det from the blurred plane).  Both return 0 when the case is not covered.
+int level_blur_flow(cudaStream_t st, int mode, const float* src, int sw, int sh, int sp, long long splane,
+                    float* ltdst, float* flowp, float* smooth, int type, const float* kc, float kscale, int nmul,
+                    int w, int h, int pitch, long long plane, int n, int int_planes = 0);
+int deriv_stream(cudaStream_t st, const float* smooth, float* lx, float* ly, float* det, int step, int w, int h, int pitch, long long plane,
+                 int n, int int_planes = 0);
 // fed.cu: all n FED steps of a level (frozen conductance) in ceil(n / 4) launches of the streaming warp kernel (k_fed4), or of the
 // tile kernel (k_fed3) when the rows are not 16-byte aligned
 int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst, float* tmp, const float* tau, int nsteps,

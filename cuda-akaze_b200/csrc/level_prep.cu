@@ -25,6 +25,7 @@
 // The arithmetic is the pinned sequence of common.cuh: results are bit-identical to the staged kernels.
 #include "common.cuh"
 #include "kernels.h"
+#include "level_math.cuh"
 
 using namespace akz;
 
@@ -42,8 +43,8 @@ struct Prep2Args {
     float *flow, *lx, *ly, *det;         // flow may be null
     const float* kc;                     // per-frame contrast factor
     long long splane, plane;
-    float kscale, fac1, fac2, k0, k1, k2;
-    int ik0, ik1, ik2, ifac1, ifac2;     // INT: 16.16 fixed-point taps and derivative factors (akazed.cu:3896, :4184)
+    LevelMathArgs m;                     // taps and derivative factors, float and 16.16
+    float kscale;
     int nmul, type, vec_ok;
     int sw, sh, sp;                      // source dims (== w, h, pitch unless PM_DOWN)
     int w, h, pitch;
@@ -69,69 +70,6 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_sr
 __device__ __forceinline__ void cp_async_wait_all()
 {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
-
-// ---- arithmetic of the two pipelines ---------------------------------------------------------------------------------------
-// INT = false: the float pipeline, pinned operation order of common.cuh.  INT = true: the integer pipeline (namespace fastakaze,
-// akazed.cu:2781-4366): planes are int32 whose bit patterns travel through the same float registers / shared-memory tiles;
-// every product sum is shifted right by 16, integer addition is associative, so only the truncation points matter.
-__device__ __forceinline__ int fi(float v) { return __float_as_int(v); }
-__device__ __forceinline__ float fb(int v) { return __int_as_float(v); }
-
-template <bool INT>
-__device__ __forceinline__ float p2_gauss(float m2, float m1, float c, float p1, float p2, const Prep2Args& a)
-{
-    if (!INT) return gauss_r2(m2, m1, c, p1, p2, a.k0, a.k1, a.k2);
-    return fb((a.ik0 * fi(c) + a.ik1 * (fi(m1) + fi(p1)) + a.ik2 * (fi(m2) + fi(p2))) >> 16);        // akazed.cu:2786-3076
-}
-// conductance of one pixel from its 3 x 3 neighbourhood of the smoothed level; ikc = 1 / k^2
-template <bool INT>
-__device__ __forceinline__ float p2_flow(float ul, float uc, float ur, float cl, float cr, float ll, float lc, float lr, int type, float ikc)
-{
-    if (!INT) {
-        float dx = scharr_dx(ul, ur, cl, cr, ll, lr);
-        float dy = scharr_dy(ul, uc, ur, ll, lc, lr);
-        return conductance(type, __fmul_rn(grad_sq(dx, dy), ikc));
-    }
-    // gFlowNaive akazed.cu:3406-3446, written in the reference's form (same contraction by nvcc as k_fflow)
-    const int dx = 10 * (fi(cr) - fi(cl)) + 3 * (fi(ur) + fi(lr) - fi(ul) - fi(ll));
-    const int dy = 10 * (fi(lc) - fi(uc)) + 3 * (fi(ll) + fi(lr) - fi(ul) - fi(ur));
-    const float dif2 = (dx * dx + dy * dy) * ikc;
-    int g;
-    if (type == 0) g = (int)(__expf(-dif2) * 65536 + 0.5f);
-    else if (type == 1) g = (int)(1.f / (1.f + dif2) * 65536 + 0.5f);
-    else if (type == 2) g = (int)((1.f - __expf(-3.315f / __powf(dif2, 4))) * 65536 + 0.5f);
-    else g = (int)(1.f / __fsqrt_rn(1.f + dif2) * 65536 + 0.5f);
-    return fb(g);
-}
-// first derivatives (x: sum_x / cr - cl, y: sum_y / lc - uc)
-template <bool INT>
-__device__ __forceinline__ void p2_deriv1(float ul, float uc, float ur, float cl, float cr, float ll, float lc, float lr, const Prep2Args& a, float& vx, float& vy)
-{
-    if (!INT) {
-        vx = deriv1(sum_x(ul, ur, ll, lr), __fsub_rn(cr, cl), a.fac1, a.fac2);
-        vy = deriv1(sum_y(ul, ur, ll, lr), __fsub_rn(lc, uc), a.fac1, a.fac2);
-    } else {                                                                                         // gDerivate akazed.cu:3339-3368
-        vx = fb((a.ifac1 * (fi(ur) + fi(lr) - fi(ul) - fi(ll)) + a.ifac2 * (fi(cr) - fi(cl))) >> 16);
-        vy = fb((a.ifac1 * (fi(lr) + fi(ll) - fi(ur) - fi(ul)) + a.ifac2 * (fi(lc) - fi(uc))) >> 16);
-    }
-}
-// determinant of the Hessian from the neighbourhoods of Lx (xu*, xc*, xl*) and Ly (yu*, yl*)
-template <bool INT>
-__device__ __forceinline__ float p2_det(float xul, float xuc, float xur, float xcl, float xcr, float xll, float xlc, float xlr,
-                                        float yul, float yuc, float yur, float yll, float ylc, float ylr, const Prep2Args& a)
-{
-    if (!INT) {
-        float dxx = deriv2(sum_x(xul, xur, xll, xlr), __fsub_rn(xcr, xcl), a.fac1, a.fac2);
-        float dxy = deriv2(sum_y(xul, xur, xll, xlr), __fsub_rn(xlc, xuc), a.fac1, a.fac2);
-        float dyy = deriv2(sum_y(yul, yur, yll, ylr), __fsub_rn(ylc, yuc), a.fac1, a.fac2);
-        return hess_det(dxx, dyy, dxy);
-    }
-    // gHessianDeterminant akazed.cu:3371-3403
-    const int dxx = (a.ifac1 * (fi(xur) + fi(xlr) - fi(xul) - fi(xll)) + a.ifac2 * (fi(xcr) - fi(xcl))) >> 16;
-    const int dxy = (a.ifac1 * (fi(xlr) + fi(xll) - fi(xur) - fi(xul)) + a.ifac2 * (fi(xlc) - fi(xuc))) >> 16;
-    const int dyy = (a.ifac1 * (fi(ylr) + fi(yll) - fi(yur) - fi(yul)) + a.ifac2 * (fi(ylc) - fi(yuc))) >> 16;
-    return fb(dxx * dyy - dxy * dxy);
 }
 
 // source-coordinate reflect of a coarse index (gDownWithSmooth reflects 2x+-2, 2x+-4 in the SOURCE image)
@@ -248,8 +186,8 @@ __global__ void __launch_bounds__(P2_NT, 3) k_prep2(const __grid_constant__ Prep
             const float* p = A + r * SP + 4 + 4 * g;
             float4 v0 = lds4(p - 4), v1 = lds4(p), v2 = lds4(p + 4);
             sts4(Bf + r * SP + 4 + 4 * g,
-                 p2_gauss<INT>(v0.z, v0.w, v1.x, v1.y, v1.z, a), p2_gauss<INT>(v0.w, v1.x, v1.y, v1.z, v1.w, a),
-                 p2_gauss<INT>(v1.x, v1.y, v1.z, v1.w, v2.x, a), p2_gauss<INT>(v1.y, v1.z, v1.w, v2.x, v2.y, a));
+                 p2_gauss<INT>(v0.z, v0.w, v1.x, v1.y, v1.z, a.m), p2_gauss<INT>(v0.w, v1.x, v1.y, v1.z, v1.w, a.m),
+                 p2_gauss<INT>(v1.x, v1.y, v1.z, v1.w, v2.x, a.m), p2_gauss<INT>(v1.y, v1.z, v1.w, v2.x, v2.y, a.m));
         }
         __syncthreads();
         // ---- 3. column pass: Sm rows [2, AR-2), four rows per item (8 loads + 4 stores per 4 rows; two-row items: 2 x (6 + 2)) ----
@@ -265,8 +203,8 @@ __global__ void __launch_bounds__(P2_NT, 3) k_prep2(const __grid_constant__ Prep
             float* q = Sm + r * SP + 4 + 4 * g;
 #pragma unroll
             for (int t = 0; t < 4; t++)
-                sts4(q + t * SP, p2_gauss<INT>(b[t].x, b[t + 1].x, b[t + 2].x, b[t + 3].x, b[t + 4].x, a), p2_gauss<INT>(b[t].y, b[t + 1].y, b[t + 2].y, b[t + 3].y, b[t + 4].y, a),
-                     p2_gauss<INT>(b[t].z, b[t + 1].z, b[t + 2].z, b[t + 3].z, b[t + 4].z, a), p2_gauss<INT>(b[t].w, b[t + 1].w, b[t + 2].w, b[t + 3].w, b[t + 4].w, a));
+                sts4(q + t * SP, p2_gauss<INT>(b[t].x, b[t + 1].x, b[t + 2].x, b[t + 3].x, b[t + 4].x, a.m), p2_gauss<INT>(b[t].y, b[t + 1].y, b[t + 2].y, b[t + 3].y, b[t + 4].y, a.m),
+                     p2_gauss<INT>(b[t].z, b[t + 1].z, b[t + 2].z, b[t + 3].z, b[t + 4].z, a.m), p2_gauss<INT>(b[t].w, b[t + 1].w, b[t + 2].w, b[t + 3].w, b[t + 4].w, a.m));
         }
         __syncthreads();
     }
@@ -348,7 +286,7 @@ __global__ void __launch_bounds__(P2_NT, 3) k_prep2(const __grid_constant__ Prep
             for (int j = 0; j < 4; j++) {
                 const int m = 4 + j;
                 float ul = u[m - S], uc = u[m], ur = u[m + S], cl = c[m - S], cr = c[m + S], ll = l[m - S], lc = l[m], lr = l[m + S];
-                p2_deriv1<INT>(ul, uc, ur, cl, cr, ll, lc, lr, a, vx[j], vy[j]);
+                p2_deriv1<INT>(ul, uc, ur, cl, cr, ll, lc, lr, a.m, vx[j], vy[j]);
             }
             sts4(LX + sr * SP + c4, vx[0], vx[1], vx[2], vx[3]);
             sts4(LY + sr * SP + c4, vy[0], vy[1], vy[2], vy[3]);
@@ -394,7 +332,7 @@ __global__ void __launch_bounds__(P2_NT, 3) k_prep2(const __grid_constant__ Prep
             for (int j = 0; j < 4; j++) {
                 const int m = 4 + j;
                 o[j] = p2_det<INT>(xu[m - S], xu[m], xu[m + S], xc[m - S], xc[m + S], xl[m - S], xl[m], xl[m + S],
-                                   yu[m - S], yu[m], yu[m + S], yl[m - S], yl[m], yl[m + S], a);
+                                   yu[m - S], yu[m], yu[m + S], yl[m - S], yl[m], yl[m + S], a.m);
             }
             int y = Y0 + r, x = X0 + 4 * g;
             float* d = dg + (long long)y * a.pitch + x;
@@ -405,6 +343,220 @@ __global__ void __launch_bounds__(P2_NT, 3) k_prep2(const __grid_constant__ Prep
             }
         }
     }
+}
+
+// =====================================================================================================================
+// k_prep3<MODE>: the blur half of a level for the split pipeline -- sigma = 1 blur (or octave transition) of the predecessor
+// tile, the conductance plane g, and the blurred plane itself written to global memory for the streaming derivative kernel
+// (deriv_stream.cu).  Same phases 1-4, arithmetic and border treatment as k_prep2, on a frame that only carries the halo
+// the blur (2) and the Scharr conductance (1) need: 64 x 48 output tile, rows [-4, 52), columns [-8, 72), 80 floats per
+// shared-memory row; the blurred tile overwrites the input tile.  Subsumes gConv2d<2> | gDownWithSmooth (akazed.cu:204, :449)
+// and gFlowNaive (:1068).
+// =====================================================================================================================
+constexpr int P3_OX = 8, P3_OY = 4;
+constexpr int P3_SP = P2_W + 2 * P3_OX;       // 80
+constexpr int P3_AR = P2_H + 2 * P3_OY;       // 56
+constexpr int P3_C0 = 4, P3_C1 = 76;          // columns of the frame that are computed (18 groups of 4)
+constexpr int P3_NG = (P3_C1 - P3_C0) / 4;
+
+// out-of-image cells of the blurred tile := value of their reflect-101 mirror cell (border tiles only; see ghost_fix)
+__device__ __forceinline__ void ghost_fix3(float* T, int r0, int r1, int X0, int Y0, int w, int h, int tid)
+{
+    constexpr int GC0 = P3_OX - 1, GC1 = P3_OX + P2_W + 1;          // the conductance stencil reads one column beyond the tile
+    constexpr int nc = GC1 - GC0;
+    const int nr = r1 - r0;
+    const int gy0 = Y0 - P3_OY + r0, gx0 = X0 - P3_OX + GC0;
+    const int top = min(max(-gy0, 0), nr), bot = min(max(h - gy0, top), nr);
+    const int lft = min(max(-gx0, 0), nc), rgt = min(max(w - gx0, lft), nc);
+    auto fix = [&](int rr, int cc) {
+        int r = r0 + rr, c = GC0 + cc;
+        int mr = min(max(refl(gy0 + rr, h) - Y0 + P3_OY, r0), r1 - 1);
+        int mc = min(max(refl(gx0 + cc, w) - X0 + P3_OX, GC0), GC1 - 1);
+        T[r * P3_SP + c] = T[mr * P3_SP + mc];
+    };
+    const int nghost_rows = top + (nr - bot);
+    for (int i = tid; i < nghost_rows * nc; i += P2_NT) {
+        int rr = i / nc, cc = i - rr * nc;
+        if (rr >= top) rr += bot - top;
+        fix(rr, cc);
+    }
+    const int nghost_cols = lft + (nc - rgt);
+    if (nghost_cols > 0) {
+        for (int i = tid; i < (bot - top) * nghost_cols; i += P2_NT) {
+            int rr = i / nghost_cols, cc = i - rr * nghost_cols;
+            if (cc >= lft) cc += rgt - lft;
+            fix(top + rr, cc);
+        }
+    }
+}
+
+struct Prep3Args {
+    const float* src;                    // predecessor Lt (same resolution) or source octave (PM_DOWN)
+    float* ltdst;                        // PM_DOWN: subsampled Lt
+    float *flow, *smooth;                // conductance and blurred plane of the level
+    const float* kc;                     // per-frame contrast factor
+    long long splane, plane;
+    LevelMathArgs m;
+    float kscale;
+    int nmul, type, vec_ok;
+    int sw, sh, sp;                      // source dims (== w, h, pitch unless PM_DOWN)
+    int w, h, pitch;
+};
+
+template <int MODE, bool INT>
+__global__ void __launch_bounds__(P2_NT, 3) k_prep3(const __grid_constant__ Prep3Args a)
+{
+    constexpr int OY = P3_OY, AR = P3_AR, SP = P3_SP, OX = P3_OX;
+    extern __shared__ __align__(16) float sm[];
+    float* A = sm;                                    // input tile, later the blurred tile
+    float* Bf = A + AR * SP;                          // row-filtered
+    float* Sm = A;
+
+    const int tid = threadIdx.x;
+    const int frame = blockIdx.z;
+    const int X0 = blockIdx.x * P2_W, Y0 = blockIdx.y * P2_H;
+    const int w = a.w, h = a.h;
+    const bool interior = X0 - OX >= 0 && X0 + P2_W + OX <= w && Y0 - OY >= 0 && Y0 + P2_H + OY <= h;
+    const bool fast = interior && a.vec_ok;
+    const float* __restrict__ src = a.src + (long long)frame * a.splane;
+
+    // ---- 1. input tile: rows [0, AR), columns [C0, C1) ----------------------------------------------
+    if (MODE != PM_DOWN && fast) {
+        for (int i = tid; i < AR * P3_NG; i += P2_NT) {
+            int r = i / P3_NG, g = i - r * P3_NG;
+            cp_async16(A + r * SP + P3_C0 + 4 * g, src + (long long)(Y0 - OY + r) * a.sp + (X0 - OX + P3_C0 + 4 * g));
+        }
+        cp_async_wait_all();
+    } else if (MODE == PM_DOWN) {
+        for (int i = tid; i < AR * (P3_C1 - P3_C0); i += P2_NT) {
+            int r = i / (P3_C1 - P3_C0), c = P3_C0 + i - r * (P3_C1 - P3_C0);
+            int sy = coarse_src2(Y0 - OY + r, a.sh), sx = coarse_src2(X0 - OX + c, a.sw);
+            A[r * SP + c] = __ldg(src + (long long)sy * a.sp + sx);
+        }
+    } else {
+        for (int i = tid; i < AR * P3_NG; i += P2_NT) {
+            int r = i / P3_NG, g = i - r * P3_NG;
+            int sy = min(max(refl(Y0 - OY + r, h), 0), h - 1), gx = X0 - OX + P3_C0 + 4 * g;
+            const float* row = src + (long long)sy * a.sp;
+            float* d = A + r * SP + P3_C0 + 4 * g;
+            if (a.vec_ok && gx >= 0 && gx + 3 < w) *reinterpret_cast<float4*>(d) = __ldg(reinterpret_cast<const float4*>(row + gx));
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) d[j] = __ldg(row + min(max(refl(gx + j, w), 0), w - 1));
+            }
+        }
+    }
+    __syncthreads();
+
+    if (MODE == PM_DOWN) {
+        // subsampled plane: dst(x, y) = src(2x, 2y)   (akazed.cu:505)
+        float* ltd = a.ltdst + (long long)frame * a.plane;
+        for (int i = tid; i < P2_H * P2_W; i += P2_NT) {
+            int r = i >> 6, c = i & 63;
+            int y = Y0 + r, x = X0 + c;
+            if (y < h && x < w) ltd[(long long)y * a.pitch + x] = A[(r + OY) * SP + OX + c];
+        }
+    }
+
+    // ---- 2. row pass: Bf[r][8, 72) from A[r][4, 76) (16 groups; the two outer groups only feed it) ----------------
+    for (int i = tid; i < AR * 16; i += P2_NT) {
+        int r = i >> 4, g = i & 15;
+        const float* p = A + r * SP + OX + 4 * g;
+        float4 v0 = lds4(p - 4), v1 = lds4(p), v2 = lds4(p + 4);
+        sts4(Bf + r * SP + OX + 4 * g,
+             p2_gauss<INT>(v0.z, v0.w, v1.x, v1.y, v1.z, a.m), p2_gauss<INT>(v0.w, v1.x, v1.y, v1.z, v1.w, a.m),
+             p2_gauss<INT>(v1.x, v1.y, v1.z, v1.w, v2.x, a.m), p2_gauss<INT>(v1.y, v1.z, v1.w, v2.x, v2.y, a.m));
+    }
+    // the blur is also needed one column beyond the tile on either side (conductance stencil): columns 7 and 72
+    for (int i = tid; i < AR * 2; i += P2_NT) {
+        int r = i >> 1, c = (i & 1) ? OX + P2_W : OX - 1;
+        const float* p = A + r * SP + c;
+        Bf[r * SP + c] = p2_gauss<INT>(p[-2], p[-1], p[0], p[1], p[2], a.m);
+    }
+    __syncthreads();
+    // ---- 3. column pass: Sm rows [2, AR-2) (over the input tile), four rows per item; 16 groups + the two edge columns ----
+    static_assert((AR - 4) % 4 == 0, "column pass works in groups of four rows");
+    for (int i = tid; i < ((AR - 4) / 4) * 16; i += P2_NT) {
+        int rb = i >> 4, g = i & 15;
+        int r = 2 + 4 * rb;
+        const float* p = Bf + (r - 2) * SP + OX + 4 * g;
+        float4 b[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) b[k] = lds4(p + k * SP);
+        float* q = Sm + r * SP + OX + 4 * g;
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+            sts4(q + t * SP, p2_gauss<INT>(b[t].x, b[t + 1].x, b[t + 2].x, b[t + 3].x, b[t + 4].x, a.m), p2_gauss<INT>(b[t].y, b[t + 1].y, b[t + 2].y, b[t + 3].y, b[t + 4].y, a.m),
+                 p2_gauss<INT>(b[t].z, b[t + 1].z, b[t + 2].z, b[t + 3].z, b[t + 4].z, a.m), p2_gauss<INT>(b[t].w, b[t + 1].w, b[t + 2].w, b[t + 3].w, b[t + 4].w, a.m));
+    }
+    for (int i = tid; i < (AR - 4) * 2; i += P2_NT) {
+        int r = 2 + (i >> 1), c = (i & 1) ? OX + P2_W : OX - 1;
+        const float* p = Bf + r * SP + c;
+        Sm[r * SP + c] = p2_gauss<INT>(p[-2 * SP], p[-SP], p[0], p[SP], p[2 * SP], a.m);
+    }
+    __syncthreads();
+    if (!interior) {
+        ghost_fix3(Sm, OY - 1, OY + P2_H + 1, X0, Y0, w, h, tid);
+        __syncthreads();
+    }
+
+    // ---- 4. blurred plane to global memory + conductance of the output pixels -------------------------------------
+    float ikc;
+    if (!INT) {
+        float k = a.kc[frame];
+        for (int i = 0; i < a.nmul; i++) k = __fmul_rn(k, a.kscale);
+        ikc = __fdiv_rn(1.f, __fmul_rn(k, k));
+    } else {
+        int k = reinterpret_cast<const int*>(a.kc)[frame];
+        for (int i = 0; i < a.nmul; i++) k = (int)__fadd_rn(__fmul_rn((float)k, 0.75f), 0.5f);       // akaze.cpp:649
+        ikc = __fdiv_rn(1.f, (float)(k * k));                                                        // akazed.cu:4218 (host)
+    }
+    float* fl = a.flow + (long long)frame * a.plane;
+    float* smg = a.smooth + (long long)frame * a.plane;
+    static_assert(P2_H % 2 == 0, "conductance phase works on row pairs");
+    for (int i = tid; i < (P2_H / 2) * 16; i += P2_NT) {
+        int r = 2 * (i >> 4), g = i & 15;
+        const float* p = Sm + (r + OY) * SP + OX + 4 * g;
+        float rw[4][6];
+        float4 ctr[2];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float* q = p + (k - 1) * SP;
+            float4 v = lds4(q);
+            float lft = __shfl_up_sync(0xffffffffu, v.w, 1), rgt = __shfl_down_sync(0xffffffffu, v.x, 1);
+            if (g == 0) lft = q[-1];
+            if (g == 15) rgt = q[4];
+            rw[k][0] = lft; rw[k][1] = v.x; rw[k][2] = v.y; rw[k][3] = v.z; rw[k][4] = v.w; rw[k][5] = rgt;
+            if (k == 1) ctr[0] = v;
+            if (k == 2) ctr[1] = v;
+        }
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                o[j] = p2_flow<INT>(rw[t][j], rw[t][j + 1], rw[t][j + 2], rw[t + 1][j], rw[t + 1][j + 2], rw[t + 2][j], rw[t + 2][j + 1], rw[t + 2][j + 2], a.type, ikc);
+            int y = Y0 + r + t, x = X0 + 4 * g;
+            long long off = (long long)y * a.pitch + x;
+            if (fast) {
+                *reinterpret_cast<float4*>(fl + off) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(smg + off) = ctr[t];
+            } else if (y < h) {
+                const float cv[4] = { ctr[t].x, ctr[t].y, ctr[t].z, ctr[t].w };
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (x + j < w) { fl[off + j] = o[j]; smg[off + j] = cv[j]; }
+            }
+        }
+    }
+}
+
+constexpr int prep3_smem() { return 2 * P3_AR * P3_SP * (int)sizeof(float); }
+
+template <int MODE, bool INT>
+void prep3_launch(cudaStream_t st, const Prep3Args& a, int n)
+{
+    dim3 g((a.w + P2_W - 1) / P2_W, (a.h + P2_H - 1) / P2_H, n);
+    k_prep3<MODE, INT><<<g, P2_NT, prep3_smem(), st>>>(a);
 }
 
 template <int S>
@@ -445,15 +597,15 @@ int level_prep2(cudaStream_t st, int mode, const float* src, int sw, int sh, int
     a.src = src; a.ltdst = ltdst; a.flow = flowp; a.lx = lx; a.ly = ly; a.det = det; a.kc = kc;
     a.splane = splane; a.plane = plane; a.kscale = kscale; a.nmul = nmul; a.type = type;
     a.sw = sw; a.sh = sh; a.sp = sp; a.w = w; a.h = h; a.pitch = pitch;
-    hessian_factors(&a.fac1, &a.fac2);
+    hessian_factors(&a.m.fac1, &a.m.fac2);
     float k[3];
     akz_gauss_taps(1.f, 2, k);
-    a.k0 = k[0]; a.k1 = k[1]; a.k2 = k[2];
+    a.m.k0 = k[0]; a.m.k1 = k[1]; a.m.k2 = k[2];
     auto al16 = [](const void* p) { return p == nullptr || ((uintptr_t)p % 16) == 0; };
     a.vec_ok = (pitch % 4 == 0) && (plane % 4 == 0) && (sp % 4 == 0) && (splane % 4 == 0) &&
                al16(src) && al16(flowp) && al16(lx) && al16(ly) && al16(det);
-    a.ik0 = (int)(k[0] * 65536 + 0.5f); a.ik1 = (int)(k[1] * 65536 + 0.5f); a.ik2 = (int)(k[2] * 65536 + 0.5f);      // akazed.cu:3896
-    a.ifac1 = (int)(a.fac1 * 65536 + 0.5f); a.ifac2 = (int)(a.fac2 * 65536 + 0.5f);                                  // akazed.cu:4184-4185
+    a.m.ik0 = (int)(k[0] * 65536 + 0.5f); a.m.ik1 = (int)(k[1] * 65536 + 0.5f); a.m.ik2 = (int)(k[2] * 65536 + 0.5f);      // akazed.cu:3896
+    a.m.ifac1 = (int)(a.m.fac1 * 65536 + 0.5f); a.m.ifac2 = (int)(a.m.fac2 * 65536 + 0.5f);                                  // akazed.cu:4184-4185
     bool ok;
     if (int_planes)
         ok = mode == 0 ? prep2_dispatch<PM_BASE, true>(st, a, step, n) : mode == 1 ? prep2_dispatch<PM_BLUR, true>(st, a, step, n)
@@ -462,6 +614,28 @@ int level_prep2(cudaStream_t st, int mode, const float* src, int sw, int sh, int
         ok = mode == 0 ? prep2_dispatch<PM_BASE, false>(st, a, step, n) : mode == 1 ? prep2_dispatch<PM_BLUR, false>(st, a, step, n)
                                                                                   : prep2_dispatch<PM_DOWN, false>(st, a, step, n);
     return ok ? 1 : 0;
+}
+
+// Blur half of a level (k_prep3): mode 1 = same-resolution blur, 2 = octave transition.  Writes the conductance plane and
+// the blurred plane (for deriv_stream).  Returns 1 when launched, 0 when not covered.
+int level_blur_flow(cudaStream_t st, int mode, const float* src, int sw, int sh, int sp, long long splane,
+                    float* ltdst, float* flowp, float* smooth, int type, const float* kc, float kscale, int nmul,
+                    int w, int h, int pitch, long long plane, int n, int int_planes)
+{
+    if ((mode != 1 && mode != 2) || w < 24 || h < 24 || !flowp || !smooth) return 0;
+    Prep3Args a = {};
+    a.src = src; a.ltdst = ltdst; a.flow = flowp; a.smooth = smooth; a.kc = kc;
+    a.splane = splane; a.plane = plane; a.kscale = kscale; a.nmul = nmul; a.type = type;
+    a.sw = sw; a.sh = sh; a.sp = sp; a.w = w; a.h = h; a.pitch = pitch;
+    float k[3];
+    akz_gauss_taps(1.f, 2, k);
+    a.m.k0 = k[0]; a.m.k1 = k[1]; a.m.k2 = k[2];
+    a.m.ik0 = (int)(k[0] * 65536 + 0.5f); a.m.ik1 = (int)(k[1] * 65536 + 0.5f); a.m.ik2 = (int)(k[2] * 65536 + 0.5f);      // akazed.cu:3896
+    auto al16 = [](const void* p) { return p == nullptr || ((uintptr_t)p % 16) == 0; };
+    a.vec_ok = (pitch % 4 == 0) && (plane % 4 == 0) && (sp % 4 == 0) && (splane % 4 == 0) && al16(src) && al16(flowp) && al16(smooth);
+    if (int_planes) { if (mode == 1) prep3_launch<PM_BLUR, true>(st, a, n); else prep3_launch<PM_DOWN, true>(st, a, n); }
+    else { if (mode == 1) prep3_launch<PM_BLUR, false>(st, a, n); else prep3_launch<PM_DOWN, false>(st, a, n); }
+    return 1;
 }
 
 }  // namespace akzk
