@@ -15,6 +15,16 @@ batch of 256 frames, frame-sharded: weak scaling, no data-path collective).  One
   cpu_baseline  OpenCV cv::AKAZE (the reference's own CPU arm, main.cpp:344-399) and the C oracle port, on a
                 bounded sample of the same frames on the box's host cores (rank 0, N=1 only)
 
+  noise         the same step on SURVEY 8(d)'s keypoint-heavy input (blurred uniform noise, ~21 k keypoints per frame, max_pts
+                32768) with its own per-class times: the default "shapes" frames carry ~1.8 k keypoints and hide the keypoint stages
+  single_frame  ms per frame of the synchronous drop-in entry point akaze::Akazer::detectAndCompute (include/akaze.h) on one
+                resident 1080p frame -- the reference's own timed loop, main.cpp:199-205
+  match         BASELINE metric 2: 10k x 10k on one GPU; 10k x 1M with the train set sharded over the ranks through
+                akz_match_sharded (one ncclAllGather inside the library), asserted equal to the unsharded result
+
+--config stream runs BASELINE configs[4] instead (synthetic 3840x2160 stream, 5 octaves x 4 sublevels, detect + describe +
+match of consecutive frames, the stream split over the GPUs with a one-frame overlap).
+
 --impl reference runs the UNMODIFIED reference CUDA library (oracle/_ref/libref_akaze.so, built from
 /root/reference by oracle/Makefile for sm_100a) through its own Akazer::detectAndCompute, frame by frame as
 main.cpp:199-205 does, on the same frames.  The reference has no CPU implementation of its own.
@@ -115,6 +125,29 @@ def dist_setup(ngpus):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return rank, world, local
+
+
+def bind_near_gpu(local, world):
+    """Pin this process (and the pinned buffers it allocates afterwards: first touch) to the CPUs of the GPU's NUMA node,
+    and when several ranks share a node give each its own slice of those CPUs.  Returns a short description."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(base + "/numa_node").read())
+        cpus = []
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0)) or sorted(os.sched_getaffinity(0))
+        if world > 1 and len(allowed) >= world:
+            per = len(allowed) // world
+            allowed = allowed[local * per:(local + 1) * per]
+        os.sched_setaffinity(0, allowed)
+        return {"pci": bdf, "numa_node": node, "cpus": f"{allowed[0]}-{allowed[-1]}" if allowed else "", "ncpus": len(allowed)}
+    except Exception as e:
+        return {"error": repr(e)[:100]}
 
 
 def barrier_max(ms, world, device):
@@ -223,18 +256,38 @@ def match_metric(ab, device, rank, world, clock_mhz):
     tl[:, 60] &= 0x3F
     if world > 1:
         import torch.distributed as dist
-        fn = lambda: D.match_sharded_gpu(ctx, q, tl, lo, ab.MATCH_KNN2)
-        for _ in range(2):
-            fn()
-        barrier(world)
-        t0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        D.comm_init_from_group(ctx)                       # the library's own communicator: id from rank 0, broadcast by torch
+        fn = lambda: ctx.match_sharded(q, tl, lo, ab.MATCH_KNN2, out=res)
         for _ in range(3):
             fn()
-        e1.record()
+        ctx.sync()
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(10):
+            fn()
+        e1.record(stream)
         e1.synchronize()
-        ms = barrier_max(e0.elapsed_time(e1) / 3, world, device)
+        ms = barrier_max(e0.elapsed_time(e1) / 10, world, device)
+        # the sharded result must equal the unsharded one: gather the whole train set once (outside the timed region) and match
+        # it on this rank alone; also in the reference-compatible mode
+        sizes = [D.shard_bounds(nt_total, world, r)[1] - D.shard_bounds(nt_total, world, r)[0] for r in range(world)]
+        full = [torch.empty(n, 64, dtype=torch.uint8, device=device) for n in sizes]
+        dist.all_gather(full, tl)
+        tfull = torch.cat(full)
+        exact = True
+        for mode, cols in ((ab.MATCH_KNN2, 4), (ab.MATCH_COMPAT, 2)):
+            a = ctx.match_sharded(q, tl, lo, mode).clone()
+            b = ctx.match(q, tfull, mode)
+            ctx.sync()
+            exact = exact and bool(torch.equal(a[:, :cols], b[:, :cols]))
+        flag = torch.tensor([1 if exact else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        assert int(flag.item()) == 1, "train-sharded matching differs from the unsharded result"
+        out["knn2_10kx1M_sharded_equals_unsharded"] = True
+        out["knn2_10kx1M_how"] = "akz_match_sharded: akz_match(finalize=0) -> ncclAllGather(nq x 16 B per rank) on the library stream -> k_match_merge; no host sync"
+        del full, tfull
+        ctx.comm_destroy()
     else:
         ms = time_it(lambda: ctx.match(q, tl, ab.MATCH_KNN2, out=res), 3)
     out["knn2_10kx1M_ms"] = round(ms, 3)
@@ -245,11 +298,73 @@ def match_metric(ab, device, rank, world, clock_mhz):
     return out
 
 
+def class_times(ctx, dev, res, F, chunk):
+    """per-class device time: one extra pass with event pairs around every kernel group, chunk by chunk (so that with two lanes
+    the kernels of this pass do not overlap each other: a kernel's time is its own)"""
+    ctx.profile(True)
+    for f0 in range(0, F, chunk):
+        ctx.detect_and_compute(dev[f0:f0 + chunk], True, out=tuple(r[f0:f0 + chunk] for r in res))
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    return prof
+
+
+def noise_workload(ab, device, local, world, args):
+    """SURVEY 8(d)'s primary input: uniform noise blurred with sigma 2 (~21 k keypoints per frame), max_pts 32768."""
+    import torch
+    F, mp = args.noise_frames, 32768
+    frames8 = make_frames(F, "noise", seed0=0)
+    dev = (torch.from_numpy(frames8).to(device).float() * (1.0 / 255.0)).contiguous()
+    ctx = ab.Context(W, H, max_batch=args.chunk, max_pts=mp, device=local, lanes=args.lanes)
+    res = ctx.alloc_results(F, True)
+    step = lambda: ctx.detect_and_compute(dev, True, out=res)
+    for _ in range(3):
+        step()
+    ctx.sync()
+    steps = max(2, args.steps // 2)
+    ms = timed(step, steps, ctx.torch_stream(), world, device)
+    counts = res[0].cpu().numpy()
+    prof = class_times(ctx, dev, res, F, args.chunk)
+    tot = sum(v[0] for v in prof.values())
+    out = {"value": round(F * world * steps / (ms * 1e-3), 2), "unit": "images/s", "frames_per_gpu": F, "max_pts": mp,
+           "keypoints_per_frame_mean": round(float(counts.mean()), 1), "clipped_frames": int((counts >= mp).sum()),
+           "workload": "uniform u8 noise, Gaussian sigma 2, min-max stretched (tests/bindings.synth_noise_u8, seeds 0..7, rolled)",
+           "classes_ms_per_step": {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
+           "keypoint_stage_share": round((prof.get("describe", (0, 0))[0] + prof.get("orient", (0, 0))[0]) / tot, 3) if tot else None}
+    ctx.close()
+    return out
+
+
+def single_frame(device):
+    """Batch-1 latency of the drop-in C++ surface (include/akaze.h through tests/cpp/dropin_shim.cu), as main.cpp:199-205 times it."""
+    import torch
+    import bindings as B
+    if not B.have_dropin():
+        return {"unavailable": "tests/cpp/build/libdropin_shim.so not built"}
+    img = B.u8_to_unit(B.synth_shapes_u8(W, H, seed=1))
+    pitch = (W + 127) // 128 * 128
+    buf = np.zeros((H, pitch), dtype=np.float32)
+    buf[:, :W] = img
+    t = torch.from_numpy(buf).to(device)
+    data = B.DropinData(10000)
+    az = B.DropinAkazer(W, H, pitch)
+    az.detect_and_compute(t, data)
+    az.time(t, data, iters=5)
+    ms = az.time(t, data, iters=50)
+    ms_nodesc = az.time(t, data, iters=50, desc=False)
+    out = {"ms_per_frame": round(ms, 4), "detect_only_ms_per_frame": round(ms_nodesc, 4), "keypoints": int(data.num),
+           "call": "akaze::Akazer::detectAndCompute(float*, AkazeData&, int3, true): device image in, AkazeData device + host records out, synchronous"}
+    az.close()
+    data.close()
+    return out
+
+
 def run_ours(args):
     import torch
     import akaze_b200 as ab
     rank, world, local = dist_setup(args.gpus)
     device = torch.device("cuda", local)
+    numa = bind_near_gpu(local, world)             # before the pinned allocations below
     F = args.frames
     frames8 = make_frames(F, args.content, seed0=100 * rank)
     dtype = np.float32 if args.dtype == "f32" else np.uint8
@@ -300,13 +415,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     nkp_mean = float(counts.mean())
 
-    # per-class device time: one extra pass of the same step with event pairs around every kernel group
-    # (chunk by chunk, so that with two lanes the kernels of this pass do not overlap each other: a kernel's time is its own)
-    ctx.profile(True)
-    for f0 in range(0, F, args.chunk):
-        ctx.detect_and_compute(dev[f0:f0 + args.chunk], True, out=tuple(r[f0:f0 + args.chunk] for r in res))
-    prof = ctx.profile_read()
-    ctx.profile(False)
+    prof = class_times(ctx, dev, res, F, args.chunk)
     tot_ms = sum(v[0] for v in prof.values())
     top = max(prof, key=lambda k: prof[k][0])
     top_ms, top_launches = prof[top]
@@ -355,6 +464,13 @@ def run_ours(args):
     }
     ctx.close()
     del dev
+    line["config"]["binding"] = numa
+    line["e2e"]["h2d_gbs_per_rank"] = round(host.numel() * host.element_size() / (ms_e2e / args.steps * 1e-3) / 1e9, 2)
+    del host
+    if not args.no_noise:
+        line["noise"] = noise_workload(ab, device, local, world, args)
+    if rank == 0 and world == 1:
+        line["single_frame"] = single_frame(device)
     if not args.no_match:
         m = match_metric(ab, device, rank, world, (clocks or {}).get("sm_mhz") if clocks else None)
         line["match"] = m
@@ -402,6 +518,31 @@ def cpu_baseline(frames8, nsample):
             out.update(port)
     except Exception as e:
         out["port_error"] = repr(e)[:120]
+    # the CPU matcher beside metric 2, and configs[0] (left.pgm + right.pgm through OpenCV: detect, describe, match)
+    try:
+        import cv2
+        import bindings as B
+        q, t = B.random_descriptors(10000, 0)[:, :61].copy(), B.random_descriptors(10000, 1)[:, :61].copy()
+        bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+        t0 = time.perf_counter()
+        mm = bf.knnMatch(q, t, k=2)
+        out["bfmatcher_knn2_10kx10k_ms"] = round((time.perf_counter() - t0) * 1e3, 1)
+        out["bfmatcher_note"] = f"cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2), 61-byte rows, {cv2.getNumThreads()} threads, {len(mm)} queries"
+        l, r = os.path.join(B.REF_DATA, "left.pgm"), os.path.join(B.REF_DATA, "right.pgm")
+        if os.path.exists(l) and os.path.exists(r):
+            a, b = B.read_pgm(l), B.read_pgm(r)
+            ak = cv2.AKAZE_create()
+            t0 = time.perf_counter()
+            k1, d1 = ak.detectAndCompute(a, None)
+            k2, d2 = ak.detectAndCompute(b, None)
+            t1 = time.perf_counter()
+            m = bf.match(d1, d2)
+            t2 = time.perf_counter()
+            out["configs0_left_right_pgm"] = {"detect_describe_ms_per_image": round((t1 - t0) * 500, 1), "match_ms": round((t2 - t1) * 1e3, 1),
+                                              "keypoints": [len(k1), len(k2)], "matches": len(m),
+                                              "how": "cv2.AKAZE_create() defaults + BFMatcher(NORM_HAMMING).match, 1280x960 u8 (main.cpp:344-399)"}
+    except Exception as e:
+        out["cpu_match_error"] = repr(e)[:120]
     return out
 
 
@@ -469,8 +610,35 @@ def run_reference(args):
             L.ref_hMatch(C.c_void_p(dq.data_ptr()), 10000, C.c_void_p(dt.data_ptr()), 10000)
         e1.record(); e1.synchronize()
         match = {"compat_10kx10k_ms": round(e0.elapsed_time(e1) / 5, 4), "how": "akaze::hMatch (gHammingMatch, 16 threads per query), 1-NN with the uniqueness gate"}
+    # the keypoint-heavy input and the single-frame latency, same definitions as in the main arm
+    noise = None
+    if not args.no_noise:
+        Fn = min(16, args.noise_frames)
+        n8 = make_frames(Fn, "noise", seed0=0)
+        hn = torch.zeros((Fn, H, pitch), dtype=torch.float32)
+        hn.numpy()[:, :, :W] = n8.astype(np.float32) * np.float32(1.0 / 255.0)
+        dn = hn.to(device)
+        npts = torch.zeros(32768 * 104, dtype=torch.uint8, device=device)
+        ncnt = np.zeros(Fn, dtype=np.int64)
+
+        def nstep():
+            for f in range(Fn):
+                ncnt[f] = L.ref_akazer_detectAndCompute(ref.hnd, C.c_void_p(dn[f].data_ptr()), W, H, pitch, 1, C.c_void_p(npts.data_ptr()), None, 32768)
+        nstep()
+        nms = timed(nstep, 2, stream, world, device)
+        noise = {"value": round(Fn * world * 2 / (nms * 1e-3), 2), "unit": "images/s", "frames_per_gpu": Fn, "max_pts": 32768,
+                 "keypoints_per_frame_mean": round(float(ncnt.mean()), 1)}
+        del dn, npts
+    sf = None
+    if rank == 0 and world == 1:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            L.ref_akazer_detectAndCompute(ref.hnd, C.c_void_p(dev[0].data_ptr()), W, H, pitch, 1, C.c_void_p(d_pts.data_ptr()), C.c_void_p(h_pts.data_ptr()), mp)
+        torch.cuda.synchronize()
+        sf = {"ms_per_frame": round((time.perf_counter() - t0) * 50.0, 4), "call": "Akazer::detectAndCompute of the reference, device image in, host records out"}
     line = {
-        "impl": "reference", "match": match, "metric": "1080p detect+describe images/sec", "value": round(v, 2), "unit": "images/s",
+        "impl": "reference", "match": match, "noise": noise, "single_frame": sf, "metric": "1080p detect+describe images/sec", "value": round(v, 2), "unit": "images/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"configs[2]: synthetic 1920x1080 grayscale, {F} frames per GPU per step ({args.content}), "
@@ -508,10 +676,17 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-match", action="store_true", help="skip the brute-force matching metric (BASELINE metric 2)")
+    ap.add_argument("--no-noise", action="store_true", help="skip the keypoint-heavy noise workload")
+    ap.add_argument("--noise-frames", type=int, default=64, help="frames per GPU of the noise workload")
+    ap.add_argument("--config", default="frames", choices=["frames", "stream"], help="frames = configs[2] (default), stream = configs[4]")
+    ap.add_argument("--stream-frames", type=int, default=32, help="configs[4]: frames of the stream per GPU (plus the overlap frame)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = max(args.warmup, 1)
-    if args.impl == "reference":
+    if args.config == "stream":
+        import bench_stream
+        bench_stream.run(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -39,6 +39,7 @@ EXPORTS = [
     "akz_unpack_desc", "akz_scatter_matches", "akz_orient", "akz_describe", "akz_detect_keypoints",
     "akz_profile_enable", "akz_profile_read", "akz_profile_class_name", "akz_keypoints_to_opencv", "akz_matches_to_opencv",
     "akz_set_match_kernel", "akz_plan_chunks", "akz_plan_match", "akz_fast_detect_and_compute", "akz_fast_detect_and_compute_host", "akz_fast_build_scale_space", "akz_fast_get_kcontrast", "akz_fast_lowpass",
+    "akz_match_pairs", "akz_comm_unique_id", "akz_comm_init", "akz_comm_attach", "akz_comm_destroy", "akz_match_sharded",
     "akz_fast_down_with_smooth", "akz_fast_scharr_contrast", "akz_fast_flow", "akz_fast_nld_step", "akz_fast_hessian",
 ]
 NUM_KCLASS = 13
@@ -91,6 +92,12 @@ def lib():
     L.akz_match.argtypes = [vp, vp, i, vp, i, i, i, i, vp]
     L.akz_match_merge.argtypes = [vp, vp, i, i, i, i, vp]
     L.akz_match_host.argtypes = [vp, vp, i, vp, i, i, vp]
+    L.akz_match_pairs.argtypes = [vp, vp, vp, i, i, vp]
+    L.akz_comm_unique_id.argtypes = [vp]
+    L.akz_comm_init.argtypes = [vp, i, i, vp]
+    L.akz_comm_attach.argtypes = [vp, vp, i, i]
+    L.akz_comm_destroy.argtypes = [vp]
+    L.akz_match_sharded.argtypes = [vp, vp, i, vp, i, i, i, vp]
     L.akz_pack_points.argtypes = [vp, vp, vp, vp, vp, i, i]
     L.akz_unpack_desc.argtypes = [vp, vp, i, vp]
     L.akz_scatter_matches.argtypes = [vp, vp, i, vp, vp]
@@ -381,12 +388,46 @@ class Context:
         _check(lib().akz_match_merge(self.h, _ptr(parts), nparts, nq, mode, int(finalize), _ptr(res)))
         return res
 
+    def match_pairs(self, desc, counts, mode=MATCH_COMPAT, out=None):
+        """desc (nf, max_pts, 64), counts (nf,) as detect_and_compute returned them -> (nf, max_pts, 4) int32: frame f matched
+        against frame f - 1 (row 0 unused); counts are read on the device."""
+        torch = self.torch
+        nf = desc.shape[0]
+        res = out if out is not None else torch.zeros(nf, self.opt.max_pts, 4, dtype=torch.int32, device=self.device)
+        _check(lib().akz_match_pairs(self.h, _ptr(desc), _ptr(counts), nf, mode, _ptr(res)))
+        return res
+
+    # ---- train-sharded matching (one process per GPU): the gather runs inside the library on its stream ----
+    def comm_init(self, nranks, rank, unique_id):
+        """unique_id: the 128 bytes akaze_b200.comm_unique_id() produced on one rank, handed to all ranks by the caller."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        _check(lib().akz_comm_init(self.h, nranks, rank, buf))
+
+    def comm_destroy(self):
+        _check(lib().akz_comm_destroy(self.h))
+
+    def match_sharded(self, q, t_local, t_index_base, mode=MATCH_KNN2, out=None):
+        """q: (nq, 64) all queries, t_local: this rank's contiguous train range starting at global index t_index_base.
+        akz_match(finalize=0) -> ncclAllGather -> akz_match_merge(finalize=1), all on the context's stream; no host sync."""
+        torch = self.torch
+        nq = q.shape[0]
+        res = out if out is not None else torch.zeros(nq, 4, dtype=torch.int32, device=self.device)
+        _check(lib().akz_match_sharded(self.h, _ptr(q), nq, _ptr(t_local), t_local.shape[0], t_index_base, mode, _ptr(res)))
+        return res
+
     def match_host(self, q, t, mode=MATCH_COMPAT):
         nq, nt = q.shape[0], t.shape[0]
         res = np.zeros((nq, 4), dtype=np.int32)
         _check(lib().akz_match_host(self.h, C.c_void_p(q.ctypes.data), nq, C.c_void_p(t.ctypes.data), nt, mode,
                                     C.c_void_p(res.ctypes.data)))
         return res
+
+
+def comm_unique_id():
+    """128-byte NCCL id for Context.comm_init (create on one rank, distribute to the others)."""
+    buf = (C.c_char * 128)()
+    _check(lib().akz_comm_unique_id(buf))
+    return bytes(buf.raw)
 
 
 def _host_ptr(a):

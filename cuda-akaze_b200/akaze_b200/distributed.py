@@ -34,8 +34,25 @@ def match_sharded(q, t_local, t_base, mode, local_fn, merge_fn, group=None):
     return merge_fn(parts, mode)
 
 
+def comm_init_from_group(ctx, group=None):
+    """Create the context's NCCL communicator for the ranks of a torch.distributed group: rank 0 makes the id
+    (akz_comm_unique_id), the group broadcasts its 128 bytes, every rank calls akz_comm_init."""
+    import torch.distributed as dist
+    import akaze_b200 as ab
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = ctx.device if backend == "nccl" else torch.device("cpu")
+    idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        idt = torch.frombuffer(bytearray(ab.comm_unique_id()), dtype=torch.uint8).to(dev)
+    dist.broadcast(idt, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ctx.comm_init(world, rank, bytes(idt.cpu().numpy().tobytes()))
+
+
 def match_sharded_gpu(ctx, q, t_local, t_base, mode, group=None):
-    """GPU instance: akz_match(finalize=0) -> all_gather (NCCL) -> akz_match_merge(finalize=1)."""
+    """Python-side variant kept for comparison: akz_match(finalize=0) -> torch all_gather -> akz_match_merge(finalize=1), with
+    two host synchronisations.  The production path is Context.match_sharded (akz_match_sharded: the gather runs inside the
+    library on the context's stream)."""
     def local_fn(q_, t_, base_, mode_):
         r = ctx.match(q_, t_, mode_, t_index_base=base_, finalize=False)
         ctx.sync()

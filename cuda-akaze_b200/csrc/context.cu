@@ -13,6 +13,9 @@
 #include <algorithm>
 #include <atomic>
 #include <mutex>
+#include <dlfcn.h>
+
+struct akz_nccl_id { char internal[128]; };      // layout of ncclUniqueId (nccl.h): passed by value to ncclCommInitRank
 
 // ---- errors ---------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -156,6 +159,9 @@ struct akz_ctx {
     akz_match_t* match_parts;
     size_t match_parts_n;
     void* match_stage; size_t match_stage_bytes;
+    // train-sharded matching: communicator (NCCL, loaded at run time) and the gather buffers
+    void* comm; int comm_ranks, comm_rank; bool comm_owned;
+    akz_match_t* shard_buf; size_t shard_buf_n;          // [1 + nranks][nq]: own partial result, then the gathered ones
     int last_frames;
     long long launches;
     AkzLevelTable tab;
@@ -266,6 +272,7 @@ int akz_create(const akz_options* o, akz_ctx** out)
     c->h2d_stream = c->d2h_stream = nullptr; c->h_cnt_pinned = nullptr;
     for (int i = 0; i < AKZ_NSET; i++) { c->ev_h2d[i] = c->ev_comp[i] = c->ev_cnt[i] = c->ev_d2h[i] = nullptr; }
     c->match_stage = nullptr; c->match_stage_bytes = 0;
+    c->comm = nullptr; c->comm_ranks = 0; c->comm_rank = 0; c->comm_owned = false; c->shard_buf = nullptr; c->shard_buf_n = 0;
     int rc = AKZ_OK;
     do {
         if (o->device >= 0) { if (cudaSetDevice(o->device) != cudaSuccess) { rc = akz_set_error(AKZ_E_CUDA, "cudaSetDevice(%d) failed", o->device); break; } }
@@ -356,6 +363,8 @@ void akz_destroy(akz_ctx* c)
     if (c->h_cnt_pinned) cudaFreeHost(c->h_cnt_pinned);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    akz_comm_destroy(c);
+    if (c->shard_buf) cudaFree(c->shard_buf);
     if (c->match_parts) cudaFree(c->match_parts);
     if (c->match_stage) cudaFree(c->match_stage);
     for (auto& pp : c->prof_pairs) { cudaEventDestroy(pp.a); cudaEventDestroy(pp.b); }
@@ -1079,6 +1088,143 @@ int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt
     if (kern == 3) { LAUNCHED(AKZ_K_MATCH, akzk::match_partial_tc5(c->stream, d_q, nq, d_t, nt, t_index_base, mode, c->match_parts, tc5_filter)); }
     else { LAUNCHED(AKZ_K_MATCH, akzk::match_partial(c->stream, d_q, nq, d_t, nt, t_index_base, mode, nsplit, c->match_parts, use_mma)); }
     LAUNCHED(AKZ_K_MATCH, akzk::match_merge(c->stream, c->match_parts, nsplit, nq, mode, finalize, d_out));
+    STAGE_EPILOGUE();
+}
+
+int akz_match_pairs(akz_ctx* c, const uint8_t* d_desc, const int* d_counts, int nframes, int mode, akz_match_t* d_out)
+{
+    STAGE_PROLOGUE();
+    if (mode != AKZ_MATCH_COMPAT && mode != AKZ_MATCH_KNN2 && mode != AKZ_MATCH_UNIQUE2) return akz_set_error(AKZ_E_INVALID, "bad matcher mode");
+    if (!d_desc || !d_counts || !d_out || nframes < 0) return akz_set_error(AKZ_E_INVALID, "bad matcher arguments");
+    if (nframes < 2) return AKZ_OK;
+    const int npairs = nframes - 1, mp = c->opt.max_pts;
+    const int nsplit = npairs >= 16 ? 2 : npairs >= 4 ? 4 : 8;        // enough blocks for the 148 SMs when there are few pairs
+    const size_t need = (size_t)npairs * nsplit * mp;
+    if (c->match_parts_n < need) {
+        if (c->match_parts) { cudaStreamSynchronize(c->stream); cudaFree(c->match_parts); }
+        c->match_parts = nullptr; c->match_parts_n = 0;
+        AKZ_CUDA_TRY(cudaMalloc((void**)&c->match_parts, need * sizeof(akz_match_t)));
+        c->match_parts_n = need;
+    }
+    LAUNCHED(AKZ_K_MATCH, akzk::match_pairs(c->stream, d_desc, d_counts, nframes, mp, mode, nsplit, c->match_parts, d_out));
+    STAGE_EPILOGUE();
+}
+
+// ---- train-sharded matching: NCCL through dlopen ----------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, akz_nccl_id, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    int (*GetVersion)(int*) = nullptr;
+};
+std::mutex g_nccl_mutex;
+NcclApi g_nccl;
+
+// dlopen by soname: glibc returns the copy already mapped into the process (e.g. the one a framework brought) before it
+// searches the library path, so a communicator handed to akz_comm_attach and the calls below go to the same NCCL
+int nccl_api(NcclApi** out)
+{
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
+    if (!g_nccl.lib) {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+        if (!h) return akz_set_error(AKZ_E_UNSUPPORTED, "NCCL is not available: %s", dlerror());
+        NcclApi a;
+        a.lib = h;
+        a.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+        a.CommInitRank = (int (*)(void**, int, akz_nccl_id, int))dlsym(h, "ncclCommInitRank");
+        a.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+        a.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+        a.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+        a.GetVersion = (int (*)(int*))dlsym(h, "ncclGetVersion");
+        if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather || !a.GetErrorString)
+            return akz_set_error(AKZ_E_UNSUPPORTED, "libnccl.so.2 lacks an expected entry point");
+        g_nccl = a;
+    }
+    *out = &g_nccl;
+    return AKZ_OK;
+}
+int nccl_fail(NcclApi* n, int code, const char* what) { return akz_set_error(AKZ_E_CUDA, "NCCL error %d (%s) in %s", code, n->GetErrorString(code), what); }
+}  // namespace
+
+int akz_comm_unique_id(void* id128)
+{
+    if (!id128) return akz_set_error(AKZ_E_INVALID, "null argument");
+    NcclApi* n;
+    int rc = nccl_api(&n);
+    if (rc != AKZ_OK) return rc;
+    static_assert(sizeof(akz_nccl_id) == AKZ_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+    int e = n->GetUniqueId(id128);
+    return e == 0 ? AKZ_OK : nccl_fail(n, e, "ncclGetUniqueId");
+}
+
+int akz_comm_init(akz_ctx* c, int nranks, int rank, const void* id128)
+{
+    STAGE_PROLOGUE();
+    if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return akz_set_error(AKZ_E_INVALID, "bad communicator arguments");
+    NcclApi* n;
+    int rc = nccl_api(&n);
+    if (rc != AKZ_OK) return rc;
+    akz_comm_destroy(c);
+    akz_nccl_id id;
+    memcpy(&id, id128, sizeof(id));
+    void* comm = nullptr;
+    int e = n->CommInitRank(&comm, nranks, id, rank);
+    if (e != 0) return nccl_fail(n, e, "ncclCommInitRank");
+    c->comm = comm; c->comm_ranks = nranks; c->comm_rank = rank; c->comm_owned = true;
+    return AKZ_OK;
+}
+
+int akz_comm_attach(akz_ctx* c, void* nccl_comm, int nranks, int rank)
+{
+    if (!c || !nccl_comm || nranks < 1 || rank < 0 || rank >= nranks) return akz_set_error(AKZ_E_INVALID, "bad communicator arguments");
+    NcclApi* n;
+    int rc = nccl_api(&n);
+    if (rc != AKZ_OK) return rc;
+    akz_comm_destroy(c);
+    c->comm = nccl_comm; c->comm_ranks = nranks; c->comm_rank = rank; c->comm_owned = false;
+    return AKZ_OK;
+}
+
+int akz_comm_destroy(akz_ctx* c)
+{
+    if (!c) return akz_set_error(AKZ_E_INVALID, "null context");
+    if (c->comm && c->comm_owned && g_nccl.CommDestroy) {
+        if (c->stream) cudaStreamSynchronize(c->stream);
+        g_nccl.CommDestroy(c->comm);
+    }
+    c->comm = nullptr; c->comm_ranks = 0; c->comm_rank = 0; c->comm_owned = false;
+    return AKZ_OK;
+}
+
+int akz_match_sharded(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t_local, int nt_local, int t_index_base, int mode, akz_match_t* d_out)
+{
+    STAGE_PROLOGUE();
+    if (!c->comm) return akz_set_error(AKZ_E_INVALID, "no communicator: call akz_comm_init or akz_comm_attach first");
+    if (nq < 0 || nt_local < 0 || !d_out) return akz_set_error(AKZ_E_INVALID, "bad matcher arguments");
+    if (nq == 0) return AKZ_OK;
+    NcclApi* n;
+    int rc = nccl_api(&n);
+    if (rc != AKZ_OK) return rc;
+    const size_t need = (size_t)(1 + c->comm_ranks) * nq;
+    if (c->shard_buf_n < need) {
+        if (c->shard_buf) { cudaStreamSynchronize(c->stream); cudaFree(c->shard_buf); }
+        c->shard_buf = nullptr; c->shard_buf_n = 0;
+        AKZ_CUDA_TRY(cudaMalloc((void**)&c->shard_buf, need * sizeof(akz_match_t)));
+        c->shard_buf_n = need;
+    }
+    akz_match_t* mine = c->shard_buf;
+    akz_match_t* all = c->shard_buf + nq;
+    // local range -> associative partial form (KNN2: two best (distance, index); COMPAT: best + the mask of index classes)
+    if ((rc = akz_match(c, d_q, nq, d_t_local, nt_local, t_index_base, mode, 0, mine)) != AKZ_OK) return rc;
+    // the one exchange of the path: nq x 16 bytes per rank, stream-ordered
+    int e = n->AllGather(mine, all, (size_t)nq * sizeof(akz_match_t), 0 /* ncclInt8 / ncclChar */, c->comm, c->stream);
+    if (e != 0) return nccl_fail(n, e, "ncclAllGather");
+    LAUNCHED(AKZ_K_MATCH, akzk::match_merge(c->stream, all, c->comm_ranks, nq, mode, 1, d_out));
     STAGE_EPILOGUE();
 }
 

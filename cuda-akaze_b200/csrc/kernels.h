@@ -99,6 +99,8 @@ int scatter_matches(cudaStream_t st, const akz_match_t* m, int nq, void* pq, con
 // ---- match.cu ----------------------------------------------------------------------------------------
 int match_partial(cudaStream_t st, const unsigned char* q, int nq, const unsigned char* t, int nt, int tbase, int mode,
                   int nsplit, akz_match_t* parts, int use_mma = 0);
+int match_pairs(cudaStream_t st, const unsigned char* desc, const int* counts, int nframes, int max_pts, int mode, int nsplit,
+                akz_match_t* parts, akz_match_t* out);
 // match_tc5.cu: tcgen05 / tensor-memory matcher (same partial-result contract)
 int match_tc5_plan(int nq, int nt, int* nsplit, int* tiles, int* per_cta, int* grid);     // returns the number of partial results per query
 int match_partial_tc5(cudaStream_t st, const unsigned char* q, int nq, const unsigned char* t, int nt, int tbase, int mode, akz_match_t* parts,

@@ -89,17 +89,18 @@ __device__ __forceinline__ void consider(Best& b, int d, int jrel, unsigned clas
     }
 }
 
+// body of the LOP3/POPC kernel: query block bx against the train range [by * per_split, (by + 1) * per_split) of t;
+// the partial results of that range go to parts[qi]
 template <int MODE>
-__global__ void __launch_bounds__(NTH) k_match(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t, int nt, int tbase,
-                                               int per_split, akz_match_t* __restrict__ parts)
+__device__ __forceinline__ void match_block(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t, int nt, int tbase,
+                                            int per_split, akz_match_t* __restrict__ parts, int bx, int by, uint4* tile)
 {
-    __shared__ uint4 tile[TILE * 4];
     unsigned qa[QPT][16];
     int qi[QPT];
     Best b[QPT];
 #pragma unroll
     for (int k = 0; k < QPT; k++) {
-        qi[k] = blockIdx.x * QPB + k * NTH + threadIdx.x;
+        qi[k] = bx * QPB + k * NTH + threadIdx.x;
 #pragma unroll
         for (int v = 0; v < 4; v++) {
             uint4 w = qi[k] < nq ? __ldg(q + 4 * (long long)qi[k] + v) : make_uint4(0, 0, 0, 0);
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(NTH) k_match(const uint4* __restrict__ q, int 
         }
         b[k].k1 = KEY_NONE; b[k].k2 = (MODE == AKZ_MATCH_KNN2) ? KEY_NONE : 0u;
     }
-    const int t0 = blockIdx.y * per_split, t1 = min(nt, t0 + per_split);
+    const int t0 = by * per_split, t1 = min(nt, t0 + per_split);
     for (int base = t0; base < t1; base += TILE) {
         int cnt = min(TILE, t1 - base);
         __syncthreads();
@@ -142,9 +143,34 @@ __global__ void __launch_bounds__(NTH) k_match(const uint4* __restrict__ q, int 
             } else {
                 m.idx2 = (int)b[k].k2; m.dist2 = 0;
             }
-            parts[(long long)blockIdx.y * nq + qi[k]] = m;
+            parts[qi[k]] = m;
         }
     }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NTH) k_match(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t, int nt, int tbase,
+                                               int per_split, akz_match_t* __restrict__ parts)
+{
+    __shared__ uint4 tile[TILE * 4];
+    match_block<MODE>(q, nq, t, nt, tbase, per_split, parts + (long long)blockIdx.y * nq, blockIdx.x, blockIdx.y, tile);
+}
+
+// Batched matching of consecutive frames of a stream (BASELINE configs[4]): pair p = blockIdx.z matches the descriptors of
+// frame p + 1 (queries) against those of frame p (train).  The counts are read on the device: no host round trip between the
+// detector and the matcher.  desc: [nframes][max_pts][64]; parts: [npairs][nsplit][max_pts].
+template <int MODE>
+__global__ void __launch_bounds__(NTH) k_match_pairs(const uint4* __restrict__ desc, const int* __restrict__ counts, int max_pts, int nsplit,
+                                                     akz_match_t* __restrict__ parts)
+{
+    __shared__ uint4 tile[TILE * 4];
+    const int p = blockIdx.z;
+    const int nq = min(counts[p + 1], max_pts), nt = min(counts[p], max_pts);
+    if ((int)blockIdx.x * QPB >= nq) return;                        // whole blocks leave before any barrier
+    int per = (nt + nsplit - 1) / nsplit;
+    per = max(((per + TILE - 1) / TILE) * TILE, TILE);
+    match_block<MODE>(desc + (long long)(p + 1) * max_pts * 4, nq, desc + (long long)p * max_pts * 4, nt, 0, per,
+                      parts + ((long long)p * nsplit + blockIdx.y) * max_pts, blockIdx.x, blockIdx.y, tile);
 }
 
 // =====================================================================================================================
@@ -379,9 +405,66 @@ __global__ void k_match_merge(const akz_match_t* __restrict__ parts, int nparts,
     out[qi] = r;
 }
 
+// merge of k_match_pairs: out[(p + 1) * max_pts + qi] for the queries of frame p + 1 (acceptance rule applied)
+__global__ void k_match_merge_pairs(const akz_match_t* __restrict__ parts, const int* __restrict__ counts, int max_pts, int nsplit, int mode,
+                                    akz_match_t* __restrict__ out)
+{
+    const int p = blockIdx.y;
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nq = min(counts[p + 1], max_pts);
+    if (qi >= nq) return;
+    const akz_match_t* pp = parts + (long long)p * nsplit * max_pts;
+    akz_match_t r;
+    const bool top2 = mode != AKZ_MATCH_COMPAT;
+    r.idx1 = -1; r.dist1 = -1; r.idx2 = top2 ? -1 : 0; r.dist2 = top2 ? -1 : 0;
+    for (int k = 0; k < nsplit; k++) {
+        const int4 b = __ldg(reinterpret_cast<const int4*>(pp + (long long)k * max_pts + qi));
+        akz_match_t m;
+        m.idx1 = b.x; m.dist1 = b.y; m.idx2 = b.z; m.dist2 = b.w;
+        if (m.idx1 < 0) continue;
+        if (top2) {
+            int cd[4] = { r.dist1, r.dist2, m.dist1, m.dist2 };
+            int ci[4] = { r.idx1, r.idx2, m.idx1, m.idx2 };
+            int bd1 = 1 << 20, bi1 = -1, bd2 = 1 << 20, bi2 = -1;
+            for (int c = 0; c < 4; c++) {
+                if (ci[c] < 0) continue;
+                if (bi1 < 0 || lex_less(cd[c], ci[c], bd1, bi1)) { bd2 = bd1; bi2 = bi1; bd1 = cd[c]; bi1 = ci[c]; }
+                else if (bi2 < 0 || lex_less(cd[c], ci[c], bd2, bi2)) { bd2 = cd[c]; bi2 = ci[c]; }
+            }
+            r.idx1 = bi1; r.dist1 = bi1 < 0 ? -1 : bd1; r.idx2 = bi2; r.dist2 = bi2 < 0 ? -1 : bd2;
+        } else {
+            if (r.idx1 < 0 || m.dist1 < r.dist1) r = m;
+            else if (m.dist1 == r.dist1) { r.idx1 = min(r.idx1, m.idx1); r.idx2 |= m.idx2; }
+        }
+    }
+    if (mode == AKZ_MATCH_UNIQUE2) {
+        bool ok = r.idx1 >= 0 && r.dist1 < AKZ_MAX_DIST && (r.idx2 < 0 || r.dist1 < r.dist2);
+        if (!ok) { r.idx1 = -1; r.dist1 = -1; }
+    }
+    if (mode == AKZ_MATCH_COMPAT) {
+        bool ok = r.idx1 >= 0 && __popc((unsigned)r.idx2) == 1 && r.dist1 < AKZ_MAX_DIST;
+        if (!ok) { r.idx1 = -1; r.dist1 = -1; }
+    }
+    out[(long long)(p + 1) * max_pts + qi] = r;
+}
+
 }  // namespace
 
 namespace akzk {
+
+// consecutive-frame matching of a batch (see k_match_pairs); parts must hold npairs * nsplit * max_pts records
+int match_pairs(cudaStream_t st, const unsigned char* desc, const int* counts, int nframes, int max_pts, int mode, int nsplit,
+                akz_match_t* parts, akz_match_t* out)
+{
+    const int npairs = nframes - 1;
+    if (npairs <= 0) return 0;
+    if (max_pts >= (1 << KEY_IDX_BITS)) return akz_set_error(AKZ_E_UNSUPPORTED, "max_pts too large for the batched matcher");
+    dim3 g((max_pts + QPB - 1) / QPB, nsplit, npairs);
+    if (mode != AKZ_MATCH_COMPAT) k_match_pairs<AKZ_MATCH_KNN2><<<g, NTH, 0, st>>>((const uint4*)desc, counts, max_pts, nsplit, parts);
+    else k_match_pairs<AKZ_MATCH_COMPAT><<<g, NTH, 0, st>>>((const uint4*)desc, counts, max_pts, nsplit, parts);
+    k_match_merge_pairs<<<dim3((max_pts + 127) / 128, npairs), 128, 0, st>>>(parts, counts, max_pts, nsplit, mode, out);
+    return 2;
+}
 
 // use_mma != 0: tensor-core kernel (large problems); the split is in units of 128 train descriptors either way
 int match_partial(cudaStream_t st, const unsigned char* q, int nq, const unsigned char* t, int nt, int tbase, int mode,

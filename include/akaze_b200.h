@@ -206,6 +206,30 @@ AKZ_API int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t
  * finalize != 0 applies the acceptance rule of the mode (COMPAT: unique class and < 96) */
 AKZ_API int akz_match_merge(akz_ctx* c, const akz_match_t* d_parts, int nparts, int nq, int mode,
                             int finalize, akz_match_t* d_out);
+/* Consecutive-frame matching of a batch (BASELINE configs[4], the 4K stream): the descriptors of frame f (queries) against
+ * those of frame f - 1 (train) for f = 1 .. nframes-1, in one batched launch; the keypoint counts are read on the device, so the
+ * call can follow akz_detect_and_compute on the same stream without a host round trip.  d_desc [nframes][max_pts][64] and
+ * d_counts [nframes] as akz_detect_and_compute wrote them (max_pts = the context's); d_out [nframes][max_pts], row 0 unused. */
+AKZ_API int akz_match_pairs(akz_ctx* c, const uint8_t* d_desc, const int* d_counts, int nframes, int mode, akz_match_t* d_out);
+
+/* ---- train-sharded matching across GPUs (one process per GPU; SURVEY 8e, BASELINE configs[3]) -------------------------------
+ * Every rank holds all nq queries and a contiguous range of the train set starting at global index t_index_base.
+ * akz_match_sharded = akz_match(finalize = 0) on the local range -> ONE ncclAllGather of nq x 16 bytes per rank on the context's
+ * stream (NCCL over NVLink / NVSwitch) -> akz_match_merge(finalize = 1): every rank ends with the same final result in d_out.
+ * Nothing synchronises with the host; the only exchange is the gather of the per-shard candidates.
+ * The communicator belongs to the context.  akz_comm_unique_id fills a 128-byte id on one rank (ncclGetUniqueId); the caller
+ * hands it to the other ranks by its own means (MPI, torch.distributed, a file ...) and every rank calls akz_comm_init.
+ * akz_comm_attach uses a communicator the caller already owns (an ncclComm_t of the NCCL library loaded in the process).
+ * NCCL is loaded at run time (libnccl.so.2, the copy already in the process if there is one): the library has no link-time
+ * dependency on it and everything else works without it. */
+#define AKZ_COMM_ID_BYTES 128
+AKZ_API int akz_comm_unique_id(void* id128);
+AKZ_API int akz_comm_init(akz_ctx* c, int nranks, int rank, const void* id128);
+AKZ_API int akz_comm_attach(akz_ctx* c, void* nccl_comm, int nranks, int rank);
+AKZ_API int akz_comm_destroy(akz_ctx* c);
+AKZ_API int akz_match_sharded(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t_local, int nt_local,
+                              int t_index_base, int mode, akz_match_t* d_out);
+
 /* kernel selection of akz_match: 0 = by problem size (default), 1 = LOP3/POPC kernel, 2 = mma.sync (IMMA) kernel,
  * 3 = tcgen05 kernel (tensor-memory accumulators).
  * Both produce identical results; the switch exists for tests and measurements. */

@@ -40,6 +40,17 @@ def test_c_abi_exports_every_declared_symbol():
     assert L.akz_version() >= 100
 
 
+def test_communicator_id_needs_no_gpu():
+    """akz_comm_unique_id (NCCL loaded at run time, no link-time dependency): 128 bytes, different on every call."""
+    try:
+        a, b = ab().comm_unique_id(), ab().comm_unique_id()
+    except ab().AkazeError as e:
+        pytest.skip(f"NCCL not available: {e}")
+    assert len(a) == 128 and a != b and any(a)
+    out = subprocess.check_output(["ldd", ab().LIB_PATH]).decode()
+    assert "nccl" not in out
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():

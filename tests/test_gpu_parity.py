@@ -942,3 +942,64 @@ def test_matcher_full_size_properties():
     assert np.array_equal(r[:, 0], perm_inv) and not r[:, 1].any()          # every query finds its own copy at distance 0
     assert (r[:, 3] > 150).all()                                           # second best of random 486-bit strings
     ctx.close()
+
+
+def test_match_pairs_equals_per_pair_matching():
+    """akz_match_pairs (batched consecutive-frame matcher of the 4K stream, counts read on the device) against akz_match pair by
+    pair, all modes; frames with zero, few and many keypoints."""
+    rng = np.random.default_rng(11)
+    mp, nf = 3000, 6
+    counts = np.array([1500, 2999, 0, 17, 3000, 700], dtype=np.int32)
+    desc = np.zeros((nf, mp, 64), dtype=np.uint8)
+    base = B.random_descriptors(3000, 3)
+    for f in range(nf):
+        d = base[rng.permutation(3000)].copy()
+        flip = rng.random((3000, 64)) < 0.02
+        d ^= (flip * rng.integers(0, 256, (3000, 64))).astype(np.uint8)
+        d[:, 61:] = 0
+        d[:, 60] &= 0x3F
+        desc[f, :counts[f]] = d[:counts[f]]
+    ctx = ab().Context(0, 0, max_pts=mp)
+    dd, dc = torch.from_numpy(desc).cuda(), torch.from_numpy(counts).cuda()
+    for mode in (ab().MATCH_COMPAT, ab().MATCH_KNN2, ab().MATCH_UNIQUE2):
+        out = torch.full((nf, mp, 4), -7, dtype=torch.int32, device="cuda")
+        ctx.match_pairs(dd, dc, mode, out=out)
+        ctx.sync()
+        out = out.cpu().numpy()
+        for f in range(1, nf):
+            if counts[f] == 0:
+                continue
+            r = ctx.match(dd[f, :counts[f]], dd[f - 1, :counts[f - 1]], mode)
+            ctx.sync()
+            r = r.cpu().numpy()
+            cols = slice(0, 2) if mode == ab().MATCH_COMPAT else slice(0, 4)
+            assert np.array_equal(out[f, :counts[f], cols], r[:, cols]), (mode, f)
+            assert (out[f, counts[f]:] == -7).all()                    # rows beyond the count are not touched
+    ctx.close()
+
+
+def test_match_sharded_with_a_one_rank_communicator():
+    """akz_match_sharded end to end on one GPU: NCCL communicator of one rank created through akz_comm_unique_id / akz_comm_init,
+    akz_match(finalize = 0) -> ncclAllGather on the context's stream -> akz_match_merge.  Must equal akz_match.  (World sizes
+    2..8 run in bench.py under torchrun, which asserts the same equality against the unsharded result.)"""
+    q, t = _planted(3000, 20000, seed=5)
+    ctx = ab().Context(0, 0)
+    try:
+        ctx.comm_init(1, 0, ab().comm_unique_id())
+    except ab().AkazeError as e:
+        ctx.close()
+        pytest.skip(f"NCCL not usable here: {e}")
+    dq, dt = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+    for mode in (ab().MATCH_KNN2, ab().MATCH_COMPAT):
+        a = ctx.match_sharded(dq, dt, 0, mode)
+        b_ = ctx.match(dq, dt, mode)
+        ctx.sync()
+        cols = 2 if mode == ab().MATCH_COMPAT else 4
+        assert torch.equal(a[:, :cols], b_[:, :cols])
+        # a train range that starts at a global offset keeps global indices
+        c = ctx.match_sharded(dq, dt[1024:], 1024, mode)
+        d = ctx.match(dq, dt[1024:], mode, t_index_base=1024)
+        ctx.sync()
+        assert torch.equal(c[:, :cols], d[:, :cols])
+    ctx.comm_destroy()
+    ctx.close()
