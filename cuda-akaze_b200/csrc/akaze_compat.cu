@@ -171,6 +171,8 @@ namespace akaze
         int* d_count = nullptr;
         akz_keypoint* d_kpts = nullptr;
         uint8_t* d_desc = nullptr;
+        int* h_count = nullptr;                 // pinned landing zone of the keypoint count
+        unsigned char* h_stage = nullptr;       // pinned landing zone of the AkazePoint records (cap x 104 bytes)
         int cap = 0;
         void release()
         {
@@ -178,7 +180,9 @@ namespace akaze
             if (d_count) cudaFree(d_count);
             if (d_kpts) cudaFree(d_kpts);
             if (d_desc) cudaFree(d_desc);
-            ctx = nullptr; d_count = nullptr; d_kpts = nullptr; d_desc = nullptr; cap = 0;
+            if (h_count) cudaFreeHost(h_count);
+            if (h_stage) cudaFreeHost(h_stage);
+            ctx = nullptr; d_count = nullptr; d_kpts = nullptr; d_desc = nullptr; h_count = nullptr; h_stage = nullptr; cap = 0;
         }
         void ensure(int w, int h, int max_pts)
         {
@@ -189,11 +193,19 @@ namespace akaze
             CHECK(cudaMalloc((void**)&d_count, sizeof(int)));
             CHECK(cudaMalloc((void**)&d_kpts, sizeof(akz_keypoint) * (size_t)max_pts));
             CHECK(cudaMalloc((void**)&d_desc, (size_t)64 * max_pts));
+            CHECK(cudaMallocHost((void**)&h_count, sizeof(int)));
+            CHECK(cudaMallocHost((void**)&h_stage, sizeof(AkazePoint) * (size_t)max_pts));
             cap = max_pts;
         }
+        // One frame through the batched pipeline (a context of batch 1: octave chains on their own streams, the whole chunk
+        // replayed as a CUDA graph from the second call with the same buffers on), then the reference's result contract
+        // (akaze.cpp:128-139): num_pts, AkazePoint records in result.d_data, and the first 24 (+61) bytes of every record in
+        // result.h_data.  The host copy is one contiguous transfer of the records into pinned memory and a strided copy on the
+        // host (the reference's cudaMemcpy2D of 85-byte rows is a row-by-row transfer).
         void run(const void* image, int dtype, AkazeData& result, int3 whp0, bool desc, bool fast = false)
         {
             ensure(whp0.x, whp0.y, result.max_pts);
+            cudaStream_t st = (cudaStream_t)akz_stream(ctx);
             if (fast)
                 AKZ_DO(akz_fast_detect_and_compute(ctx, (const uint8_t*)image, 1, whp0.x, whp0.y, whp0.z, (long long)whp0.y * whp0.z,
                                                    desc ? 1 : 0, d_count, d_kpts, d_desc));
@@ -201,12 +213,16 @@ namespace akaze
                 AKZ_DO(akz_detect_and_compute(ctx, image, dtype, 1, whp0.x, whp0.y, whp0.z, (long long)whp0.y * whp0.z,
                                               desc ? 1 : 0, d_count, d_kpts, d_desc));
             AKZ_DO(akz_pack_points(ctx, d_count, d_kpts, d_desc, result.d_data, result.max_pts, desc ? 1 : 0));
-            CHECK(cudaMemcpyAsync(&result.num_pts, d_count, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)akz_stream(ctx)));
+            CHECK(cudaMemcpyAsync(h_count, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
             AKZ_DO(akz_sync(ctx));
+            result.num_pts = *h_count;
             if (result.h_data != NULL && result.num_pts > 0) {
-                // the first 24 (+61) bytes of every record, as akaze.cpp:134-139
-                CHECK(cudaMemcpy2D(&result.h_data[0].x, sizeof(AkazePoint), &result.d_data[0].x, sizeof(AkazePoint),
-                                   (desc ? FLEN * sizeof(unsigned char) : 0) + 6 * sizeof(float), result.num_pts, cudaMemcpyDeviceToHost));
+                const size_t n = (size_t)result.num_pts;
+                const size_t ncopy = (desc ? FLEN * sizeof(unsigned char) : 0) + 6 * sizeof(float);      // akaze.cpp:134-139
+                CHECK(cudaMemcpyAsync(h_stage, result.d_data, n * sizeof(AkazePoint), cudaMemcpyDeviceToHost, st));
+                AKZ_DO(akz_sync(ctx));
+                unsigned char* dst = reinterpret_cast<unsigned char*>(result.h_data);
+                for (size_t i = 0; i < n; i++) memcpy(dst + i * sizeof(AkazePoint), h_stage + i * sizeof(AkazePoint), ncopy);
             }
         }
     };

@@ -139,7 +139,18 @@ struct akz_ctx {
     long long mplane;
     // device memory
     std::vector<void*> allocs;
-    float *smooth, *flow, *tmpA, *tmpB;
+    float *smooth, *flow, *tmpA, *tmpB;            // scratch planes of the octave whose launches are being issued (= sc[k])
+    // Small-batch contexts (max_batch <= 4, e.g. the one behind akaze::Akazer): every octave has its own scratch planes and
+    // stream, so the octave chains -- octave o + 1 only needs level (o, 0) -- run side by side, and a whole chunk is captured
+    // once per argument set as a CUDA graph and replayed (a single frame is launch bound: ~90 launches of a few microseconds)
+    struct Scratch { float *smooth, *flow, *tmpA, *tmpB; } sc[8];
+    cudaStream_t cur;                               // stream the pipeline launches go to (c->stream, or an octave stream)
+    cudaStream_t ostream[8];
+    cudaEvent_t ev_lvl0[8], ev_oct[8];
+    bool opar;
+    struct GraphEntry { unsigned long long key[10]; int seen; cudaGraphExec_t exec; int launches; };
+    std::vector<GraphEntry> graphs;
+    bool graph_ok;
     unsigned long long* map;
     unsigned* rowmask;
     int *rowcount, *prefix, *hist, *counts_own;      // counts_own / kpts_own / desc_own: AKZ_NSET result sets (host API pipeline)
@@ -272,12 +283,15 @@ int akz_create(const akz_options* o, akz_ctx** out)
     c->h2d_stream = c->d2h_stream = nullptr; c->h_cnt_pinned = nullptr;
     for (int i = 0; i < AKZ_NSET; i++) { c->ev_h2d[i] = c->ev_comp[i] = c->ev_cnt[i] = c->ev_d2h[i] = nullptr; }
     c->match_stage = nullptr; c->match_stage_bytes = 0;
+    c->cur = nullptr; c->opar = false; c->graph_ok = false;
+    for (int i = 0; i < 8; i++) { c->ostream[i] = nullptr; c->ev_lvl0[i] = c->ev_oct[i] = nullptr; c->sc[i] = { nullptr, nullptr, nullptr, nullptr }; }
     c->comm = nullptr; c->comm_ranks = 0; c->comm_rank = 0; c->comm_owned = false; c->shard_buf = nullptr; c->shard_buf_n = 0;
     int rc = AKZ_OK;
     do {
         if (o->device >= 0) { if (cudaSetDevice(o->device) != cudaSuccess) { rc = akz_set_error(AKZ_E_CUDA, "cudaSetDevice(%d) failed", o->device); break; } }
         cudaGetDevice(&c->device);
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamDefault) != cudaSuccess) { rc = akz_set_error(AKZ_E_CUDA, "stream creation failed"); break; }
+        c->cur = c->stream;
         const int B = o->max_batch;
         // small per-frame scalars: needed by the stage seams even without a pyramid
         if ((rc = dalloc(c, &c->prefix, (size_t)2 * B + 2)) != AKZ_OK) break;
@@ -300,6 +314,30 @@ int akz_create(const akz_options* o, akz_ctx** out)
         if ((rc = dalloc(c, &c->flow, n0)) != AKZ_OK) break;
         if ((rc = dalloc(c, &c->tmpA, n0)) != AKZ_OK) break;
         if ((rc = dalloc(c, &c->tmpB, n0)) != AKZ_OK) break;
+        c->sc[0] = { c->smooth, c->flow, c->tmpA, c->tmpB };
+        for (int k = 1; k < 8; k++) c->sc[k] = c->sc[0];
+        {
+            static const bool small_on = [] { const char* e = getenv("AKZ_SMALL_BATCH"); return !e || atoi(e) != 0; }();
+            if (small_on && B <= 4 && o->fused == 1 && c->noct > 1) {
+                for (int k = 1; k < c->noct && rc == AKZ_OK; k++) {
+                    const size_t nk = (size_t)c->lev[k * o->max_scale].plane * B;
+                    if ((rc = dalloc(c, &c->sc[k].smooth, nk)) != AKZ_OK) break;
+                    if ((rc = dalloc(c, &c->sc[k].flow, nk)) != AKZ_OK) break;
+                    if ((rc = dalloc(c, &c->sc[k].tmpA, nk)) != AKZ_OK) break;
+                    if ((rc = dalloc(c, &c->sc[k].tmpB, nk)) != AKZ_OK) break;
+                }
+                if (rc != AKZ_OK) break;
+                c->ostream[0] = c->stream;
+                for (int k = 0; k < c->noct; k++) {
+                    if (k > 0 && cudaStreamCreateWithFlags(&c->ostream[k], cudaStreamNonBlocking) != cudaSuccess) { rc = akz_set_error(AKZ_E_CUDA, "stream creation failed"); break; }
+                    cudaEventCreateWithFlags(&c->ev_lvl0[k], cudaEventDisableTiming);
+                    cudaEventCreateWithFlags(&c->ev_oct[k], cudaEventDisableTiming);
+                }
+                if (rc != AKZ_OK) break;
+                c->opar = true;
+                c->graph_ok = true;
+            }
+        }
         c->mpitch = c->lev[0].pitch;
         c->mplane = (long long)c->mpitch * o->height;
         if ((rc = dalloc(c, &c->map, (size_t)c->mplane * B)) != AKZ_OK) break;
@@ -350,6 +388,12 @@ void akz_destroy(akz_ctx* c)
     if (c->lane1) akz_destroy(c->lane1);
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (int k = 0; k < 8; k++) {
+        if (k > 0 && c->ostream[k]) { cudaStreamSynchronize(c->ostream[k]); cudaStreamDestroy(c->ostream[k]); }
+        if (c->ev_lvl0[k]) cudaEventDestroy(c->ev_lvl0[k]);
+        if (c->ev_oct[k]) cudaEventDestroy(c->ev_oct[k]);
+    }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (void* p : c->allocs) cudaFree(p);
@@ -408,11 +452,11 @@ const float* akz_level_plane(const akz_ctx* c, int l, int which, int frame)
 // ---- pipeline ------------------------------------------------------------------------------------------
 #define LAUNCHED(cls_, expr) do {                                                              \
         cudaEvent_t ea_ = nullptr;                                                             \
-        if (c->prof_on) { ea_ = prof_event(c); cudaEventRecord(ea_, c->stream); }              \
+        if (c->prof_on) { ea_ = prof_event(c); cudaEventRecord(ea_, c->cur); }              \
         int r_ = (expr);                                                                       \
         if (r_ < 0) return r_;                                                                 \
         c->launches += r_;                                                                     \
-        if (ea_) { cudaEvent_t eb_ = prof_event(c); cudaEventRecord(eb_, c->stream);           \
+        if (ea_) { cudaEvent_t eb_ = prof_event(c); cudaEventRecord(eb_, c->cur);           \
                    c->prof_pairs.push_back({ ea_, eb_, (cls_), r_ }); }                        \
     } while (0)
 
@@ -438,7 +482,7 @@ static int prep_level_split(akz_ctx* c, int mode, const float* src, int sw, int 
                             float* lx, float* ly, float* det, int nmul, int step, int w, int h, int pitch, long long plane, int nf, int int_planes)
 {
     if (!prep_split_enabled() || step < 2 || step > 4 || w < 32 || h < 32 || (w % 4) != 0) return 0;
-    cudaStream_t st = c->stream;
+    cudaStream_t st = c->cur;
     if (mode == 0) return akzk::deriv_stream(st, src, lx, ly, det, step, w, h, pitch, plane, nf, int_planes);
     if (!c->smooth || !flowp) return 0;
     // both halves must take the level: probe the derivative half's conditions first (it has the stricter ones)
@@ -459,7 +503,7 @@ static int prep_level(akz_ctx* c, int mode, const float* src, int sw, int sh, in
                       float* lx, float* ly, float* det, int nmul, int step, int w, int h, int pitch, long long plane, int nf)
 {
     const akz_options& o = c->opt;
-    cudaStream_t st = c->stream;
+    cudaStream_t st = c->cur;
     if (o.fused == 1) {
         // split pipeline: tile kernel for the blur / octave transition + conductance (blurred plane to c->smooth), streaming warp
         // kernel for the derivatives and the determinant; the single tile kernel k_prep2 takes what they do not cover
@@ -487,13 +531,27 @@ static int prep_level(akz_ctx* c, int mode, const float* src, int sw, int sh, in
     return launches + r;
 }
 
-static int scale_space_chunk(akz_ctx* c, const void* img, int dtype, int nf, int ipitch, long long istride)
+// Octave switch of the pipeline: the launches that follow go to the octave's stream and scratch planes.  Without per-octave
+// resources (large-batch contexts) every octave uses the context's stream and the one scratch set.
+static int enter_octave(akz_ctx* c, int oc)
 {
-    cudaStream_t st = c->stream;
+    const int k = c->opar ? oc : 0;
+    c->smooth = c->sc[k].smooth; c->flow = c->sc[k].flow; c->tmpA = c->sc[k].tmpA; c->tmpB = c->sc[k].tmpB;
+    c->cur = c->opar ? c->ostream[oc] : c->stream;
+    // octave oc starts from level (oc - 1, 0) (akaze.cpp:371-392) and the contrast factor: both are ready at that octave's event
+    if (c->opar && oc > 0) AKZ_CUDA_TRY(cudaStreamWaitEvent(c->cur, c->ev_lvl0[oc - 1], 0));
+    return AKZ_OK;
+}
+
+static int scale_space_levels(akz_ctx* c, const void* img, int dtype, int nf, int ipitch, long long istride)
+{
     const akz_options& o = c->opt;
     const int S = o.max_scale, fused = o.fused;
     AkzLevel& L0 = c->lev[0];
     const int w0 = L0.w, h0 = L0.h, p0 = L0.pitch;
+    int rc = enter_octave(c, 0);
+    if (rc != AKZ_OK) return rc;
+    cudaStream_t st = c->cur;
     // level (0,0): akaze.cpp:325-346
     const float var0 = o.soffset * o.soffset;
     const int ksz0 = (int)(2 * ceilf((o.soffset - 0.8f) / 0.3f) + 3);
@@ -520,6 +578,7 @@ static int scale_space_chunk(akz_ctx* c, const void* img, int dtype, int nf, int
         }
         LAUNCHED(AKZ_K_CONTRAST, akzk::contrast(st, c->smooth, c->hmax, c->hist, c->kc, o.per, o.kcontrast_override, w0, h0, p0, L0.plane, nf));
     }
+    if (c->opar) AKZ_CUDA_TRY(cudaEventRecord(c->ev_lvl0[0], st));            // Lt(0,0) and the contrast factors are ready
     if (fused) LAUNCHED(AKZ_K_PREP, prep_level(c, 0, L0.lt, w0, h0, p0, L0.plane, nullptr, nullptr, L0.lx, L0.ly, L0.det, 0, L0.sigma_size, w0, h0, p0, L0.plane, nf));
     else LAUNCHED(AKZ_K_HESSIAN, akzk::hessian(st, L0.lt, L0.lx, L0.ly, L0.det, L0.sigma_size, w0, h0, p0, L0.plane, nf));
 
@@ -529,6 +588,8 @@ static int scale_space_chunk(akz_ctx* c, const void* img, int dtype, int nf, int
         const int w = L.w, h = L.h, p = L.pitch;
         if (L.sub == 0) {
             // new octave (akaze.cpp:371-392): source is sublevel 0 of the previous octave; kcontrast *= 0.75
+            if ((rc = enter_octave(c, L.octave)) != AKZ_OK) return rc;
+            st = c->cur;
             AkzLevel& P = c->lev[l - S];
             if (fused) {
                 LAUNCHED(AKZ_K_PREP, prep_level(c, 2, P.lt, P.w, P.h, P.pitch, P.plane, c->tmpB, c->flow, L.lx, L.ly, L.det, L.octave,
@@ -538,6 +599,7 @@ static int scale_space_chunk(akz_ctx* c, const void* img, int dtype, int nf, int
                 LAUNCHED(AKZ_K_FLOW, akzk::flow(st, c->smooth, c->flow, o.diffusivity, c->kc, 0.75f, L.octave, w, h, p, L.plane, nf));
             }
             LAUNCHED(AKZ_K_FED, akzk::fed_cycle(st, c->tmpB, c->flow, L.lt, c->tmpA, tau, L.nsteps, w, h, p, L.plane, nf, fused));
+            if (c->opar) AKZ_CUDA_TRY(cudaEventRecord(c->ev_lvl0[L.octave], st));
         } else {
             // next sublevel (akaze.cpp:393-421)
             AkzLevel& P = c->lev[l - 1];
@@ -553,6 +615,21 @@ static int scale_space_chunk(akz_ctx* c, const void* img, int dtype, int nf, int
     }
     c->last_frames = nf;
     return AKZ_OK;
+}
+
+static int scale_space_chunk(akz_ctx* c, const void* img, int dtype, int nf, int ipitch, long long istride)
+{
+    const int rc = scale_space_levels(c, img, dtype, nf, ipitch, istride);
+    // back to the context's stream and scratch set; the octave streams join it (also after an error: nothing stays forked)
+    int rj = AKZ_OK;
+    if (c->opar)
+        for (int k = 1; k < c->noct; k++) {
+            if (cudaEventRecord(c->ev_oct[k], c->ostream[k]) != cudaSuccess || cudaStreamWaitEvent(c->stream, c->ev_oct[k], 0) != cudaSuccess)
+                rj = akz_set_error(AKZ_E_CUDA, "joining the octave streams failed");
+        }
+    c->cur = c->stream;
+    c->smooth = c->sc[0].smooth; c->flow = c->sc[0].flow; c->tmpA = c->sc[0].tmpA; c->tmpB = c->sc[0].tmpB;
+    return rc != AKZ_OK ? rc : rj;
 }
 
 // integer pipeline, Akazer::fastDetect (akaze.cpp:506-743): the plane buffers of the context are reused as int32 planes
@@ -663,6 +740,50 @@ static int detect_chunk(akz_ctx* c, int nf, int describe, int* d_counts, akz_key
     return AKZ_OK;
 }
 
+// Replay of a whole chunk as a CUDA graph (small-batch contexts).  The first call with an argument set runs eagerly (lazy
+// per-device initialisation stays outside any capture) and remembers the set; the second one captures the same launches --
+// kernels, memsets and the fork / join of the octave streams -- instantiates the graph and launches it; later ones launch it.
+template <class F>
+static int run_graphed(akz_ctx* c, const unsigned long long (&key)[10], F&& body)
+{
+    if (!c->graph_ok || c->prof_on) return body();
+    for (auto& g : c->graphs) {
+        if (memcmp(g.key, key, sizeof(key)) != 0) continue;
+        if (!g.exec) {
+            cudaGraph_t graph = nullptr;
+            const long long l0 = c->launches;
+            if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); c->graph_ok = false; return body(); }
+            const int rc = body();
+            const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+            const int nl = (int)(c->launches - l0);
+            c->launches = l0;
+            if (rc != AKZ_OK || e != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                c->graph_ok = false;                       // this context keeps working without graphs
+                return rc != AKZ_OK ? rc : body();
+            }
+            cudaGraphExec_t exec = nullptr;
+            const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ei != cudaSuccess || !exec) { cudaGetLastError(); c->graph_ok = false; return body(); }
+            g.exec = exec; g.launches = nl;
+        }
+        AKZ_CUDA_TRY(cudaGraphLaunch(g.exec, c->stream));
+        c->launches += g.launches;
+        return AKZ_OK;
+    }
+    if (c->graphs.size() >= 8) {
+        if (c->graphs.front().exec) { cudaStreamSynchronize(c->stream); cudaGraphExecDestroy(c->graphs.front().exec); }
+        c->graphs.erase(c->graphs.begin());
+    }
+    akz_ctx::GraphEntry g = {};
+    memcpy(g.key, key, sizeof(key));
+    g.seen = 1; g.exec = nullptr; g.launches = 0;
+    c->graphs.push_back(g);
+    return body();
+}
+
 extern "C" {
 
 int akz_build_scale_space(akz_ctx* c, const void* d_images, int dtype, int nframes, int w, int h, int pitch, long long stride)
@@ -715,6 +836,17 @@ int akz_detect_and_compute(akz_ctx* c, const void* d_images, int dtype, int nfra
     AKZ_CUDA_TRY(cudaSetDevice(c->device));
     const int B = c->opt.max_batch;
     const size_t esz = dtype == AKZ_U8 ? 1 : 4;
+    if (nframes >= 1 && nframes <= B && c->graph_ok) {
+        const unsigned long long key[10] = { (unsigned long long)(uintptr_t)d_images, (unsigned long long)dtype, (unsigned long long)nframes,
+                                             (unsigned long long)pitch, (unsigned long long)stride, (unsigned long long)describe,
+                                             (unsigned long long)(uintptr_t)d_counts, (unsigned long long)(uintptr_t)d_kpts,
+                                             (unsigned long long)(uintptr_t)d_desc, 0ull };
+        return run_graphed(c, key, [&]() -> int {
+            int r = scale_space_chunk(c, d_images, dtype, nframes, pitch, stride);
+            if (r != AKZ_OK) return r;
+            return detect_chunk(c, nframes, describe, d_counts, d_kpts, d_desc);
+        });
+    }
     // two lanes: chunks alternate between the parent and the child context, each on its own stream
     const bool two = c->lane1 != nullptr && nframes > B;
     if (two) {
@@ -767,6 +899,17 @@ int akz_fast_detect_and_compute(akz_ctx* c, const uint8_t* d_images, int nframes
     akz_device_guard dev_guard_;
     AKZ_CUDA_TRY(cudaSetDevice(c->device));
     const int B = c->opt.max_batch;
+    if (nframes >= 1 && nframes <= B && c->graph_ok) {
+        const unsigned long long key[10] = { (unsigned long long)(uintptr_t)d_images, (unsigned long long)AKZ_U8, (unsigned long long)nframes,
+                                             (unsigned long long)pitch, (unsigned long long)stride, (unsigned long long)describe,
+                                             (unsigned long long)(uintptr_t)d_counts, (unsigned long long)(uintptr_t)d_kpts,
+                                             (unsigned long long)(uintptr_t)d_desc, 1ull };
+        return run_graphed(c, key, [&]() -> int {
+            int r = fast_scale_space_chunk(c, d_images, nframes, pitch, stride);
+            if (r != AKZ_OK) return r;
+            return detect_chunk(c, nframes, describe, d_counts, d_kpts, d_desc, 1);
+        });
+    }
     const bool two = c->lane1 != nullptr && nframes > B;
     if (two) {
         AKZ_CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
@@ -1197,6 +1340,8 @@ int akz_comm_destroy(akz_ctx* c)
         if (c->stream) cudaStreamSynchronize(c->stream);
         g_nccl.CommDestroy(c->comm);
     }
+    c->cur = nullptr; c->opar = false; c->graph_ok = false;
+    for (int i = 0; i < 8; i++) { c->ostream[i] = nullptr; c->ev_lvl0[i] = c->ev_oct[i] = nullptr; c->sc[i] = { nullptr, nullptr, nullptr, nullptr }; }
     c->comm = nullptr; c->comm_ranks = 0; c->comm_rank = 0; c->comm_owned = false;
     return AKZ_OK;
 }

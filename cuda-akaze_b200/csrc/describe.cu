@@ -495,7 +495,16 @@ __global__ void k_pack(const int* __restrict__ count, const akz_keypoint* __rest
         akz_keypoint k = kpts[i];
         RefPoint* p = pts + i;
         p->x = k.x; p->y = k.y; p->octave = k.layer; p->size = k.size; p->angle = k.angle;
-        if (with_desc) for (int b = 0; b < 61; b++) p->features[b] = desc[(long long)i * 64 + b];
+        if (with_desc) {
+            // 61 bytes = 15 words + 1 byte; features[] starts at offset 24 of a 104-byte record: word stores are aligned.
+            // Bytes 85..87 (padding before `match`) are left alone.
+            const uint4* d4 = reinterpret_cast<const uint4*>(desc + (long long)i * 64);
+            const uint4 a = __ldg(d4), b = __ldg(d4 + 1), c = __ldg(d4 + 2), d = __ldg(d4 + 3);
+            unsigned* f = reinterpret_cast<unsigned*>(p->features);
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+            f[8] = c.x; f[9] = c.y; f[10] = c.z; f[11] = c.w; f[12] = d.x; f[13] = d.y; f[14] = d.z;
+            p->features[60] = (unsigned char)(d.w & 0xFFu);
+        }
     }
 }
 

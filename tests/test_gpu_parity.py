@@ -1003,3 +1003,40 @@ def test_match_sharded_with_a_one_rank_communicator():
         assert torch.equal(c[:, :cols], d[:, :cols])
     ctx.comm_destroy()
     ctx.close()
+
+
+@pytest.mark.parametrize("fast", [False, True])
+def test_small_batch_graph_path_equals_the_batched_path(fast):
+    """Contexts of batch <= 4 run the octave chains on their own streams and replay a chunk as a CUDA graph from the second
+    call with the same buffers on (the path behind akaze::Akazer).  Every call -- eager, captured, replayed, and after the
+    input buffer's CONTENT changed -- must give exactly what a large-batch context (one stream, no graph) gives."""
+    w, h = 1280, 960
+    imgs = [B.read_pgm(os.path.join(B.REF_DATA, n)) if os.path.exists(os.path.join(B.REF_DATA, n)) else B.synth_shapes_u8(w, h, seed=7 + i)
+            for i, n in enumerate(("left.pgm", "right.pgm"))]
+    conv = (lambda a: a) if fast else B.u8_to_unit
+    big = ab().Context(w, h, max_batch=8, max_pts=8000)
+    run_big = big.fast_detect_and_compute if fast else big.detect_and_compute
+    expect = []
+    for im in imgs:
+        c, k, d = run_big(torch.from_numpy(conv(im)[None]).cuda())
+        big.sync()
+        n = int(c[0].cpu())
+        expect.append((n, k[0, :n].cpu().numpy().copy(), d[0, :n].cpu().numpy().copy()))
+    big.close()
+    for nb in (1, 2):
+        small = ab().Context(w, h, max_batch=nb, max_pts=8000)
+        run_small = small.fast_detect_and_compute if fast else small.detect_and_compute
+        buf = torch.from_numpy(conv(imgs[0])[None]).cuda()
+        out = small.alloc_results(1, True)
+        l0 = small.launches
+        for it in range(5):
+            src = imgs[it % 2]
+            buf.copy_(torch.from_numpy(conv(src)[None]).cuda())
+            torch.cuda.synchronize()
+            c, k, d = run_small(buf, out=out)
+            small.sync()
+            n, ek, ed = expect[it % 2]
+            assert int(c[0].cpu()) == n, (nb, it)
+            assert np.array_equal(k[0, :n].cpu().numpy(), ek) and np.array_equal(d[0, :n].cpu().numpy(), ed), (nb, it)
+        assert small.launches - l0 > 5 * 40                              # replayed launches are counted too
+        small.close()
