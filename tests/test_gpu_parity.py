@@ -395,17 +395,13 @@ def test_keypoints_vs_reference(ref_left):
         return missed
 
     assert not dm[:, 61:].any()
-    # up to three runs of the (racy) reference: a run that misses a statistical bar was seen about once in fifteen fresh boxes
+    # REPORT ONLY for the statistical bars: the whole-pipeline reference run merges sublevels with a live data race, its outcome
+    # differs from run to run, and a bar it misses says nothing about this library.  The exact statements (set equality,
+    # positions, descriptors against the race-free reference) are test_detector_vs_serialized_reference and the 1920x1088 test;
+    # the descriptor comparison inside compare() is exact and stays asserted.
     missed = compare(ref_left["pts"])
-    for attempt in range(2):
-        if not missed:
-            break
-        print(f"[keypoints] reference run missed {missed}; running the reference again")
-        r = B.RefAkazer(w, h, w)
-        pts, _, _ = r.detect_keep(dev(img)[0], max_pts=30000)
-        r.close()
-        missed = compare(pts)
-    assert not missed, missed
+    if missed:
+        print(f"[keypoints] (report only) the racy reference run differs beyond the usual bars: {missed}")
 
 
 def test_detector_vs_serialized_reference():
@@ -1040,3 +1036,81 @@ def test_small_batch_graph_path_equals_the_batched_path(fast):
             assert np.array_equal(k[0, :n].cpu().numpy(), ek) and np.array_equal(d[0, :n].cpu().numpy(), ed), (nb, it)
         assert small.launches - l0 > 5 * 40                              # replayed launches are counted too
         small.close()
+
+
+def _full_parity_vs_serialised_reference(img, noct, tag, clean_level, kp_region, min_common=1.0):
+    """Whole pipeline against the reference run race-free (bindings.RefAkazer.detect_serialized) on one frame: every plane of
+    every level that the reference computes without reading uninitialised memory (clean_level(l) -> fraction of rows from the
+    top that must agree, 1.0 = all), the keypoint SET inside kp_region(points) -> mask, positions <= 1e-4 px, and the descriptors
+    of all keypoints with bit-identical (x, y, angle)."""
+    from scipy.spatial import cKDTree
+    h, w = img.shape
+    r = B.RefAkazer(w, h, w, noctaves=noct)
+    rp, planes, k = r.detect_serialized(dev(img)[0], max_pts=60000)
+    r.close()
+    ctx = ab().Context(w, h, noctaves=noct, max_batch=1, max_pts=60000, kcontrast_override=k)
+    counts, kpts, desc = ctx.detect_and_compute(dev(img))
+    ctx.sync()
+    assert ctx.num_levels == len(planes) == 4 * noct
+    names = ["Lt", "det", "Lx", "Ly"]
+    nfull = 0
+    for l in range(ctx.num_levels):
+        frac = clean_level(l)
+        for which in range(4):
+            a, b = bits(ctx.plane(l, which)), bits(planes[l][which])
+            top = int(round(a.shape[0] * frac))
+            if frac >= 1.0:
+                assert_bits_equal(ctx.plane(l, which), planes[l][which], f"{tag} level {l} {names[which]}")
+                nfull += 1
+            else:
+                assert np.array_equal(a[:top], b[:top]), f"{tag} level {l} {names[which]}: differs above the reference's band"
+    mine = _kp_array(counts, kpts)
+    dm = desc[0].cpu().numpy()
+    ctx.close()
+    mm, rm = kp_region(mine, "layer"), kp_region(rp, "octave")
+    key = lambda a, f, m: {(int(q[f]), q["y"].view(np.uint32).item(), q["x"].view(np.uint32).item()) for q in a[m]}
+    ours, theirs = key(mine, "layer", mm), key(rp, "octave", rm)
+    d, j = cKDTree(np.stack([mine["x"], mine["y"]], 1)).query(np.stack([rp["x"][rm], rp["y"][rm]], 1))
+    rr = rp[rm]
+    exact = (d == 0) & (mine["layer"][j] == rr["octave"]) & (mine["angle"][j].view(np.uint32) == rr["angle"].view(np.uint32))
+    nbad = int((dm[j[exact]][:, :61] != rr["features"][exact]).any(axis=1).sum())
+    da = np.abs(mine["angle"][j] - rr["angle"])
+    da = np.minimum(da, 2 * np.pi - da)
+    print(f"\n[{tag}] planes compared in full: {nfull} of {4 * len(planes)}; keypoints ours={len(ours)} reference={len(theirs)} common={len(ours & theirs)}; "
+          f"angles within 1e-4 rad: {(da <= 1e-4).mean():.5f}; descriptors compared (identical x, y, angle): {int(exact.sum())}, differing: {nbad}")
+    assert len(theirs) > 200
+    if min_common >= 1.0:
+        assert ours == theirs
+    else:
+        assert len(ours & theirs) >= min_common * max(len(ours), len(theirs))
+    assert (da[d == 0] <= 1e-4).mean() >= 0.995
+    assert nbad == 0 and exact.mean() >= 0.7
+    return len(theirs)
+
+
+@needs_ref
+@pytest.mark.parametrize("content", ["shapes", "noise"])
+def test_benchmark_scale_1920x1088_vs_reference_complete(content):
+    """The benchmark-scale frame at the nearest size where the reference reads no uninitialised rows (1088 / 544 / 272 / 136 rows,
+    SURVEY App. B-7): ALL 64 planes bit for bit, the COMPLETE keypoint set and every comparable descriptor, no band excluded.
+    Both synthetic inputs of bench.py (shapes ~2 k keypoints, noise ~20 k)."""
+    w, h = 1920, 1088
+    gen = B.synth_noise_u8 if content == "noise" else B.synth_shapes_u8
+    img = B.u8_to_unit(gen(w, h, seed=51))
+    n = _full_parity_vs_serialised_reference(img, 4, f"1920x1088 {content}", lambda l: 1.0, lambda a, f: np.ones(len(a), dtype=bool))
+    assert n > (10000 if content == "noise" else 1000)
+
+
+@needs_ref
+def test_4k_five_octaves_vs_reference():
+    """BASELINE configs[4] geometry: 3840x2160, 5 octaves x 4 sublevels.  The reference reads uninitialised rows at octave 3
+    (270 rows, App. B-7) and octave 4 inherits them through the octave transition: octaves 0-2 (48 planes) are compared in
+    full, octaves 3 and 4 above the band the garbage reaches (it climbs one row per diffusion step from the bottom edge; the
+    last level of octave 4, 57 steps on 135 rows, is left out).  Keypoints of octaves 0-2 in the upper 55 % of the frame: a
+    contaminated coarse candidate can still suppress a true fine keypoint near it through the radius NMS, so the sets must
+    agree to 99.5 % there rather than exactly; descriptors of all keypoints with identical (x, y, angle) are exact."""
+    w, h = 3840, 2160
+    img = B.u8_to_unit(B.synth_shapes_u8(w, h, seed=21, nshapes=600))
+    top = {12: 0.75, 13: 0.6, 14: 0.42, 15: 0.2, 16: 0.7, 17: 0.45, 18: 0.15, 19: 0.0}
+    _full_parity_vs_serialised_reference(img, 5, "3840x2160 5x4", lambda l: top.get(l, 1.0),
+                                         lambda a, f: (a["y"] < 0.55 * h) & (a[f] < 12), min_common=0.995)
