@@ -487,7 +487,11 @@ static int prep_level_split(akz_ctx* c, int mode, const float* src, int sw, int 
     if (!c->smooth || !flowp) return 0;
     // both halves must take the level: probe the derivative half's conditions first (it has the stricter ones)
     if ((pitch % 4) != 0 || (plane % 4) != 0 || (((uintptr_t)c->smooth | (uintptr_t)lx | (uintptr_t)ly | (uintptr_t)det) % 16) != 0) return 0;
-    int r1 = akzk::level_blur_flow(st, mode, src, sw, sh, sp, splane, ltdst, flowp, c->smooth, c->opt.diffusivity, c->kc, 0.75f, nmul,
+    static const bool blur_stream_on = [] { const char* e = getenv("AKZ_BLUR_STREAM"); return !e || atoi(e) != 0; }();      // A/B knob
+    int r1 = blur_stream_on ? akzk::blur_stream(st, mode, src, sw, sh, sp, splane, ltdst, flowp, c->smooth, c->opt.diffusivity, c->kc, 0.75f, nmul,
+                                                w, h, pitch, plane, nf, int_planes) : 0;
+    if (r1 == 0)
+        r1 = akzk::level_blur_flow(st, mode, src, sw, sh, sp, splane, ltdst, flowp, c->smooth, c->opt.diffusivity, c->kc, 0.75f, nmul,
                                    w, h, pitch, plane, nf, int_planes);
     if (r1 <= 0) return r1;
     int r2 = akzk::deriv_stream(st, c->smooth, lx, ly, det, step, w, h, pitch, plane, nf, int_planes);

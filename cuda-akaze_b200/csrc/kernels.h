@@ -57,6 +57,10 @@ int level_prep2(cudaStream_t st, int mode, const float* src, int sw, int sh, int
 int level_blur_flow(cudaStream_t st, int mode, const float* src, int sw, int sh, int sp, long long splane,
                     float* ltdst, float* flowp, float* smooth, int type, const float* kc, float kscale, int nmul,
                     int w, int h, int pitch, long long plane, int n, int int_planes = 0);
+// blur_stream.cu: the same half as a streaming warp kernel (k_blur4); 0 when not covered
+int blur_stream(cudaStream_t st, int mode, const float* src, int sw, int sh, int sp, long long splane,
+                float* ltdst, float* flowp, float* smooth, int type, const float* kc, float kscale, int nmul,
+                int w, int h, int pitch, long long plane, int n, int int_planes = 0);
 int deriv_stream(cudaStream_t st, const float* smooth, float* lx, float* ly, float* det, int step, int w, int h, int pitch, long long plane,
                  int n, int int_planes = 0);
 // fed.cu: all n FED steps of a level (frozen conductance) in ceil(n / 4) launches of the streaming warp kernel (k_fed4), or of the
