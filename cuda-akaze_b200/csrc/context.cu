@@ -147,6 +147,12 @@ struct akz_ctx {
     cudaStream_t cur;                               // stream the pipeline launches go to (c->stream, or an octave stream)
     cudaStream_t ostream[8];
     cudaEvent_t ev_lvl0[8], ev_oct[8];
+    // side streams of the border-ring kernels (deriv_stream.cu), one per octave stream; rk = the one in use, ring_pending[k]:
+    // ev_ring_join[k] has to be waited for before the blurred plane is overwritten / the level's planes are read
+    cudaStream_t ring_stream[8];
+    cudaEvent_t ev_ring_fork[8], ev_ring_join[8];
+    bool ring_pending[8];
+    int rk;
     bool opar;
     struct GraphEntry { unsigned long long key[10]; int seen; cudaGraphExec_t exec; int launches; };
     std::vector<GraphEntry> graphs;
@@ -285,6 +291,8 @@ int akz_create(const akz_options* o, akz_ctx** out)
     c->match_stage = nullptr; c->match_stage_bytes = 0;
     c->cur = nullptr; c->opar = false; c->graph_ok = false;
     for (int i = 0; i < 8; i++) { c->ostream[i] = nullptr; c->ev_lvl0[i] = c->ev_oct[i] = nullptr; c->sc[i] = { nullptr, nullptr, nullptr, nullptr }; }
+    for (int i = 0; i < 8; i++) { c->ring_stream[i] = nullptr; c->ev_ring_fork[i] = c->ev_ring_join[i] = nullptr; c->ring_pending[i] = false; }
+    c->rk = 0;
     c->comm = nullptr; c->comm_ranks = 0; c->comm_rank = 0; c->comm_owned = false; c->shard_buf = nullptr; c->shard_buf_n = 0;
     int rc = AKZ_OK;
     do {
@@ -314,6 +322,16 @@ int akz_create(const akz_options* o, akz_ctx** out)
         if ((rc = dalloc(c, &c->flow, n0)) != AKZ_OK) break;
         if ((rc = dalloc(c, &c->tmpA, n0)) != AKZ_OK) break;
         if ((rc = dalloc(c, &c->tmpB, n0)) != AKZ_OK) break;
+        {
+            static const bool ring_side = [] { const char* e = getenv("AKZ_RING_SIDE"); return !e || atoi(e) != 0; }();
+            const int nring = ring_side ? ((B <= 4) ? c->noct : 1) : 0;
+            for (int k = 0; k < nring && k < 8; k++) {
+                if (cudaStreamCreateWithFlags(&c->ring_stream[k], cudaStreamNonBlocking) != cudaSuccess) { rc = akz_set_error(AKZ_E_CUDA, "stream creation failed"); break; }
+                cudaEventCreateWithFlags(&c->ev_ring_fork[k], cudaEventDisableTiming);
+                cudaEventCreateWithFlags(&c->ev_ring_join[k], cudaEventDisableTiming);
+            }
+            if (rc != AKZ_OK) break;
+        }
         c->sc[0] = { c->smooth, c->flow, c->tmpA, c->tmpB };
         for (int k = 1; k < 8; k++) c->sc[k] = c->sc[0];
         {
@@ -389,6 +407,11 @@ void akz_destroy(akz_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (int k = 0; k < 8; k++) {
+        if (c->ring_stream[k]) { cudaStreamSynchronize(c->ring_stream[k]); cudaStreamDestroy(c->ring_stream[k]); }
+        if (c->ev_ring_fork[k]) cudaEventDestroy(c->ev_ring_fork[k]);
+        if (c->ev_ring_join[k]) cudaEventDestroy(c->ev_ring_join[k]);
+    }
     for (int k = 0; k < 8; k++) {
         if (k > 0 && c->ostream[k]) { cudaStreamSynchronize(c->ostream[k]); cudaStreamDestroy(c->ostream[k]); }
         if (c->ev_lvl0[k]) cudaEventDestroy(c->ev_lvl0[k]);
@@ -483,7 +506,15 @@ static int prep_level_split(akz_ctx* c, int mode, const float* src, int sw, int 
 {
     if (!prep_split_enabled() || step < 2 || step > 4 || w < 32 || h < 32 || (w % 4) != 0) return 0;
     cudaStream_t st = c->cur;
-    if (mode == 0) return akzk::deriv_stream(st, src, lx, ly, det, step, w, h, pitch, plane, nf, int_planes);
+    const int rk = c->rk;
+    cudaStream_t rst = c->prof_on ? nullptr : c->ring_stream[rk];         // per-class timing keeps the ring kernels on the main stream
+    // the ring kernels of the previous level (side stream) read the blurred plane this level is about to overwrite
+    if (c->ring_pending[rk]) { AKZ_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_ring_join[rk], 0)); c->ring_pending[rk] = false; }
+    if (mode == 0) {
+        int r0 = akzk::deriv_stream(st, src, lx, ly, det, step, w, h, pitch, plane, nf, int_planes, rst, c->ev_ring_fork[rk], c->ev_ring_join[rk]);
+        if (r0 > 0 && rst) c->ring_pending[rk] = true;
+        return r0;
+    }
     if (!c->smooth || !flowp) return 0;
     // both halves must take the level: probe the derivative half's conditions first (it has the stricter ones)
     if ((pitch % 4) != 0 || (plane % 4) != 0 || (((uintptr_t)c->smooth | (uintptr_t)lx | (uintptr_t)ly | (uintptr_t)det) % 16) != 0) return 0;
@@ -494,9 +525,10 @@ static int prep_level_split(akz_ctx* c, int mode, const float* src, int sw, int 
         r1 = akzk::level_blur_flow(st, mode, src, sw, sh, sp, splane, ltdst, flowp, c->smooth, c->opt.diffusivity, c->kc, 0.75f, nmul,
                                    w, h, pitch, plane, nf, int_planes);
     if (r1 <= 0) return r1;
-    int r2 = akzk::deriv_stream(st, c->smooth, lx, ly, det, step, w, h, pitch, plane, nf, int_planes);
+    int r2 = akzk::deriv_stream(st, c->smooth, lx, ly, det, step, w, h, pitch, plane, nf, int_planes, rst, c->ev_ring_fork[rk], c->ev_ring_join[rk]);
     if (r2 < 0) return r2;
     if (r2 == 0) return akz_set_error(AKZ_E_UNSUPPORTED, "split level pipeline: derivative half refused a level the blur half took");
+    if (rst) c->ring_pending[rk] = true;
     return r1 + r2;
 }
 
@@ -542,6 +574,7 @@ static int enter_octave(akz_ctx* c, int oc)
     const int k = c->opar ? oc : 0;
     c->smooth = c->sc[k].smooth; c->flow = c->sc[k].flow; c->tmpA = c->sc[k].tmpA; c->tmpB = c->sc[k].tmpB;
     c->cur = c->opar ? c->ostream[oc] : c->stream;
+    c->rk = c->opar ? oc : 0;
     // octave oc starts from level (oc - 1, 0) (akaze.cpp:371-392) and the contrast factor: both are ready at that octave's event
     if (c->opar && oc > 0) AKZ_CUDA_TRY(cudaStreamWaitEvent(c->cur, c->ev_lvl0[oc - 1], 0));
     return AKZ_OK;
@@ -621,23 +654,35 @@ static int scale_space_levels(akz_ctx* c, const void* img, int dtype, int nf, in
     return AKZ_OK;
 }
 
+// the side streams of the border-ring kernels join the stream of their octave (also after an error: nothing stays forked)
+static int join_rings(akz_ctx* c)
+{
+    int rj = AKZ_OK;
+    for (int k = 0; k < 8; k++)
+        if (c->ring_pending[k]) {
+            if (cudaStreamWaitEvent(c->opar ? c->ostream[k] : c->stream, c->ev_ring_join[k], 0) != cudaSuccess) rj = akz_set_error(AKZ_E_CUDA, "joining a ring stream failed");
+            c->ring_pending[k] = false;
+        }
+    return rj;
+}
+
 static int scale_space_chunk(akz_ctx* c, const void* img, int dtype, int nf, int ipitch, long long istride)
 {
     const int rc = scale_space_levels(c, img, dtype, nf, ipitch, istride);
     // back to the context's stream and scratch set; the octave streams join it (also after an error: nothing stays forked)
-    int rj = AKZ_OK;
+    int rj = join_rings(c);
     if (c->opar)
         for (int k = 1; k < c->noct; k++) {
             if (cudaEventRecord(c->ev_oct[k], c->ostream[k]) != cudaSuccess || cudaStreamWaitEvent(c->stream, c->ev_oct[k], 0) != cudaSuccess)
                 rj = akz_set_error(AKZ_E_CUDA, "joining the octave streams failed");
         }
-    c->cur = c->stream;
+    c->cur = c->stream; c->rk = 0;
     c->smooth = c->sc[0].smooth; c->flow = c->sc[0].flow; c->tmpA = c->sc[0].tmpA; c->tmpB = c->sc[0].tmpB;
     return rc != AKZ_OK ? rc : rj;
 }
 
 // integer pipeline, Akazer::fastDetect (akaze.cpp:506-743): the plane buffers of the context are reused as int32 planes
-static int fast_scale_space_chunk(akz_ctx* c, const unsigned char* img, int nf, int ipitch, long long istride)
+static int fast_scale_space_levels(akz_ctx* c, const unsigned char* img, int nf, int ipitch, long long istride)
 {
     cudaStream_t st = c->stream;
     const akz_options& o = c->opt;
@@ -714,6 +759,14 @@ static int fast_scale_space_chunk(akz_ctx* c, const unsigned char* img, int nf, 
     }
     c->last_frames = nf;
     return AKZ_OK;
+}
+
+static int fast_scale_space_chunk(akz_ctx* c, const unsigned char* img, int nf, int ipitch, long long istride)
+{
+    c->rk = 0;                                   // the integer pipeline runs its octaves on the context's stream
+    const int rc = fast_scale_space_levels(c, img, nf, ipitch, istride);
+    const int rj = join_rings(c);                // ring index 0 belongs to the context's stream in either mode
+    return rc != AKZ_OK ? rc : rj;
 }
 
 static int detect_chunk(akz_ctx* c, int nf, int describe, int* d_counts, akz_keypoint* d_kpts, unsigned char* d_desc, int fast = 0)
@@ -1116,6 +1169,10 @@ int akz_hessian(akz_ctx* c, const float* smooth, float* lx, float* ly, float* de
         return akz_set_error(AKZ_E_INVALID, "the fused level kernel cannot work in place: outputs must not alias the input (use fused = 0)");
     if (c->opt.fused) LAUNCHED(AKZ_K_PREP, prep_level(c, 0, smooth, w, h, pitch, stride, nullptr, nullptr, lx, ly, det, 0, step, w, h, pitch, stride, n));
     else LAUNCHED(AKZ_K_HESSIAN, akzk::hessian(c->stream, smooth, lx, ly, det, step, w, h, pitch, stride, n));
+    {
+        const int rj = join_rings(c);
+        if (rj != AKZ_OK) return rj;
+    }
     STAGE_EPILOGUE();
 }
 
@@ -1346,6 +1403,8 @@ int akz_comm_destroy(akz_ctx* c)
     }
     c->cur = nullptr; c->opar = false; c->graph_ok = false;
     for (int i = 0; i < 8; i++) { c->ostream[i] = nullptr; c->ev_lvl0[i] = c->ev_oct[i] = nullptr; c->sc[i] = { nullptr, nullptr, nullptr, nullptr }; }
+    for (int i = 0; i < 8; i++) { c->ring_stream[i] = nullptr; c->ev_ring_fork[i] = c->ev_ring_join[i] = nullptr; c->ring_pending[i] = false; }
+    c->rk = 0;
     c->comm = nullptr; c->comm_ranks = 0; c->comm_rank = 0; c->comm_owned = false;
     return AKZ_OK;
 }

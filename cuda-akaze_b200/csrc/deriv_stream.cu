@@ -266,8 +266,11 @@ __global__ void __launch_bounds__(256) k_det_ring(const float* __restrict__ lx, 
     det[base + (long long)y * pitch + x] = p2_det<INT>(a.ul, a.uc, a.ur, a.cl, a.cr, a.ll, a.lc, a.lr, b.ul, b.uc, b.ur, b.ll, b.lc, b.lr, m);
 }
 
+// The two border-ring kernels are a few microseconds of work that depend on the main kernel: with a side stream they are forked
+// off (event after the main kernel) and run under whatever the main stream does next -- the diffusion cycle of the level, which
+// touches none of these planes.  The caller joins ev_join before it overwrites the blurred plane or reads Lx / Ly / det.
 template <int S, bool INT>
-void deriv4_launch(cudaStream_t st, Deriv4Args& a, int n)
+void deriv4_launch(cudaStream_t st, Deriv4Args& a, int n, cudaStream_t ring_st, cudaEvent_t ev_fork, cudaEvent_t ev_join)
 {
     a.nstrips = (a.w + D4<S>::OC - 1) / D4<S>::OC;
     // bands of at most ~270 rows (a multiple of 12, so that every band starts on residue 0 of every S): two row times of
@@ -278,19 +281,27 @@ void deriv4_launch(cudaStream_t st, Deriv4Args& a, int n)
     a.nunits = n * a.nbands * S * a.nstrips;
     k_deriv4<S, INT><<<(a.nunits + D4_WARPS - 1) / D4_WARPS, 32 * D4_WARPS, 0, st>>>(a);
     const int c1 = ring_count(S, a.w, a.h), c2 = ring_count(2 * S, a.w, a.h);
-    k_deriv_ring<INT><<<dim3((c1 + 255) / 256, n), 256, 0, st>>>(a.sm, a.lx, a.ly, S, a.m, a.w, a.h, a.pitch, a.plane, c1);
-    k_det_ring<INT><<<dim3((c2 + 255) / 256, n), 256, 0, st>>>(a.lx, a.ly, a.det, S, a.m, a.w, a.h, a.pitch, a.plane, c2);
+    cudaStream_t rs = st;
+    if (ring_st && ev_fork && ev_join) {
+        cudaEventRecord(ev_fork, st);
+        cudaStreamWaitEvent(ring_st, ev_fork, 0);
+        rs = ring_st;
+    }
+    k_deriv_ring<INT><<<dim3((c1 + 255) / 256, n), 256, 0, rs>>>(a.sm, a.lx, a.ly, S, a.m, a.w, a.h, a.pitch, a.plane, c1);
+    k_det_ring<INT><<<dim3((c2 + 255) / 256, n), 256, 0, rs>>>(a.lx, a.ly, a.det, S, a.m, a.w, a.h, a.pitch, a.plane, c2);
+    if (rs != st) cudaEventRecord(ev_join, rs);
 }
 
 }  // namespace
 
 namespace akzk {
 
-// Lx, Ly, det of a level from its smoothed plane.  Returns the number of launches (3), or 0 when the case is not covered
+// Lx, Ly, det of a level from its smoothed plane.  ring_st / ev_fork / ev_join (optional): side stream for the border-ring
+// kernels, see deriv4_launch.  Returns the number of launches (3), or 0 when the case is not covered
 // (derivative step outside 2..4, rows not 16-byte aligned, width not a multiple of 4, tiny planes): the caller then uses the
 // tile kernel or the per-stage kernels.
 int deriv_stream(cudaStream_t st, const float* smooth, float* lx, float* ly, float* det, int step, int w, int h, int pitch, long long plane,
-                 int n, int int_planes)
+                 int n, int int_planes, cudaStream_t ring_st, cudaEvent_t ev_fork, cudaEvent_t ev_join)
 {
     if (step < 2 || step > 4 || w < 32 || h < 32 || (w % 4) != 0 || (pitch % 4) != 0 || (plane % 4) != 0) return 0;
     if ((((uintptr_t)smooth | (uintptr_t)lx | (uintptr_t)ly | (uintptr_t)det) % 16) != 0) return 0;
@@ -300,9 +311,9 @@ int deriv_stream(cudaStream_t st, const float* smooth, float* lx, float* ly, flo
     hessian_factors(&a.m.fac1, &a.m.fac2);
     a.m.ifac1 = (int)(a.m.fac1 * 65536 + 0.5f); a.m.ifac2 = (int)(a.m.fac2 * 65536 + 0.5f);          // akazed.cu:4184-4185
     if (int_planes) {
-        if (step == 2) deriv4_launch<2, true>(st, a, n); else if (step == 3) deriv4_launch<3, true>(st, a, n); else deriv4_launch<4, true>(st, a, n);
+        if (step == 2) deriv4_launch<2, true>(st, a, n, ring_st, ev_fork, ev_join); else if (step == 3) deriv4_launch<3, true>(st, a, n, ring_st, ev_fork, ev_join); else deriv4_launch<4, true>(st, a, n, ring_st, ev_fork, ev_join);
     } else {
-        if (step == 2) deriv4_launch<2, false>(st, a, n); else if (step == 3) deriv4_launch<3, false>(st, a, n); else deriv4_launch<4, false>(st, a, n);
+        if (step == 2) deriv4_launch<2, false>(st, a, n, ring_st, ev_fork, ev_join); else if (step == 3) deriv4_launch<3, false>(st, a, n, ring_st, ev_fork, ev_join); else deriv4_launch<4, false>(st, a, n, ring_st, ev_fork, ev_join);
     }
     return 3;
 }
