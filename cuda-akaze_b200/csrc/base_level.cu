@@ -11,6 +11,8 @@
 // value at the mirrored pixel bit for bit; no border fix-up is needed here.
 #include "common.cuh"
 #include "kernels.h"
+#include <algorithm>
+#include <cstdlib>
 
 using namespace akz;
 
@@ -245,6 +247,181 @@ __global__ void __launch_bounds__(B2_NT, 2) k_base2(const __grid_constant__ Base
     }
 }
 
+// =====================================================================================================================
+// k_base4<Tin>: the same base level as a streaming warp kernel (structure of k_blur4 / k_fed4: a warp owns a strip of 128
+// columns, 4 per lane, one halo lane at either end for the radius-4 row pass, and marches down a band of rows; rows arrive
+// through a cp.async landing ring; vertical windows live in registers).  At row time t: both row passes of input row t from
+// the lane's four pixels and the two neighbour lanes' (8 shuffles), the sigma0 column pass over nine row-filtered rows ->
+// Lt row t-4, the sigma = 1 column pass over five -> blurred row t-2, and the Scharr magnitude of row t-3 from three
+// blurred rows (+ running maximum, one atomicMax per warp).  Both blurs are symmetric, so the mirrored rows (reflected row
+// index) and the mirrored neighbours of the border lanes give the reference's reflect-101 values bit for bit, also for the
+// Scharr taps on the blurred plane.  The row loop is unrolled by 12 (ring of the nine-row window).
+// =====================================================================================================================
+constexpr int B4_WARPS = 4, B4_COLS = 120, B4_RING = 6;
+
+struct Base4Args {
+    Base2Args b;
+    int nstrips, nbands, band_h, nunits;
+};
+
+template <typename Tin> struct B4in { static constexpr int LANEB = sizeof(Tin) == 4 ? 16 : 4; static constexpr int SLOTB = 32 * LANEB; };
+
+struct Base4Regs {
+    float R0[12][4];        // sigma0 row pass, rows t-8 .. t (ring by row time mod 12)
+    float R1[6][4];         // sigma = 1 row pass, rows t-4 .. t (mod 6)
+    float S1[3][6];         // blurred rows t-4, t-3, t-2 with their left / right neighbour (production time mod 3)
+};
+
+struct Base4Lane {
+    const unsigned char* psrc;      // frame base + clamped column of this lane, in bytes
+    long long obase;
+    unsigned ring;
+    int y0, y1, t0;
+    bool bl, br, store;
+};
+
+template <typename Tin>
+__device__ __forceinline__ void b4_request(const Base2Args& a, const Base4Lane& ln, int row_time, int slot)
+{
+    const int r = min(max(refl(row_time, a.h), 0), a.h - 1);
+    const unsigned char* g = ln.psrc + (long long)r * a.ipitch * (int)sizeof(Tin);
+    const unsigned d = ln.ring + slot * B4in<Tin>::SLOTB;
+    if (sizeof(Tin) == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(g) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(g) : "memory");
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+
+template <typename Tin, bool INT, bool MAG, int PH>
+__device__ __forceinline__ void b4_row(Base4Regs& R, const Base2Args& a, const Base4Lane& ln, int t, unsigned& best)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    b4_request<Tin>(a, ln, t + B4_RING - 1, (PH + B4_RING - 1) % B4_RING);
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(B4_RING - 1) : "memory");
+    float v[4];
+    {
+        const unsigned sa = ln.ring + (PH % B4_RING) * B4in<Tin>::SLOTB;
+        if (sizeof(Tin) == 4) {
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(sa) : "memory");
+        } else {
+            unsigned w4;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w4) : "r"(sa) : "memory");
+            v[0] = b2_px<INT>((unsigned char)w4); v[1] = b2_px<INT>((unsigned char)(w4 >> 8));
+            v[2] = b2_px<INT>((unsigned char)(w4 >> 16)); v[3] = b2_px<INT>((unsigned char)(w4 >> 24));
+        }
+    }
+    // ---- both row passes
+    {
+        float e[12];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            e[j] = __shfl_up_sync(FULL, v[j], 1);
+            e[4 + j] = v[j];
+            e[8 + j] = __shfl_down_sync(FULL, v[j], 1);
+        }
+        if (ln.bl) { const float r0 = e[8]; e[0] = r0; e[1] = v[3]; e[2] = v[2]; e[3] = v[1]; }           // x = -4 .. -1 -> 4, 3, 2, 1
+        if (ln.br) { const float l3 = e[3]; e[8] = v[2]; e[9] = v[1]; e[10] = v[0]; e[11] = l3; }         // x = w .. w+3 -> w-2 .. w-5
+        float* r0 = R.R0[PH % 12];
+#pragma unroll
+        for (int j = 0; j < 4; j++) r0[j] = b2_gauss4<INT>(e[j], e[1 + j], e[2 + j], e[3 + j], e[4 + j], e[5 + j], e[6 + j], e[7 + j], e[8 + j], a);
+        if (MAG) {
+            float* r1 = R.R1[PH % 6];
+#pragma unroll
+            for (int j = 0; j < 4; j++) r1[j] = b2_gauss2<INT>(e[2 + j], e[3 + j], e[4 + j], e[5 + j], e[6 + j], a);
+        }
+    }
+    // ---- sigma0 column pass -> Lt row t-4
+    {
+        const int rl = t - 4;
+        float o[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            o[c] = b2_gauss4<INT>(R.R0[(PH + 4) % 12][c], R.R0[(PH + 5) % 12][c], R.R0[(PH + 6) % 12][c], R.R0[(PH + 7) % 12][c], R.R0[(PH + 8) % 12][c],
+                                  R.R0[(PH + 9) % 12][c], R.R0[(PH + 10) % 12][c], R.R0[(PH + 11) % 12][c], R.R0[PH % 12][c], a);
+        if (ln.store && rl >= ln.y0 && rl < ln.y1)
+            *reinterpret_cast<float4*>(a.lt + ln.obase + (long long)rl * a.pitch) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    if (MAG) {
+        // ---- sigma = 1 column pass -> blurred row t-2 (kept with its left / right neighbours)
+        float* s = R.S1[PH % 3];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            s[1 + c] = b2_gauss2<INT>(R.R1[(PH + 2) % 6][c], R.R1[(PH + 3) % 6][c], R.R1[(PH + 4) % 6][c], R.R1[(PH + 5) % 6][c], R.R1[PH % 6][c], a);
+        s[0] = __shfl_up_sync(FULL, s[4], 1);
+        s[5] = __shfl_down_sync(FULL, s[1], 1);
+        if (ln.bl) s[0] = s[2];
+        if (ln.br) s[5] = s[3];
+        // ---- Scharr magnitude of row t-3
+        const int rm = t - 3;
+        if (ln.store && rm >= ln.y0 && rm < ln.y1) {
+            const float* up = R.S1[(PH + 1) % 3];
+            const float* ce = R.S1[(PH + 2) % 3];
+            const float* dn = R.S1[PH % 3];
+            float o[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                o[c] = b2_mag<INT>(up[c], up[c + 1], up[c + 2], ce[c], ce[c + 2], dn[c], dn[c + 1], dn[c + 2]);
+                best = max(best, __float_as_uint(o[c]));
+            }
+            *reinterpret_cast<float4*>(a.mag + ln.obase + (long long)rm * a.pitch) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+template <typename Tin, bool INT, bool MAG>
+__global__ void __launch_bounds__(32 * B4_WARPS, 4) k_base4(const __grid_constant__ Base4Args aa)
+{
+    const Base2Args& a = aa.b;
+    const int lane = threadIdx.x & 31;
+    const int unit = blockIdx.x * B4_WARPS + (threadIdx.x >> 5);
+    if (unit >= aa.nunits) return;
+    const int per = aa.nstrips * aa.nbands;
+    const int frame = unit / per, rem = unit - frame * per;
+    const int band = rem / aa.nstrips, strip = rem - band * aa.nstrips;
+    Base4Lane ln;
+    const int gx0 = strip * B4_COLS - 4 + 4 * lane;
+    const int gxl = min(max(gx0, 0), min(a.pitch, a.ipitch) - 4);
+    ln.psrc = (const unsigned char*)a.img + ((long long)frame * a.istride + gxl) * (int)sizeof(Tin);
+    ln.obase = (long long)frame * a.plane + gx0;
+    ln.y0 = band * aa.band_h; ln.y1 = min(a.h, ln.y0 + aa.band_h); ln.t0 = ln.y0 - 4;
+    ln.bl = gx0 == 0;
+    ln.br = gx0 + 3 == a.w - 1;
+    ln.store = lane >= 1 && lane <= 30 && gx0 >= 0 && gx0 < a.w;
+    __shared__ __align__(16) unsigned char ring_mem[B4_WARPS * B4_RING * B4in<Tin>::SLOTB];
+    ln.ring = (unsigned)__cvta_generic_to_shared(ring_mem + (threadIdx.x >> 5) * (B4_RING * B4in<Tin>::SLOTB) + lane * B4in<Tin>::LANEB);
+    Base4Regs R;
+#pragma unroll
+    for (int i = 0; i < 12; i++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) { R.R0[i][c] = 0.f; R.R1[i % 6][c] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) R.S1[i][c] = 0.f;
+#pragma unroll
+    for (int k = 0; k < B4_RING - 1; k++) b4_request<Tin>(a, ln, ln.t0 + k, k);
+    unsigned best = 0u;
+    // Lt row y0 needs input rows y0-4 .. y0+4; Lt row y1-1 is complete at row time y1+3
+    const int T = (ln.y1 - ln.y0) + 8;
+    for (int it = 0; it < T; it += 12) {
+        b4_row<Tin, INT, MAG, 0>(R, a, ln, ln.t0 + it, best);
+        b4_row<Tin, INT, MAG, 1>(R, a, ln, ln.t0 + it + 1, best);
+        b4_row<Tin, INT, MAG, 2>(R, a, ln, ln.t0 + it + 2, best);
+        b4_row<Tin, INT, MAG, 3>(R, a, ln, ln.t0 + it + 3, best);
+        b4_row<Tin, INT, MAG, 4>(R, a, ln, ln.t0 + it + 4, best);
+        b4_row<Tin, INT, MAG, 5>(R, a, ln, ln.t0 + it + 5, best);
+        b4_row<Tin, INT, MAG, 6>(R, a, ln, ln.t0 + it + 6, best);
+        b4_row<Tin, INT, MAG, 7>(R, a, ln, ln.t0 + it + 7, best);
+        b4_row<Tin, INT, MAG, 8>(R, a, ln, ln.t0 + it + 8, best);
+        b4_row<Tin, INT, MAG, 9>(R, a, ln, ln.t0 + it + 9, best);
+        b4_row<Tin, INT, MAG, 10>(R, a, ln, ln.t0 + it + 10, best);
+        b4_row<Tin, INT, MAG, 11>(R, a, ln, ln.t0 + it + 11, best);
+    }
+    if (MAG) {
+        best = __reduce_max_sync(0xffffffffu, best);
+        if (lane == 0) atomicMax(a.hmax_bits + frame, best);
+    }
+}
+
 // 300-bin histogram of mag * 300 / hmax (truncating multiply, clamp to 299) over the in-image pixels (akazed.cu:901-938,
 // App. B-3); one block bins 8 rows; per-warp privatised shared histograms keep the atomics apart.
 __global__ void __launch_bounds__(256) k_hist2(const float* __restrict__ mag, const unsigned* __restrict__ hmax_bits, int* __restrict__ hist,
@@ -324,13 +501,31 @@ int base_level2(cudaStream_t st, const void* img, int dtype, int w, int h, int i
                ((uintptr_t)img % 16 == 0) && (((size_t)ipitch * esz) % 16 == 0) && (((size_t)istride * esz) % 16 == 0);
     int launches = 0;
     dim3 g((w + B2_T - 1) / B2_T, (h + B2_T - 1) / B2_T, n);
+    // streaming warp kernel when the rows are 16-byte aligned and there are enough (strip, band, frame) units; else the tile kernel
+    Base4Args s4 = {};
+    s4.b = a;
+    s4.nstrips = (w + B4_COLS - 1) / B4_COLS;
+    {
+        const int nb = std::max(1, (h + 50) / 100);                       // bands of ~100 rows: 8 rows of warm-up each, row loop unrolled by 12
+        s4.band_h = (h + nb - 1) / nb;
+        s4.nbands = (h + s4.band_h - 1) / s4.band_h;
+    }
+    const long long units = (long long)n * s4.nstrips * s4.nbands;
+    static const int min_units = [] { const char* e = getenv("AKZ_BASE_MIN_UNITS"); return e ? atoi(e) : 1024; }();
+    const bool stream = a.vec_ok && (w % 4) == 0 && w >= 32 && h >= 16 && units >= min_units && units < (1ll << 30);
+    s4.nunits = (int)units;
+    const int g4 = (int)((units + B4_WARPS - 1) / B4_WARPS);
     if (int_planes) {
         // integer pipeline: the caller zeroes the maximum / histogram before and runs the integer histogram + scan after
-        k_base2<unsigned char, true><<<g, B2_NT, B2_SMEM, st>>>(a);
+        if (stream) { if (mag) k_base4<unsigned char, true, true><<<g4, 32 * B4_WARPS, 0, st>>>(s4); else k_base4<unsigned char, true, false><<<g4, 32 * B4_WARPS, 0, st>>>(s4); }
+        else k_base2<unsigned char, true><<<g, B2_NT, B2_SMEM, st>>>(a);
         return 1;
     }
     if (mag) { int tot = n * AKZ_NBINS; k_contrast_init2<<<(tot + 255) / 256, 256, 0, st>>>(hmax_bits, hist, n); launches++; }
-    if (dtype == AKZ_U8) k_base2<unsigned char, false><<<g, B2_NT, B2_SMEM, st>>>(a);
+    if (stream) {
+        if (dtype == AKZ_U8) { if (mag) k_base4<unsigned char, false, true><<<g4, 32 * B4_WARPS, 0, st>>>(s4); else k_base4<unsigned char, false, false><<<g4, 32 * B4_WARPS, 0, st>>>(s4); }
+        else { if (mag) k_base4<float, false, true><<<g4, 32 * B4_WARPS, 0, st>>>(s4); else k_base4<float, false, false><<<g4, 32 * B4_WARPS, 0, st>>>(s4); }
+    } else if (dtype == AKZ_U8) k_base2<unsigned char, false><<<g, B2_NT, B2_SMEM, st>>>(a);
     else k_base2<float, false><<<g, B2_NT, B2_SMEM, st>>>(a);
     launches++;
     if (mag) {
