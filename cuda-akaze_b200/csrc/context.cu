@@ -324,7 +324,7 @@ int akz_create(const akz_options* o, akz_ctx** out)
         if ((rc = dalloc(c, &c->tmpB, n0)) != AKZ_OK) break;
         {
             static const bool ring_side = [] { const char* e = getenv("AKZ_RING_SIDE"); return !e || atoi(e) != 0; }();
-            const int nring = ring_side ? ((B <= 4) ? c->noct : 1) : 0;
+            const int nring = ring_side ? c->noct : 0;
             for (int k = 0; k < nring && k < 8; k++) {
                 if (cudaStreamCreateWithFlags(&c->ring_stream[k], cudaStreamNonBlocking) != cudaSuccess) { rc = akz_set_error(AKZ_E_CUDA, "stream creation failed"); break; }
                 cudaEventCreateWithFlags(&c->ev_ring_fork[k], cudaEventDisableTiming);
@@ -336,7 +336,8 @@ int akz_create(const akz_options* o, akz_ctx** out)
         for (int k = 1; k < 8; k++) c->sc[k] = c->sc[0];
         {
             static const bool small_on = [] { const char* e = getenv("AKZ_SMALL_BATCH"); return !e || atoi(e) != 0; }();
-            if (small_on && B <= 4 && o->fused == 1 && c->noct > 1) {
+            static const bool opar_all = [] { const char* e = getenv("AKZ_OPAR_ALL"); return e && atoi(e) != 0; }();
+            if (small_on && (B <= 4 || opar_all) && o->fused == 1 && c->noct > 1) {
                 for (int k = 1; k < c->noct && rc == AKZ_OK; k++) {
                     const size_t nk = (size_t)c->lev[k * o->max_scale].plane * B;
                     if ((rc = dalloc(c, &c->sc[k].smooth, nk)) != AKZ_OK) break;
@@ -353,7 +354,7 @@ int akz_create(const akz_options* o, akz_ctx** out)
                 }
                 if (rc != AKZ_OK) break;
                 c->opar = true;
-                c->graph_ok = true;
+                c->graph_ok = B <= 4;
             }
         }
         c->mpitch = c->lev[0].pitch;
@@ -384,6 +385,7 @@ int akz_create(const akz_options* o, akz_ctx** out)
             D.w = L.w; D.h = L.h; D.pitch = L.pitch; D.octave = L.octave; D.size = L.size;
         }
         akzk::orient_table_init(c->stream);
+        if ((rc = akzk::describe_prepare(o->descriptor_pattern_size)) != AKZ_OK) break;
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = akz_set_cuda_error(cudaGetLastError(), "context init", __FILE__, __LINE__); break; }
     } while (0);
     if (rc == AKZ_OK && !matcher_only && o->lanes >= 2) {

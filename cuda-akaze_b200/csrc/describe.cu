@@ -3,6 +3,12 @@
 // comparison tables (:65-159), AkazePoint layout (akaze_structures.h:19-39).
 #include "common.cuh"
 #include "kernels.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <utility>
+#include <vector>
 #include <math_constants.h>
 
 using namespace akz;
@@ -153,88 +159,6 @@ __global__ void __launch_bounds__(ORI_WARPS * 32) k_orient(const __grid_constant
 
 // ---- M-LDB -------------------------------------------------------------------------------------------
 __constant__ short c_cmp[2][488];
-
-// 64 threads per keypoint exactly as the reference lays the work out; the per-thread accumulation
-// order and the reduction tree decide the bits, so both are kept (SURVEY A-13):
-//   a_t = acc_t + acc_{t+32} (t = 0..31), then the shuffle-down tree 1,2,4,8,16 -> lane 0.
-// Accumulators are stored value-major ([90][64]) so neighbouring threads hit different banks.
-__global__ void __launch_bounds__(64) k_describe(const __grid_constant__ AkzLevelTable tab, const int* __restrict__ prefix, int nframes,
-                                                 const akz_keypoint* __restrict__ kpts, unsigned char* __restrict__ desc,
-                                                 int max_pts, int size2, int size3, int size4)
-{
-    __shared__ float acc[90][64];
-    __shared__ float val[96];
-    int tix = threadIdx.x;
-    int total = prefix[nframes];
-    for (int g = blockIdx.x; g < total; g += gridDim.x) {
-        int frame = find_frame(prefix, nframes, g);
-        int local = g - prefix[frame];
-        const akz_keypoint* kp = kpts + (long long)frame * max_pts + local;
-        const AkzLevelDev& L = tab.lv[kp->layer];
-        int o = L.octave, p = L.pitch;
-        float iratio = 1.f / (1 << o);
-        int scale = (int)__fadd_rn(kp->size, 0.5f);
-        float xf = __fmul_rn(kp->x, iratio), yf = __fmul_rn(kp->y, iratio);
-        float ang = kp->angle;
-        float co = __cosf(ang), si = __sinf(ang);
-        const float* imd = L.lt + (long long)frame * L.plane;
-        const float* dxd = L.lx + (long long)frame * L.plane;
-        const float* dyd = L.ly + (long long)frame * L.plane;
-        int win = max(3 * size3, 4 * size4);
-#pragma unroll 6
-        for (int v = 0; v < 90; v++) acc[v][tix] = 0.f;
-        float fscale = (float)scale;
-        for (int i = tix; i < win * win; i += 64) {
-            int y = i / win, x = i - win * y, m = max(x, y);
-            if (m >= win) continue;
-            float l = (float)(x - size2), k = (float)(y - size2);
-            int xp = (int)__fadd_rn(__fmaf_rn(fscale, __fmaf_rn(co, k, -__fmul_rn(si, l)), xf), 0.5f);
-            int yp = (int)__fadd_rn(__fmaf_rn(fscale, __fmaf_rn(si, k, __fmul_rn(co, l)), yf), 0.5f);
-            xp = min(max(xp, 0), L.w - 1); yp = min(max(yp, 0), L.h - 1);       // no-op for in-range patches (border test)
-            long long pos = (long long)yp * p + xp;
-            float im = __ldg(imd + pos), dx = __ldg(dxd + pos), dy = __ldg(dyd + pos);
-            float rx = __fmaf_rn(co, dy, -__fmul_rn(si, dx));
-            float ry = __fmaf_rn(co, dx, __fmul_rn(si, dy));
-            if (m < 2 * size2) {
-                int c = 3 * ((y < size2 ? 0 : 1) * 2 + (x < size2 ? 0 : 1));
-                acc[c][tix] = __fadd_rn(acc[c][tix], im); acc[c + 1][tix] = __fadd_rn(acc[c + 1][tix], rx); acc[c + 2][tix] = __fadd_rn(acc[c + 2][tix], ry);
-            }
-            if (m < 3 * size3) {
-                int x3 = (x < size3 ? 0 : (x < 2 * size3 ? 1 : 2)), y3 = (y < size3 ? 0 : (y < 2 * size3 ? 1 : 2));
-                int c = 3 * (4 + y3 * 3 + x3);
-                acc[c][tix] = __fadd_rn(acc[c][tix], im); acc[c + 1][tix] = __fadd_rn(acc[c + 1][tix], rx); acc[c + 2][tix] = __fadd_rn(acc[c + 2][tix], ry);
-            }
-            if (m < 4 * size4) {
-                int x4 = (x < 2 * size4 ? (x < size4 ? 0 : 1) : (x < 3 * size4 ? 2 : 3));
-                int y4 = (y < 2 * size4 ? (y < size4 ? 0 : 1) : (y < 3 * size4 ? 2 : 3));
-                int c = 3 * (13 + y4 * 4 + x4);
-                acc[c][tix] = __fadd_rn(acc[c][tix], im); acc[c + 1][tix] = __fadd_rn(acc[c + 1][tix], rx); acc[c + 2][tix] = __fadd_rn(acc[c + 2][tix], ry);
-            }
-        }
-        __syncthreads();
-        // warp w reduces the values v = w, w+2, ...
-        int lane = tix & 31, w = tix >> 5;
-        for (int v = w; v < 87; v += 2) {
-            float a = __fadd_rn(acc[v][lane], acc[v][lane + 32]);
-            a = __fadd_rn(a, __shfl_down_sync(0xffffffffu, a, 1));
-            a = __fadd_rn(a, __shfl_down_sync(0xffffffffu, a, 2));
-            a = __fadd_rn(a, __shfl_down_sync(0xffffffffu, a, 4));
-            a = __fadd_rn(a, __shfl_down_sync(0xffffffffu, a, 8));
-            a = __fadd_rn(a, __shfl_down_sync(0xffffffffu, a, 16));
-            if (lane == 0) val[v] = a;
-        }
-        __syncthreads();
-        unsigned char* out = desc + ((long long)frame * max_pts + local) * 64;
-        unsigned r = 0;
-        if (tix < 61) {
-            int nb = (tix == 60 ? 6 : 8);
-            for (int i = 0; i < nb; i++)
-                r |= (val[c_cmp[0][tix * 8 + i]] > val[c_cmp[1][tix * 8 + i]] ? 1u : 0u) << i;
-        }
-        out[tix] = (unsigned char)r;                      // bytes 61..63 are written as zero
-        __syncthreads();
-    }
-}
 
 // ---- M-LDB, pattern size fixed at compile time (PAT = 10 is the reference default, akaze.h:54) ---------------
 // Same numbers as k_describe, produced with a third of the instructions (ncu r01b: 2160 thread-instructions per
@@ -400,82 +324,205 @@ __global__ void __launch_bounds__(64) k_describe_t(const __grid_constant__ AkzLe
     }
 }
 
-// ---- M-LDB of the integer pipeline (gDescribe2 akazed.cu:3723-3855): int planes, int rotated derivatives
-// (float product sums truncated to int), int cell sums (associative: any reduction order), int comparisons.
-__global__ void __launch_bounds__(64) k_describe_int(const __grid_constant__ AkzLevelTable tab, const int* __restrict__ prefix, int nframes,
-                                                     const akz_keypoint* __restrict__ kpts, unsigned char* __restrict__ desc,
-                                                     int max_pts, int size2, int size3, int size4)
+// ---- M-LDB, sample-major: k_describe_s ----------------------------------------------------------------------------------------
+// The reference accumulates the (2 P + 1)^2 samples of a keypoint with 64 threads -- thread t takes samples t, t + 64, ... in
+// order and adds each to the cell of the 2x2, 3x3 and 4x4 grid it falls into -- and reduces every cell value over the 64
+// threads with a fixed tree: a_t = acc_t + acc_(t+32), then pairs, fours, ... (gDescribe2 akazed.cu:1869-2001).  The float
+// sums pin that order.  WHICH samples of which thread fall into which cell is static (sample i sits at column i mod W, row
+// i / W of the unrotated grid), so the whole reduction is a fixed expression over the sample values.  k_describe_s evaluates
+// it directly: 128 threads gather the samples into a sample-major shared array (5.3 KB per channel set at P = 10, not the
+// 87 x 64 accumulator matrix: 22.6 KB, read-modify-write per sample, zero fill, 64 reads per output value), then four threads
+// per cell walk a table of 16-bit masks -- bit m of mask[cell][lane] = sample lane + 64 m belongs to the cell -- rebuild the per-
+// lane sums in sample order, add the two halves, run the tree over their eight lanes in registers and join by shuffle.
+// ~1240 sample reads per channel instead of ~8200 shared-memory operations per keypoint; the same bits.
+// Any pattern size with (2 P + 1)^2 <= 1024 samples (P <= 14); the tables are built on the host for the context's pattern.
+constexpr int DS_NT = 128;
+constexpr int DS_CELLS = 29;                                 // 4 + 9 + 16
+constexpr int DS_MAXNS = 1024;                               // mask bits: sample = lane + 64 m, m < 16
+
+struct DescTables {
+    unsigned short mask[DS_CELLS][4][16];                    // [cell][quarter q][slot k]: lane = 8 q + (k >> 1) + 32 (k & 1)
+};
+
+struct DescArgs {
+    const int* prefix;
+    const akz_keypoint* kpts;
+    unsigned char* desc;
+    const DescTables* tables;
+    int nframes, max_pts;
+    int s2, s3, s4, win, ns;
+};
+
+// sample i lives at ds_val[i + (i >> 5)]: the reduction reads samples 64 m apart (lane + 64 m), which would all sit in one bank
+__device__ __forceinline__ int dsi(int i) { return i + (i >> 5); }
+
+template <bool INT, int NK>
+__global__ void __launch_bounds__(DS_NT, (NK <= 4 ? 8 : 4)) k_describe_s(const __grid_constant__ AkzLevelTable tab, const __grid_constant__ DescArgs a)
 {
-    __shared__ int acc[87][65];
-    __shared__ int val[96];
-    const int tix = threadIdx.x;
-    const int total = prefix[nframes];
+    extern __shared__ __align__(16) float ds_val[];          // [3][nsp]: im, rx, ry of every sample
+    __shared__ __align__(16) DescTables s_tab;
+    __shared__ float s_cell[96];
+    __shared__ int s_prefix[AKZ_MAX_FRAMES_SEARCH + 1];
+    const int tid = threadIdx.x;
+    const int nsp = (a.ns + (a.ns >> 5) + 4) & ~3;
+    for (int i = tid; i <= a.nframes && i <= AKZ_MAX_FRAMES_SEARCH; i += DS_NT) s_prefix[i] = a.prefix[i];
+    for (int i = tid; i < (int)(sizeof(DescTables) / 4); i += DS_NT) reinterpret_cast<unsigned*>(&s_tab)[i] = reinterpret_cast<const unsigned*>(a.tables)[i];
+    __syncthreads();
+    const int total = s_prefix[min(a.nframes, AKZ_MAX_FRAMES_SEARCH)];
+    // this thread's 8 comparison pairs, fetched once (per-lane different constant addresses serialise in the constant cache)
+    unsigned cmp[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int b = min(tid, 60) * 8 + i;
+        cmp[i] = (unsigned)c_cmp[0][b] | ((unsigned)c_cmp[1][b] << 16);
+    }
+    const int S2 = a.s2, WIN = a.win, NS = a.ns;
+    struct Kp { float co, si; int frame, local; };
+    // gather of keypoint g into registers: all NK x 3 loads are issued back to back
+    auto gather = [&](int g, Kp& K, float (&im)[NK], float (&dx)[NK], float (&dy)[NK]) {
+        int lo = 0, hi = a.nframes - 1;                    // largest f with s_prefix[f] <= g
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_prefix[mid] <= g) lo = mid; else hi = mid - 1; }
+        K.frame = lo; K.local = g - s_prefix[lo];
+        const akz_keypoint* kp = a.kpts + (long long)K.frame * a.max_pts + K.local;
+        const AkzLevelDev& L = tab.lv[kp->layer];
+        const int o = L.octave, p = L.pitch;
+        const float iratio = 1.f / (1 << o);
+        const float fscale = (float)(int)__fadd_rn(kp->size, 0.5f);
+        const int iscale = (int)(kp->size + 0.5f);
+        const float xf = INT ? kp->x * iratio : __fmul_rn(kp->x, iratio), yf = INT ? kp->y * iratio : __fmul_rn(kp->y, iratio);
+        const float ang = kp->angle;
+        const float co = __cosf(ang), si = __sinf(ang);
+        K.co = co; K.si = si;
+        const float* imd = L.lt + (long long)K.frame * L.plane;
+        const float* dxd = L.lx + (long long)K.frame * L.plane;
+        const float* dyd = L.ly + (long long)K.frame * L.plane;
+#pragma unroll
+        for (int k = 0; k < NK; k++) {
+            int i = tid + DS_NT * k;
+            im[k] = 0.f; dx[k] = 0.f; dy[k] = 0.f;
+            if (i < NS) {
+                int y = i / WIN, x = i - WIN * y;
+                int xp, yp;
+                if (!INT) {
+                    float l = (float)(x - S2), kk = (float)(y - S2);
+                    xp = (int)__fadd_rn(__fmaf_rn(fscale, __fmaf_rn(co, kk, -__fmul_rn(si, l)), xf), 0.5f);
+                    yp = (int)__fadd_rn(__fmaf_rn(fscale, __fmaf_rn(si, kk, __fmul_rn(co, l)), yf), 0.5f);
+                } else {                                   // integer pipeline: the reference's own float expressions truncated to int
+                    const int li = x - S2, ki = y - S2;
+                    xp = (int)(xf + iscale * (ki * co - li * si) + 0.5f);
+                    yp = (int)(yf + iscale * (ki * si + li * co) + 0.5f);
+                }
+                xp = min(max(xp, 0), L.w - 1); yp = min(max(yp, 0), L.h - 1);       // no-op for in-range patches (border test)
+                long long pos = (long long)yp * p + xp;
+                im[k] = __ldg(imd + pos); dx[k] = __ldg(dxd + pos); dy[k] = __ldg(dyd + pos);
+            }
+        }
+    };
+    // the gathers of the block's NEXT keypoint are in flight while the current one is reduced
+    Kp cur, nxt;
+    float im[NK], dx[NK], dy[NK], nim[NK], ndx[NK], ndy[NK];
+    if ((int)blockIdx.x < total) gather(blockIdx.x, cur, im, dx, dy);
+    // role of this thread in the reduction: quarter q of cell
+    const int cell = min(tid >> 2, DS_CELLS - 1), q = tid & 3;
     for (int g = blockIdx.x; g < total; g += gridDim.x) {
-        int frame = find_frame(prefix, nframes, g);
-        int local = g - prefix[frame];
-        const akz_keypoint* pt = kpts + (long long)frame * max_pts + local;
-        const AkzLevelDev& L = tab.lv[pt->layer];
-        int o = L.octave, p = L.pitch;
-        float iratio = 1.f / (1 << o);
-        int scale = (int)(pt->size + 0.5f);
-        float xf = pt->x * iratio;
-        float yf = pt->y * iratio;
-        float ang = pt->angle;
-        float co = __cosf(ang);
-        float si = __sinf(ang);
-        const int* imd = reinterpret_cast<const int*>(L.lt) + (long long)frame * L.plane;
-        const int* dxd = reinterpret_cast<const int*>(L.lx) + (long long)frame * L.plane;
-        const int* dyd = reinterpret_cast<const int*>(L.ly) + (long long)frame * L.plane;
-        int winsize = max(3 * size3, 4 * size4);
-        for (int v = 0; v < 87; v++) acc[v][tix] = 0;
-        for (int i = tix; i < winsize * winsize; i += 64) {
-            int y = i / winsize;
-            int x = i - winsize * y;
-            int m = max(x, y);
-            if (m >= winsize) continue;
-            int l = x - size2;
-            int k = y - size2;
-            int xp = (int)(xf + scale * (k * co - l * si) + 0.5f);
-            int yp = (int)(yf + scale * (k * si + l * co) + 0.5f);
-            xp = min(max(xp, 0), L.w - 1); yp = min(max(yp, 0), L.h - 1);       // no-op for in-range patches (border test)
-            long long pos = (long long)yp * p + xp;
-            int im = __ldg(imd + pos);
-            int dx = __ldg(dxd + pos);
-            int dy = __ldg(dyd + pos);
-            int rx = -dx * si + dy * co;
-            int ry = dx * co + dy * si;
-            if (m < 2 * size2) {
-                int c = 3 * ((y < size2 ? 0 : 1) * 2 + (x < size2 ? 0 : 1));
-                acc[c][tix] += im; acc[c + 1][tix] += rx; acc[c + 2][tix] += ry;
-            }
-            if (m < 3 * size3) {
-                int x3 = (x < size3 ? 0 : (x < 2 * size3 ? 1 : 2)), y3 = (y < size3 ? 0 : (y < 2 * size3 ? 1 : 2));
-                int c = 3 * (4 + y3 * 3 + x3);
-                acc[c][tix] += im; acc[c + 1][tix] += rx; acc[c + 2][tix] += ry;
-            }
-            if (m < 4 * size4) {
-                int x4 = (x < 2 * size4 ? (x < size4 ? 0 : 1) : (x < 3 * size4 ? 2 : 3));
-                int y4 = (y < 2 * size4 ? (y < size4 ? 0 : 1) : (y < 3 * size4 ? 2 : 3));
-                int c = 3 * (13 + y4 * 4 + x4);
-                acc[c][tix] += im; acc[c + 1][tix] += rx; acc[c + 2][tix] += ry;
+        const bool more = g + (int)gridDim.x < total;
+        if (more) gather(g + gridDim.x, nxt, nim, ndx, ndy);
+        const float co = cur.co, si = cur.si;
+        // 1. rotated derivatives, sample-major into shared memory
+#pragma unroll
+        for (int k = 0; k < NK; k++) {
+            int i = tid + DS_NT * k;
+            if (i < NS) {
+                float rx, ry;
+                if (!INT) {
+                    rx = __fmaf_rn(co, dy[k], -__fmul_rn(si, dx[k]));
+                    ry = __fmaf_rn(co, dx[k], __fmul_rn(si, dy[k]));
+                } else {
+                    const int dxi = __float_as_int(dx[k]), dyi = __float_as_int(dy[k]);
+                    const int rxi = -dxi * si + dyi * co, ryi = dxi * co + dyi * si;          // float expressions truncated to int
+                    rx = __int_as_float(rxi); ry = __int_as_float(ryi);
+                }
+                const int si_ = dsi(i);
+                ds_val[si_] = im[k]; ds_val[nsp + si_] = rx; ds_val[2 * nsp + si_] = ry;
             }
         }
         __syncthreads();
-        for (int v = tix; v < 87; v += 64) {
-            int sum = 0;
-            for (int t = 0; t < 64; t++) sum += acc[v][t];
-            val[v] = sum;
+        // 2. the reference's reduction for this thread's eight lane pairs of its cell
+        {
+            const uint4 w0 = *reinterpret_cast<const uint4*>(&s_tab.mask[cell][q][0]);
+            const uint4 w1 = *reinterpret_cast<const uint4*>(&s_tab.mask[cell][q][8]);
+            const unsigned mw[8] = { w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w };       // two 16-bit masks per word: lane tt (low), lane tt + 32 (high)
+            float r[8][3];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int tt = 8 * q + j;
+                float plo[3] = { 0.f, 0.f, 0.f }, phi[3] = { 0.f, 0.f, 0.f };
+                unsigned mk = mw[j] & 0xFFFFu;
+                while (mk) {                                              // samples tt + 64 m of lane tt, in order
+                    const int m = __ffs(mk) - 1;
+                    mk &= mk - 1;
+                    const int id = dsi(tt + 64 * m);
+                    plo[0] = dsum<INT>(plo[0], ds_val[id]); plo[1] = dsum<INT>(plo[1], ds_val[nsp + id]); plo[2] = dsum<INT>(plo[2], ds_val[2 * nsp + id]);
+                }
+                mk = mw[j] >> 16;
+                while (mk) {                                              // lane tt + 32
+                    const int m = __ffs(mk) - 1;
+                    mk &= mk - 1;
+                    const int id = dsi(tt + 32 + 64 * m);
+                    phi[0] = dsum<INT>(phi[0], ds_val[id]); phi[1] = dsum<INT>(phi[1], ds_val[nsp + id]); phi[2] = dsum<INT>(phi[2], ds_val[2 * nsp + id]);
+                }
+#pragma unroll
+                for (int c = 0; c < 3; c++) r[j][c] = dsum<INT>(plo[c], phi[c]);              // a_t = acc_t + acc_(t+32)
+            }
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1)
+#pragma unroll
+                for (int j = 0; j + d < 8; j += 2 * d)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) r[j][c] = dsum<INT>(r[j][c], r[j + d][c]);
+            // lanes 8 q .. 8 q + 7 are done; the quarters of a cell sit in four consecutive threads: steps d = 8 and d = 16 of the tree
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                float v = r[0][c];
+                v = dsum<INT>(v, __shfl_down_sync(0xffffffffu, v, 1));        // q0 + q1, q2 + q3
+                v = dsum<INT>(v, __shfl_down_sync(0xffffffffu, v, 2));        // (q0 + q1) + (q2 + q3)
+                if (q == 0 && tid < 4 * DS_CELLS) s_cell[3 * cell + c] = v;
+            }
         }
         __syncthreads();
-        unsigned char* out = desc + ((long long)frame * max_pts + local) * 64;
-        unsigned r = 0;
-        if (tix < 61) {
-            int nb = (tix == 60 ? 6 : 8);
-            for (int i = 0; i < nb; i++)
-                r |= (val[c_cmp[0][tix * 8 + i]] > val[c_cmp[1][tix * 8 + i]] ? 1u : 0u) << i;
+        // 3. the 486 comparisons
+        if (tid < 64) {
+            unsigned char* out = a.desc + ((long long)cur.frame * a.max_pts + cur.local) * 64;
+            unsigned rbits = 0;
+            if (tid < 61) {
+                const int nb = (tid == 60 ? 6 : 8);
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    if (i < nb) rbits |= (dgreater<INT>(s_cell[cmp[i] & 0xFFFFu], s_cell[cmp[i] >> 16]) ? 1u : 0u) << i;
+            }
+            out[tid] = (unsigned char)rbits;                  // bytes 61..63 are written as zero
         }
-        out[tix] = (unsigned char)r;
-        __syncthreads();
+        if (more) {
+            cur = nxt;
+#pragma unroll
+            for (int k = 0; k < NK; k++) { im[k] = nim[k]; dx[k] = ndx[k]; dy[k] = ndy[k]; }
+        }
+    }
+}
+
+// masks of the static reduction for a pattern (host)
+static void build_desc_tables(int s2, int s3, int s4, int win, DescTables& T)
+{
+    memset(&T, 0, sizeof(T));
+    const int ns = win * win;
+    for (int i = 0; i < ns; i++) {
+        const int y = i / win, x = i - win * y, m = x > y ? x : y;
+        const int lane = i & 63, mm = i >> 6;
+        const int qd = (lane & 31) >> 3, k = 2 * (lane & 7) + (lane >> 5);
+        auto set = [&](int cell) { T.mask[cell][qd][k] |= (unsigned short)(1u << mm); };
+        if (m < 2 * s2) set((y < s2 ? 0 : 1) * 2 + (x < s2 ? 0 : 1));
+        if (m < 3 * s3) set(4 + (y < s3 ? 0 : (y < 2 * s3 ? 1 : 2)) * 3 + (x < s3 ? 0 : (x < 2 * s3 ? 1 : 2)));
+        if (m < 4 * s4) set(13 + (y < 2 * s4 ? (y < s4 ? 0 : 1) : (y < 3 * s4 ? 2 : 3)) * 4 + (x < 2 * s4 ? (x < s4 ? 0 : 1) : (x < 3 * s4 ? 2 : 3)));
     }
 }
 
@@ -553,20 +600,58 @@ int orient(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const i
     return 1;
 }
 
+// per-device cache of the reduction tables of a pattern size (tiny, built on first use; never freed)
+static const DescTables* desc_tables_for(int pattern, int s2, int s3, int s4, int win)
+{
+    static std::mutex mu;
+    static std::vector<std::pair<long long, const DescTables*>> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const long long key = (long long)dev * 1000 + pattern;
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto& e : cache) if (e.first == key) return e.second;
+    DescTables h;
+    build_desc_tables(s2, s3, s4, win, h);
+    DescTables* d = nullptr;
+    if (cudaMalloc((void**)&d, sizeof(DescTables)) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, &h, sizeof(DescTables), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+    cache.push_back({ key, d });
+    return d;
+}
+
+// warm the table cache (akz_create): no allocation or blocking copy later, e.g. inside a stream capture
+int describe_prepare(int pattern)
+{
+    const int s2 = pattern, s3 = (int)ceilf(2.0f * pattern / 3.0f), s4 = (int)ceilf(0.5f * pattern);
+    const int win = std::max(3 * s3, 4 * s4);
+    if (win * win > DS_MAXNS) return akz_set_error(AKZ_E_UNSUPPORTED, "descriptor_pattern_size %d: (%d x %d samples) exceeds the %d the M-LDB kernel supports", pattern, win, win, DS_MAXNS);
+    return desc_tables_for(pattern, s2, s3, s4, win) ? 0 : akz_set_error(AKZ_E_NOMEM, "descriptor tables");
+}
+
 int describe(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const int* prefix, const akz_keypoint* kpts,
              unsigned char* desc, int max_pts, int n, int pattern, int fast)
 {
     (void)counts;
-    int size2 = pattern;                                          // akazed.cu:2681-2683
-    int size3 = (int)ceilf(2.0f * pattern / 3.0f);
-    int size4 = (int)ceilf(0.5f * pattern);
-    if (fast) {
-        if (pattern == 10 && n <= AKZ_MAX_FRAMES_SEARCH) k_describe_t<10, true><<<148 * 9, 64, 0, st>>>(tab, prefix, n, kpts, desc, max_pts);
-        else k_describe_int<<<148 * 8, 64, 0, st>>>(tab, prefix, n, kpts, desc, max_pts, size2, size3, size4);
-        return 1;
+    const int s2 = pattern;                                       // akazed.cu:2681-2683
+    const int s3 = (int)ceilf(2.0f * pattern / 3.0f);
+    const int s4 = (int)ceilf(0.5f * pattern);
+    const int win = std::max(3 * s3, 4 * s4), ns = win * win;
+    if (ns > DS_MAXNS) return akz_set_error(AKZ_E_UNSUPPORTED, "descriptor_pattern_size %d is not supported (at most %d samples)", pattern, DS_MAXNS);
+    if (n > AKZ_MAX_FRAMES_SEARCH) return akz_set_error(AKZ_E_UNSUPPORTED, "more than %d frames per chunk", AKZ_MAX_FRAMES_SEARCH);
+    DescArgs a;
+    a.prefix = prefix; a.kpts = kpts; a.desc = desc; a.nframes = n; a.max_pts = max_pts;
+    a.s2 = s2; a.s3 = s3; a.s4 = s4; a.win = win; a.ns = ns;
+    a.tables = desc_tables_for(pattern, s2, s3, s4, win);
+    if (!a.tables) return akz_set_error(AKZ_E_NOMEM, "descriptor tables");
+    const size_t smem = 3 * (size_t)((ns + (ns >> 5) + 4) & ~3) * sizeof(float);
+    const int grid = 148 * 8;
+    if (ns <= 4 * DS_NT) {
+        if (fast) k_describe_s<true, 4><<<grid, DS_NT, smem, st>>>(tab, a);
+        else k_describe_s<false, 4><<<grid, DS_NT, smem, st>>>(tab, a);
+    } else {
+        if (fast) k_describe_s<true, 8><<<grid, DS_NT, smem, st>>>(tab, a);
+        else k_describe_s<false, 8><<<grid, DS_NT, smem, st>>>(tab, a);
     }
-    if (pattern == 10 && n <= AKZ_MAX_FRAMES_SEARCH) k_describe_t<10, false><<<148 * 9, 64, 0, st>>>(tab, prefix, n, kpts, desc, max_pts);
-    else k_describe<<<148 * 8, 64, 0, st>>>(tab, prefix, n, kpts, desc, max_pts, size2, size3, size4);
     return 1;
 }
 

@@ -96,6 +96,7 @@ int orient_table_init(cudaStream_t st);
 int orient(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const int* prefix, akz_keypoint* kpts, int max_pts, int n, int fast = 0);
 int describe(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const int* prefix, const akz_keypoint* kpts,
              unsigned char* desc, int max_pts, int n, int pattern, int fast = 0);
+int describe_prepare(int pattern);      // builds the pattern's reduction tables on the current device (call outside stream capture)
 int pack_points(cudaStream_t st, const int* count, const akz_keypoint* kpts, const unsigned char* desc, void* points, int max_pts, int with_desc);
 int unpack_desc(cudaStream_t st, const void* points, int n, unsigned char* desc);
 int scatter_matches(cudaStream_t st, const akz_match_t* m, int nq, void* pq, const void* pt);
