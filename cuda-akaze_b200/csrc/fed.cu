@@ -340,6 +340,11 @@ struct Fed4Lane {
     const float *psrc, *pflow;      // frame base + clamped column of this lane
     float* pdst;                    // frame base + column of this lane
     unsigned ring;                  // shared-memory address of this lane's 16 bytes of Lt in slot 0 of its warp's landing ring (g: + 512)
+    // TMA variant (A/B, AKZ_FED_TMA=1): the row segment of the whole warp is one bulk copy per plane issued by lane 0
+    const float *wsrc, *wflow;      // frame base + first in-row column of the warp's segment
+    unsigned wring, mbar;           // shared-memory address of the segment's first byte in slot 0; of the warp's six mbarriers
+    unsigned wbytes;                // bytes of the segment that lie inside the row
+    unsigned par;                   // parity of the current pass over the ring
     int y0, y1, t0;                 // band: output rows [y0, y1), first row time
     int ir;                         // GEN: index of the image's last column inside this lane's four (-1: none)
     bool bl, br, store;             // lane holds x = 0 / x = w-1 (as its last column) / lane writes output
@@ -349,14 +354,38 @@ struct Fed4Lane {
 // row being consumed.  A lane only ever reads back the bytes it copied itself, so cp.async.wait_group is all the
 // synchronisation there is (no barrier, no cross-lane visibility).  Five rows x 1 KB x 16 warps = 80 KB in flight per SM:
 // with loads issued from registers two rows ahead (first version) the kernel sat at 2.7 TB/s, bound by the memory latency.
+template <bool TMA>
 __device__ __forceinline__ void f4_request(const Fed4Args& a, const Fed4Lane& ln, int row_time, int slot)
 {
     const int row = min(max(row_time, 0), a.h - 1);
     const long long o = (long long)row * a.pitch;
-    const unsigned d = ln.ring + slot * F4_ROWB;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(ln.psrc + o) : "memory");
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + 512u), "l"(ln.pflow + o) : "memory");
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    if (!TMA) {
+        const unsigned d = ln.ring + slot * F4_ROWB;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(ln.psrc + o) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d + 512u), "l"(ln.pflow + o) : "memory");
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    } else {
+        // one elected lane: expect 2 x wbytes on the slot's mbarrier, then one bulk copy (TMA, SASS UBLKCP) per plane
+        if ((threadIdx.x & 31) == 0) {
+            const unsigned mb = ln.mbar + slot * 8, d = ln.wring + slot * F4_ROWB;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mb), "r"(2u * ln.wbytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                         ::"r"(d), "l"(ln.wsrc + o), "r"(ln.wbytes), "r"(mb) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                         ::"r"(d + 512u), "l"(ln.wflow + o), "r"(ln.wbytes), "r"(mb) : "memory");
+        }
+    }
+}
+
+template <bool TMA>
+__device__ __forceinline__ void f4_wait(const Fed4Lane& ln, int slot)
+{
+    if (!TMA) {
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(F4_RING - 1) : "memory");
+    } else {
+        const unsigned mb = ln.mbar + slot * 8;
+        asm volatile("{\n.reg .pred p;\nAKZ_W_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@!p bra AKZ_W_%=;\n}\n" ::"r"(mb), "r"(ln.par) : "memory");
+    }
 }
 
 // one row time: request row t + 5, take row t out of the landing ring, form its pair sums, then step s = 1..N advances to its
@@ -364,15 +393,16 @@ __device__ __forceinline__ void f4_request(const Fed4Args& a, const Fed4Lane& ln
 // PH = (row time - first row time) mod 6.  SLOW = this row time touches the first / last image row or lies in the warm-up /
 // padding of the band: border substitutions are applied and the store is range-checked.  Rows outside the image or the band
 // are computed like any other (their values are never consumed by a valid row).
-template <int N, bool INT, bool GEN, int PH, bool SLOW>
+template <int N, bool INT, bool GEN, bool TMA, int PH, bool SLOW>
 __device__ __forceinline__ void f4_row(Fed4Regs<N>& R, const Fed4Args& a, const Fed4Lane& ln, int t)
 {
     constexpr unsigned FULL = 0xffffffffu;
     const int h = a.h;
     // ---- landing ring
     {
-        f4_request(a, ln, t + F4_RING - 1, (PH + F4_RING - 1) % F4_RING);
-        asm volatile("cp.async.wait_group %0;\n" ::"n"(F4_RING - 1) : "memory");
+        if (TMA) __syncwarp();                 // every lane has read the slot that is requested again (row t - 1)
+        f4_request<TMA>(a, ln, t + F4_RING - 1, (PH + F4_RING - 1) % F4_RING);
+        f4_wait<TMA>(ln, PH);
         float4 v, g;
         const unsigned sa = ln.ring + PH * F4_ROWB;
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sa) : "memory");
@@ -447,17 +477,17 @@ __device__ __forceinline__ void f4_row(Fed4Regs<N>& R, const Fed4Args& a, const 
     }
 }
 
-template <int N, bool INT, bool GEN, int PH>
+template <int N, bool INT, bool GEN, bool TMA, int PH>
 __device__ __forceinline__ void f4_phase(Fed4Regs<N>& R, const Fed4Args& a, const Fed4Lane& ln, int it, int T)
 {
     // every row time writes the same ring slots on both paths (no early outs: a skipped write would keep the old value of
     // the slot alive around the loop and cost its register for the whole iteration)
     const int i = it + PH, t = ln.t0 + i;
-    if (i <= 2 * N || t >= a.h || i >= T) f4_row<N, INT, GEN, PH, true>(R, a, ln, t);
-    else f4_row<N, INT, GEN, PH, false>(R, a, ln, t);
+    if (i <= 2 * N || t >= a.h || i >= T) f4_row<N, INT, GEN, TMA, PH, true>(R, a, ln, t);
+    else f4_row<N, INT, GEN, TMA, PH, false>(R, a, ln, t);
 }
 
-template <int N, bool INT, bool GEN>
+template <int N, bool INT, bool GEN, bool TMA>
 __global__ void __launch_bounds__(32 * F4_WARPS, (N <= 3 ? 4 : 3)) k_fed4(const __grid_constant__ Fed4Args a)
 {
     const int lane = threadIdx.x & 31;
@@ -481,6 +511,22 @@ __global__ void __launch_bounds__(32 * F4_WARPS, (N <= 3 ? 4 : 3)) k_fed4(const 
 
     __shared__ __align__(16) unsigned char ring_mem[F4_WARPS * F4_RING * F4_ROWB];
     ln.ring = (unsigned)__cvta_generic_to_shared(ring_mem + (threadIdx.x >> 5) * (F4_RING * F4_ROWB) + lane * 16);
+    ln.wsrc = ln.wflow = nullptr; ln.wring = ln.mbar = ln.wbytes = ln.par = 0;
+    if (TMA) {
+        __shared__ __align__(8) unsigned long long mbars[F4_WARPS * F4_RING];
+        const int gs = strip * F4_COLS - 4;                                // first column of the warp's 128-column segment
+        const int c0 = max(gs, 0), c1 = min(gs + 128, a.pitch);            // part of it inside the row (multiples of 4 columns)
+        ln.wsrc = a.src + base + c0; ln.wflow = a.flow + base + c0;
+        ln.wbytes = (unsigned)(c1 - c0) * 4u;
+        ln.wring = (unsigned)__cvta_generic_to_shared(ring_mem + (threadIdx.x >> 5) * (F4_RING * F4_ROWB)) + (unsigned)(c0 - gs) * 4u;
+        ln.mbar = (unsigned)__cvta_generic_to_shared(mbars + (threadIdx.x >> 5) * F4_RING);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < F4_RING; k++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(ln.mbar + k * 8) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncwarp();
+    }
 
     Fed4Regs<N> R;
 #pragma unroll
@@ -504,15 +550,16 @@ __global__ void __launch_bounds__(32 * F4_WARPS, (N <= 3 ? 4 : 3)) k_fed4(const 
     for (int s = 0; s < N; s++) { R.NL[s] = 0.f; R.NR[s] = 0.f; }
     // rows t0 .. t0 + 4 are requested up front, one commit group per row
 #pragma unroll
-    for (int k = 0; k < F4_RING - 1; k++) f4_request(a, ln, ln.t0 + k, k);
+    for (int k = 0; k < F4_RING - 1; k++) f4_request<TMA>(a, ln, ln.t0 + k, k);
     const int T = (ln.y1 - ln.y0) + 2 * N;
     for (int it = 0; it < T; it += 6) {
-        f4_phase<N, INT, GEN, 0>(R, a, ln, it, T);
-        f4_phase<N, INT, GEN, 1>(R, a, ln, it, T);
-        f4_phase<N, INT, GEN, 2>(R, a, ln, it, T);
-        f4_phase<N, INT, GEN, 3>(R, a, ln, it, T);
-        f4_phase<N, INT, GEN, 4>(R, a, ln, it, T);
-        f4_phase<N, INT, GEN, 5>(R, a, ln, it, T);
+        f4_phase<N, INT, GEN, TMA, 0>(R, a, ln, it, T);
+        f4_phase<N, INT, GEN, TMA, 1>(R, a, ln, it, T);
+        f4_phase<N, INT, GEN, TMA, 2>(R, a, ln, it, T);
+        f4_phase<N, INT, GEN, TMA, 3>(R, a, ln, it, T);
+        f4_phase<N, INT, GEN, TMA, 4>(R, a, ln, it, T);
+        f4_phase<N, INT, GEN, TMA, 5>(R, a, ln, it, T);
+        ln.par ^= 1u;
     }
 }
 
@@ -520,6 +567,7 @@ akz_once_t g_attr_done;
 int g_fed_rb = 4;                            // rows per thread block of k_fed3 (AKZ_FED_RB=2 selects the 4 x 2 variant)
 int g_fed_band = 0;                          // rows per band of k_fed4 (AKZ_FED_BAND; 0 = chosen per launch)
 int g_fed_stream = 1;                        // AKZ_FED_STREAM=0 forces the tile kernel (A/B measurements)
+int g_fed_tma = 0;                           // AKZ_FED_TMA=1: landing ring filled by cp.async.bulk (TMA) + mbarrier instead of cp.async
 int g_fed_min_units = 1024;                  // fewer (strip, band, frame) units than this: the tile kernel (AKZ_FED_MIN_UNITS)
 
 }  // namespace
@@ -533,6 +581,7 @@ static void set_attrs()
     if (const char* e = getenv("AKZ_FED_RB")) g_fed_rb = atoi(e) == 2 ? 2 : 4;
     if (const char* e = getenv("AKZ_FED_BAND")) g_fed_band = std::max(8, atoi(e));
     if (const char* e = getenv("AKZ_FED_MIN_UNITS")) g_fed_min_units = atoi(e);
+    if (const char* e = getenv("AKZ_FED_TMA")) g_fed_tma = atoi(e);
     if (const char* e = getenv("AKZ_FED_STREAM")) g_fed_stream = atoi(e);
     cudaFuncSetAttribute(k_fed3<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
     cudaFuncSetAttribute(k_fed3<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
@@ -544,12 +593,16 @@ template <int N>
 static void fed4_launch(cudaStream_t st, const Fed4Args& a, bool int_planes, bool gen)
 {
     const int grid = (a.nunits + F4_WARPS - 1) / F4_WARPS;
+    if (g_fed_tma && !int_planes && !gen) {                 // measured alternative: rows by TMA bulk copies + mbarriers
+        k_fed4<N, false, false, true><<<grid, 32 * F4_WARPS, 0, st>>>(a);
+        return;
+    }
     if (int_planes) {
-        if (gen) k_fed4<N, true, true><<<grid, 32 * F4_WARPS, 0, st>>>(a);
-        else k_fed4<N, true, false><<<grid, 32 * F4_WARPS, 0, st>>>(a);
+        if (gen) k_fed4<N, true, true, false><<<grid, 32 * F4_WARPS, 0, st>>>(a);
+        else k_fed4<N, true, false, false><<<grid, 32 * F4_WARPS, 0, st>>>(a);
     } else {
-        if (gen) k_fed4<N, false, true><<<grid, 32 * F4_WARPS, 0, st>>>(a);
-        else k_fed4<N, false, false><<<grid, 32 * F4_WARPS, 0, st>>>(a);
+        if (gen) k_fed4<N, false, true, false><<<grid, 32 * F4_WARPS, 0, st>>>(a);
+        else k_fed4<N, false, false, false><<<grid, 32 * F4_WARPS, 0, st>>>(a);
     }
 }
 

@@ -1114,3 +1114,29 @@ def test_4k_five_octaves_vs_reference():
     top = {12: 0.75, 13: 0.6, 14: 0.42, 15: 0.2, 16: 0.7, 17: 0.45, 18: 0.15, 19: 0.0}
     _full_parity_vs_serialised_reference(img, 5, "3840x2160 5x4", lambda l: top.get(l, 1.0),
                                          lambda a, f: (a["y"] < 0.55 * h) & (a[f] < 12), min_common=0.995)
+
+
+def test_fed_tma_variant_is_exact():
+    """The measured alternative of k_fed4 (AKZ_FED_TMA=1: rows by cp.async.bulk + mbarrier instead of cp.async, see
+    profiles/r02_fed4_tma_ab.txt) must give the same bits.  The knob is read once per process: run it in a child process."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, "cuda-akaze_b200"); sys.path.insert(0, "tests")
+import akaze_b200 as ab
+for (w, h, n) in ((1920, 200, 3), (480, 270, 4), (250 * 4, 97, 7)):
+    g = torch.Generator(device="cuda"); g.manual_seed(n)
+    L = torch.rand(3, h, w, device="cuda", generator=g); G = torch.rand(3, h, w, device="cuda", generator=g)
+    tau = (np.random.default_rng(n).random(n) * 0.2 + 0.01).astype(np.float32)
+    outs = []
+    for fused in (1, 0):
+        c = ab.Context(0, 0, fused=fused, max_batch=3)
+        d, t = torch.zeros_like(L), torch.zeros_like(L)
+        c.fed_cycle(L, G, d, t, w, tau); c.sync(); outs.append(d); c.close()
+    assert torch.equal(outs[0].view(torch.int32), outs[1].view(torch.int32)), (w, h, n)
+print("tma-ok")
+'''
+    env = dict(os.environ, AKZ_FED_TMA="1", AKZ_FED_MIN_UNITS="0")
+    out = subprocess.run([sys.executable, "-c", code], cwd=B.ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "tma-ok" in out.stdout, out.stderr[-1500:]
