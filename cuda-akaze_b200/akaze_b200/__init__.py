@@ -38,7 +38,7 @@ EXPORTS = [
     "akz_fed_cycle", "akz_hessian", "akz_match", "akz_match_merge", "akz_match_host", "akz_pack_points",
     "akz_unpack_desc", "akz_scatter_matches", "akz_orient", "akz_describe", "akz_detect_keypoints",
     "akz_profile_enable", "akz_profile_read", "akz_profile_class_name", "akz_keypoints_to_opencv", "akz_matches_to_opencv",
-    "akz_set_match_kernel", "akz_plan_chunks", "akz_plan_match", "akz_fast_detect_and_compute", "akz_fast_detect_and_compute_host", "akz_fast_build_scale_space", "akz_fast_get_kcontrast", "akz_fast_lowpass",
+    "akz_set_match_kernel", "akz_set_describe_kernel", "akz_plan_chunks", "akz_plan_match", "akz_fast_detect_and_compute", "akz_fast_detect_and_compute_host", "akz_fast_build_scale_space", "akz_fast_get_kcontrast", "akz_fast_lowpass",
     "akz_match_pairs", "akz_comm_unique_id", "akz_comm_init", "akz_comm_attach", "akz_comm_destroy", "akz_match_sharded",
     "akz_fast_down_with_smooth", "akz_fast_scharr_contrast", "akz_fast_flow", "akz_fast_nld_step", "akz_fast_hessian",
 ]
@@ -115,6 +115,8 @@ def lib():
     L.akz_plan_chunks.argtypes = [i, i, i, C.POINTER(C.c_int), C.POINTER(C.c_int), i]
     L.akz_plan_match.argtypes = [i, i, C.POINTER(C.c_int)]
     L.akz_set_match_kernel.restype = None
+    L.akz_set_describe_kernel.argtypes = [i]
+    L.akz_set_describe_kernel.restype = None
     L.akz_keypoints_to_opencv.argtypes = [vp, i, i, vp]
     L.akz_matches_to_opencv.argtypes = [vp, i, vp]
     L.akz_profile_enable.argtypes = [vp, i]

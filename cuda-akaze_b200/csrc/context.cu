@@ -159,7 +159,7 @@ struct akz_ctx {
     bool graph_ok;
     unsigned long long* map;
     unsigned* rowmask;
-    int *rowcount, *prefix, *hist, *counts_own;      // counts_own / kpts_own / desc_own: AKZ_NSET result sets (host API pipeline)
+    int *rowcount, *prefix, *order, *hist, *counts_own;      // counts_own / kpts_own / desc_own: AKZ_NSET result sets (host API pipeline)
     unsigned* hmax;
     float* kc;
     akz_keypoint* kpts_own;
@@ -303,6 +303,7 @@ int akz_create(const akz_options* o, akz_ctx** out)
         const int B = o->max_batch;
         // small per-frame scalars: needed by the stage seams even without a pyramid
         if ((rc = dalloc(c, &c->prefix, (size_t)2 * B + 2)) != AKZ_OK) break;
+        if (!matcher_only && (rc = dalloc(c, &c->order, (size_t)B * o->max_pts)) != AKZ_OK) break;      // processing order of the keypoint stages
         if ((rc = dalloc(c, &c->hist, (size_t)AKZ_NBINS * B)) != AKZ_OK) break;
         if ((rc = dalloc(c, &c->hmax, (size_t)B)) != AKZ_OK) break;
         if ((rc = dalloc(c, &c->kc, (size_t)B)) != AKZ_OK) break;
@@ -793,8 +794,9 @@ static int detect_chunk(akz_ctx* c, int nf, int describe, int* d_counts, akz_key
     LAUNCHED(AKZ_K_NMS, akzk::nms_emit(st, c->map, c->mpitch, c->mplane, o.width, o.height, c->psz, c->tab, c->rowmask, c->rowcount,
                             d_counts, c->prefix, d_kpts, o.max_pts, nf, fast));
     if (describe) {
-        LAUNCHED(AKZ_K_ORIENT, akzk::orient(st, c->tab, d_counts, c->prefix, d_kpts, o.max_pts, nf, fast));
-        LAUNCHED(AKZ_K_DESCRIBE, akzk::describe(st, c->tab, d_counts, c->prefix, d_kpts, d_desc, o.max_pts, nf, o.descriptor_pattern_size, fast));
+        LAUNCHED(AKZ_K_ORIENT, akzk::layer_order(st, d_counts, d_kpts, c->order, o.max_pts, nf));
+        LAUNCHED(AKZ_K_ORIENT, akzk::orient(st, c->tab, d_counts, c->prefix, d_kpts, o.max_pts, nf, fast, c->order));
+        LAUNCHED(AKZ_K_DESCRIBE, akzk::describe(st, c->tab, d_counts, c->prefix, d_kpts, d_desc, o.max_pts, nf, o.descriptor_pattern_size, fast, c->order));
     }
     return AKZ_OK;
 }
@@ -1248,6 +1250,7 @@ int akz_detect_keypoints(akz_ctx* c, int n, int* d_counts, akz_keypoint* d_kpts)
 // ---- matcher ----------------------------------------------------------------------------------------------
 static std::atomic<int> g_match_kernel{0};   // 0 = by problem size, 1 = POPC/LOP3 kernel, 2 = mma.sync kernel, 3 = tcgen05 kernel
 void akz_set_match_kernel(int which) { g_match_kernel.store(which, std::memory_order_relaxed); }
+void akz_set_describe_kernel(int which) { akzk::set_describe_kernel(which); }
 
 int akz_match(akz_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int t_index_base, int mode, int finalize, akz_match_t* d_out)
 {

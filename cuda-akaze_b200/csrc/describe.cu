@@ -5,6 +5,7 @@
 #include "kernels.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <utility>
@@ -51,12 +52,51 @@ __device__ __forceinline__ float fast_atan2(float y, float x)     // akazed.cu:1
     return r;
 }
 
+// Gathers of the keypoint stages.  ncu (profiles/r02n_*): k_orient and both M-LDB kernels sit at the same 1.1 TB/s of DRAM reads
+// whatever their instruction count: scattered 32-byte sector fetches bound them, not bytes.  The patches of neighbouring
+// keypoints cover every sector of a row segment sooner or later, so a miss asks L2 to fetch the whole 256-byte neighbourhood.
+__device__ __forceinline__ float ldg_wide(const float* p)
+{
+    float v;
+    asm("ld.global.nc.L2::256B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // locate keypoint g of the chunk: frame by linear search over the prefix (n <= a few dozen)
 __device__ __forceinline__ int find_frame(const int* __restrict__ prefix, int n, int g)
 {
     int f = 0;
     while (f + 1 < n && g >= prefix[f + 1]) f++;
     return f;
+}
+
+// ---- processing order of the keypoint stages ------------------------------------------------------------------------------
+// Keypoints are stored in raster order (App. B-5); consecutive ones sit on different levels, i.e. in different planes.  Gathering
+// in that order thrashes: scripts/probes/gather_probe.cu -- the M-LDB access pattern alone, 19 k keypoints per frame -- takes
+// 3.1 ns per keypoint when they share one level, 7-9 ns when twelve levels alternate.  order[frame][j] lists the frame's
+// keypoints grouped by layer (counting sort, one block per frame; within a layer raster order is kept from one group of 1024 to
+// the next, which is all locality needs).  Orientation and descriptors walk the frame through it; results and their positions
+// in the output do not depend on it.
+__global__ void __launch_bounds__(1024) k_layer_order(const int* __restrict__ counts, const akz_keypoint* __restrict__ kpts, int* __restrict__ order, int max_pts)
+{
+    __shared__ int s_cnt[AKZ_MAX_LEVELS], s_cur[AKZ_MAX_LEVELS];
+    const int frame = blockIdx.x, n = min(counts[frame], max_pts);
+    const akz_keypoint* kp = kpts + (long long)frame * max_pts;
+    int* ord = order + (long long)frame * max_pts;
+    if (threadIdx.x < AKZ_MAX_LEVELS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 1024) atomicAdd(&s_cnt[kp[i].layer], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int sum = 0;
+        for (int l = 0; l < AKZ_MAX_LEVELS; l++) { s_cur[l] = sum; sum += s_cnt[l]; }
+    }
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        if (i < n) ord[atomicAdd(&s_cur[kp[i].layer], 1)] = i;
+        __syncthreads();
+    }
 }
 
 constexpr int ORI_WARPS = 4;
@@ -67,7 +107,7 @@ constexpr int ORI_WARPS = 4;
 // polynomial dFastAtan2 for the bin as well as for the final angle
 template <bool FAST>
 __global__ void __launch_bounds__(ORI_WARPS * 32) k_orient(const __grid_constant__ AkzLevelTable tab, const int* __restrict__ prefix, int nframes,
-                                                          akz_keypoint* __restrict__ kpts, int max_pts)
+                                                          akz_keypoint* __restrict__ kpts, int max_pts, const int* __restrict__ order)
 {
     __shared__ float4 s_samp[ORI_WARPS][128];
     __shared__ float s_res[ORI_WARPS][2][64];
@@ -75,7 +115,9 @@ __global__ void __launch_bounds__(ORI_WARPS * 32) k_orient(const __grid_constant
     int total = prefix[nframes];
     for (int g = blockIdx.x * ORI_WARPS + wid; g < total; g += gridDim.x * ORI_WARPS) {
         int frame = find_frame(prefix, nframes, g);
-        akz_keypoint* kp = kpts + (long long)frame * max_pts + (g - prefix[frame]);
+        int local = g - prefix[frame];
+        if (order) local = order[(long long)frame * max_pts + local];
+        akz_keypoint* kp = kpts + (long long)frame * max_pts + local;
         const AkzLevelDev& L = tab.lv[kp->layer];
         int o = L.octave, p = L.pitch;
         const float* lx = L.lx + (long long)frame * L.plane;
@@ -92,12 +134,12 @@ __global__ void __launch_bounds__(ORI_WARPS * 32) k_orient(const __grid_constant
                 long long pos = (long long)yy * p + xx;
                 float dx, dy, ang;
                 if (FAST) {
-                    dx = gw * __ldg(reinterpret_cast<const int*>(lx) + pos);
-                    dy = gw * __ldg(reinterpret_cast<const int*>(ly) + pos);
+                    dx = gw * __float_as_int(ldg_wide(lx + pos));
+                    dy = gw * __float_as_int(ldg_wide(ly + pos));
                     ang = fast_atan2(dy, dx);
                 } else {
-                    dx = gw * __ldg(lx + pos);
-                    dy = gw * __ldg(ly + pos);
+                    dx = gw * ldg_wide(lx + pos);
+                    dy = gw * ldg_wide(ly + pos);
                     ang = atan2f(dy, dx);
                 }
                 int a = max(min((int)(ang * (21 / 3.14159265358979323846)) + 21, 41), 0);   // akazed.cu:1702
@@ -160,14 +202,9 @@ __global__ void __launch_bounds__(ORI_WARPS * 32) k_orient(const __grid_constant
 // ---- M-LDB -------------------------------------------------------------------------------------------
 __constant__ short c_cmp[2][488];
 
-// ---- M-LDB, pattern size fixed at compile time (PAT = 10 is the reference default, akaze.h:54) ---------------
-// Same numbers as k_describe, produced with a third of the instructions (ncu r01b: 2160 thread-instructions per
-// thread per keypoint, 18.7 % issue utilisation, stalls on the global gathers and on shared memory):
-//   * all 7 x 3 gathers of a thread are issued before the first accumulation (memory-level parallelism 21);
-//   * window size and cell geometry are immediates (no runtime division);
-//   * the reduction is transposed: thread v owns output value v and evaluates the reference's tree itself,
-//     a_t = acc_t + acc_{t+32}, then the shuffle-down pairing ((a0+a1)+(a2+a3))+... serially from shared memory
-//     (row stride 65: conflict-free both for the per-thread accumulation columns and for the transposed reads).
+// float / integer pipeline arithmetic of the cell sums: INT = true is the integer pipeline's M-LDB (gDescribe2 akazed.cu:3723-3855):
+// int planes (bit patterns travel in float registers), sample positions and rotated derivatives in the reference's own float
+// expressions truncated to int, int cell sums (associative), int comparisons.
 template <bool INT> __device__ __forceinline__ float dsum(float a, float b)
 {
     return INT ? __int_as_float(__float_as_int(a) + __float_as_int(b)) : __fadd_rn(a, b);
@@ -175,153 +212,6 @@ template <bool INT> __device__ __forceinline__ float dsum(float a, float b)
 template <bool INT> __device__ __forceinline__ bool dgreater(float a, float b)
 {
     return INT ? __float_as_int(a) > __float_as_int(b) : a > b;
-}
-
-// INT = true: the integer pipeline's M-LDB (gDescribe2 akazed.cu:3723-3855): int planes (bit patterns in the float registers and
-// accumulators), sample positions and rotated derivatives in the reference's own float expressions truncated to int, int
-// cell sums (associative: any reduction order), int comparisons.
-template <int PAT, bool INT>
-__global__ void __launch_bounds__(64) k_describe_t(const __grid_constant__ AkzLevelTable tab, const int* __restrict__ prefix, int nframes,
-                                                   const akz_keypoint* __restrict__ kpts, unsigned char* __restrict__ desc, int max_pts)
-{
-    constexpr int S2 = PAT, S3 = (2 * PAT + 2) / 3, S4 = (PAT + 1) / 2;      // akazed.cu:2681-2683 (ceil)
-    constexpr int WIN = (3 * S3 > 4 * S4) ? 3 * S3 : 4 * S4;
-    constexpr int NS = WIN * WIN, NK = (NS + 63) / 64, RS = 65;
-    __shared__ __align__(16) float acc[87 * RS + 4];
-    __shared__ float val[96];
-    const int tix = threadIdx.x;
-    // frame of a keypoint: binary search in a shared-memory copy of the prefix (the linear search through global memory
-    // was 14 % of the stall samples, ncu r01f; one block per frame instead leaves the busiest frame as a long tail)
-    __shared__ int s_prefix[AKZ_MAX_FRAMES_SEARCH + 1];
-    for (int i = tix; i <= nframes && i <= AKZ_MAX_FRAMES_SEARCH; i += 64) s_prefix[i] = prefix[i];
-    __syncthreads();
-    const int total = s_prefix[min(nframes, AKZ_MAX_FRAMES_SEARCH)];
-    // this thread's 8 comparison pairs, fetched once (per-lane different constant addresses serialise in the constant cache)
-    unsigned cmp[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        int b = min(tix, 60) * 8 + i;
-        cmp[i] = (unsigned)c_cmp[0][b] | ((unsigned)c_cmp[1][b] << 16);
-    }
-    // 1. gather of keypoint g into registers (all 7 x 3 loads issued back to back)
-    struct Kp { float co, si; int frame, local; };
-    auto gather = [&](int g, Kp& K, float (&im)[NK], float (&dx)[NK], float (&dy)[NK]) {
-        int lo = 0, hi = nframes - 1;                      // largest f with s_prefix[f] <= g
-        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_prefix[mid] <= g) lo = mid; else hi = mid - 1; }
-        K.frame = lo; K.local = g - s_prefix[lo];
-        const akz_keypoint* kp = kpts + (long long)K.frame * max_pts + K.local;
-        const AkzLevelDev& L = tab.lv[kp->layer];
-        const int o = L.octave, p = L.pitch;
-        const float iratio = 1.f / (1 << o);
-        const float fscale = (float)(int)__fadd_rn(kp->size, 0.5f);
-        const int iscale = (int)(kp->size + 0.5f);
-        const float xf = INT ? kp->x * iratio : __fmul_rn(kp->x, iratio), yf = INT ? kp->y * iratio : __fmul_rn(kp->y, iratio);
-        const float ang = kp->angle;
-        const float co = __cosf(ang), si = __sinf(ang);
-        K.co = co; K.si = si;
-        const float* imd = L.lt + (long long)K.frame * L.plane;
-        const float* dxd = L.lx + (long long)K.frame * L.plane;
-        const float* dyd = L.ly + (long long)K.frame * L.plane;
-#pragma unroll
-        for (int k = 0; k < NK; k++) {
-            int i = tix + 64 * k;
-            im[k] = 0.f; dx[k] = 0.f; dy[k] = 0.f;
-            if (i < NS) {
-                int y = i / WIN, x = i - WIN * y;
-                float l = (float)(x - S2), kk = (float)(y - S2);
-                int xp, yp;
-                if (!INT) {
-                    xp = (int)__fadd_rn(__fmaf_rn(fscale, __fmaf_rn(co, kk, -__fmul_rn(si, l)), xf), 0.5f);
-                    yp = (int)__fadd_rn(__fmaf_rn(fscale, __fmaf_rn(si, kk, __fmul_rn(co, l)), yf), 0.5f);
-                } else {                                                   // the reference's expressions, as k_describe_int writes them
-                    const int li = x - S2, ki = y - S2;
-                    xp = (int)(xf + iscale * (ki * co - li * si) + 0.5f);
-                    yp = (int)(yf + iscale * (ki * si + li * co) + 0.5f);
-                }
-                xp = min(max(xp, 0), L.w - 1); yp = min(max(yp, 0), L.h - 1);       // no-op for in-range patches (border test)
-                long long pos = (long long)yp * p + xp;
-                im[k] = __ldg(imd + pos); dx[k] = __ldg(dxd + pos); dy[k] = __ldg(dyd + pos);
-            }
-        }
-    };
-    // Software pipeline: the gathers of the block's NEXT keypoint are issued before the current one is accumulated, so their
-    // DRAM latency overlaps the shared-memory work (ncu r01f: 14 % issue utilisation, 8 warps per issue on the long scoreboard
-    // with ten 64-thread blocks per SM and a strictly serial gather -> accumulate -> reduce loop per block).
-    Kp cur, nxt;
-    float im[NK], dx[NK], dy[NK], nim[NK], ndx[NK], ndy[NK];
-    if ((int)blockIdx.x < total) gather(blockIdx.x, cur, im, dx, dy);
-    for (int g = blockIdx.x; g < total; g += gridDim.x) {
-        const bool more = g + (int)gridDim.x < total;
-        if (more) gather(g + gridDim.x, nxt, nim, ndx, ndy);
-        const float co = cur.co, si = cur.si;
-        const int frame = cur.frame, local = cur.local;
-        // 2. clear the accumulators: the block zeroes the whole array with 128-bit stores (22 per thread instead of 87 scalar)
-        for (int i = tix; i < (87 * RS + 3) / 4; i += 64) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        __syncthreads();
-        // 3. accumulate in sample order (each thread touches only its own column: no synchronisation needed)
-#pragma unroll
-        for (int k = 0; k < NK; k++) {
-            int i = tix + 64 * k;
-            if (i < NS) {
-                int y = i / WIN, x = i - WIN * y, m = max(x, y);
-                float rx, ry;
-                if (!INT) {
-                    rx = __fmaf_rn(co, dy[k], -__fmul_rn(si, dx[k]));
-                    ry = __fmaf_rn(co, dx[k], __fmul_rn(si, dy[k]));
-                } else {
-                    const int dxi = __float_as_int(dx[k]), dyi = __float_as_int(dy[k]);
-                    const int rxi = -dxi * si + dyi * co, ryi = dxi * co + dyi * si;          // float expressions truncated to int
-                    rx = __int_as_float(rxi); ry = __int_as_float(ryi);
-                }
-                // The cells of the three grids live in disjoint rows of acc, but the compiler cannot know that and would
-                // serialise the three read-modify-write groups of a sample (load after the previous group's store: ncu r01j,
-                // 6.3 warps per issue on the short scoreboard).  All nine loads first, then the adds, then the stores.
-                const bool g2 = m < 2 * S2, g3 = m < 3 * S3, g4 = m < 4 * S4;
-                const int x3 = (x < S3 ? 0 : (x < 2 * S3 ? 1 : 2)), y3 = (y < S3 ? 0 : (y < 2 * S3 ? 1 : 2));
-                const int x4 = (x < 2 * S4 ? (x < S4 ? 0 : 1) : (x < 3 * S4 ? 2 : 3));
-                const int y4 = (y < 2 * S4 ? (y < S4 ? 0 : 1) : (y < 3 * S4 ? 2 : 3));
-                float* a2 = acc + (3 * ((y < S2 ? 0 : 1) * 2 + (x < S2 ? 0 : 1))) * RS + tix;
-                float* a3 = acc + (3 * (4 + y3 * 3 + x3)) * RS + tix;
-                float* a4 = acc + (3 * (13 + y4 * 4 + x4)) * RS + tix;
-                float v2[3] = { 0.f, 0.f, 0.f }, v3[3] = { 0.f, 0.f, 0.f }, v4[3] = { 0.f, 0.f, 0.f };
-                if (g2) { v2[0] = a2[0]; v2[1] = a2[RS]; v2[2] = a2[2 * RS]; }
-                if (g3) { v3[0] = a3[0]; v3[1] = a3[RS]; v3[2] = a3[2 * RS]; }
-                if (g4) { v4[0] = a4[0]; v4[1] = a4[RS]; v4[2] = a4[2 * RS]; }
-                if (g2) { a2[0] = dsum<INT>(v2[0], im[k]); a2[RS] = dsum<INT>(v2[1], rx); a2[2 * RS] = dsum<INT>(v2[2], ry); }
-                if (g3) { a3[0] = dsum<INT>(v3[0], im[k]); a3[RS] = dsum<INT>(v3[1], rx); a3[2 * RS] = dsum<INT>(v3[2], ry); }
-                if (g4) { a4[0] = dsum<INT>(v4[0], im[k]); a4[RS] = dsum<INT>(v4[1], rx); a4[2 * RS] = dsum<INT>(v4[2], ry); }
-            }
-        }
-        __syncthreads();
-        // 4. transposed reduction: the reference's tree for value v, evaluated by one thread
-        for (int v = tix; v < 87; v += 64) {
-            const float* a = acc + v * RS;
-            float r[32];
-#pragma unroll
-            for (int t = 0; t < 32; t++) r[t] = dsum<INT>(a[t], a[t + 32]);
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1)
-#pragma unroll
-                for (int t = 0; t + d < 32; t += 2 * d) r[t] = dsum<INT>(r[t], r[t + d]);
-            val[v] = r[0];
-        }
-        __syncthreads();
-        unsigned char* out = desc + ((long long)frame * max_pts + local) * 64;
-        unsigned rbits = 0;
-        if (tix < 61) {
-            const int nb = (tix == 60 ? 6 : 8);
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-                if (i < nb) rbits |= (dgreater<INT>(val[cmp[i] & 0xFFFFu], val[cmp[i] >> 16]) ? 1u : 0u) << i;
-        }
-        out[tix] = (unsigned char)rbits;                  // bytes 61..63 are written as zero
-        __syncthreads();
-        if (more) {
-            cur = nxt;
-#pragma unroll
-            for (int k = 0; k < NK; k++) { im[k] = nim[k]; dx[k] = ndx[k]; dy[k] = ndy[k]; }
-        }
-    }
 }
 
 // ---- M-LDB, sample-major: k_describe_s ----------------------------------------------------------------------------------------
@@ -349,6 +239,7 @@ struct DescArgs {
     const akz_keypoint* kpts;
     unsigned char* desc;
     const DescTables* tables;
+    const int* order;                                        // processing order within a frame (k_layer_order), or null
     int nframes, max_pts;
     int s2, s3, s4, win, ns;
 };
@@ -383,6 +274,7 @@ __global__ void __launch_bounds__(DS_NT, (NK <= 4 ? 8 : 4)) k_describe_s(const _
         int lo = 0, hi = a.nframes - 1;                    // largest f with s_prefix[f] <= g
         while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (s_prefix[mid] <= g) lo = mid; else hi = mid - 1; }
         K.frame = lo; K.local = g - s_prefix[lo];
+        if (a.order) K.local = a.order[(long long)K.frame * a.max_pts + K.local];
         const akz_keypoint* kp = a.kpts + (long long)K.frame * a.max_pts + K.local;
         const AkzLevelDev& L = tab.lv[kp->layer];
         const int o = L.octave, p = L.pitch;
@@ -414,7 +306,7 @@ __global__ void __launch_bounds__(DS_NT, (NK <= 4 ? 8 : 4)) k_describe_s(const _
                 }
                 xp = min(max(xp, 0), L.w - 1); yp = min(max(yp, 0), L.h - 1);       // no-op for in-range patches (border test)
                 long long pos = (long long)yp * p + xp;
-                im[k] = __ldg(imd + pos); dx[k] = __ldg(dxd + pos); dy[k] = __ldg(dyd + pos);
+                im[k] = ldg_wide(imd + pos); dx[k] = ldg_wide(dxd + pos); dy[k] = ldg_wide(dyd + pos);
             }
         }
     };
@@ -510,6 +402,198 @@ __global__ void __launch_bounds__(DS_NT, (NK <= 4 ? 8 : 4)) k_describe_s(const _
     }
 }
 
+constexpr int DW_RS = 64;                                    // floats per row of the (cell value x reference thread) matrix: bank = thread mod 32
+constexpr int DW_ROWS = 90;                                  // 87 values + 3 trash rows for samples outside a grid
+
+// ---- M-LDB, block per keypoint with register run sums: k_describe_b (pattern size 10) ---------------------------------------
+// ncu of k_describe_s on the keypoint-heavy input (profiles/r02n_k_describe_s_raw.txt): 6950 warp instructions per keypoint at
+// 61 % issue utilisation -- its table-driven reduction walks masks with divergent loops.  Here everything that depends on a
+// sample's place in the 21 x 21 grid is a per-thread constant computed once per kernel:
+//   gather:     as k_describe_s -- 128 threads gather the 441 samples (the NEXT keypoint's gathers are in flight while the
+//               current one is reduced) and store them sample-major, rotated, in shared memory;
+//   accumulate: reference thread t's samples (t, t + 64, ...) visit every cell of a grid in ONE contiguous run (x advances by 1
+//               and y by 3 per sample, with at most one wrap), so the per-(cell, thread) sums are running sums in registers,
+//               stored once when the run ends into an 87 x 64 matrix in shared memory (row = 3 cell + channel, column =
+//               reference thread: conflict-free; samples outside a grid go to three trash rows).  Threads 0..63 take grids
+//               2 x 2 and 3 x 3, threads 64..127 grid 4 x 4.  Starting every run from zero is exact (0 + s = s);
+//   reduce:     thread v < 87 reads row v (16 LDS.128, float4 index XOR v so that the eight threads of a quarter warp hit
+//               different banks), writes zeros back (the matrix is clean for the next keypoint) and runs the reference's tree
+//               in registers: a_t = acc_t + acc_(t+32), pairs, fours, ...  The tree is a butterfly, invariant under an XOR
+//               permutation of its leaves, and fadd commutes: same bits;
+//   compare:    61 threads form one descriptor byte each.
+// What is left is the gather itself (scripts/probes/gather_probe.cu: the access pattern alone costs 3-4 ns per keypoint; with the
+// samples forced onto one pixel the kernel runs four times faster): misses fetch 256-byte neighbourhoods (ldg_wide) and the
+// frame is walked level by level (k_layer_order).  Five CTAs per SM: six need register spills that cost more than they hide.
+constexpr int DB_NSP = 448;                                  // floats per channel of the sample array
+constexpr int DB_CTAS = 5;                                   // CTAs per SM (102 registers: no spills; 6 spills the row reduce)
+constexpr size_t DB_SMEM = (size_t)(3 * DB_NSP + DW_ROWS * DW_RS + 96 + AKZ_MAX_FRAMES_SEARCH + 4) * 4;
+
+template <bool INT>
+__global__ void __launch_bounds__(DS_NT, DB_CTAS) k_describe_b(const __grid_constant__ AkzLevelTable tab, const __grid_constant__ DescArgs a)
+{
+    constexpr int P = 10, S3 = 7, S4 = 5, WIN = 21, NS = WIN * WIN, NK = 4;
+    extern __shared__ __align__(16) float db_smem[];
+    float* ds_val = db_smem;                                 // [3][DB_NSP]: im, rx, ry of every sample
+    float* s_acc = ds_val + 3 * DB_NSP;                      // [90][64]
+    float* s_cell = s_acc + DW_ROWS * DW_RS;                 // [96]
+    int* s_prefix = reinterpret_cast<int*>(s_cell + 96);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < DW_ROWS * DW_RS / 4; i += DS_NT) reinterpret_cast<float4*>(s_acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i <= a.nframes && i <= AKZ_MAX_FRAMES_SEARCH; i += DS_NT) s_prefix[i] = a.prefix[i];
+    __syncthreads();
+    const int total = s_prefix[min(a.nframes, AKZ_MAX_FRAMES_SEARCH)];
+    unsigned cmp[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        int b = min(tid, 60) * 8 + i;
+        cmp[i] = (unsigned)c_cmp[0][b] | ((unsigned)c_cmp[1][b] << 16);
+    }
+    // reference thread t = tid & 63; threads 0..63 own grids 2 x 2 and 3 x 3 (offA, offB), threads 64..127 grid 4 x 4 (offA)
+    const int col = tid & 63, hi = tid >> 6;
+    unsigned offs[7];
+    unsigned lastA = 0, lastB = 0;
+#pragma unroll
+    for (int m = 0; m < 7; m++) {
+        const int i = col + 64 * m;
+        const int y = i / WIN, x = i - WIN * y, mx = max(x, y);
+        const bool in = i < NS;
+        const int r2 = (in && mx < 2 * P) ? 3 * ((y < P ? 0 : 1) * 2 + (x < P ? 0 : 1)) : 87;
+        const int r3 = in ? 3 * (4 + (y < S3 ? 0 : (y < 2 * S3 ? 1 : 2)) * 3 + (x < S3 ? 0 : (x < 2 * S3 ? 1 : 2))) : 87;
+        const int r4 = (in && mx < 4 * S4) ? 3 * (13 + (y < 2 * S4 ? (y < S4 ? 0 : 1) : (y < 3 * S4 ? 2 : 3)) * 4 + (x < 2 * S4 ? (x < S4 ? 0 : 1) : (x < 3 * S4 ? 2 : 3))) : 87;
+        offs[m] = hi ? (unsigned)(r4 * DW_RS + col) : ((unsigned)(r2 * DW_RS + col) | ((unsigned)(r3 * DW_RS + col) << 16));
+    }
+#pragma unroll
+    for (int m = 0; m < 7; m++) {
+        const int mn = m == 6 ? m : m + 1;
+        if (m == 6 || (offs[mn] & 0xFFFFu) != (offs[m] & 0xFFFFu)) lastA |= 1u << m;
+        if (m == 6 || (offs[mn] >> 16) != (offs[m] >> 16)) lastB |= 1u << m;
+    }
+    struct Kp { float co, si; int frame, local; };
+    auto gather = [&](int g, Kp& K, float (&im)[NK], float (&dx)[NK], float (&dy)[NK]) {
+        int lo = 0, hh = a.nframes - 1;                    // largest f with s_prefix[f] <= g
+        while (lo < hh) { int mid = (lo + hh + 1) >> 1; if (s_prefix[mid] <= g) lo = mid; else hh = mid - 1; }
+        K.frame = lo; K.local = g - s_prefix[lo];
+        if (a.order) K.local = a.order[(long long)K.frame * a.max_pts + K.local];
+        const akz_keypoint* kp = a.kpts + (long long)K.frame * a.max_pts + K.local;
+        const AkzLevelDev& L = tab.lv[kp->layer];
+        const int o = L.octave, p = L.pitch;
+        const float iratio = 1.f / (1 << o);
+        const float fscale = (float)(int)__fadd_rn(kp->size, 0.5f);
+        const int iscale = (int)(kp->size + 0.5f);
+        const float xf = INT ? kp->x * iratio : __fmul_rn(kp->x, iratio), yf = INT ? kp->y * iratio : __fmul_rn(kp->y, iratio);
+        const float ang = kp->angle;
+        const float co = __cosf(ang), si = __sinf(ang);
+        K.co = co; K.si = si;
+        const float* imd = L.lt + (long long)K.frame * L.plane;
+        const float* dxd = L.lx + (long long)K.frame * L.plane;
+        const float* dyd = L.ly + (long long)K.frame * L.plane;
+#pragma unroll
+        for (int k = 0; k < NK; k++) {
+            int i = tid + DS_NT * k;
+            im[k] = 0.f; dx[k] = 0.f; dy[k] = 0.f;
+            if (i < NS) {
+                int y = i / WIN, x = i - WIN * y;
+                int xp, yp;
+                if (!INT) {
+                    float l = (float)(x - P), kk = (float)(y - P);
+                    xp = (int)__fadd_rn(__fmaf_rn(fscale, __fmaf_rn(co, kk, -__fmul_rn(si, l)), xf), 0.5f);
+                    yp = (int)__fadd_rn(__fmaf_rn(fscale, __fmaf_rn(si, kk, __fmul_rn(co, l)), yf), 0.5f);
+                } else {                                   // integer pipeline: the reference's own float expressions truncated to int
+                    const int li = x - P, ki = y - P;
+                    xp = (int)(xf + iscale * (ki * co - li * si) + 0.5f);
+                    yp = (int)(yf + iscale * (ki * si + li * co) + 0.5f);
+                }
+                xp = min(max(xp, 0), L.w - 1); yp = min(max(yp, 0), L.h - 1);       // no-op for in-range patches (border test)
+                long long pos = (long long)yp * p + xp;
+                im[k] = ldg_wide(imd + pos); dx[k] = ldg_wide(dxd + pos); dy[k] = ldg_wide(dyd + pos);
+            }
+        }
+    };
+    Kp cur, nxt;
+    float im[NK], dx[NK], dy[NK], nim[NK], ndx[NK], ndy[NK];
+    if ((int)blockIdx.x < total) gather(blockIdx.x, cur, im, dx, dy);
+    for (int g = blockIdx.x; g < total; g += gridDim.x) {
+        const bool more = g + (int)gridDim.x < total;
+        if (more) gather(g + gridDim.x, nxt, nim, ndx, ndy);
+        const float co = cur.co, si = cur.si;
+        // 1. rotated derivatives, sample-major into shared memory (samples 441..447 of a channel are never read as members of a cell)
+#pragma unroll
+        for (int k = 0; k < NK; k++) {
+            int i = tid + DS_NT * k;
+            if (i < DB_NSP) {
+                float rx, ry;
+                if (!INT) {
+                    rx = __fmaf_rn(co, dy[k], -__fmul_rn(si, dx[k]));
+                    ry = __fmaf_rn(co, dx[k], __fmul_rn(si, dy[k]));
+                } else {
+                    const int dxi = __float_as_int(dx[k]), dyi = __float_as_int(dy[k]);
+                    const int rxi = -dxi * si + dyi * co, ryi = dxi * co + dyi * si;          // float expressions truncated to int
+                    rx = __int_as_float(rxi); ry = __int_as_float(ryi);
+                }
+                ds_val[i] = im[k]; ds_val[DB_NSP + i] = rx; ds_val[2 * DB_NSP + i] = ry;
+            }
+        }
+        __syncthreads();
+        // 2. running sums of reference thread col over its seven samples, in order; a sum is stored when its run ends
+        {
+            float aA[3] = { 0.f, 0.f, 0.f }, aB[3] = { 0.f, 0.f, 0.f };
+            bool eA = false, eB = false;
+#pragma unroll
+            for (int m = 0; m < 7; m++) {
+                const int i = col + 64 * m;
+                const float s3[3] = { ds_val[i], ds_val[DB_NSP + i], ds_val[2 * DB_NSP + i] };
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    aA[c] = dsum<INT>(eA ? 0.f : aA[c], s3[c]);
+                    aB[c] = dsum<INT>(eB ? 0.f : aB[c], s3[c]);
+                }
+                eA = (lastA >> m) & 1u; eB = (lastB >> m) & 1u;
+                if (eA) { float* q = s_acc + (offs[m] & 0xFFFFu); q[0] = aA[0]; q[DW_RS] = aA[1]; q[2 * DW_RS] = aA[2]; }
+                if (eB && !hi) { float* q = s_acc + (offs[m] >> 16); q[0] = aB[0]; q[DW_RS] = aB[1]; q[2 * DW_RS] = aB[2]; }
+            }
+        }
+        __syncthreads();
+        // 3. the reference's reduction tree for value tid, in registers; the row is handed back zeroed
+        if (tid < 87) {
+            float4* row = reinterpret_cast<float4*>(s_acc + tid * DW_RS);
+            const int sw = tid & 7;
+            float r[32];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {                                    // a_t = acc_t + acc_(t+32): float4 k and k + 8 of the row
+                const float4 q = row[k ^ sw], u = row[(k ^ sw) + 8];
+                r[4 * k] = dsum<INT>(q.x, u.x); r[4 * k + 1] = dsum<INT>(q.y, u.y); r[4 * k + 2] = dsum<INT>(q.z, u.z); r[4 * k + 3] = dsum<INT>(q.w, u.w);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) row[k ^ sw] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+#pragma unroll
+                for (int t = 0; t + d < 32; t += 2 * d) r[t] = dsum<INT>(r[t], r[t + d]);
+            s_cell[tid] = r[0];
+        }
+        __syncthreads();
+        // 4. the 486 comparisons
+        if (tid < 64) {
+            unsigned char* out = a.desc + ((long long)cur.frame * a.max_pts + cur.local) * 64;
+            unsigned rbits = 0;
+            if (tid < 61) {
+                const int nb = (tid == 60 ? 6 : 8);
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    if (i < nb) rbits |= (dgreater<INT>(s_cell[cmp[i] & 0xFFFFu], s_cell[cmp[i] >> 16]) ? 1u : 0u) << i;
+            }
+            out[tid] = (unsigned char)rbits;                  // bytes 61..63 are written as zero
+        }
+        if (more) {
+            cur = nxt;
+#pragma unroll
+            for (int k = 0; k < NK; k++) { im[k] = nim[k]; dx[k] = ndx[k]; dy[k] = ndy[k]; }
+        }
+    }
+}
+
+akz_once_t g_dw_attr;                     // per device: the opt-in to more than 48 KB of dynamic shared memory
+
 // masks of the static reduction for a pattern (host)
 static void build_desc_tables(int s2, int s3, int s4, int win, DescTables& T)
 {
@@ -573,10 +657,13 @@ __global__ void k_scatter(const akz_match_t* __restrict__ m, int nq, RefPoint* _
 }
 
 akz_once_t g_cmp_uploaded;                // per device: constant memory is per device
+std::atomic<int> g_describe_generic{getenv("AKZ_DESCRIBE_S") != nullptr ? 1 : 0};      // akz_set_describe_kernel: the generic kernel also for pattern 10
 
 }  // namespace
 
 namespace akzk {
+
+void set_describe_kernel(int which) { g_describe_generic.store(which ? 1 : 0, std::memory_order_relaxed); }
 
 int orient_table_init(cudaStream_t st)
 {
@@ -592,11 +679,18 @@ int orient_table_init(cudaStream_t st)
     return 1;
 }
 
-int orient(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const int* prefix, akz_keypoint* kpts, int max_pts, int n, int fast)
+int layer_order(cudaStream_t st, const int* counts, const akz_keypoint* kpts, int* order, int max_pts, int n)
+{
+    k_layer_order<<<n, 1024, 0, st>>>(counts, kpts, order, max_pts);
+    return 1;
+}
+
+int orient(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const int* prefix, akz_keypoint* kpts, int max_pts, int n, int fast, const int* order)
 {
     (void)counts;
-    if (fast) k_orient<true><<<148 * 8, ORI_WARPS * 32, 0, st>>>(tab, prefix, n, kpts, max_pts);
-    else k_orient<false><<<148 * 8, ORI_WARPS * 32, 0, st>>>(tab, prefix, n, kpts, max_pts);
+    static const int ctas = getenv("AKZ_ORI_CTAS") ? atoi(getenv("AKZ_ORI_CTAS")) : 8;      // tuning knob
+    if (fast) k_orient<true><<<148 * ctas, ORI_WARPS * 32, 0, st>>>(tab, prefix, n, kpts, max_pts, order);
+    else k_orient<false><<<148 * ctas, ORI_WARPS * 32, 0, st>>>(tab, prefix, n, kpts, max_pts, order);
     return 1;
 }
 
@@ -629,7 +723,7 @@ int describe_prepare(int pattern)
 }
 
 int describe(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const int* prefix, const akz_keypoint* kpts,
-             unsigned char* desc, int max_pts, int n, int pattern, int fast)
+             unsigned char* desc, int max_pts, int n, int pattern, int fast, const int* order)
 {
     (void)counts;
     const int s2 = pattern;                                       // akazed.cu:2681-2683
@@ -639,10 +733,20 @@ int describe(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const
     if (ns > DS_MAXNS) return akz_set_error(AKZ_E_UNSUPPORTED, "descriptor_pattern_size %d is not supported (at most %d samples)", pattern, DS_MAXNS);
     if (n > AKZ_MAX_FRAMES_SEARCH) return akz_set_error(AKZ_E_UNSUPPORTED, "more than %d frames per chunk", AKZ_MAX_FRAMES_SEARCH);
     DescArgs a;
-    a.prefix = prefix; a.kpts = kpts; a.desc = desc; a.nframes = n; a.max_pts = max_pts;
+    a.prefix = prefix; a.kpts = kpts; a.desc = desc; a.nframes = n; a.max_pts = max_pts; a.order = order;
     a.s2 = s2; a.s3 = s3; a.s4 = s4; a.win = win; a.ns = ns;
     a.tables = desc_tables_for(pattern, s2, s3, s4, win);
     if (!a.tables) return akz_set_error(AKZ_E_NOMEM, "descriptor tables");
+    if (pattern == 10 && !g_describe_generic.load(std::memory_order_relaxed)) {                          // the reference default: k_describe_b
+        if (akz_once_guard once{g_dw_attr}) {
+            cudaFuncSetAttribute(k_describe_b<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM);
+            cudaFuncSetAttribute(k_describe_b<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DB_SMEM);
+        }
+        static const int ctas = getenv("AKZ_DB_CTAS") ? atoi(getenv("AKZ_DB_CTAS")) : DB_CTAS;      // tuning knob
+        if (fast) k_describe_b<true><<<148 * ctas, DS_NT, DB_SMEM, st>>>(tab, a);
+        else k_describe_b<false><<<148 * ctas, DS_NT, DB_SMEM, st>>>(tab, a);
+        return 1;
+    }
     const size_t smem = 3 * (size_t)((ns + (ns >> 5) + 4) & ~3) * sizeof(float);
     const int grid = 148 * 8;
     if (ns <= 4 * DS_NT) {

@@ -93,9 +93,11 @@ int frame_prefix(cudaStream_t st, const int* counts, int* prefix, int n);
 
 // ---- describe.cu -------------------------------------------------------------------------------------
 int orient_table_init(cudaStream_t st);
-int orient(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const int* prefix, akz_keypoint* kpts, int max_pts, int n, int fast = 0);
+int layer_order(cudaStream_t st, const int* counts, const akz_keypoint* kpts, int* order, int max_pts, int n);     // order[frame][j]: keypoints grouped by layer
+int orient(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const int* prefix, akz_keypoint* kpts, int max_pts, int n, int fast = 0, const int* order = nullptr);
 int describe(cudaStream_t st, const AkzLevelTable& tab, const int* counts, const int* prefix, const akz_keypoint* kpts,
-             unsigned char* desc, int max_pts, int n, int pattern, int fast = 0);
+             unsigned char* desc, int max_pts, int n, int pattern, int fast = 0, const int* order = nullptr);
+void set_describe_kernel(int which);    // 1 = the generic kernel for every pattern size
 int describe_prepare(int pattern);      // builds the pattern's reduction tables on the current device (call outside stream capture)
 int pack_points(cudaStream_t st, const int* count, const akz_keypoint* kpts, const unsigned char* desc, void* points, int max_pts, int with_desc);
 int unpack_desc(cudaStream_t st, const void* points, int n, unsigned char* desc);

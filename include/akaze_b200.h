@@ -234,6 +234,9 @@ AKZ_API int akz_match_sharded(akz_ctx* c, const uint8_t* d_q, int nq, const uint
  * 3 = tcgen05 kernel (tensor-memory accumulators).
  * Both produce identical results; the switch exists for tests and measurements. */
 AKZ_API void akz_set_match_kernel(int which);
+/* kernel selection of the M-LDB stage: 0 = by pattern size (default: k_describe_b for the reference's pattern 10, the generic
+ * k_describe_s otherwise), 1 = always the generic kernel.  Identical results; for tests and measurements. */
+AKZ_API void akz_set_describe_kernel(int which);
 /* Host-side planning, exposed for tests (no device work).
  * akz_plan_chunks: the chunk plan of a batch of nframes frames (max_batch per chunk, ramp_up = the host pipeline's short first
  *   chunks); writes starts / sizes (up to cap entries) and returns the number of chunks.

@@ -523,6 +523,59 @@ def test_orientation_and_descriptor_given_reference_keypoints(ref_left):
     ctx.close()
 
 
+def _describe_given(ctx, refp):
+    n = len(refp)
+    kp = np.zeros(n, dtype=ab().KEYPOINT_DTYPE)
+    kp["x"], kp["y"], kp["size"], kp["angle"], kp["layer"] = refp["x"], refp["y"], refp["size"], refp["angle"], refp["octave"]
+    kt = torch.from_numpy(kp.view(np.int32).reshape(1, n, 8)).cuda()
+    ct = torch.tensor([n], dtype=torch.int32, device="cuda")
+    dt = torch.zeros(1, n, 64, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.describe(ct, kt, dt)
+    ctx.sync()
+    return dt[0].cpu().numpy()
+
+
+def test_descriptor_kernels_agree_and_other_pattern_sizes_vs_reference(ref_left):
+    """M-LDB has two kernels: k_describe_b (pattern size 10, the reference default) and the generic table-driven k_describe_s.
+    Both must give the reference's bits on the reference's keypoints + angles; other pattern sizes (akaze.h:54 is a
+    constructor argument) are checked against the reference built with the same size."""
+    img = ref_left["img"]
+    h, w = img.shape
+    L = ab().lib()
+    try:
+        for generic in (0, 1):
+            L.akz_set_describe_kernel(generic)
+            ctx = ab().Context(w, h, max_batch=1, max_pts=len(ref_left["pts"]), kcontrast_override=ref_left["k"])
+            ctx.build_scale_space(dev(img))
+            ours = _describe_given(ctx, ref_left["pts"])
+            ctx.close()
+            assert np.array_equal(ours[:, :61], ref_left["pts"]["features"]), f"generic={generic}"
+            assert not ours[:, 61:].any()
+    finally:
+        L.akz_set_describe_kernel(0)
+    for pattern in (6, 13):
+        r = B.RefAkazer(w, h, w, pattern=pattern)
+        pts, planes, k = r.detect_keep(dev(img)[0], max_pts=30000)
+        r.close()
+        ctx = ab().Context(w, h, max_batch=1, max_pts=len(pts), kcontrast_override=k, descriptor_pattern_size=pattern)
+        ctx.build_scale_space(dev(img))
+        ours = _describe_given(ctx, pts)
+        ctx.close()
+        bad = (ours[:, :61] != pts["features"]).any(axis=1)
+        # The reference does not clamp sample positions (akazed.cu:1917-1919): patches larger than the detector's border margin
+        # (which is sized for pattern 10) read whatever lies beside the plane in its pyramid.  We clamp (DESIGN: deliberate
+        # differences), so only keypoints whose rotated patch stays inside the level are comparable.
+        o = pts["octave"] // 4
+        ratio = 1.0 / (1 << o)
+        reach = np.floor(pts["size"] + 0.5) * pattern * np.sqrt(2.0) + 2.0
+        xf, yf = pts["x"] * ratio, pts["y"] * ratio
+        inside = (xf - reach >= 0) & (yf - reach >= 0) & (xf + reach <= (w >> o) - 1) & (yf + reach <= (h >> o) - 1)
+        print(f"\n[M-LDB | pattern {pattern}] {len(pts)} keypoints, {int(bad.sum())} descriptors differ, {int((bad & inside).sum())} of them "
+              f"among the {int(inside.sum())} whose patch stays inside the level")
+        assert inside.mean() > 0.8 and not (bad & inside).any(), pattern
+
+
 def test_keypoints_equal_cpu_oracle():
     """Detector (extrema merge, NMS, refinement, raster order) is bit-identical to the CPU oracle."""
     for (w, h, seed) in [(640, 480, 5), (333, 250, 6)]:
