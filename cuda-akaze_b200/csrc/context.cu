@@ -158,7 +158,7 @@ struct akz_ctx {
     std::vector<GraphEntry> graphs;
     bool graph_ok;
     unsigned long long* map;
-    unsigned* rowmask;
+    unsigned *rowmask, *occ;      // survivor masks; occupancy bitmap of the key map (one bit per pixel with a candidate)
     int *rowcount, *prefix, *order, *hist, *counts_own;      // counts_own / kpts_own / desc_own: AKZ_NSET result sets (host API pipeline)
     unsigned* hmax;
     float* kc;
@@ -363,6 +363,7 @@ int akz_create(const akz_options* o, akz_ctx** out)
         if ((rc = dalloc(c, &c->map, (size_t)c->mplane * B)) != AKZ_OK) break;
         int mwords = (o->width + 31) / 32;
         if ((rc = dalloc(c, &c->rowmask, (size_t)mwords * o->height * B)) != AKZ_OK) break;
+        if ((rc = dalloc(c, &c->occ, (size_t)mwords * o->height * B)) != AKZ_OK) break;
         if ((rc = dalloc(c, &c->rowcount, (size_t)o->height * B)) != AKZ_OK) break;
         if ((rc = dalloc(c, &c->counts_own, (size_t)AKZ_NSET * B)) != AKZ_OK) break;
         if ((rc = dalloc(c, &c->kpts_own, (size_t)AKZ_NSET * o->max_pts * B)) != AKZ_OK) break;
@@ -376,6 +377,9 @@ int akz_create(const akz_options* o, akz_ctx** out)
         if (cudaMallocHost((void**)&c->h_cnt_pinned, sizeof(int) * AKZ_NSET * B) != cudaSuccess) { rc = akz_set_error(AKZ_E_NOMEM, "pinned allocation failed"); break; }
         cudaMemsetAsync(c->rowcount, 0, sizeof(int) * (size_t)o->height * B, c->stream);
         cudaMemsetAsync(c->rowmask, 0, sizeof(unsigned) * (size_t)mwords * o->height * B, c->stream);
+        // the key map and its occupancy bitmap start clean and every chunk leaves them clean (k_clear_map)
+        cudaMemsetAsync(c->occ, 0, sizeof(unsigned) * (size_t)mwords * o->height * B, c->stream);
+        cudaMemsetAsync(c->map, 0, sizeof(unsigned long long) * (size_t)c->mplane * B, c->stream);
         // level table for the keypoint kernels
         memset(&c->tab, 0, sizeof(c->tab));
         c->tab.nlevels = c->nlev; c->tab.max_scale = o->max_scale;
@@ -777,7 +781,7 @@ static int detect_chunk(akz_ctx* c, int nf, int describe, int* d_counts, akz_key
     cudaStream_t st = c->stream;
     const akz_options& o = c->opt;
     const int S = o.max_scale;
-    AKZ_CUDA_TRY(cudaMemsetAsync(c->map, 0, sizeof(unsigned long long) * (size_t)c->mplane * nf, st));
+    const int mwords = (o.width + 31) / 32;
     for (int oc = 0; oc < c->noct; oc++) {
         AkzExtremaArgs a;
         memset(&a, 0, sizeof(a));
@@ -789,9 +793,9 @@ static int detect_chunk(akz_ctx* c, int nf, int describe, int* d_counts, akz_key
             a.lv[j].det = L.det; a.lv[j].plane = L.plane; a.lv[j].border = L.border; a.lv[j].threshold = o.dthreshold;
             a.lv[j].layer = oc * S + j; a.lv[j].ithreshold = 65;                      // akaze.cpp:560
         }
-        LAUNCHED(AKZ_K_EXTREMA, akzk::extrema(st, a, c->map, c->mpitch, c->mplane, nf));
+        LAUNCHED(AKZ_K_EXTREMA, akzk::extrema(st, a, c->map, c->mpitch, c->mplane, c->occ, mwords, o.height, nf));
     }
-    LAUNCHED(AKZ_K_NMS, akzk::nms_emit(st, c->map, c->mpitch, c->mplane, o.width, o.height, c->psz, c->tab, c->rowmask, c->rowcount,
+    LAUNCHED(AKZ_K_NMS, akzk::nms_emit(st, c->map, c->mpitch, c->mplane, o.width, o.height, c->psz, c->tab, c->occ, c->rowmask, c->rowcount,
                             d_counts, c->prefix, d_kpts, o.max_pts, nf, fast));
     if (describe) {
         LAUNCHED(AKZ_K_ORIENT, akzk::layer_order(st, d_counts, d_kpts, c->order, o.max_pts, nf));

@@ -5,7 +5,11 @@
 //   - the three float/int maps are one 64-bit key map merged with atomicMax: arg-max over levels,
 //     ties to the lowest layer, no tearing;
 //   - survivors are compacted in raster order (row counts -> scan -> emit), not atomicInc order;
-//   - the keypoint count never leaves the device.
+//   - the keypoint count never leaves the device;
+//   - the key map is sparse (a few thousand candidates per 2 M pixels): k_extrema also sets the candidate's bit in an occupancy
+//     bitmap (one word per 32 pixels); the NMS pass reads the bitmap and touches the 64-bit map only around candidates, and
+//     k_clear_map zeroes exactly the entries that were written.  Round 1 cleared the whole map (531 MB per 32 frames) and
+//     read all of it again (k_nms_mark: 2.5 ms per 256 frames, 1.7 TB/s).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -28,7 +32,8 @@ __device__ __forceinline__ float ext_thr(const AkzExtremaLevel& L, float) { retu
 __device__ __forceinline__ int ext_thr(const AkzExtremaLevel& L, int) { return L.ithreshold; }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_extrema(const __grid_constant__ AkzExtremaArgs a, unsigned long long* __restrict__ map, int mpitch, long long mplane)
+__global__ void __launch_bounds__(256) k_extrema(const __grid_constant__ AkzExtremaArgs a, unsigned long long* __restrict__ map, int mpitch, long long mplane,
+                                                 unsigned* __restrict__ occ, int mwords, int H)
 {
     typedef typename ExtVec<T>::type V4;
     int frame = blockIdx.z / a.nsub, sub = blockIdx.z - frame * a.nsub;
@@ -59,54 +64,75 @@ __global__ void __launch_bounds__(256) k_extrema(const __grid_constant__ AkzExtr
         int right_x = (int)(__fadd_rn(__fadd_rn((float)ix, border), 0.5f)) + 1;
         if (left_x < 0 || right_x >= a.w) continue;
         if (v > u[j + 1] && v > d[j + 1] && v > c[j] && v > c[j + 2] && v > u[j] && v > u[j + 2] && v > d[j] && v > d[j + 2]) {
-            long long oi = (long long)frame * mplane + (long long)(iy << a.octave) * mpitch + (ix << a.octave);
+            const int Y = iy << a.octave, X = ix << a.octave;
+            long long oi = (long long)frame * mplane + (long long)Y * mpitch + X;
             atomicMax(map + oi, ext_key(v, L.layer));
+            atomicOr(occ + ((long long)frame * H + Y) * mwords + (X >> 5), 1u << (X & 31));
         }
     }
 }
 
-// one block per (row, frame): radius NMS decision per pixel -> bit mask + row count
+// one thread per word of the occupancy bitmap (32 pixels of a row): radius NMS decision for its candidates -> survivor mask.
+// (no block barrier and no counter: the row counts are popcounts of the masks, taken by k_row_scan)
 __global__ void __launch_bounds__(256) k_nms_mark(const unsigned long long* __restrict__ map, int mpitch, long long mplane,
                                                   int W, int H, int psz, const __grid_constant__ AkzLevelTable tab,
-                                                  unsigned* __restrict__ rowmask, int mwords)
+                                                  const unsigned* __restrict__ occ, unsigned* __restrict__ rowmask, int mwords)
 {
-    int iy = blockIdx.x + psz, frame = blockIdx.y;
+    const int frame = blockIdx.y;
+    const int wi = blockIdx.x * 256 + threadIdx.x;               // word of rows [psz, H - psz)
+    if (wi >= (H - 2 * psz) * mwords) return;
+    const int iy = psz + wi / mwords, word = wi - (iy - psz) * mwords;
+    const long long wpos = ((long long)frame * H + iy) * mwords + word;
+    unsigned cand = __ldg(occ + wpos), keepmask = 0;
     const unsigned long long* m = map + (long long)frame * mplane;
-    // (no block barrier: the row count is taken from the bit masks by k_row_scan.  With a shared counter and two
-    // __syncthreads every warp waited for the one warp of the row that walks an NMS neighbourhood: ncu r01j, 13 warps per
-    // issue stalled at the barrier)
-    int xend = W - psz;                                   // ix + psz < W
-    for (int x0 = 0; x0 < mwords * 32; x0 += 256) {
-        int ix = x0 + threadIdx.x;
-        bool keep = false;
-        if (ix >= psz && ix < xend) {
-            unsigned long long key = m[(long long)iy * mpitch + ix];
-            if (key != 0ull) {
-                unsigned rc = (unsigned)(key >> 32);          // positive float bits and positive ints order like unsigned
-                float fsz = tab.lv[key_layer(key)].size;
-                int isz = (int)__fadd_rn(fsz, 0.5f);
-                int sq = (int)__fmul_rn(fsz, fsz);
-                keep = true;
-                for (int i = -isz; i <= isz && keep; i++) {
-                    const unsigned long long* row = m + (long long)(iy + i) * mpitch + ix;
-                    for (int j = -isz; j <= isz; j++) {
-                        if ((i == 0 && j == 0) || i * i + j * j >= sq) continue;
-                        // akazed.cu:1578-1581: the reference's `continue` at the centre skips its `new_idx++`, so on
-                        // the centre row every j > 0 examines the pixel at offset j-1 (the centre itself for j = 1)
-                        // under the distance test of j.  Reproduced: the keypoint SET must equal the reference's.
-                        unsigned long long kn = row[(i == 0 && j > 0) ? j - 1 : j];
-                        if (kn == 0ull) continue;
-                        unsigned rn = (unsigned)(kn >> 32);
-                        if (rn > rc || (rn == rc && i <= 0 && j <= 0)) { keep = false; break; }
-                    }
-                }
+    const int xend = W - psz;                                     // ix + psz < W
+    while (cand) {
+        const int bit = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const int ix = word * 32 + bit;
+        if (ix < psz || ix >= xend) continue;
+        const unsigned long long key = m[(long long)iy * mpitch + ix];
+        if (key == 0ull) continue;
+        const unsigned rc = (unsigned)(key >> 32);                // positive float bits and positive ints order like unsigned
+        const float fsz = tab.lv[key_layer(key)].size;
+        const int isz = (int)__fadd_rn(fsz, 0.5f);
+        const int sq = (int)__fmul_rn(fsz, fsz);
+        bool keep = true;
+        for (int i = -isz; i <= isz && keep; i++) {
+            const unsigned long long* row = m + (long long)(iy + i) * mpitch + ix;
+            for (int j = -isz; j <= isz; j++) {
+                if ((i == 0 && j == 0) || i * i + j * j >= sq) continue;
+                // akazed.cu:1578-1581: the reference's `continue` at the centre skips its `new_idx++`, so on
+                // the centre row every j > 0 examines the pixel at offset j-1 (the centre itself for j = 1)
+                // under the distance test of j.  Reproduced: the keypoint SET must equal the reference's.
+                const unsigned long long kn = row[(i == 0 && j > 0) ? j - 1 : j];
+                if (kn == 0ull) continue;
+                const unsigned rn = (unsigned)(kn >> 32);
+                if (rn > rc || (rn == rc && i <= 0 && j <= 0)) { keep = false; break; }
             }
         }
-        unsigned b = __ballot_sync(0xffffffffu, keep);
-        if ((threadIdx.x & 31) == 0) {
-            int word = (x0 + threadIdx.x) >> 5;
-            if (word < mwords) rowmask[((long long)frame * H + iy) * mwords + word] = b;
-        }
+        if (keep) keepmask |= 1u << bit;
+    }
+    rowmask[wpos] = keepmask;
+}
+
+// zero the map entries that k_extrema wrote and the bitmap itself: the map is clean for the next chunk without a memset
+__global__ void __launch_bounds__(256) k_clear_map(unsigned long long* __restrict__ map, int mpitch, long long mplane, int H,
+                                                   unsigned* __restrict__ occ, int mwords)
+{
+    const int frame = blockIdx.y;
+    const int wi = blockIdx.x * 256 + threadIdx.x;
+    if (wi >= H * mwords) return;
+    const int iy = wi / mwords, word = wi - iy * mwords;
+    unsigned* o = occ + (long long)frame * H * mwords + wi;
+    unsigned cand = *o;
+    if (!cand) return;
+    *o = 0u;
+    unsigned long long* row = map + (long long)frame * mplane + (long long)iy * mpitch + word * 32;
+    while (cand) {
+        const int bit = __ffs(cand) - 1;
+        cand &= cand - 1;
+        row[bit] = 0ull;
     }
 }
 
@@ -261,14 +287,14 @@ __global__ void __launch_bounds__(128) k_emit_refine(const unsigned long long* _
 
 namespace akzk {
 
-int extrema(cudaStream_t st, const AkzExtremaArgs& a, unsigned long long* map, int mpitch, long long mplane, int n)
+int extrema(cudaStream_t st, const AkzExtremaArgs& a, unsigned long long* map, int mpitch, long long mplane, unsigned* occ, int mwords, int H, int n)
 {
     int ew = a.w - 2 * a.psz, eh = a.h - 2 * a.psz;
     if (ew <= 0 || eh <= 0) return 0;
     int xb = a.psz & ~3;
     dim3 g((a.w - xb + 127) / 128, (eh + 7) / 8, n * a.nsub);
-    if (a.int_planes) k_extrema<int><<<g, dim3(32, 8), 0, st>>>(a, map, mpitch, mplane);
-    else k_extrema<float><<<g, dim3(32, 8), 0, st>>>(a, map, mpitch, mplane);
+    if (a.int_planes) k_extrema<int><<<g, dim3(32, 8), 0, st>>>(a, map, mpitch, mplane, occ, mwords, H);
+    else k_extrema<float><<<g, dim3(32, 8), 0, st>>>(a, map, mpitch, mplane, occ, mwords, H);
     return 1;
 }
 
@@ -278,8 +304,8 @@ int frame_prefix(cudaStream_t st, const int* counts, int* prefix, int n)
     return 1;
 }
 
-int nms_emit(cudaStream_t st, const unsigned long long* map, int mpitch, long long mplane, int W, int H, int psz,
-             const AkzLevelTable& tab, unsigned* rowmask, int* rowcount, int* counts, int* prefix,
+int nms_emit(cudaStream_t st, unsigned long long* map, int mpitch, long long mplane, int W, int H, int psz,
+             const AkzLevelTable& tab, unsigned* occ, unsigned* rowmask, int* rowcount, int* counts, int* prefix,
              akz_keypoint* kpts, int max_pts, int n, int int_planes)
 {
     int mwords = (W + 31) / 32;
@@ -287,7 +313,7 @@ int nms_emit(cudaStream_t st, const unsigned long long* map, int mpitch, long lo
     int rows = H - 2 * psz;
     int launches = 0;
     if (rows > 0) {
-        k_nms_mark<<<dim3(rows, n), 256, 0, st>>>(map, mpitch, mplane, W, H, psz, tab, rowmask, mwords);
+        k_nms_mark<<<dim3((rows * mwords + 255) / 256, n), 256, 0, st>>>(map, mpitch, mplane, W, H, psz, tab, occ, rowmask, mwords);
         launches++;
     }
     k_row_scan<<<n, 1024, 0, st>>>(rowcount, rowmask, mwords, H, rows > 0 ? psz : H, counts, prefix + n + 1, max_pts);
@@ -298,6 +324,8 @@ int nms_emit(cudaStream_t st, const unsigned long long* map, int mpitch, long lo
         else k_emit_refine<false><<<dim3(rows, n), 128, 0, st>>>(map, mpitch, mplane, H, psz, tab, rowmask, mwords, rowcount, kpts, max_pts);
         launches++;
     }
+    k_clear_map<<<dim3((H * mwords + 255) / 256, n), 256, 0, st>>>(map, mpitch, mplane, H, occ, mwords);
+    launches++;
     return launches;
 }
 

@@ -84,9 +84,9 @@ int fast_nld_step(cudaStream_t st, const int* src, const int* flow, int* dst, fl
 int fast_hessian(cudaStream_t st, const int* smooth, int* lx, int* ly, int* det, int step, int w, int h, int pitch, long long stride, int n);
 
 // ---- detect.cu ---------------------------------------------------------------------------------------
-int extrema(cudaStream_t st, const AkzExtremaArgs& a, unsigned long long* map, int mpitch, long long mplane, int n);
-int nms_emit(cudaStream_t st, const unsigned long long* map, int mpitch, long long mplane, int W, int H, int psz,
-             const AkzLevelTable& tab, unsigned* rowmask, int* rowcount, int* counts, int* prefix,
+int extrema(cudaStream_t st, const AkzExtremaArgs& a, unsigned long long* map, int mpitch, long long mplane, unsigned* occ, int mwords, int H, int n);
+int nms_emit(cudaStream_t st, unsigned long long* map, int mpitch, long long mplane, int W, int H, int psz,
+             const AkzLevelTable& tab, unsigned* occ, unsigned* rowmask, int* rowcount, int* counts, int* prefix,
              akz_keypoint* kpts, int max_pts, int n, int int_planes = 0);
 
 int frame_prefix(cudaStream_t st, const int* counts, int* prefix, int n);
