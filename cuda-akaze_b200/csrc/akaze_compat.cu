@@ -174,6 +174,7 @@ namespace akaze
         int* h_count = nullptr;                 // pinned landing zone of the keypoint count
         unsigned char* h_stage = nullptr;       // pinned landing zone of the AkazePoint records (cap x 104 bytes)
         int cap = 0;
+        int last_n = 0;                         // keypoints of the previous frame (size of the speculative record copy)
         void release()
         {
             if (ctx) akz_destroy(ctx);
@@ -214,13 +215,21 @@ namespace akaze
                                               desc ? 1 : 0, d_count, d_kpts, d_desc));
             AKZ_DO(akz_pack_points(ctx, d_count, d_kpts, d_desc, result.d_data, result.max_pts, desc ? 1 : 0));
             CHECK(cudaMemcpyAsync(h_count, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+            // The records follow the count in the same stream: as many as the previous frame had (+ 25 %), so that a stream of
+            // similar frames needs one synchronisation per frame, not two; the rest, if any, in a second copy.
+            const bool want = result.h_data != NULL;
+            const size_t guess = want ? std::min((size_t)result.max_pts, (size_t)last_n + (size_t)last_n / 4 + 256) : 0;
+            if (guess) CHECK(cudaMemcpyAsync(h_stage, result.d_data, guess * sizeof(AkazePoint), cudaMemcpyDeviceToHost, st));
             AKZ_DO(akz_sync(ctx));
             result.num_pts = *h_count;
-            if (result.h_data != NULL && result.num_pts > 0) {
+            last_n = result.num_pts;
+            if (want && result.num_pts > 0) {
                 const size_t n = (size_t)result.num_pts;
                 const size_t ncopy = (desc ? FLEN * sizeof(unsigned char) : 0) + 6 * sizeof(float);      // akaze.cpp:134-139
-                CHECK(cudaMemcpyAsync(h_stage, result.d_data, n * sizeof(AkazePoint), cudaMemcpyDeviceToHost, st));
-                AKZ_DO(akz_sync(ctx));
+                if (n > guess) {
+                    CHECK(cudaMemcpyAsync(h_stage + guess * sizeof(AkazePoint), result.d_data + guess, (n - guess) * sizeof(AkazePoint), cudaMemcpyDeviceToHost, st));
+                    AKZ_DO(akz_sync(ctx));
+                }
                 unsigned char* dst = reinterpret_cast<unsigned char*>(result.h_data);
                 for (size_t i = 0; i < n; i++) memcpy(dst + i * sizeof(AkazePoint), h_stage + i * sizeof(AkazePoint), ncopy);
             }

@@ -782,6 +782,10 @@ static int detect_chunk(akz_ctx* c, int nf, int describe, int* d_counts, akz_key
     const akz_options& o = c->opt;
     const int S = o.max_scale;
     const int mwords = (o.width + 31) / 32;
+    // Small-batch contexts (octave streams): the four extrema kernels merge into the same map with atomicMax and are independent,
+    // so octaves 1.. run beside octave 0 on their octave streams; k_clear_map runs on a side stream under the keypoint stages.
+    const bool par = c->opar && c->noct > 1;
+    if (par) AKZ_CUDA_TRY(cudaEventRecord(c->ev_lvl0[0], st));
     for (int oc = 0; oc < c->noct; oc++) {
         AkzExtremaArgs a;
         memset(&a, 0, sizeof(a));
@@ -793,15 +797,27 @@ static int detect_chunk(akz_ctx* c, int nf, int describe, int* d_counts, akz_key
             a.lv[j].det = L.det; a.lv[j].plane = L.plane; a.lv[j].border = L.border; a.lv[j].threshold = o.dthreshold;
             a.lv[j].layer = oc * S + j; a.lv[j].ithreshold = 65;                      // akaze.cpp:560
         }
-        LAUNCHED(AKZ_K_EXTREMA, akzk::extrema(st, a, c->map, c->mpitch, c->mplane, c->occ, mwords, o.height, nf));
+        cudaStream_t so = (par && oc > 0) ? c->ostream[oc] : st;
+        if (so != st) AKZ_CUDA_TRY(cudaStreamWaitEvent(so, c->ev_lvl0[0], 0));
+        c->cur = so;
+        LAUNCHED(AKZ_K_EXTREMA, akzk::extrema(so, a, c->map, c->mpitch, c->mplane, c->occ, mwords, o.height, nf));
+        c->cur = st;
+        if (so != st) { AKZ_CUDA_TRY(cudaEventRecord(c->ev_oct[oc], so)); AKZ_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_oct[oc], 0)); }
     }
     LAUNCHED(AKZ_K_NMS, akzk::nms_emit(st, c->map, c->mpitch, c->mplane, o.width, o.height, c->psz, c->tab, c->occ, c->rowmask, c->rowcount,
                             d_counts, c->prefix, d_kpts, o.max_pts, nf, fast));
+    cudaStream_t sc = (par && describe) ? c->ostream[1] : st;
+    if (sc != st) { AKZ_CUDA_TRY(cudaEventRecord(c->ev_lvl0[0], st)); AKZ_CUDA_TRY(cudaStreamWaitEvent(sc, c->ev_lvl0[0], 0)); }
+    c->cur = sc;
+    LAUNCHED(AKZ_K_NMS, akzk::clear_map(sc, c->map, c->mpitch, c->mplane, o.width, o.height, c->occ, nf));
+    c->cur = st;
+    if (sc != st) AKZ_CUDA_TRY(cudaEventRecord(c->ev_oct[1], sc));
     if (describe) {
         LAUNCHED(AKZ_K_ORIENT, akzk::layer_order(st, d_counts, d_kpts, c->order, o.max_pts, nf));
         LAUNCHED(AKZ_K_ORIENT, akzk::orient(st, c->tab, d_counts, c->prefix, d_kpts, o.max_pts, nf, fast, c->order));
         LAUNCHED(AKZ_K_DESCRIBE, akzk::describe(st, c->tab, d_counts, c->prefix, d_kpts, d_desc, o.max_pts, nf, o.descriptor_pattern_size, fast, c->order));
     }
+    if (sc != st) AKZ_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_oct[1], 0));
     return AKZ_OK;
 }
 
@@ -873,7 +889,8 @@ int akz_get_kcontrast(akz_ctx* c, float* h_k, int nframes)
 // Chunk plan of a batch: full chunks of B frames; small chunks (B/8, B/4, B/2) at the start when the first upload has nothing
 // to hide behind (host pipeline).  A mirrored ramp-down (so that the last chunk, which runs alone on its lane, is short) is
 // implemented but off: measured at 256 frames it costs more in small-chunk inefficiency than the shorter tail returns
-// (4705 -> 4636 images/s resident, 4308 -> 4322 host to host).
+// (round 1: 4705 -> 4636 images/s resident, 4308 -> 4322 host to host; round 2, copy-bound float frames: 5754 -> 5683,
+// scripts/probes/e2e_rampdown.sh).
 static void chunk_plan(int nframes, int B, bool ramp_up, bool ramp_down, std::vector<int>& start, std::vector<int>& size)
 {
     start.clear(); size.clear();

@@ -274,9 +274,13 @@ void deriv4_launch(cudaStream_t st, Deriv4Args& a, int n, cudaStream_t ring_st, 
 {
     a.nstrips = (a.w + D4<S>::OC - 1) / D4<S>::OC;
     // bands of at most ~270 rows (a multiple of 12, so that every band starts on residue 0 of every S): two row times of
-    // warm-up per residue class and band
-    const int nb = std::max(1, (a.h + 269) / 270);
-    a.band_h = ((a.h + nb - 1) / nb + 11) / 12 * 12;
+    // warm-up per residue class and band.  With few frames or small levels the bands are shortened (down to 24 rows) until there
+    // are ~2000 (strip, band, residue) units: a handful of warps marching down long bands left the GPU idle (one 1080p frame:
+    // 120-240 units, 22-30 us per launch on the critical path of the single-frame graph).
+    const long long per_band = (long long)n * S * a.nstrips;
+    const int nb_fill = (int)std::min<long long>((a.h + 23) / 24, (2048 + per_band - 1) / per_band);
+    const int nb = std::max(std::max(1, (a.h + 269) / 270), nb_fill);
+    a.band_h = std::max(24, ((a.h + nb - 1) / nb + 11) / 12 * 12);
     a.nbands = (a.h + a.band_h - 1) / a.band_h;
     a.nunits = n * a.nbands * S * a.nstrips;
     k_deriv4<S, INT><<<(a.nunits + D4_WARPS - 1) / D4_WARPS, 32 * D4_WARPS, 0, st>>>(a);

@@ -89,6 +89,7 @@ int nms_emit(cudaStream_t st, unsigned long long* map, int mpitch, long long mpl
              const AkzLevelTable& tab, unsigned* occ, unsigned* rowmask, int* rowcount, int* counts, int* prefix,
              akz_keypoint* kpts, int max_pts, int n, int int_planes = 0);
 
+int clear_map(cudaStream_t st, unsigned long long* map, int mpitch, long long mplane, int W, int H, unsigned* occ, int n);
 int frame_prefix(cudaStream_t st, const int* counts, int* prefix, int n);
 
 // ---- describe.cu -------------------------------------------------------------------------------------

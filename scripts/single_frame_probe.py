@@ -36,3 +36,13 @@ t = torch.from_numpy(buf).cuda()
 data = B.DropinData(10000); az = B.DropinAkazer(W, H, pitch)
 az.detect_and_compute(t, data); az.time(t, data, iters=5)
 print(f"Akazer::detectAndCompute {az.time(t, data, iters=50):.3f} ms/frame; detect only {az.time(t, data, iters=50, desc=False):.3f}")
+# per-class device time of one frame (event pairs around every kernel group; no graph, octaves serialised on one stream)
+ctx = ab.Context(W, H, max_batch=1, max_pts=10000)
+dev = torch.from_numpy(img[None]).cuda()
+out = ctx.alloc_results(1, True)
+for _ in range(3):
+    ctx.detect_and_compute(dev, True, out=out)
+ctx.sync(); ctx.profile(True)
+ctx.detect_and_compute(dev, True, out=out); ctx.sync()
+prof = ctx.profile_read(); ctx.profile(False)
+print("classes (ms, launches):", {k: (round(v[0], 3), v[1]) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])})
