@@ -1065,7 +1065,8 @@ static int detect_and_compute_host_impl(akz_ctx* c, const void* h_images, int dt
     // the upload of the first chunk is not hidden behind anything (a full first chunk of 32 float frames is 265 MB = 5 ms
     // exposed): see chunk_plan
     std::vector<int> cstart, csize;
-    chunk_plan(nframes, B, true, false, cstart, csize);
+    static const bool ramp_down = getenv("AKZ_RAMP_DOWN") != nullptr;      // tuning knob (scripts/probes/e2e_rampdown.sh): off, see chunk_plan
+    chunk_plan(nframes, B, true, ramp_down, cstart, csize);
     const int nchunks = (int)cstart.size();
     auto chunk_frames = [&](int i) { return csize[i]; };
     auto issue_h2d = [&](int i) -> int {
