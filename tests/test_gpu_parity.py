@@ -662,6 +662,30 @@ def test_u8_ingest_batching_host_api_and_determinism():
     ctx.close()
 
 
+def test_sparse_detector_leaves_the_key_map_clean():
+    """The detector's key map and its occupancy bitmap are cleared only where k_extrema wrote them (k_clear_map): a context that
+    has seen keypoint-heavy frames, full chunks and partial chunks must return exactly what a fresh context returns."""
+    w, h = 640, 480
+    noise = B.u8_to_unit(np.stack([B.synth_noise_u8(w, h, seed=s) for s in range(4)]))
+    shapes = B.u8_to_unit(np.stack([B.synth_shapes_u8(w, h, seed=70 + s) for s in range(3)]))
+    fresh = ab().Context(w, h, max_batch=4, max_pts=20000)
+    want = [t.clone() for t in fresh.detect_and_compute(torch.from_numpy(shapes).cuda())]
+    fresh.sync()
+    fresh.close()
+    ctx = ab().Context(w, h, max_batch=4, max_pts=20000)
+    cn, _, _ = ctx.detect_and_compute(torch.from_numpy(noise).cuda())              # a full chunk with many candidates everywhere
+    ctx.sync()
+    assert int(cn.min()) > int(want[0].max())
+    ctx.detect_and_compute(torch.from_numpy(noise[:1]).cuda(), False)               # detect only, one frame
+    got = ctx.detect_and_compute(torch.from_numpy(shapes).cuda())                   # a partial chunk
+    ctx.sync()
+    assert torch.equal(got[0], want[0])
+    for f in range(3):
+        n = int(want[0][f])
+        assert torch.equal(got[1][f, :n], want[1][f, :n]) and torch.equal(got[2][f, :n], want[2][f, :n])
+    ctx.close()
+
+
 def test_two_lanes_equal_one_lane():
     """akz_options.lanes = 2 (chunks alternate between two streams with their own pyramids, AKZ_NSET staging buffers and
     result sets in the host pipeline) returns exactly what the single-lane context returns: device API, host API with
