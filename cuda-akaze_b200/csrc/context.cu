@@ -158,6 +158,8 @@ struct akz_ctx {
     std::vector<GraphEntry> graphs;
     bool graph_ok;
     unsigned long long* map;
+    unsigned char* hot[AKZ_MAX_LEVELS];   // per level: one byte per four pixels written by k_deriv4 ("a determinant of the group > threshold")
+    bool hot_valid[AKZ_MAX_LEVELS];       // ... of the chunk in flight (set by the level's derivative kernel, used by detect_chunk right after)
     unsigned *rowmask, *occ;      // survivor masks; occupancy bitmap of the key map (one bit per pixel with a candidate)
     int *rowcount, *prefix, *order, *hist, *counts_own;      // counts_own / kpts_own / desc_own: AKZ_NSET result sets (host API pipeline)
     unsigned* hmax;
@@ -316,6 +318,7 @@ int akz_create(const akz_options* o, akz_ctx** out)
             if ((rc = dalloc(c, &L.det, n)) != AKZ_OK) break;
             if ((rc = dalloc(c, &L.lx, n)) != AKZ_OK) break;
             if ((rc = dalloc(c, &L.ly, n)) != AKZ_OK) break;
+            if (o->fused == 1 && (L.pitch % 4) == 0 && (rc = dalloc(c, &c->hot[l], (size_t)(L.pitch / 4) * L.h * B)) != AKZ_OK) break;
         }
         if (rc != AKZ_OK) break;
         size_t n0 = (size_t)c->lev[0].plane * B;
@@ -514,15 +517,23 @@ static bool prep_split_enabled()
 static int prep_level_split(akz_ctx* c, int mode, const float* src, int sw, int sh, int sp, long long splane, float* ltdst, float* flowp,
                             float* lx, float* ly, float* det, int nmul, int step, int w, int h, int pitch, long long plane, int nf, int int_planes)
 {
+    // the context's own level?  then its `hot` plane is written along with the determinant (and is stale until it has been)
+    int li = -1;
+    for (int l = 0; l < c->nlev; l++) if (c->lev[l].det == det && c->lev[l].w == w && c->lev[l].h == h && c->lev[l].pitch == pitch) li = l;
+    if (li >= 0) c->hot_valid[li] = false;
     if (!prep_split_enabled() || step < 2 || step > 4 || w < 32 || h < 32 || (w % 4) != 0) return 0;
     cudaStream_t st = c->cur;
     const int rk = c->rk;
     cudaStream_t rst = c->prof_on ? nullptr : c->ring_stream[rk];         // per-class timing keeps the ring kernels on the main stream
     // the ring kernels of the previous level (side stream) read the blurred plane this level is about to overwrite
     if (c->ring_pending[rk]) { AKZ_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_ring_join[rk], 0)); c->ring_pending[rk] = false; }
+    unsigned char* hot = li >= 0 ? c->hot[li] : nullptr;
+    const float thr = c->opt.dthreshold;
+    const int ithr = 65;                                                  // akaze.cpp:560
     if (mode == 0) {
-        int r0 = akzk::deriv_stream(st, src, lx, ly, det, step, w, h, pitch, plane, nf, int_planes, rst, c->ev_ring_fork[rk], c->ev_ring_join[rk]);
+        int r0 = akzk::deriv_stream(st, src, lx, ly, det, step, w, h, pitch, plane, nf, int_planes, rst, c->ev_ring_fork[rk], c->ev_ring_join[rk], hot, thr, ithr);
         if (r0 > 0 && rst) c->ring_pending[rk] = true;
+        if (r0 > 0 && hot) c->hot_valid[li] = true;
         return r0;
     }
     if (!c->smooth || !flowp) return 0;
@@ -535,10 +546,11 @@ static int prep_level_split(akz_ctx* c, int mode, const float* src, int sw, int 
         r1 = akzk::level_blur_flow(st, mode, src, sw, sh, sp, splane, ltdst, flowp, c->smooth, c->opt.diffusivity, c->kc, 0.75f, nmul,
                                    w, h, pitch, plane, nf, int_planes);
     if (r1 <= 0) return r1;
-    int r2 = akzk::deriv_stream(st, c->smooth, lx, ly, det, step, w, h, pitch, plane, nf, int_planes, rst, c->ev_ring_fork[rk], c->ev_ring_join[rk]);
+    int r2 = akzk::deriv_stream(st, c->smooth, lx, ly, det, step, w, h, pitch, plane, nf, int_planes, rst, c->ev_ring_fork[rk], c->ev_ring_join[rk], hot, thr, ithr);
     if (r2 < 0) return r2;
     if (r2 == 0) return akz_set_error(AKZ_E_UNSUPPORTED, "split level pipeline: derivative half refused a level the blur half took");
     if (rst) c->ring_pending[rk] = true;
+    if (hot) c->hot_valid[li] = true;
     return r1 + r2;
 }
 
@@ -779,7 +791,8 @@ static int fast_scale_space_chunk(akz_ctx* c, const unsigned char* img, int nf, 
     return rc != AKZ_OK ? rc : rj;
 }
 
-static int detect_chunk(akz_ctx* c, int nf, int describe, int* d_counts, akz_keypoint* d_kpts, unsigned char* d_desc, int fast = 0)
+// fresh: the scale space of these frames was built by the same entry point just before (the `hot` planes describe these determinants)
+static int detect_chunk(akz_ctx* c, int nf, int describe, int* d_counts, akz_keypoint* d_kpts, unsigned char* d_desc, int fast = 0, bool fresh = true)
 {
     cudaStream_t st = c->stream;
     const akz_options& o = c->opt;
@@ -799,6 +812,7 @@ static int detect_chunk(akz_ctx* c, int nf, int describe, int* d_counts, akz_key
             const AkzLevel& L = c->lev[oc * S + j];
             a.lv[j].det = L.det; a.lv[j].plane = L.plane; a.lv[j].border = L.border; a.lv[j].threshold = o.dthreshold;
             a.lv[j].layer = oc * S + j; a.lv[j].ithreshold = 65;                      // akaze.cpp:560
+            a.lv[j].hot = (fresh && c->hot_valid[oc * S + j]) ? c->hot[oc * S + j] : nullptr;
         }
         cudaStream_t so = (par && oc > 0) ? c->ostream[oc] : st;
         if (so != st) AKZ_CUDA_TRY(cudaStreamWaitEvent(so, c->ev_lvl0[0], 0));
@@ -1267,7 +1281,7 @@ int akz_detect_keypoints(akz_ctx* c, int n, int* d_counts, akz_keypoint* d_kpts)
 {
     STAGE_PROLOGUE();
     if (n < 1 || n > c->opt.max_batch || c->nlev == 0) return akz_set_error(AKZ_E_INVALID, "bad frame count");
-    int rc = detect_chunk(c, n, 0, d_counts, d_kpts, nullptr);
+    int rc = detect_chunk(c, n, 0, d_counts, d_kpts, nullptr, 0, false);      // the planes may have been written by the caller
     if (rc != AKZ_OK) return rc;
     STAGE_EPILOGUE();
 }

@@ -31,6 +31,9 @@ constexpr int D4_SLOTB = 512 + 32;          // bytes per slot: 16 bytes of paddi
 struct Deriv4Args {
     const float* sm;
     float *lx, *ly, *det;
+    unsigned char* hot;                     // optional: one byte per four pixels, "some determinant of the group passes the detector
+                                            // threshold" -- k_extrema reads it instead of the determinant plane
+    float thr; int ithr;
     long long plane;
     int w, h, pitch;
     int nstrips, nbands, band_h, nunits;
@@ -52,6 +55,7 @@ struct Deriv4Regs {
 struct Deriv4Lane {
     const float* psm;                       // frame base + clamped column of this lane
     long long obase;                        // frame base + column of this lane (outputs)
+    long long hbase;                        // frame base + group of this lane in the `hot` plane
     unsigned ring;                          // shared-memory address of this lane's 16 bytes in slot 0 of its warp's ring
     int y0, y1, r0;                         // band rows [y0, y1), row of time 0
     bool store;                             // lane writes output columns
@@ -153,8 +157,14 @@ __device__ __forceinline__ void d4_row(Deriv4Regs<S>& R, const Deriv4Args& a, co
             o[c] = p2_det<INT>(xu[m - S], xu[m], xu[m + S], xc[m - S], xc[m + S], xl[m - S], xl[m], xl[m + S],
                                yu[m - S], yu[m], yu[m + S], yl[m - S], yl[m], yl[m + S], a.m);
         }
-        if (ln.store && r2 >= ln.y0 && r2 < ln.y1)
+        if (ln.store && r2 >= ln.y0 && r2 < ln.y1) {
             *reinterpret_cast<float4*>(a.det + ln.obase + (long long)r2 * a.pitch) = make_float4(o[0], o[1], o[2], o[3]);
+            if (a.hot) {
+                const bool h = INT ? (fi(o[0]) > a.ithr || fi(o[1]) > a.ithr || fi(o[2]) > a.ithr || fi(o[3]) > a.ithr)
+                                   : (o[0] > a.thr || o[1] > a.thr || o[2] > a.thr || o[3] > a.thr);
+                a.hot[ln.hbase + (long long)r2 * (a.pitch >> 2)] = h ? 1 : 0;
+            }
+        }
     }
 }
 
@@ -176,6 +186,7 @@ __global__ void __launch_bounds__(32 * D4_WARPS, (S <= 3 ? 4 : 3)) k_deriv4(cons
     const long long base = (long long)frame * a.plane;
     ln.psm = a.sm + base + gxl;
     ln.obase = base + gx0;
+    ln.hbase = (long long)frame * (a.pitch >> 2) * a.h + (gx0 >> 2);
     ln.y0 = band * a.band_h; ln.y1 = min(a.h, ln.y0 + a.band_h);
     ln.r0 = ln.y0 + rho - 2 * S;
     ln.store = lane >= D4<S>::HL && lane < 32 - D4<S>::HL && gx0 >= 0 && gx0 < a.w;
@@ -305,13 +316,14 @@ namespace akzk {
 // (derivative step outside 2..4, rows not 16-byte aligned, width not a multiple of 4, tiny planes): the caller then uses the
 // tile kernel or the per-stage kernels.
 int deriv_stream(cudaStream_t st, const float* smooth, float* lx, float* ly, float* det, int step, int w, int h, int pitch, long long plane,
-                 int n, int int_planes, cudaStream_t ring_st, cudaEvent_t ev_fork, cudaEvent_t ev_join)
+                 int n, int int_planes, cudaStream_t ring_st, cudaEvent_t ev_fork, cudaEvent_t ev_join, unsigned char* hot, float thr, int ithr)
 {
     if (step < 2 || step > 4 || w < 32 || h < 32 || (w % 4) != 0 || (pitch % 4) != 0 || (plane % 4) != 0) return 0;
     if ((((uintptr_t)smooth | (uintptr_t)lx | (uintptr_t)ly | (uintptr_t)det) % 16) != 0) return 0;
     if (smooth == det || smooth == lx || smooth == ly) return 0;      // not an in-place kernel
     Deriv4Args a = {};
     a.sm = smooth; a.lx = lx; a.ly = ly; a.det = det; a.plane = plane; a.w = w; a.h = h; a.pitch = pitch;
+    a.hot = hot; a.thr = thr; a.ithr = ithr;
     hessian_factors(&a.m.fac1, &a.m.fac2);
     a.m.ifac1 = (int)(a.m.fac1 * 65536 + 0.5f); a.m.ifac2 = (int)(a.m.fac2 * 65536 + 0.5f);          // akazed.cu:4184-4185
     if (int_planes) {

@@ -12,6 +12,7 @@ struct AkzLevelTable {
 
 struct AkzExtremaLevel {
     const float* det;
+    const unsigned char* hot;           // optional (k_deriv4): one byte per four pixels, set when a determinant of the group passes the threshold
     long long plane;
     float border, threshold;
     int layer, ithreshold;              // ithreshold: integer pipeline (akaze.cpp:560: 65)
@@ -62,7 +63,8 @@ int blur_stream(cudaStream_t st, int mode, const float* src, int sw, int sh, int
                 float* ltdst, float* flowp, float* smooth, int type, const float* kc, float kscale, int nmul,
                 int w, int h, int pitch, long long plane, int n, int int_planes = 0);
 int deriv_stream(cudaStream_t st, const float* smooth, float* lx, float* ly, float* det, int step, int w, int h, int pitch, long long plane,
-                 int n, int int_planes = 0, cudaStream_t ring_st = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr);
+                 int n, int int_planes = 0, cudaStream_t ring_st = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr,
+                 unsigned char* hot = nullptr, float thr = 0.f, int ithr = 0);     // hot: one byte per 4 pixels, "a determinant of the group > threshold"
 // fed.cu: all n FED steps of a level (frozen conductance) in ceil(n / 4) launches of the streaming warp kernel (k_fed4), or of the
 // tile kernel (k_fed3) when the rows are not 16-byte aligned
 int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst, float* tmp, const float* tau, int nsteps,
