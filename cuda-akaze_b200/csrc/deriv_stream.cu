@@ -284,14 +284,25 @@ template <int S, bool INT>
 void deriv4_launch(cudaStream_t st, Deriv4Args& a, int n, cudaStream_t ring_st, cudaEvent_t ev_fork, cudaEvent_t ev_join)
 {
     a.nstrips = (a.w + D4<S>::OC - 1) / D4<S>::OC;
-    // bands of at most ~270 rows (a multiple of 12, so that every band starts on residue 0 of every S): two row times of
-    // warm-up per residue class and band.  With few frames or small levels the bands are shortened (down to 24 rows) until there
-    // are ~2000 (strip, band, residue) units: a handful of warps marching down long bands left the GPU idle (one 1080p frame:
-    // 120-240 units, 22-30 us per launch on the critical path of the single-frame graph).
+    // Bands are multiples of 12 rows (every band starts on residue 0 of every S) and cost two row times of warm-up before and
+    // after per residue class.  Their number is chosen by a small model: (waves of CTAs the GPU needs) x (row times of a unit).
+    // Many frames: ~270-row bands (octave 0 of 32 frames: 4 bands, 3 waves).  Few frames or small levels: shorter bands until the
+    // units fill one wave -- but not 1.1 waves (960 x 540, S = 3, 32 frames: 3 bands = 648 CTAs for 592 slots took 58 us, 2 bands
+    // 48 us; one 1080p frame with 270-row bands: 120-240 units, 22-30 us per launch on the critical path of the graph).
+    static const int nsm = [] { int d = 0, v = 148; cudaGetDevice(&d); if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || v <= 0) v = 148; return v; }();
     const long long per_band = (long long)n * S * a.nstrips;
-    const int nb_fill = (int)std::min<long long>((a.h + 23) / 24, (2048 + per_band - 1) / per_band);
-    const int nb = std::max(std::max(1, (a.h + 269) / 270), nb_fill);
-    a.band_h = std::max(24, ((a.h + nb - 1) / nb + 11) / 12 * 12);
+    const long long slots = (long long)nsm * (S <= 3 ? 4 : 3);          // resident CTAs (launch bounds of k_deriv4)
+    const int nb_lo = std::max(1, (a.h + 269) / 270), nb_hi = std::max(nb_lo, (a.h + 23) / 24);
+    long long best_cost = -1;
+    int best_bh = a.h;
+    for (int nb = nb_lo; nb <= nb_hi; nb++) {
+        const int bh = std::max(24, ((a.h + nb - 1) / nb + 11) / 12 * 12);
+        const int nbands = (a.h + bh - 1) / bh;
+        const long long ctas = (per_band * nbands + D4_WARPS - 1) / D4_WARPS;
+        const long long cost = ((ctas + slots - 1) / slots) * (bh / S + 4);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_bh = bh; }
+    }
+    a.band_h = best_bh;
     a.nbands = (a.h + a.band_h - 1) / a.band_h;
     a.nunits = n * a.nbands * S * a.nstrips;
     k_deriv4<S, INT><<<(a.nunits + D4_WARPS - 1) / D4_WARPS, 32 * D4_WARPS, 0, st>>>(a);
