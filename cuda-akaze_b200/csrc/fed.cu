@@ -639,14 +639,28 @@ int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst,
     // units) is faster on the tile kernel, as are rows that are not 16-byte aligned.
     const int nstrips = (w + F4_COLS - 1) / F4_COLS;
     int band_h = g_fed_band;
+    int nbands;
     if (band_h <= 0) {
-        const long long want = 1200;
-        const long long nb = std::max<long long>(1, (want + (long long)n * nstrips - 1) / ((long long)n * nstrips));
-        band_h = (int)std::min<long long>(96, std::max<long long>(32, (h + nb - 1) / nb));
+        // (waves of CTAs) x (row times of a unit), bands of 32 rows or more: 1920x1080 x 32 frames -> 9 bands of 120 rows = 1152
+        // CTAs = two waves (0.152 ms per 3-step cycle; 11 bands of 99 rows = 2.4 waves: 0.160 ms); 480x270 -> bands of 30-32 rows
+        static const int nsm = [] { int d = 0, v = 148; cudaGetDevice(&d); if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || v <= 0) v = 148; return v; }();
+        const int N = std::min(nsteps, F4_MAXN);
+        const long long slots = (long long)nsm * (N <= 3 ? 4 : 3);
+        long long best = -1;
+        band_h = h;
+        for (int nb = 1; nb <= std::max(1, h / 32); nb++) {
+            const int bh = (h + nb - 1) / nb;
+            const int nbd = (h + bh - 1) / bh;
+            const long long ctas = ((long long)n * nstrips * nbd + F4_WARPS - 1) / F4_WARPS;
+            const long long cost = ((ctas + slots - 1) / slots) * (bh + 2 * N);
+            if (best < 0 || cost < best) { best = cost; band_h = bh; }
+        }
+        nbands = (h + band_h - 1) / band_h;
+    } else {
+        nbands = std::max(1, (h + band_h / 2) / band_h);
+        band_h = (h + nbands - 1) / nbands;
+        nbands = (h + band_h - 1) / band_h;
     }
-    int nbands = std::max(1, (h + band_h / 2) / band_h);
-    band_h = (h + nbands - 1) / nbands;
-    nbands = (h + band_h - 1) / band_h;
     const long long units = (long long)n * nstrips * nbands;
     const bool stream = vec_ok && g_fed_stream && w >= 8 && h >= 8 && units >= g_fed_min_units && units < (1ll << 30);
     const int maxk = stream ? F4_MAXN : FE_MAXK;
