@@ -539,6 +539,18 @@ static int prep_level_split(akz_ctx* c, int mode, const float* src, int sw, int 
     if (!c->smooth || !flowp) return 0;
     // both halves must take the level: probe the derivative half's conditions first (it has the stricter ones)
     if ((pitch % 4) != 0 || (plane % 4) != 0 || (((uintptr_t)c->smooth | (uintptr_t)lx | (uintptr_t)ly | (uintptr_t)det) % 16) != 0) return 0;
+    // same-resolution levels: both halves in one streaming kernel (no round trip of the blurred plane) when there are enough CTAs
+    static const int level4 = [] { const char* e = getenv("AKZ_LEVEL4"); return e ? atoi(e) : 0; }();      // A/B knob: 0 off (default until it beats the pair), 1 on, 2 forced (tests)
+    if (mode == 1 && level4 && src != c->smooth) {
+        const int r4 = akzk::level_stream(st, src, flowp, c->smooth, lx, ly, det, c->opt.diffusivity, c->kc, 0.75f, nmul, step, w, h, pitch, plane, nf, int_planes,
+                                          rst, c->ev_ring_fork[rk], c->ev_ring_join[rk], hot, thr, ithr, level4 == 2);
+        if (r4 < 0) return r4;
+        if (r4 > 0) {
+            if (rst) c->ring_pending[rk] = true;
+            if (hot) c->hot_valid[li] = true;
+            return r4;
+        }
+    }
     static const bool blur_stream_on = [] { const char* e = getenv("AKZ_BLUR_STREAM"); return !e || atoi(e) != 0; }();      // A/B knob
     int r1 = blur_stream_on ? akzk::blur_stream(st, mode, src, sw, sh, sp, splane, ltdst, flowp, c->smooth, c->opt.diffusivity, c->kc, 0.75f, nmul,
                                                 w, h, pitch, plane, nf, int_planes) : 0;

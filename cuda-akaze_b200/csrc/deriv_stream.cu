@@ -280,6 +280,22 @@ __global__ void __launch_bounds__(256) k_det_ring(const float* __restrict__ lx, 
 // The two border-ring kernels are a few microseconds of work that depend on the main kernel: with a side stream they are forked
 // off (event after the main kernel) and run under whatever the main stream does next -- the diffusion cycle of the level, which
 // touches none of these planes.  The caller joins ev_join before it overwrites the blurred plane or reads Lx / Ly / det.
+template <bool INT>
+void rings_launch(cudaStream_t st, const float* sm, float* lx, float* ly, float* det, int S, const LevelMathArgs& m, int w, int h, int pitch, long long plane,
+                  int n, cudaStream_t ring_st, cudaEvent_t ev_fork, cudaEvent_t ev_join)
+{
+    const int c1 = ring_count(S, w, h), c2 = ring_count(2 * S, w, h);
+    cudaStream_t rs = st;
+    if (ring_st && ev_fork && ev_join) {
+        cudaEventRecord(ev_fork, st);
+        cudaStreamWaitEvent(ring_st, ev_fork, 0);
+        rs = ring_st;
+    }
+    k_deriv_ring<INT><<<dim3((c1 + 255) / 256, n), 256, 0, rs>>>(sm, lx, ly, S, m, w, h, pitch, plane, c1);
+    k_det_ring<INT><<<dim3((c2 + 255) / 256, n), 256, 0, rs>>>(lx, ly, det, S, m, w, h, pitch, plane, c2);
+    if (rs != st) cudaEventRecord(ev_join, rs);
+}
+
 template <int S, bool INT>
 void deriv4_launch(cudaStream_t st, Deriv4Args& a, int n, cudaStream_t ring_st, cudaEvent_t ev_fork, cudaEvent_t ev_join)
 {
@@ -306,16 +322,7 @@ void deriv4_launch(cudaStream_t st, Deriv4Args& a, int n, cudaStream_t ring_st, 
     a.nbands = (a.h + a.band_h - 1) / a.band_h;
     a.nunits = n * a.nbands * S * a.nstrips;
     k_deriv4<S, INT><<<(a.nunits + D4_WARPS - 1) / D4_WARPS, 32 * D4_WARPS, 0, st>>>(a);
-    const int c1 = ring_count(S, a.w, a.h), c2 = ring_count(2 * S, a.w, a.h);
-    cudaStream_t rs = st;
-    if (ring_st && ev_fork && ev_join) {
-        cudaEventRecord(ev_fork, st);
-        cudaStreamWaitEvent(ring_st, ev_fork, 0);
-        rs = ring_st;
-    }
-    k_deriv_ring<INT><<<dim3((c1 + 255) / 256, n), 256, 0, rs>>>(a.sm, a.lx, a.ly, S, a.m, a.w, a.h, a.pitch, a.plane, c1);
-    k_det_ring<INT><<<dim3((c2 + 255) / 256, n), 256, 0, rs>>>(a.lx, a.ly, a.det, S, a.m, a.w, a.h, a.pitch, a.plane, c2);
-    if (rs != st) cudaEventRecord(ev_join, rs);
+    rings_launch<INT>(st, a.sm, a.lx, a.ly, a.det, S, a.m, a.w, a.h, a.pitch, a.plane, n, ring_st, ev_fork, ev_join);
 }
 
 }  // namespace
@@ -343,6 +350,18 @@ int deriv_stream(cudaStream_t st, const float* smooth, float* lx, float* ly, flo
         if (step == 2) deriv4_launch<2, false>(st, a, n, ring_st, ev_fork, ev_join); else if (step == 3) deriv4_launch<3, false>(st, a, n, ring_st, ev_fork, ev_join); else deriv4_launch<4, false>(st, a, n, ring_st, ev_fork, ev_join);
     }
     return 3;
+}
+
+// the border-ring kernels alone (k_level4 in level_stream.cu computes the interior itself); returns the number of launches
+int deriv_rings(cudaStream_t st, const float* smooth, float* lx, float* ly, float* det, int step, int w, int h, int pitch, long long plane,
+                int n, int int_planes, cudaStream_t ring_st, cudaEvent_t ev_fork, cudaEvent_t ev_join)
+{
+    LevelMathArgs m = {};
+    hessian_factors(&m.fac1, &m.fac2);
+    m.ifac1 = (int)(m.fac1 * 65536 + 0.5f); m.ifac2 = (int)(m.fac2 * 65536 + 0.5f);
+    if (int_planes) rings_launch<true>(st, smooth, lx, ly, det, step, m, w, h, pitch, plane, n, ring_st, ev_fork, ev_join);
+    else rings_launch<false>(st, smooth, lx, ly, det, step, m, w, h, pitch, plane, n, ring_st, ev_fork, ev_join);
+    return 2;
 }
 
 }  // namespace akzk

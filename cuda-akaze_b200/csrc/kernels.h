@@ -65,6 +65,13 @@ int blur_stream(cudaStream_t st, int mode, const float* src, int sw, int sh, int
 int deriv_stream(cudaStream_t st, const float* smooth, float* lx, float* ly, float* det, int step, int w, int h, int pitch, long long plane,
                  int n, int int_planes = 0, cudaStream_t ring_st = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr,
                  unsigned char* hot = nullptr, float thr = 0.f, int ithr = 0);     // hot: one byte per 4 pixels, "a determinant of the group > threshold"
+int deriv_rings(cudaStream_t st, const float* smooth, float* lx, float* ly, float* det, int step, int w, int h, int pitch, long long plane,
+                int n, int int_planes, cudaStream_t ring_st, cudaEvent_t ev_fork, cudaEvent_t ev_join);
+// level_stream.cu: both halves of a same-resolution level in one streaming kernel (k_level4) + the border rings; the blurred plane
+// is written only near the image border.  0 when not covered (few CTAs unless force, derivative step outside 2..4, alignment)
+int level_stream(cudaStream_t st, const float* src, float* flowp, float* smooth, float* lx, float* ly, float* det, int type,
+                 const float* kc, float kscale, int nmul, int step, int w, int h, int pitch, long long plane, int n, int int_planes,
+                 cudaStream_t ring_st, cudaEvent_t ev_fork, cudaEvent_t ev_join, unsigned char* hot, float thr, int ithr, int force);
 // fed.cu: all n FED steps of a level (frozen conductance) in ceil(n / 4) launches of the streaming warp kernel (k_fed4), or of the
 // tile kernel (k_fed3) when the rows are not 16-byte aligned
 int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst, float* tmp, const float* tau, int nsteps,

@@ -1217,3 +1217,55 @@ print("tma-ok")
     env = dict(os.environ, AKZ_FED_TMA="1", AKZ_FED_MIN_UNITS="0")
     out = subprocess.run([sys.executable, "-c", code], cwd=B.ROOT, env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "tma-ok" in out.stdout, out.stderr[-1500:]
+
+
+_LEVEL4_CHILD = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, "cuda-akaze_b200"); sys.path.insert(0, "tests")
+import akaze_b200 as ab, bindings as B
+total = 0
+for (w, h, n, seed) in ((1920, 1088, 2, 3), (640, 480, 3, 5), (336, 250, 2, 7), (1000, 97, 4, 9)):
+    imgs8 = np.stack([B.synth_noise_u8(w, h, seed=seed + i) if i % 2 else B.synth_shapes_u8(w, h, seed=seed + i) for i in range(n)])
+    imgs = torch.from_numpy(np.stack([B.u8_to_unit(x) for x in imgs8])).cuda()
+    imgs8 = torch.from_numpy(imgs8).cuda()
+    for fast in (False, True):
+        res = {}
+        for fused in (1, 0):
+            c = ab.Context(w, h, fused=fused, max_batch=n, max_pts=30000)
+            l0 = c.launches
+            if fast:
+                cnt, kp, de = c.fast_detect_and_compute(imgs8)
+            else:
+                cnt, kp, de = c.detect_and_compute(imgs)
+            c.sync()
+            if fused: total += c.launches - l0
+            get = c.plane_int if fast else c.plane
+            planes = [[np.ascontiguousarray(get(l, which, f)).view(np.uint32).copy() for which in range(4)] for f in range(n) for l in range(c.num_levels)]
+            res[fused] = (planes, cnt.cpu().numpy().copy(), kp.cpu().numpy().copy(), de.cpu().numpy().copy())
+            c.close()
+        for i, (a, b) in enumerate(zip(res[1][0], res[0][0])):
+            for which in range(4):
+                assert np.array_equal(a[which], b[which]), (w, h, fast, "frame/level", i, "plane", which, int((a[which] != b[which]).sum()))
+        assert np.array_equal(res[1][1], res[0][1]), (w, h, fast, res[1][1], res[0][1])
+        for f in range(n):
+            m = int(res[1][1][f])
+            assert m > 20, (w, h, fast, f, m)
+            assert np.array_equal(res[1][2][f, :m], res[0][2][f, :m]) and np.array_equal(res[1][3][f, :m], res[0][3][f, :m]), (w, h, fast, f)
+print("level4-ok", total)
+'''
+
+
+def test_level4_fused_level_kernel_is_exact():
+    """k_level4 (level_stream.cu: blur + conductance + Lx / Ly / det of a level in one streaming kernel) against the per-stage
+    kernels (fused = 0): every plane of every level bit for bit, the same keypoints and descriptors, float and integer pipeline,
+    sizes with partial bands and partial strips.  AKZ_LEVEL4=2 forces the kernel at batch sizes where the size heuristic would not
+    pick it (the knob is read once per process: child processes); with AKZ_LEVEL4=0 the same run needs more launches."""
+    import subprocess
+    import sys
+    launches = {}
+    for knob in ("2", "0"):
+        env = dict(os.environ, AKZ_LEVEL4=knob)
+        out = subprocess.run([sys.executable, "-c", _LEVEL4_CHILD], cwd=B.ROOT, env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "level4-ok" in out.stdout, (knob, out.stdout[-500:], out.stderr[-1500:])
+        launches[knob] = int(out.stdout.split("level4-ok")[1].split()[0])
+    assert launches["2"] < launches["0"], launches
