@@ -240,12 +240,25 @@ int blur_stream(cudaStream_t st, int mode, const float* src, int sw, int sh, int
     a.m.k0 = k[0]; a.m.k1 = k[1]; a.m.k2 = k[2];
     a.m.ik0 = (int)(k[0] * 65536 + 0.5f); a.m.ik1 = (int)(k[1] * 65536 + 0.5f); a.m.ik2 = (int)(k[2] * 65536 + 0.5f);      // akazed.cu:3896
     a.nstrips = (w + B4_COLS - 1) / B4_COLS;
-    // bands as in k_fed4: ~96 rows once there are ~1200 units, never below 32 rows (six rows of warm-up per band)
-    const long long nb = std::max<long long>(1, (1200 + (long long)n * a.nstrips - 1) / ((long long)n * a.nstrips));
-    int band_h = (int)std::min<long long>(96, std::max<long long>(32, (h + nb - 1) / nb));
-    int nbands = std::max(1, (h + band_h / 2) / band_h);
-    band_h = (h + nbands - 1) / nbands;
-    a.band_h = band_h; a.nbands = (h + band_h - 1) / band_h;
+    // Bands cost six rows of warm-up each.  Their number by the model of k_deriv4 / k_fed4: (waves of CTAs the GPU needs) x (row
+    // times of a unit); AKZ_BLUR_BAND=<rows> overrides (tuning knob)
+    {
+        static const int nsm = [] { int d = 0, v = 148; cudaGetDevice(&d); if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || v <= 0) v = 148; return v; }();
+        static const int forced = [] { const char* e = getenv("AKZ_BLUR_BAND"); return e ? atoi(e) : 0; }();
+        const long long per_band = (long long)n * a.nstrips, slots = (long long)nsm * 4;       // resident CTAs (launch bounds of k_blur4)
+        const int nb_lo = std::max(1, (h + 359) / 360), nb_hi = std::max(nb_lo, (h + 31) / 32);
+        long long best_cost = -1;
+        int best_bh = h;
+        for (int nb = nb_lo; nb <= nb_hi; nb++) {
+            const int bh = std::max(32, (h + nb - 1) / nb);
+            const int nbands = (h + bh - 1) / bh;
+            const long long ctas = (per_band * nbands + B4_WARPS - 1) / B4_WARPS;
+            const long long cost = ((ctas + slots - 1) / slots) * (bh + 6);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_bh = bh; }
+        }
+        if (forced >= 16) best_bh = std::min(h, forced);
+        a.band_h = best_bh; a.nbands = (h + best_bh - 1) / best_bh;
+    }
     const long long units = (long long)n * a.nstrips * a.nbands;
     if (units >= (1ll << 30)) return 0;
     a.nunits = (int)units;

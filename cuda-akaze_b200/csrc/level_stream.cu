@@ -139,19 +139,19 @@ __device__ __forceinline__ void l4_row(Level4Regs<S>& R, const Level4Args& a, co
         // the border-ring kernels read the blurred plane within 2 S <= 8 pixels of the image border
         if (ln.store && arow >= ln.y0 && arow < ln.y1 && (ln.edge || arow < 8 || arow >= a.h - 8))
             *reinterpret_cast<float4*>(a.smooth + ln.obase + (long long)arow * a.pitch) = make_float4(sm[S], sm[S + 1], sm[S + 2], sm[S + 3]);
-        __syncwarp();
         if (S == 4) {
+            __syncwarp();
             const float4 l = l4_lds4(sa - 16), r = l4_lds4(sa + 16);
             sm[0] = l.x; sm[1] = l.y; sm[2] = l.z; sm[3] = l.w;
             sm[8 % RW] = r.x; sm[9 % RW] = r.y; sm[10 % RW] = r.z; sm[11 % RW] = r.w;
-        } else if (S == 3) {
-            const float l0 = l4_lds1(sa - 12);
-            const float2 l1 = l4_lds2(sa - 8), r0 = l4_lds2(sa + 16);
-            const float r1 = l4_lds1(sa + 24);
-            sm[0] = l0; sm[1] = l1.x; sm[2] = l1.y; sm[7] = r0.x; sm[8 % RW] = r0.y; sm[9 % RW] = r1;
         } else {
-            const float2 l = l4_lds2(sa - 8), r = l4_lds2(sa + 16);
-            sm[0] = l.x; sm[1] = l.y; sm[6] = r.x; sm[7] = r.y;
+            // a 32- or 64-bit shared load at a 16-byte lane stride costs four wavefronts, a shuffle one
+#pragma unroll
+            for (int j = 0; j < S; j++) {
+                const float lo = __shfl_up_sync(FULL, sm[S + 4 - S + j], 1);      // columns x - S + j of the left neighbour lane
+                const float hi = __shfl_down_sync(FULL, sm[S + j], 1);            // columns x + 4 + j of the right neighbour lane
+                sm[j] = lo; sm[(S + 4 + j) % RW] = hi;
+            }
         }
     }
     // ---- 3. first derivatives of row arow - S, determinant of row arow - 2S (k_deriv4's row step)
@@ -183,6 +183,8 @@ __device__ __forceinline__ void l4_row(Level4Regs<S>& R, const Level4Args& a, co
             ly[(S + 4 + j) % RW] = __shfl_down_sync(FULL, vy[j], 1);
         }
     }
+    // (every stage runs in every iteration, also in the warm-up of a band: straight-line code lets the stages overlap; with
+    // branches around them the kernel was 25 % slower)
     const int r2 = arow - 2 * S;
     const bool out2 = ln.store && r2 >= ln.y0 && r2 < ln.y1;
     {
@@ -207,38 +209,40 @@ __device__ __forceinline__ void l4_row(Level4Regs<S>& R, const Level4Args& a, co
             }
         }
     }
-    // ---- 4. conductance of row r2: centre row from the register pipeline, rows r2 -+ 1 from ring BL
-    if (out2) {
+    // ---- 4. conductance of row r2: centre row from the register pipeline, rows r2 -+ 1 from ring BL (their left / right
+    // neighbours by shuffle: a 32-bit shared load at a 16-byte lane stride costs four wavefronts)
+    {
         const int qf = ((PH + 2) % 6) * S + ln.k;
-        const unsigned ua = ln.bl + l4_wrap<S>(qf - 1) * L4_BLB, da = ln.bl + l4_wrap<S>(qf + 1) * L4_BLB;
-        const float4 u4 = l4_lds4(ua), d4 = l4_lds4(da);
-        float u[6] = { l4_lds1(ua - 4), u4.x, u4.y, u4.z, u4.w, l4_lds1(ua + 16) };
-        float d[6] = { l4_lds1(da - 4), d4.x, d4.y, d4.z, d4.w, l4_lds1(da + 16) };
-        const float* ce = R.Sm[(PH + 1) % 3];
-        float cl = ce[S - 1], cr = ce[S + 4];
-        if (ln.lb) { u[0] = u[2]; d[0] = d[2]; cl = ce[S + 1]; }         // blurred(-1) := blurred(1)   (index reflection, akazed.cu:1076-1083)
-        if (ln.rb) { u[5] = u[3]; d[5] = d[3]; cr = ce[S + 2]; }         // blurred(w)  := blurred(w - 2)
-        if (r2 == 0) {                                                     // warp-uniform: row -1 := row 1
+        const float4 u4 = l4_lds4(ln.bl + l4_wrap<S>(qf - 1) * L4_BLB), d4 = l4_lds4(ln.bl + l4_wrap<S>(qf + 1) * L4_BLB);
+        float u[6] = { __shfl_up_sync(FULL, u4.w, 1), u4.x, u4.y, u4.z, u4.w, __shfl_down_sync(FULL, u4.x, 1) };
+        float d[6] = { __shfl_up_sync(FULL, d4.w, 1), d4.x, d4.y, d4.z, d4.w, __shfl_down_sync(FULL, d4.x, 1) };
+        if (out2) {
+            const float* ce = R.Sm[(PH + 1) % 3];
+            float cl = ce[S - 1], cr = ce[S + 4];
+            if (ln.lb) { u[0] = u[2]; d[0] = d[2]; cl = ce[S + 1]; }     // blurred(-1) := blurred(1)   (index reflection, akazed.cu:1076-1083)
+            if (ln.rb) { u[5] = u[3]; d[5] = d[3]; cr = ce[S + 2]; }     // blurred(w)  := blurred(w - 2)
+            if (r2 == 0) {                                                 // row -1 := row 1
 #pragma unroll
-            for (int c = 0; c < 6; c++) u[c] = d[c];
-        }
-        if (r2 == a.h - 1) {                                               // row h := row h - 2
+                for (int c = 0; c < 6; c++) u[c] = d[c];
+            }
+            if (r2 == a.h - 1) {                                           // row h := row h - 2
 #pragma unroll
-            for (int c = 0; c < 6; c++) d[c] = u[c];
+                for (int c = 0; c < 6; c++) d[c] = u[c];
+            }
+            float f[4];
+            f[0] = p2_flow<INT>(u[0], u[1], u[2], cl, ce[S + 1], d[0], d[1], d[2], type, ln.ikc);
+            f[1] = p2_flow<INT>(u[1], u[2], u[3], ce[S], ce[S + 2], d[1], d[2], d[3], type, ln.ikc);
+            f[2] = p2_flow<INT>(u[2], u[3], u[4], ce[S + 1], ce[S + 3], d[2], d[3], d[4], type, ln.ikc);
+            f[3] = p2_flow<INT>(u[3], u[4], u[5], ce[S + 2], cr, d[3], d[4], d[5], type, ln.ikc);
+            *reinterpret_cast<float4*>(a.flow + ln.obase + (long long)r2 * a.pitch) = make_float4(f[0], f[1], f[2], f[3]);
         }
-        float o[4];
-        o[0] = p2_flow<INT>(u[0], u[1], u[2], cl, ce[S + 1], d[0], d[1], d[2], type, ln.ikc);
-        o[1] = p2_flow<INT>(u[1], u[2], u[3], ce[S], ce[S + 2], d[1], d[2], d[3], type, ln.ikc);
-        o[2] = p2_flow<INT>(u[2], u[3], u[4], ce[S + 1], ce[S + 3], d[2], d[3], d[4], type, ln.ikc);
-        o[3] = p2_flow<INT>(u[3], u[4], u[5], ce[S + 2], cr, d[3], d[4], d[5], type, ln.ikc);
-        *reinterpret_cast<float4*>(a.flow + ln.obase + (long long)r2 * a.pitch) = make_float4(o[0], o[1], o[2], o[3]);
     }
     // ---- 5. rows written in this iteration become visible to the other warps; slots read in it may be rewritten
     __syncthreads();
 }
 
-template <int S, bool INT, int TYPE>
-__global__ void __launch_bounds__(32 * S, L4<S>::CTAS) k_level4(const __grid_constant__ Level4Args a)
+template <int S, bool INT, int TYPE, int CTAS>
+__global__ void __launch_bounds__(32 * S, CTAS) k_level4(const __grid_constant__ Level4Args a)
 {
     const int lane = threadIdx.x & 31;
     // strips fastest, then bands, then frames
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(32 * S, L4<S>::CTAS) k_level4(const __grid_con
     const int band = rem % a.nbands;
     const int frame = rem / a.nbands;
     Level4Lane ln;
-    ln.k = threadIdx.x >> 5;
+    ln.k = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);          // provably warp-uniform: the branches on row numbers stay uniform branches
     const int gx0 = strip * L4<S>::OC - 4 * L4<S>::HL + 4 * lane;
     const int gxl = min(max(gx0, 0), a.pitch - 4);
     const long long base = (long long)frame * a.plane;
@@ -283,12 +287,17 @@ __global__ void __launch_bounds__(32 * S, L4<S>::CTAS) k_level4(const __grid_con
     for (int q = 0; q < L4_LAND - 1; q++) l4_request(a, ln, ln.yb + q * S + ln.k, q);
     // the determinant / conductance of the band's first row of a residue leave in iteration L4_LAG
     const int T = (ln.y1 - ln.y0 + S - 1) / S + L4_LAG;
-    for (int i = 0; i < T; i += 6) {
+    for (int i = 0; i < T; i += 6) {                                      // T is the same for every warp of the CTA (block barrier inside)
         l4_row<S, INT, TYPE, 0>(R, a, ln, i);
+        if (i + 1 >= T) break;
         l4_row<S, INT, TYPE, 1>(R, a, ln, i + 1);
+        if (i + 2 >= T) break;
         l4_row<S, INT, TYPE, 2>(R, a, ln, i + 2);
+        if (i + 3 >= T) break;
         l4_row<S, INT, TYPE, 3>(R, a, ln, i + 3);
+        if (i + 4 >= T) break;
         l4_row<S, INT, TYPE, 4>(R, a, ln, i + 4);
+        if (i + 5 >= T) break;
         l4_row<S, INT, TYPE, 5>(R, a, ln, i + 5);
     }
 }
@@ -301,7 +310,10 @@ int level4_launch(cudaStream_t st, Level4Args& a, int n, int force)
     // the model of k_deriv4: (waves of CTAs the GPU needs) x (iterations of a CTA)
     static const int nsm = [] { int d = 0, v = 148; cudaGetDevice(&d); if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || v <= 0) v = 148; return v; }();
     const long long per_band = (long long)n * a.nstrips;
-    const long long slots = (long long)nsm * L4<S>::CTAS;
+    // S = 3: five CTAs per SM mean 128 registers and a few spilled values, four mean 162 registers and were 9 % faster (AKZ_L4_CTAS=5 selects five)
+    static const int ctas3 = [] { const char* e = getenv("AKZ_L4_CTAS"); return e && atoi(e) == 5 ? 5 : 4; }();
+    const int ctas = S == 3 ? ctas3 : L4<S>::CTAS;
+    const long long slots = (long long)nsm * ctas;
     const int nb_lo = std::max(1, (a.h + 287) / 288), nb_hi = std::max(nb_lo, (a.h + 47) / 48);
     long long best_cost = -1;
     int best_bh = a.h;
@@ -320,8 +332,13 @@ int level4_launch(cudaStream_t st, Level4Args& a, int n, int force)
     // (or the tile kernels behind them) is faster there
     if (!force && units < slots) return 0;
     a.nunits = (int)units;
-    if (a.type == 1) k_level4<S, INT, 1><<<a.nunits, 32 * S, 0, st>>>(a);
-    else k_level4<S, INT, -1><<<a.nunits, 32 * S, 0, st>>>(a);
+    if (S == 3 && ctas == 4) {
+        if (a.type == 1) k_level4<S, INT, 1, (S == 3 ? 4 : L4<S>::CTAS)><<<a.nunits, 32 * S, 0, st>>>(a);
+        else k_level4<S, INT, -1, (S == 3 ? 4 : L4<S>::CTAS)><<<a.nunits, 32 * S, 0, st>>>(a);
+    } else {
+        if (a.type == 1) k_level4<S, INT, 1, L4<S>::CTAS><<<a.nunits, 32 * S, 0, st>>>(a);
+        else k_level4<S, INT, -1, L4<S>::CTAS><<<a.nunits, 32 * S, 0, st>>>(a);
+    }
     return 1;
 }
 
