@@ -305,6 +305,7 @@ def class_times(ctx, dev, res, F, chunk):
     for f0 in range(0, F, chunk):
         ctx.detect_and_compute(dev[f0:f0 + chunk], True, out=tuple(r[f0:f0 + chunk] for r in res))
     prof = ctx.profile_read()
+    class_times.octaves = ctx.profile_octaves(8)          # the same pass split by octave (scale-space classes)
     ctx.profile(False)
     return prof
 
@@ -445,6 +446,24 @@ def run_ours(args):
             "classes_ms_per_step": {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
             "whole_step": {"algorithmic_gbs": round(step_alg / (ms / args.steps * 1e-3) / 1e9, 1),
                            "frac_of_hbm": round(step_alg / (ms / args.steps * 1e-3) / 1e9 / peak, 4)}}
+    # the scale-space classes by octave: octave 0 holds 75 % of the pixels and is where the streaming kernels run full waves;
+    # octaves 1-3 are small launches that the second lane and the octave streams overlap in the real step
+    px = level_pixels(W, H)
+    by_oct = {}
+    for cls in ("prep", "fed"):
+        row = getattr(class_times, "octaves", {}).get(cls)
+        if not row:
+            continue
+        out_rows = []
+        for o in range(len(px) // 4):
+            lv = px[4 * o:4 * o + 4]
+            # prep: 20 B/px per level (read Lt_prev; write g, Lx, Ly, det), level (0,0) has no g (16), octave transitions also write Lt (24)
+            b = (20 * sum(lv) - (4 * lv[0] if o == 0 else -4 * lv[0])) if cls == "prep" else 12 * (sum(lv) - (lv[0] if o == 0 else 0))
+            if row[o] > 0:
+                gbs = b * F / (row[o] * 1e-3) / 1e9
+                out_rows.append({"octave": o, "ms_per_step": round(row[o], 3), "algorithmic_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)})
+        by_oct[cls] = out_rows
+    roof["scale_space_by_octave"] = by_oct
     line = {
         "metric": "1080p detect+describe images/sec", "value": round(F * world * args.steps / (ms * 1e-3), 2), "unit": "images/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),

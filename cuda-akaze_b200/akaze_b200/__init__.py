@@ -37,7 +37,7 @@ EXPORTS = [
     "akz_get_kcontrast", "akz_lowpass", "akz_down_with_smooth", "akz_scharr_contrast", "akz_flow", "akz_nld_step",
     "akz_fed_cycle", "akz_hessian", "akz_match", "akz_match_merge", "akz_match_host", "akz_pack_points",
     "akz_unpack_desc", "akz_scatter_matches", "akz_orient", "akz_describe", "akz_detect_keypoints",
-    "akz_profile_enable", "akz_profile_read", "akz_profile_class_name", "akz_keypoints_to_opencv", "akz_matches_to_opencv",
+    "akz_profile_enable", "akz_profile_read", "akz_profile_octaves", "akz_profile_class_name", "akz_keypoints_to_opencv", "akz_matches_to_opencv",
     "akz_set_match_kernel", "akz_set_describe_kernel", "akz_plan_chunks", "akz_plan_match", "akz_fast_detect_and_compute", "akz_fast_detect_and_compute_host", "akz_fast_build_scale_space", "akz_fast_get_kcontrast", "akz_fast_lowpass",
     "akz_match_pairs", "akz_comm_unique_id", "akz_comm_init", "akz_comm_attach", "akz_comm_destroy", "akz_match_sharded",
     "akz_fast_down_with_smooth", "akz_fast_scharr_contrast", "akz_fast_flow", "akz_fast_nld_step", "akz_fast_hessian",
@@ -121,6 +121,7 @@ def lib():
     L.akz_matches_to_opencv.argtypes = [vp, i, vp]
     L.akz_profile_enable.argtypes = [vp, i]
     L.akz_profile_read.argtypes = [vp, i, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    L.akz_profile_octaves.argtypes = [vp, i, i, C.POINTER(C.c_double)]
     L.akz_profile_class_name.argtypes = [i]
     L.akz_profile_class_name.restype = C.c_char_p
     _lib = L
@@ -214,6 +215,17 @@ class Context:
         n = (C.c_longlong * NUM_KCLASS)()
         _check(lib().akz_profile_read(self.h, NUM_KCLASS, ms, n))
         return {lib().akz_profile_class_name(k).decode(): (ms[k], n[k]) for k in range(NUM_KCLASS) if n[k]}
+
+    def profile_octaves(self, noct=8):
+        """{class name: [ms of octave 0, 1, ...]} of the last profile_read."""
+        ms = (C.c_double * (NUM_KCLASS * noct))()
+        _check(lib().akz_profile_octaves(self.h, NUM_KCLASS, noct, ms))
+        out = {}
+        for k in range(NUM_KCLASS):
+            row = [ms[k * noct + o] for o in range(noct)]
+            if any(row):
+                out[lib().akz_profile_class_name(k).decode()] = row
+        return out
 
     @property
     def num_levels(self):

@@ -186,11 +186,13 @@ struct akz_ctx {
     AkzLevelTable tab;
     // per-kernel-class device timing (akz_profile_*): event pairs around every wrapper call while enabled
     bool prof_on;
-    struct ProfPair { cudaEvent_t a, b; int cls, launches; };
+    struct ProfPair { cudaEvent_t a, b; int cls, launches, oct; };
     std::vector<ProfPair> prof_pairs;
     std::vector<cudaEvent_t> prof_pool;
     double prof_ms[AKZ_NUM_KCLASS];
     long long prof_launches[AKZ_NUM_KCLASS];
+    double prof_oct_ms[AKZ_NUM_KCLASS][8], prof_oct_last[AKZ_NUM_KCLASS][8];      // the same times by octave (keypoint stages: octave 0)
+    int cur_oct = 0;                               // octave whose launches are being issued
 };
 
 static cudaEvent_t prof_event(akz_ctx* c)
@@ -285,6 +287,7 @@ int akz_create(const akz_options* o, akz_ctx** out)
     c->opt = *o;
     c->launches = 0; c->last_frames = 0; c->prof_on = false;
     memset(c->prof_ms, 0, sizeof(c->prof_ms)); memset(c->prof_launches, 0, sizeof(c->prof_launches));
+    memset(c->prof_oct_ms, 0, sizeof(c->prof_oct_ms)); memset(c->prof_oct_last, 0, sizeof(c->prof_oct_last));
     for (int i = 0; i < AKZ_NSET; i++) c->img_stage[i] = nullptr;
     c->lane1 = nullptr; c->ev_fork = c->ev_join = nullptr;
     c->img_stage_bytes = 0; c->match_parts = nullptr; c->match_parts_n = 0;
@@ -493,7 +496,7 @@ const float* akz_level_plane(const akz_ctx* c, int l, int which, int frame)
         if (r_ < 0) return r_;                                                                 \
         c->launches += r_;                                                                     \
         if (ea_) { cudaEvent_t eb_ = prof_event(c); cudaEventRecord(eb_, c->cur);           \
-                   c->prof_pairs.push_back({ ea_, eb_, (cls_), r_ }); }                        \
+                   c->prof_pairs.push_back({ ea_, eb_, (cls_), r_, c->cur_oct }); }                        \
     } while (0)
 
 static int check_frame_args(akz_ctx* c, const void* img, int dtype, int nframes, int w, int h, int pitch, long long stride)
@@ -606,6 +609,7 @@ static int prep_level(akz_ctx* c, int mode, const float* src, int sw, int sh, in
 static int enter_octave(akz_ctx* c, int oc)
 {
     const int k = c->opar ? oc : 0;
+    c->cur_oct = oc & 7;
     c->smooth = c->sc[k].smooth; c->flow = c->sc[k].flow; c->tmpA = c->sc[k].tmpA; c->tmpB = c->sc[k].tmpB;
     c->cur = c->opar ? c->ostream[oc] : c->stream;
     c->rk = c->opar ? oc : 0;
@@ -710,7 +714,7 @@ static int scale_space_chunk(akz_ctx* c, const void* img, int dtype, int nf, int
             if (cudaEventRecord(c->ev_oct[k], c->ostream[k]) != cudaSuccess || cudaStreamWaitEvent(c->stream, c->ev_oct[k], 0) != cudaSuccess)
                 rj = akz_set_error(AKZ_E_CUDA, "joining the octave streams failed");
         }
-    c->cur = c->stream; c->rk = 0;
+    c->cur = c->stream; c->rk = 0; c->cur_oct = 0;
     c->smooth = c->sc[0].smooth; c->flow = c->sc[0].flow; c->tmpA = c->sc[0].tmpA; c->tmpB = c->sc[0].tmpB;
     return rc != AKZ_OK ? rc : rj;
 }
@@ -1568,19 +1572,31 @@ int akz_profile_read(akz_ctx* c, int ncls, double* ms, long long* launches)
     for (auto& pp : c->prof_pairs) {
         float t = 0.f;
         AKZ_CUDA_TRY(cudaEventElapsedTime(&t, pp.a, pp.b));
-        c->prof_ms[pp.cls] += t; c->prof_launches[pp.cls] += pp.launches;
+        c->prof_ms[pp.cls] += t; c->prof_launches[pp.cls] += pp.launches; c->prof_oct_ms[pp.cls][pp.oct & 7] += t;
         c->prof_pool.push_back(pp.a); c->prof_pool.push_back(pp.b);
     }
     c->prof_pairs.clear();
     for (int i = 0; i < ncls && i < AKZ_NUM_KCLASS; i++) { ms[i] = c->prof_ms[i]; launches[i] = c->prof_launches[i]; }
     memset(c->prof_ms, 0, sizeof(c->prof_ms)); memset(c->prof_launches, 0, sizeof(c->prof_launches));
+    memcpy(c->prof_oct_last, c->prof_oct_ms, sizeof(c->prof_oct_ms)); memset(c->prof_oct_ms, 0, sizeof(c->prof_oct_ms));
     if (c->lane1) {
         // with two lanes the per-class times are summed over both streams (they overlap in wall-clock time)
         double ms1[AKZ_NUM_KCLASS]; long long l1[AKZ_NUM_KCLASS];
         int rc = akz_profile_read(c->lane1, AKZ_NUM_KCLASS, ms1, l1);
         if (rc != AKZ_OK) return rc;
         for (int i = 0; i < ncls && i < AKZ_NUM_KCLASS; i++) { ms[i] += ms1[i]; launches[i] += l1[i]; }
+        for (int i = 0; i < AKZ_NUM_KCLASS; i++)
+            for (int k = 0; k < 8; k++) c->prof_oct_last[i][k] += c->lane1->prof_oct_last[i][k];
     }
+    return AKZ_OK;
+}
+
+// the times of the last akz_profile_read split by octave: ms[cls * noct + octave] (scale-space classes; everything else is octave 0)
+int akz_profile_octaves(akz_ctx* c, int ncls, int noct, double* ms)
+{
+    if (!c || !ms || ncls < 0 || noct < 0) return akz_set_error(AKZ_E_INVALID, "bad argument");
+    for (int i = 0; i < ncls; i++)
+        for (int k = 0; k < noct; k++) ms[i * noct + k] = (i < AKZ_NUM_KCLASS && k < 8) ? c->prof_oct_last[i][k] : 0.0;
     return AKZ_OK;
 }
 

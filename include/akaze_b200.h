@@ -122,6 +122,8 @@ enum { AKZ_K_BASE = 0, AKZ_K_BLUR, AKZ_K_CONTRAST, AKZ_K_PREP, AKZ_K_HESSIAN, AK
        AKZ_K_NMS, AKZ_K_ORIENT, AKZ_K_DESCRIBE, AKZ_K_MATCH, AKZ_K_MISC, AKZ_NUM_KCLASS };
 AKZ_API int         akz_profile_enable(akz_ctx* c, int on);
 AKZ_API int         akz_profile_read(akz_ctx* c, int ncls, double* ms, long long* launches);
+/* the times of the last akz_profile_read by octave: ms[cls * noct + octave] (scale-space classes; the others report octave 0) */
+AKZ_API int         akz_profile_octaves(akz_ctx* c, int ncls, int noct, double* ms);
 AKZ_API const char* akz_profile_class_name(int cls);
 
 /* ---- the hot path: replaces Akazer::detectAndCompute (akaze.cpp:101-150) over a batch ------- */
