@@ -199,11 +199,12 @@ __global__ void __launch_bounds__(32 * D4_WARPS, (S <= 3 ? 4 : 3)) k_deriv4(cons
 #pragma unroll
         for (int c = 0; c < D4<S>::RW; c++) { R.Sm[i][c] = 0.f; R.Lx[i][c] = 0.f; R.Ly[i][c] = 0.f; }
     // rows of the band in this residue class, plus two row times before (derivative rows the first determinant needs) and two after
-    const int nrows = (ln.y1 - ln.y0 - rho + S - 1) / S;
-    const int T = nrows + 4;
+    // (the loop ends when the determinant row of row time j, r0 + (j - 2) S, has left the band: written with the values that are live
+    // anyway -- a trip count kept in a register was spilled by ptxas at 128 registers and reloaded every six rows: 17 % of the
+    // kernel's stall samples sat on that local load, ncu r02z)
 #pragma unroll
     for (int k = 0; k < D4_RING - 2; k++) d4_request(a, ln, ln.r0 + k * S, k);
-    for (int j = 0; j < T; j += 6) {
+    for (int j = 0; ln.r0 + (j - 2) * S < ln.y1; j += 6) {
         d4_row<S, INT, 0>(R, a, ln, j);
         d4_row<S, INT, 1>(R, a, ln, j + 1);
         d4_row<S, INT, 2>(R, a, ln, j + 2);
