@@ -483,6 +483,26 @@ def run_ours(args):
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
     }
     ctx.close()
+    # what the same kernels cost on a FULL machine: the profile pass again with one lane and chunks of 128 frames (the real step
+    # gets the same effect from its second lane and the octave streams: its time does not change with the chunk size)
+    if rank == 0 and world == 1 and F >= 128 and not args.no_full:
+        try:
+            big = ab.Context(W, H, max_batch=128, max_pts=mp, device=local, lanes=1)
+            for _ in range(2):
+                big.detect_and_compute(dev[:128], True, out=tuple(r[:128] for r in res))
+            big.sync()
+            Fb = F - F % 128
+            pf = class_times(big, dev[:Fb], tuple(r[:Fb] for r in res), Fb, 128)
+            big.close()
+            sc = F / Fb
+            alg_p = algorithmic_bytes("prep", nkp_mean) * F
+            alg_f = algorithmic_bytes("fed", nkp_mean) * F
+            roof["full_machine"] = {"chunk": 128, "lanes": 1,
+                                    "classes_ms_per_step": {k: round(v[0] * sc, 3) for k, v in sorted(pf.items(), key=lambda kv: -kv[1][0])},
+                                    "prep_frac": round(alg_p / (pf["prep"][0] * sc * 1e-3) / 1e9 / peak, 4),
+                                    "fed_frac": round(alg_f / (pf["fed"][0] * sc * 1e-3) / 1e9 / peak, 4)}
+        except Exception as e:                                   # never lose the line over the extra pass
+            roof["full_machine"] = {"unavailable": str(e)[:200]}
     del dev
     line["config"]["binding"] = numa
     line["e2e"]["h2d_gbs_per_rank"] = round(host.numel() * host.element_size() / (ms_e2e / args.steps * 1e-3) / 1e9, 2)
@@ -697,6 +717,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-match", action="store_true", help="skip the brute-force matching metric (BASELINE metric 2)")
     ap.add_argument("--no-noise", action="store_true", help="skip the keypoint-heavy noise workload")
+    ap.add_argument("--no-full", action="store_true", help="skip the extra profile pass with chunks of 128 frames (roofline.full_machine)")
     ap.add_argument("--noise-frames", type=int, default=64, help="frames per GPU of the noise workload")
     ap.add_argument("--config", default="frames", choices=["frames", "stream"], help="frames = configs[2] (default), stream = configs[4]")
     ap.add_argument("--stream-frames", type=int, default=32, help="configs[4]: frames of the stream per GPU (plus the overlap frame)")
