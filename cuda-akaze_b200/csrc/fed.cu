@@ -568,6 +568,7 @@ int g_fed_rb = 4;                            // rows per thread block of k_fed3 
 int g_fed_band = 0;                          // rows per band of k_fed4 (AKZ_FED_BAND; 0 = chosen per launch)
 int g_fed_stream = 1;                        // AKZ_FED_STREAM=0 forces the tile kernel (A/B measurements)
 int g_fed_tma = 0;                           // AKZ_FED_TMA=1: landing ring filled by cp.async.bulk (TMA) + mbarrier instead of cp.async
+int g_fed_maxn = 4;                          // steps per launch of k_fed4 (AKZ_FED_MAXN, 2..4; tuning knob)
 int g_fed_min_units = 1024;                  // fewer (strip, band, frame) units than this: the tile kernel (AKZ_FED_MIN_UNITS)
 
 }  // namespace
@@ -581,6 +582,7 @@ static void set_attrs()
     if (const char* e = getenv("AKZ_FED_RB")) g_fed_rb = atoi(e) == 2 ? 2 : 4;
     if (const char* e = getenv("AKZ_FED_BAND")) g_fed_band = std::max(8, atoi(e));
     if (const char* e = getenv("AKZ_FED_MIN_UNITS")) g_fed_min_units = atoi(e);
+    if (const char* e = getenv("AKZ_FED_MAXN")) g_fed_maxn = std::min(F4_MAXN, std::max(2, atoi(e)));
     if (const char* e = getenv("AKZ_FED_TMA")) g_fed_tma = atoi(e);
     if (const char* e = getenv("AKZ_FED_STREAM")) g_fed_stream = atoi(e);
     cudaFuncSetAttribute(k_fed3<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3_SMEM);
@@ -638,32 +640,36 @@ int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst,
     // fine, a warp's own row pipeline is what has to stay full); 480x270 wants bands of 32 rows (1152 units); 240x135 (320
     // units) is faster on the tile kernel, as are rows that are not 16-byte aligned.
     const int nstrips = (w + F4_COLS - 1) / F4_COLS;
-    int band_h = g_fed_band;
-    int nbands;
-    if (band_h <= 0) {
-        // (waves of CTAs) x (row times of a unit), bands of 32 rows or more: 1920x1080 x 32 frames -> 9 bands of 120 rows = 1152
-        // CTAs = two waves (0.152 ms per 3-step cycle; 11 bands of 99 rows = 2.4 waves: 0.160 ms); 480x270 -> bands of 30-32 rows
-        static const int nsm = [] { int d = 0, v = 148; cudaGetDevice(&d); if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || v <= 0) v = 148; return v; }();
-        const int N = std::min(nsteps, F4_MAXN);
-        const long long slots = (long long)nsm * (N <= 3 ? 4 : 3);
-        long long best = -1;
-        band_h = h;
-        for (int nb = 1; nb <= std::max(1, h / 32); nb++) {
-            const int bh = (h + nb - 1) / nb;
-            const int nbd = (h + bh - 1) / bh;
-            const long long ctas = ((long long)n * nstrips * nbd + F4_WARPS - 1) / F4_WARPS;
-            const long long cost = ((ctas + slots - 1) / slots) * (bh + 2 * N);
-            if (best < 0 || cost < best) { best = cost; band_h = bh; }
+    // band layout of a launch of N steps: (waves of CTAs) x (row times of a unit), bands of 32 rows or more: 1920x1080 x 32 frames,
+    // N = 3 -> 9 bands of 120 rows = 1152 CTAs = two waves (0.152 ms per cycle; 11 bands of 99 rows = 2.4 waves: 0.160 ms); 480x270
+    // -> bands of 30-32 rows.  Per LAUNCH, not per cycle: a 6-step cycle is two launches of 3 steps (four CTAs per SM, six warm-up
+    // rows), not of 4 (960x540: 0.098 -> 0.089 ms)
+    auto layout = [&](int N, int& band_h, int& nbands) {
+        band_h = g_fed_band;
+        if (band_h <= 0) {
+            static const int nsm = [] { int d = 0, v = 148; cudaGetDevice(&d); if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || v <= 0) v = 148; return v; }();
+            const long long slots = (long long)nsm * (N <= 3 ? 4 : 3);
+            long long best = -1;
+            band_h = h;
+            for (int nb = 1; nb <= std::max(1, h / 32); nb++) {
+                const int bh = (h + nb - 1) / nb;
+                const int nbd = (h + bh - 1) / bh;
+                const long long ctas = ((long long)n * nstrips * nbd + F4_WARPS - 1) / F4_WARPS;
+                const long long cost = ((ctas + slots - 1) / slots) * (bh + 2 * N);
+                if (best < 0 || cost < best) { best = cost; band_h = bh; }
+            }
+            nbands = (h + band_h - 1) / band_h;
+        } else {
+            nbands = std::max(1, (h + band_h / 2) / band_h);
+            band_h = (h + nbands - 1) / nbands;
+            nbands = (h + band_h - 1) / band_h;
         }
-        nbands = (h + band_h - 1) / band_h;
-    } else {
-        nbands = std::max(1, (h + band_h / 2) / band_h);
-        band_h = (h + nbands - 1) / nbands;
-        nbands = (h + band_h - 1) / band_h;
-    }
+    };
+    int band_h, nbands;
+    layout(std::min(nsteps, g_fed_maxn), band_h, nbands);
     const long long units = (long long)n * nstrips * nbands;
     const bool stream = vec_ok && g_fed_stream && w >= 8 && h >= 8 && units >= g_fed_min_units && units < (1ll << 30);
-    const int maxk = stream ? F4_MAXN : FE_MAXK;
+    const int maxk = stream ? g_fed_maxn : FE_MAXK;
     const int m = (nsteps + maxk - 1) / maxk;
     int done = 0;
     const float* cur = src;
@@ -673,7 +679,9 @@ int fed_cycle(cudaStream_t st, const float* src, const float* flowp, float* dst,
         if (stream) {
             Fed4Args a4 = {};
             a4.src = cur; a4.flow = flowp; a4.dst = out; a4.plane = plane; a4.w = w; a4.h = h; a4.pitch = pitch;
-            a4.nstrips = nstrips; a4.nbands = nbands; a4.band_h = band_h; a4.nunits = (int)units;
+            int bh, nb;
+            layout(cnt, bh, nb);
+            a4.nstrips = nstrips; a4.nbands = nb; a4.band_h = bh; a4.nunits = n * nstrips * nb;
             for (int k = 0; k < cnt; k++) a4.stepfac[k] = stepfac(done + k);
             const bool gen = (w % 4) != 0;
             switch (cnt) {
