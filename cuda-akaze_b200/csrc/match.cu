@@ -19,6 +19,7 @@
 //          the minimum and it is < 96; that test is applied once, after the last merge.
 #include "common.cuh"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace {
 
@@ -359,6 +360,9 @@ __device__ __forceinline__ bool lex_less(int d, int i, int d2, int i2) { return 
 __global__ void k_match_merge(const akz_match_t* __restrict__ parts, int nparts, int nq, int mode, int finalize, akz_match_t* __restrict__ out)
 {
     int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    // launched with programmatic stream serialisation (match_merge below): the blocks may become resident while the kernel that
+    // writes `parts` is still running; its results are visible after this wait (a no-op under a plain launch)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (qi >= nq) return;
     akz_match_t r;
     const bool top2 = mode != AKZ_MATCH_COMPAT;                // KNN2 and UNIQUE2 share the partial form
@@ -499,7 +503,23 @@ int match_partial(cudaStream_t st, const unsigned char* q, int nq, const unsigne
 int match_merge(cudaStream_t st, const akz_match_t* parts, int nparts, int nq, int mode, int finalize, akz_match_t* out)
 {
     if (nq <= 0) return 0;
-    k_match_merge<<<(nq + 127) / 128, 128, 0, st>>>(parts, nparts, nq, mode, finalize, out);
+    // programmatic dependent launch: k_match_tc5 releases its dependents when it starts (griddepcontrol.launch_dependents), so the
+    // merge blocks are resident and waiting when the last tile is written -- the launch gap of a 3 us kernel behind a 38 us one
+    static const bool pdl = [] { const char* e = getenv("AKZ_MATCH_PDL"); return !e || atoi(e) != 0; }();      // A/B knob
+    if (!pdl) {
+        k_match_merge<<<(nq + 127) / 128, 128, 0, st>>>(parts, nparts, nq, mode, finalize, out);
+        return 1;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((nq + 127) / 128); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, k_match_merge, parts, nparts, nq, mode, finalize, out) != cudaSuccess) {
+        cudaGetLastError();
+        k_match_merge<<<(nq + 127) / 128, 128, 0, st>>>(parts, nparts, nq, mode, finalize, out);
+    }
     return 1;
 }
 

@@ -245,6 +245,9 @@ struct T5Args {
 template <int MODE, bool FILTER>
 __global__ void __launch_bounds__(T5_NT, 1) k_match_tc5(const __grid_constant__ T5Args a)
 {
+    // k_match_merge is launched behind this kernel as a programmatic dependent: let its blocks become resident now (they block in
+    // griddepcontrol.wait until this grid has finished and its writes are visible)
+    asm volatile("griddepcontrol.launch_dependents;");
     extern __shared__ unsigned char t5raw[];
     unsigned char* sm = t5raw + ((1024u - (smem_u32(t5raw) & 1023u)) & 1023u);
     unsigned char* As = sm + T5_OFF_A;
