@@ -1,6 +1,6 @@
 // k_level4<S>: a whole level's "everything but the diffusion" in ONE streaming kernel -- sigma = 1 blur of the predecessor level,
 // conductance, Lx, Ly and the Hessian determinant -- without the blurred plane's round trip through HBM that the pair
-// k_blur4 (blur_stream.cu) + k_deriv4 (deriv_stream.cu) pays: 20 bytes per pixel instead of 28.  Subsumes gConv2d<2>
+// k_blur4 (blur_stream.cu) + k_deriv4 (deriv_stream.cu) pays: 20 bytes per pixel instead of 28 (see STATUS below).  Subsumes gConv2d<2>
 // (akazed.cu:204), gFlowNaive (:1068), gDerivate (:1267) and gHessianDeterminant (:1299) and their integer twins.
 //
 // The two halves want the rows in different orders: the 5-tap blur and the 3 x 3 conductance talk to NEIGHBOURING rows, the
@@ -13,8 +13,13 @@
 //     3. Lx, Ly of row a - S and det of row a - 2S from the register pipeline, exactly as k_deriv4 (halos by shuffle)
 //     4. conductance of row a - 2S: centre row from the register pipeline, rows a - 2S -+ 1 from ring BL
 //     5. one block barrier
-// Both rings hold six blocks of rows: a slot is rewritten three iterations after its last reader.  Per pixel ~82 instructions,
-// 0.4 shared-memory wavefronts (the tile kernel k_prep2 had 1.6) and 20 bytes of HBM traffic.
+// Both rings hold six blocks of rows: a slot is rewritten three iterations after its last reader.  Every stage runs in every
+// iteration, warm-up included: guarded by (warp-uniform) branches the stages no longer overlap and the kernel is 25 % slower.
+//
+// STATUS: opt-in (AKZ_LEVEL4=1; 2 = at any size, for the parity test).  Bit-exact in both pipelines, 20.4 bytes per pixel of HBM
+// traffic instead of 27.2 -- and 5 % slower than the pair on a B200 (profiles/r02z_level4_ab.txt): the level is co-limited by
+// issue slots, the fused form needs as many instructions as the pair plus wider halos (128 loaded columns per 112 stored on both
+// halves), ~0.9 shared-memory wavefronts per pixel, and runs 12-15 warps per SM.  Kept as the measured answer to "why two kernels".
 //
 // Borders as in the two kernels it replaces: the blur runs on the mirrored input (bit-identical to reflect-101, the filter is
 // symmetric), the conductance substitutes the mirror row / column of the BLURRED plane, and the derivative pixels whose taps
