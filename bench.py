@@ -316,18 +316,19 @@ def noise_workload(ab, device, local, world, args):
     F, mp = args.noise_frames, 32768
     frames8 = make_frames(F, "noise", seed0=0)
     dev = (torch.from_numpy(frames8).to(device).float() * (1.0 / 255.0)).contiguous()
-    ctx = ab.Context(W, H, max_batch=args.chunk, max_pts=mp, device=local, lanes=args.lanes)
+    chunk = min(args.chunk, max(1, F // 2))               # two chunks at least: both lanes work
+    ctx = ab.Context(W, H, max_batch=chunk, max_pts=mp, device=local, lanes=args.lanes)
     res = ctx.alloc_results(F, True)
     step = lambda: ctx.detect_and_compute(dev, True, out=res)
     for _ in range(3):
         step()
     ctx.sync()
-    steps = max(2, args.steps // 2)
+    steps = max(4, args.steps)                             # 64 frames take 17 ms: a two-step region is at the mercy of one hiccup
     ms = timed(step, steps, ctx.torch_stream(), world, device)
     counts = res[0].cpu().numpy()
-    prof = class_times(ctx, dev, res, F, args.chunk)
+    prof = class_times(ctx, dev, res, F, chunk)
     tot = sum(v[0] for v in prof.values())
-    out = {"value": round(F * world * steps / (ms * 1e-3), 2), "unit": "images/s", "frames_per_gpu": F, "max_pts": mp,
+    out = {"value": round(F * world * steps / (ms * 1e-3), 2), "unit": "images/s", "frames_per_gpu": F, "chunk": chunk, "max_pts": mp,
            "keypoints_per_frame_mean": round(float(counts.mean()), 1), "clipped_frames": int((counts >= mp).sum()),
            "workload": "uniform u8 noise, Gaussian sigma 2, min-max stretched (tests/bindings.synth_noise_u8, seeds 0..7, rolled)",
            "classes_ms_per_step": {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
@@ -708,7 +709,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step (configs[2]: 256)")
-    ap.add_argument("--chunk", type=int, default=32, help="frames processed together (akz_options.max_batch)")
+    ap.add_argument("--chunk", type=int, default=64, help="frames processed together (akz_options.max_batch); the host path caps the chunks "
+                    "of float frames at 32 (link-bound: fill / drain), see akz_detect_and_compute_host")
     ap.add_argument("--lanes", type=int, default=2, help="chunks in flight (akz_options.lanes): 2 = two streams with their own pyramids")
     ap.add_argument("--max-pts", type=int, default=10000, help="per-frame keypoint capacity (main.cpp:157)")
     ap.add_argument("--content", default="shapes", choices=["shapes", "noise"])

@@ -1099,7 +1099,12 @@ static int detect_and_compute_host_impl(akz_ctx* c, const void* h_images, int dt
     // exposed): see chunk_plan
     std::vector<int> cstart, csize;
     static const bool ramp_down = getenv("AKZ_RAMP_DOWN") != nullptr;      // tuning knob (scripts/probes/e2e_rampdown.sh): off, see chunk_plan
-    chunk_plan(nframes, B, true, ramp_down, cstart, csize);
+    // Float frames are bound by the host link (55.6 GB/s): what counts there is how soon the first kernel starts and how
+    // little is left after the last byte, so their chunks stay at 32 frames however large max_batch is (256 frames, max_batch 64:
+    // 5430 -> 5930 images/s).  u8 frames are bound by the kernels and take the full chunk.  AKZ_HOST_CHUNK_F32 overrides.
+    static const int f32_cap = [] { const char* e = getenv("AKZ_HOST_CHUNK_F32"); const int v = e ? atoi(e) : 32; return v > 0 ? v : 32; }();
+    const int Bh = (dtype == AKZ_F32 && !fast) ? std::min(B, f32_cap) : B;
+    chunk_plan(nframes, Bh, true, ramp_down, cstart, csize);
     const int nchunks = (int)cstart.size();
     auto chunk_frames = [&](int i) { return csize[i]; };
     auto issue_h2d = [&](int i) -> int {
