@@ -19,7 +19,7 @@ for l in dis[start:end]:
     if m:
         cur = (m.group(1).split('/')[-1], int(m.group(2)))
         continue
-    if re.match(r'\s+/\*[0-9a-f]{4}\*/', l):
+    if re.match(r'\s+/\*[0-9a-f]{4,6}\*/', l):
         per_inst.append(cur)
 out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'], capture_output=True, text=True).stdout
 hdr, inst, first, active = None, [], None, False
